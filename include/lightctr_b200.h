@@ -1,0 +1,148 @@
+/* include/lightctr_b200.h -- the drop-in boundary (C ABI) of the B200-native LightCTR hot path.
+ *
+ * The reference (cnkuangshi/LightCTR) has no FFI: its "API" is C++ inheritance
+ * (FM_Algo_Abst::Train() fm_algo_abst.h:137, Train_FM_Algo/Train_FFM_Algo/Train_NFM_Algo ctors
+ * train_fm_algo.h:23, train_ffm_algo.h:25, train_nfm_algo.h:21, Fully_Conn_Layer
+ * train/layer/fullyconnLayer.h:80-206, updaters util/gradientUpdater.h:128-278,
+ * util/momentumUpdater.h:172-215).  The host shims in lightctr_b200/host/ keep those class
+ * surfaces; each of their methods lowers to the entry points below.  Plain pointers and sizes
+ * only, no C++/torch types, no exceptions across the boundary.  Every function returns 0 on
+ * success, non-zero on failure (lctr_last_error() gives the message; the host shims turn that
+ * into the reference's own style: print + exit(1), fm_algo_abst.h:79-82).
+ *
+ * Threading: one ctx per trainer, driven from one host thread (the reference's Train() is
+ * synchronous and single-caller).  All device work is issued on the ctx's
+ * stream; calls that return host-visible results synchronise that stream only.
+ */
+#ifndef LIGHTCTR_B200_H
+#define LIGHTCTR_B200_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LCTR_ABI_VERSION 1
+
+typedef struct lctr_ctx lctr_ctx;
+
+enum { LCTR_MODEL_FM = 1, LCTR_MODEL_FFM = 2, LCTR_MODEL_NFM = 3 };
+/* updater = the reference's `_Num` family member (gradientUpdater.h:128-154 Adagrad,
+ * :235-278 FTRL; momentumUpdater.h:172-215 Adam) */
+enum { LCTR_OPT_ADAGRAD = 0, LCTR_OPT_FTRL = 1, LCTR_OPT_ADAM = 2 };
+enum { LCTR_ACT_SIGMOID = 0, LCTR_ACT_TANH = 1 };
+enum { LCTR_MLP_FP32 = 0, LCTR_MLP_BF16 = 1 };
+
+#define LCTR_MAX_LAYERS 8
+
+/* Snapshot of the reference's process-global statics (main.cpp:64-73; SURVEY.md 8b "Hyper-parameter
+ * sources") plus the trainer ctor arguments.  Zero-initialise, then fill. */
+typedef struct lctr_cfg {
+    uint32_t abi_version;     /* LCTR_ABI_VERSION */
+    int32_t model;            /* LCTR_MODEL_* */
+    int32_t optimizer;        /* LCTR_OPT_* for W and V (and the MLP, which the reference fixes to Adagrad) */
+    int32_t device;           /* CUDA device ordinal */
+    uint64_t feature_cnt;     /* F = max fid + 1 (fm_algo_abst.h:95) */
+    uint32_t field_cnt;       /* Fc; 0 for FM/NFM (fm_algo_abst.h:57-59) */
+    uint32_t factor_cnt;      /* k */
+    float learning_rate;      /* GradientUpdater::__global_learning_rate */
+    float l2_reg;             /* L2Reg_ratio (train_fm_algo.cpp:13) */
+    uint64_t minibatch_size;  /* updater divisor; 0 => rows of the step (FM/FFM: train_fm_algo.cpp:38) */
+    float momentum;           /* MomentumUpdater::__global_momentum       (Adam beta1 -- used for BOTH moments) */
+    float momentum_adam2;     /* MomentumUpdater::__global_momentum_adam2 (Adam bias correction only) */
+    float ftrl_alpha, ftrl_beta, ftrl_lambda1, ftrl_lambda2; /* gradientUpdater.h:275; 0 => reference defaults */
+    /* MLP (NFM deep part): dims k -> hidden[0] -> ... -> hidden[n_hidden-1] -> 1 */
+    int32_t n_hidden;
+    uint32_t hidden[LCTR_MAX_LAYERS];
+    int32_t activation;       /* LCTR_ACT_* of the hidden layers */
+    int32_t mlp_precision;    /* LCTR_MLP_FP32 (parity) or LCTR_MLP_BF16 (tensor-core perf mode) */
+    /* capacity hints (0 => grow on demand) */
+    uint64_t max_rows, max_nnz;
+    /* multi-GPU: this process' rank / world (1 process per GPU); tables are owner-sharded by fid % world */
+    int32_t rank, world;
+    uint32_t reserved[8];
+} lctr_cfg;
+
+const char* lctr_last_error(void);
+int lctr_abi_version(void);
+
+/* ---- lifetime ------------------------------------------------------------------------------- */
+int lctr_create(const lctr_cfg* cfg, lctr_ctx** out);
+int lctr_destroy(lctr_ctx* ctx);
+int lctr_sync(lctr_ctx* ctx);
+
+/* ---- parameters (replaces direct pokes at FM_Algo_Abst::W / V, fm_algo_abst.h:141,145) ------- */
+/* V layout == reference: FM/NFM V[fid*k + f] (fm_algo_abst.h:146-148); FFM V[fid*Fc*k + field*k + f] (:149-151) */
+int lctr_upload_params(lctr_ctx* ctx, const float* W, const float* V);
+int lctr_download_params(lctr_ctx* ctx, float* W, float* V);
+/* optimizer state: s1 = adagrad accum | ftrl z | adam m ; s2 = ftrl n | adam v ; each F + |V| floats, W part first
+ * (same concatenation as update_g, train_fm_algo.h:52-57).  NULL pointers are skipped. */
+int lctr_download_opt_state(lctr_ctx* ctx, float* s1, float* s2);
+int lctr_upload_opt_state(lctr_ctx* ctx, const float* s1, const float* s2);
+
+/* ---- data: CSR form of FM_Algo_Abst::dataSet / label (fm_algo_abst.h:29-35,156,170) ---------- */
+/* Copies one CSR batch (or a whole dataset) host->device into `slot` (0..3), asynchronously on the
+ * ctx stream.  row_ptr has rows+1 entries; field may be NULL for FM/NFM; val may be NULL meaning all
+ * 1.0f (the shipped data).  Indexing is bit-exact w.r.t. the reference parser. */
+int lctr_upload_batch(lctr_ctx* ctx, int slot, int64_t rows, int64_t nnz, const int64_t* row_ptr,
+                      const uint32_t* fid, const uint16_t* field, const float* val, const int32_t* label);
+
+/* ---- the hot path --------------------------------------------------------------------------- */
+/* One reference "batch": forward (gather + interaction [+ MLP]) -> loss -> backward scatter-add ->
+ * per-coordinate update on the rows [row_begin,row_end) of the resident slot.
+ *   FM : Train_FM_Algo::batchGradCompute + accumWVGrad + ApplyGrad   (train_fm_algo.cpp:63-126)
+ *   FFM: Train_FFM_Algo::...                                         (train_ffm_algo.cpp:51-126)
+ *   NFM: Train_NFM_Algo::batchGradCompute + ApplyGrad                (train_nfm_algo.cpp:56-169)
+ * loss_sum / acc_cnt (may be NULL: then no host sync happens) receive the summed logloss and the
+ * number of correct rows of this step, the quantities the reference prints per epoch. */
+int lctr_train_step(lctr_ctx* ctx, int slot, int64_t row_begin, int64_t row_end, float* loss_sum, float* acc_cnt);
+/* End-to-end convenience: upload_batch(slot 0) + train_step + result readback, host buffers in. */
+int lctr_train_batch(lctr_ctx* ctx, int64_t rows, int64_t nnz, const int64_t* row_ptr, const uint32_t* fid,
+                     const uint16_t* field, const float* val, const int32_t* label, float* loss_sum,
+                     float* acc_cnt);
+/* Forward only on a resident slot; pctr (rows floats, host) receives sigmoid(pred).
+ * quirk_sumvx_slot >= 0 reproduces FM_Predict's use of the TRAINING sumVX of the same row index
+ * (predict/fm_predict.cpp:27-32); -1 computes the proper FM prediction. */
+int lctr_predict(lctr_ctx* ctx, int slot, int quirk_sumvx_slot, float* pctr);
+/* sumVX[rows*k] of a slot as left by the last forward over it (FM_Algo_Abst::sumVX, fm_algo_abst.h:145). */
+int lctr_download_sumvx(lctr_ctx* ctx, int slot, float* sumVX);
+/* per-row sigmoid(pred) of the last forward over the slot */
+int lctr_download_pred(lctr_ctx* ctx, int slot, float* pred);
+
+/* ---- MLP (Fully_Conn_Layer chain, fullyconnLayer.h) ------------------------------------------ */
+/* layer l: weight [out][in] row-major (fullyconnLayer.h:211-216), bias[out], dropout mask[out] (1/0). */
+int lctr_mlp_upload(lctr_ctx* ctx, int layer, const float* weight, const float* bias);
+int lctr_mlp_download(lctr_ctx* ctx, int layer, float* weight, float* bias);
+int lctr_mlp_set_mask(lctr_ctx* ctx, int layer, const float* mask);
+
+/* ---- multi-GPU (replaces distribut/ring_collect.h + pull.h/push.h) ------------ */
+/* Exchange of CUDA IPC handles is done by the caller's process group (torch.distributed / MPI):
+ * export this rank's table handles, gather them, import all peers'. */
+int lctr_ipc_export(lctr_ctx* ctx, void* handles_out, size_t cap, size_t* bytes);
+int lctr_ipc_import(lctr_ctx* ctx, const void* all_handles, size_t bytes_per_rank);
+/* device pointer + element count of the fused dense-gradient buffer (the BufferFusion of
+ * fullyconnLayer.h:69-75) for an external ncclAllReduce; 0 elements when the model has no MLP */
+int lctr_dense_grad_buffer(lctr_ctx* ctx, void** dev_ptr, size_t* n_floats);
+
+/* ---- host-side ingest (fm_algo_abst.h:70-107), bit-exact indexing ----------------------------- */
+typedef struct lctr_dataset {
+    int64_t rows, nnz, label_cnt;
+    uint64_t feature_cnt, field_cnt;
+    int64_t* row_ptr;
+    uint32_t* fid;
+    uint16_t* field;
+    float* val;
+    int32_t* label;
+} lctr_dataset;
+int lctr_load_libffm(const char* path, uint64_t field_cnt_in, uint64_t feature_cnt_in, lctr_dataset** out);
+int lctr_free_dataset(lctr_dataset* d);
+
+/* introspection for tests / bench: number of kernels this library has launched on ctx so far */
+int64_t lctr_launch_count(const lctr_ctx* ctx);
+/* raw CUDA stream handle (cudaStream_t) of the ctx, for event timing on the launching stream */
+void* lctr_stream(lctr_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LIGHTCTR_B200_H */

@@ -1,0 +1,263 @@
+"""ctypes binding of the C ABI in include/lightctr_b200.h (lightctr_b200/lib/liblightctr_b200.so).
+
+This is plumbing for the Python tests and bench.py; the drop-in host side for the reference's C++
+callers is lightctr_b200/host/*.h.  There is NO CPU fallback: if the shared library is missing or
+no CUDA device is present the calls raise.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "lib", "liblightctr_b200.so")
+
+MODEL_FM, MODEL_FFM, MODEL_NFM = 1, 2, 3
+OPT_ADAGRAD, OPT_FTRL, OPT_ADAM = 0, 1, 2
+ACT_SIGMOID, ACT_TANH = 0, 1
+MLP_FP32, MLP_BF16 = 0, 1
+MAX_LAYERS = 8
+ABI_VERSION = 1
+
+# every symbol include/lightctr_b200.h declares (tests check the .so exports each of them)
+SYMBOLS = [
+    "lctr_last_error", "lctr_abi_version", "lctr_create", "lctr_destroy", "lctr_sync", "lctr_upload_params",
+    "lctr_download_params", "lctr_download_opt_state", "lctr_upload_opt_state", "lctr_upload_batch",
+    "lctr_train_step", "lctr_train_batch", "lctr_predict", "lctr_download_sumvx", "lctr_download_pred",
+    "lctr_mlp_upload", "lctr_mlp_download", "lctr_mlp_set_mask", "lctr_ipc_export", "lctr_ipc_import",
+    "lctr_dense_grad_buffer", "lctr_load_libffm", "lctr_free_dataset", "lctr_launch_count", "lctr_stream",
+]
+
+
+class Cfg(C.Structure):
+    _fields_ = [("abi_version", C.c_uint32), ("model", C.c_int32), ("optimizer", C.c_int32), ("device", C.c_int32),
+                ("feature_cnt", C.c_uint64), ("field_cnt", C.c_uint32), ("factor_cnt", C.c_uint32),
+                ("learning_rate", C.c_float), ("l2_reg", C.c_float), ("minibatch_size", C.c_uint64),
+                ("momentum", C.c_float), ("momentum_adam2", C.c_float), ("ftrl_alpha", C.c_float),
+                ("ftrl_beta", C.c_float), ("ftrl_lambda1", C.c_float), ("ftrl_lambda2", C.c_float),
+                ("n_hidden", C.c_int32), ("hidden", C.c_uint32 * MAX_LAYERS), ("activation", C.c_int32),
+                ("mlp_precision", C.c_int32), ("max_rows", C.c_uint64), ("max_nnz", C.c_uint64), ("rank", C.c_int32),
+                ("world", C.c_int32), ("reserved", C.c_uint32 * 8)]
+
+
+class DatasetC(C.Structure):
+    _fields_ = [("rows", C.c_int64), ("nnz", C.c_int64), ("label_cnt", C.c_int64), ("feature_cnt", C.c_uint64),
+                ("field_cnt", C.c_uint64), ("row_ptr", C.POINTER(C.c_int64)), ("fid", C.POINTER(C.c_uint32)),
+                ("field", C.POINTER(C.c_uint16)), ("val", C.POINTER(C.c_float)), ("label", C.POINTER(C.c_int32))]
+
+
+_lib = None
+
+
+def load_library():
+    """dlopen the CUDA extension; raises loudly when it is missing (no fallback path exists)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError("lightctr_b200: CUDA extension %s is missing -- run `python -m lightctr_b200.build` "
+                           "(there is no CPU fallback)" % LIB_PATH)
+    L = C.CDLL(LIB_PATH)
+    vp, i64, f32p = C.c_void_p, C.c_int64, C.c_void_p
+    L.lctr_last_error.restype = C.c_char_p
+    L.lctr_create.argtypes = [C.POINTER(Cfg), C.POINTER(vp)]
+    L.lctr_destroy.argtypes = [vp]
+    L.lctr_sync.argtypes = [vp]
+    L.lctr_upload_params.argtypes = [vp, f32p, f32p]
+    L.lctr_download_params.argtypes = [vp, f32p, f32p]
+    L.lctr_download_opt_state.argtypes = [vp, f32p, f32p]
+    L.lctr_upload_opt_state.argtypes = [vp, f32p, f32p]
+    L.lctr_upload_batch.argtypes = [vp, C.c_int, i64, i64, vp, vp, vp, vp, vp]
+    L.lctr_train_step.argtypes = [vp, C.c_int, i64, i64, C.POINTER(C.c_float), C.POINTER(C.c_float)]
+    L.lctr_train_batch.argtypes = [vp, i64, i64, vp, vp, vp, vp, vp, C.POINTER(C.c_float), C.POINTER(C.c_float)]
+    L.lctr_predict.argtypes = [vp, C.c_int, C.c_int, f32p]
+    L.lctr_download_sumvx.argtypes = [vp, C.c_int, f32p]
+    L.lctr_download_pred.argtypes = [vp, C.c_int, f32p]
+    L.lctr_mlp_upload.argtypes = [vp, C.c_int, f32p, f32p]
+    L.lctr_mlp_download.argtypes = [vp, C.c_int, f32p, f32p]
+    L.lctr_mlp_set_mask.argtypes = [vp, C.c_int, f32p]
+    L.lctr_ipc_export.argtypes = [vp, vp, C.c_size_t, C.POINTER(C.c_size_t)]
+    L.lctr_ipc_import.argtypes = [vp, vp, C.c_size_t]
+    L.lctr_dense_grad_buffer.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_size_t)]
+    L.lctr_load_libffm.argtypes = [C.c_char_p, C.c_uint64, C.c_uint64, C.POINTER(C.POINTER(DatasetC))]
+    L.lctr_free_dataset.argtypes = [C.POINTER(DatasetC)]
+    L.lctr_launch_count.argtypes = [vp]
+    L.lctr_launch_count.restype = C.c_int64
+    L.lctr_stream.argtypes = [vp]
+    L.lctr_stream.restype = vp
+    _lib = L
+    return L
+
+
+class LctrError(RuntimeError):
+    pass
+
+
+def _chk(rc):
+    if rc != 0:
+        raise LctrError(load_library().lctr_last_error().decode())
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data
+
+
+class HostDataset:
+    """CSR arrays as produced by lctr_load_libffm (FM_Algo_Abst::dataSet / label)."""
+
+    def __init__(self, row_ptr, fid, field, val, label, feature_cnt, field_cnt):
+        self.row_ptr = np.ascontiguousarray(row_ptr, np.int64)
+        self.fid = np.ascontiguousarray(fid, np.uint32)
+        self.field = None if field is None else np.ascontiguousarray(field, np.uint16)
+        self.val = None if val is None else np.ascontiguousarray(val, np.float32)
+        self.label = np.ascontiguousarray(label, np.int32)
+        self.feature_cnt, self.field_cnt = int(feature_cnt), int(field_cnt)
+
+    rows = property(lambda self: len(self.row_ptr) - 1)
+    nnz = property(lambda self: len(self.fid))
+
+
+def load_libffm(path, field_cnt=0, feature_cnt=0):
+    """FM_Algo_Abst::loadDataRow (fm_algo_abst.h:70-107) through the library's own parser."""
+    L = load_library()
+    dp = C.POINTER(DatasetC)()
+    _chk(L.lctr_load_libffm(path.encode(), field_cnt, feature_cnt, C.byref(dp)))
+    d = dp.contents
+    n, r, lc = d.nnz, d.rows, d.label_cnt
+    out = HostDataset(np.ctypeslib.as_array(d.row_ptr, (r + 1,)).copy(),
+                      np.ctypeslib.as_array(d.fid, (max(n, 1),))[:n].copy(),
+                      np.ctypeslib.as_array(d.field, (max(n, 1),))[:n].copy(),
+                      np.ctypeslib.as_array(d.val, (max(n, 1),))[:n].copy(),
+                      np.ctypeslib.as_array(d.label, (max(lc, 1),))[:lc].copy(), d.feature_cnt, d.field_cnt)
+    L.lctr_free_dataset(dp)
+    return out
+
+
+class Context:
+    """Owning wrapper around lctr_ctx."""
+
+    def __init__(self, model, feature_cnt, factor_cnt, field_cnt=0, optimizer=OPT_ADAGRAD, lr=0.05, l2=0.001,
+                 minibatch_size=0, momentum=0.8, momentum_adam2=0.999, hidden=(), activation=ACT_SIGMOID,
+                 mlp_precision=MLP_FP32, device=0, rank=0, world=1):
+        L = load_library()
+        cfg = Cfg()
+        cfg.abi_version = ABI_VERSION
+        cfg.model, cfg.optimizer, cfg.device = model, optimizer, device
+        cfg.feature_cnt, cfg.field_cnt, cfg.factor_cnt = feature_cnt, field_cnt, factor_cnt
+        cfg.learning_rate, cfg.l2_reg, cfg.minibatch_size = lr, l2, minibatch_size
+        cfg.momentum, cfg.momentum_adam2 = momentum, momentum_adam2
+        cfg.n_hidden = len(hidden)
+        for i, h in enumerate(hidden):
+            cfg.hidden[i] = h
+        cfg.activation, cfg.mlp_precision = activation, mlp_precision
+        cfg.rank, cfg.world = rank, world
+        self.cfg = cfg
+        self.h = C.c_void_p()
+        _chk(L.lctr_create(C.byref(cfg), C.byref(self.h)))
+        self.L = L
+        self.F, self.k, self.Fc = feature_cnt, factor_cnt, field_cnt
+        self.rowlen = factor_cnt * (field_cnt if model == MODEL_FFM else 1)
+        self.slot_rows = {}
+
+    def close(self):
+        if self.h:
+            self.L.lctr_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def sync(self):
+        _chk(self.L.lctr_sync(self.h))
+
+    def upload_params(self, W, V):
+        W = None if W is None else np.ascontiguousarray(W, np.float32)
+        V = None if V is None else np.ascontiguousarray(V, np.float32)
+        _chk(self.L.lctr_upload_params(self.h, _p(W), _p(V)))
+
+    def download_params(self):
+        W = np.empty(self.F, np.float32)
+        V = np.empty(self.F * self.rowlen, np.float32)
+        _chk(self.L.lctr_download_params(self.h, W.ctypes.data, V.ctypes.data))
+        return W, V
+
+    def download_opt_state(self):
+        n = self.F * (self.rowlen + 1)
+        s1, s2 = np.zeros(n, np.float32), np.zeros(n, np.float32)
+        _chk(self.L.lctr_download_opt_state(self.h, s1.ctypes.data, s2.ctypes.data))
+        return s1, s2
+
+    def upload_opt_state(self, s1, s2=None):
+        s1 = np.ascontiguousarray(s1, np.float32)
+        s2 = None if s2 is None else np.ascontiguousarray(s2, np.float32)
+        _chk(self.L.lctr_upload_opt_state(self.h, _p(s1), _p(s2)))
+
+    def upload_batch(self, slot, row_ptr, fid, field, val, label):
+        rows, nnz = len(row_ptr) - 1, len(fid)
+        keep = [np.ascontiguousarray(row_ptr, np.int64), np.ascontiguousarray(fid, np.uint32),
+                None if field is None else np.ascontiguousarray(field, np.uint16),
+                None if val is None else np.ascontiguousarray(val, np.float32), np.ascontiguousarray(label, np.int32)]
+        _chk(self.L.lctr_upload_batch(self.h, slot, rows, nnz, *[_p(a) for a in keep]))
+        self.sync()  # host arrays may be pageable temporaries
+        self.slot_rows[slot] = rows
+
+    def upload_dataset(self, slot, ds, all_ones_as_null=True):
+        val = ds.val
+        if val is not None and all_ones_as_null and np.all(val == 1.0):
+            val = None
+        self.upload_batch(slot, ds.row_ptr, ds.fid, ds.field, val, ds.label[:len(ds.row_ptr) - 1])
+
+    def train_step(self, slot=0, row_begin=0, row_end=None, want_stats=True):
+        if row_end is None:
+            row_end = self.slot_rows[slot]
+        if want_stats:
+            loss, acc = C.c_float(), C.c_float()
+            _chk(self.L.lctr_train_step(self.h, slot, row_begin, row_end, C.byref(loss), C.byref(acc)))
+            return loss.value, acc.value
+        _chk(self.L.lctr_train_step(self.h, slot, row_begin, row_end, None, None))
+        return None
+
+    def train_batch(self, row_ptr, fid, field, val, label):
+        """End-to-end call on host buffers (numpy arrays, ideally pinned)."""
+        loss, acc = C.c_float(), C.c_float()
+        _chk(self.L.lctr_train_batch(self.h, len(row_ptr) - 1, len(fid), _p(row_ptr), _p(fid), _p(field), _p(val),
+                                     _p(label), C.byref(loss), C.byref(acc)))
+        return loss.value, acc.value
+
+    def predict(self, slot, quirk_sumvx_slot=-1):
+        out = np.empty(self.slot_rows[slot], np.float32)
+        _chk(self.L.lctr_predict(self.h, slot, quirk_sumvx_slot, out.ctypes.data))
+        return out
+
+    def download_sumvx(self, slot):
+        out = np.empty(self.slot_rows[slot] * self.k, np.float32)
+        _chk(self.L.lctr_download_sumvx(self.h, slot, out.ctypes.data))
+        return out
+
+    def download_pred(self, slot):
+        out = np.empty(self.slot_rows[slot], np.float32)
+        _chk(self.L.lctr_download_pred(self.h, slot, out.ctypes.data))
+        return out
+
+    def mlp_upload(self, layer, weight, bias):
+        w = np.ascontiguousarray(weight, np.float32)
+        b = np.ascontiguousarray(bias, np.float32)
+        _chk(self.L.lctr_mlp_upload(self.h, layer, w.ctypes.data, b.ctypes.data))
+
+    def mlp_download(self, layer, n_in, n_out):
+        w, b = np.empty(n_in * n_out, np.float32), np.empty(n_out, np.float32)
+        _chk(self.L.lctr_mlp_download(self.h, layer, w.ctypes.data, b.ctypes.data))
+        return w, b
+
+    def mlp_set_mask(self, layer, mask):
+        m = np.ascontiguousarray(mask, np.float32)
+        _chk(self.L.lctr_mlp_set_mask(self.h, layer, m.ctypes.data))
+
+    def launch_count(self):
+        return self.L.lctr_launch_count(self.h)
+
+    def stream(self):
+        return self.L.lctr_stream(self.h)

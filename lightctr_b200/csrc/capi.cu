@@ -1,0 +1,343 @@
+// lightctr_b200/csrc/capi.cu -- the C ABI declared in include/lightctr_b200.h.
+#include <stdarg.h>
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "common.cuh"
+
+namespace lctr {
+static thread_local std::string g_err;
+void set_error(const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_err = buf;
+}
+
+template <typename T>
+static int dalloc(T** p, size_t n) {
+    *p = nullptr;
+    if (n == 0) return 0;
+    LCTR_CUDA(cudaMalloc((void**)p, n * sizeof(T)));
+    return 0;
+}
+template <typename T>
+static void dfree(T*& p) {
+    if (p) cudaFree(p);
+    p = nullptr;
+}
+
+static int slot_reserve(lctr_ctx* c, Slot& s, int64_t rows, int64_t nnz) {
+    const size_t k = c->cfg.factor_cnt;
+    if (rows > s.cap_rows) {
+        int64_t cap = std::max<int64_t>(rows, s.cap_rows + s.cap_rows / 2);
+        dfree(s.row_ptr); dfree(s.label); dfree(s.pred); dfree(s.sumvx); dfree(s.wide);
+        if (dalloc(&s.row_ptr, (size_t)cap + 1)) return 1;
+        if (dalloc(&s.label, (size_t)cap)) return 1;
+        if (dalloc(&s.pred, (size_t)cap)) return 1;
+        if (dalloc(&s.wide, (size_t)cap)) return 1;
+        if (c->cfg.model != LCTR_MODEL_FFM) {
+            if (dalloc(&s.sumvx, (size_t)cap * k)) return 1;
+            LCTR_CUDA(cudaMemsetAsync(s.sumvx, 0, (size_t)cap * k * sizeof(float), c->stream));
+        }
+        s.cap_rows = cap;
+    }
+    if (nnz > s.cap_nnz) {
+        int64_t cap = std::max<int64_t>(nnz, s.cap_nnz + s.cap_nnz / 2);
+        dfree(s.fid); dfree(s.field); dfree(s.val);
+        if (dalloc(&s.fid, (size_t)cap + 32)) return 1;
+        if (dalloc(&s.field, (size_t)cap + 32)) return 1;
+        if (dalloc(&s.val, (size_t)cap + 32)) return 1;
+        s.cap_nnz = cap;
+    }
+    return 0;
+}
+
+__global__ void label_to_float_kernel(const int32_t* in, float* out, int64_t n) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (float)in[i];
+}
+}  // namespace lctr
+
+using namespace lctr;
+
+extern "C" {
+
+const char* lctr_last_error(void) { return g_err.c_str(); }
+int lctr_abi_version(void) { return LCTR_ABI_VERSION; }
+
+int lctr_create(const lctr_cfg* cfg, lctr_ctx** out) {
+    LCTR_CHECK(cfg && out, "lctr_create: null argument");
+    LCTR_CHECK(cfg->abi_version == LCTR_ABI_VERSION, "lctr_create: abi_version %u != %u", cfg->abi_version,
+               LCTR_ABI_VERSION);
+    LCTR_CHECK(cfg->model >= LCTR_MODEL_FM && cfg->model <= LCTR_MODEL_NFM, "lctr_create: bad model %d", cfg->model);
+    LCTR_CHECK(cfg->optimizer >= LCTR_OPT_ADAGRAD && cfg->optimizer <= LCTR_OPT_ADAM, "lctr_create: bad optimizer %d",
+               cfg->optimizer);
+    LCTR_CHECK(cfg->feature_cnt > 0 && cfg->feature_cnt < (1ull << 32), "lctr_create: feature_cnt out of range");
+    LCTR_CHECK(cfg->factor_cnt > 0, "lctr_create: factor_cnt must be > 0");
+    LCTR_CHECK(cfg->model != LCTR_MODEL_FFM || cfg->field_cnt > 0, "lctr_create: FFM needs field_cnt > 0");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        set_error("lctr_create: no CUDA device available (%s); this library has no CPU fallback",
+                  cudaGetErrorString(e));
+        return 2;
+    }
+    LCTR_CHECK(cfg->device >= 0 && cfg->device < ndev, "lctr_create: device %d of %d", cfg->device, ndev);
+    LCTR_CUDA(cudaSetDevice(cfg->device));
+    lctr_ctx* c = new lctr_ctx();
+    c->cfg = *cfg;
+    if (c->cfg.ftrl_alpha == 0.f) {  // gradientUpdater.h:275
+        c->cfg.ftrl_alpha = 0.15f; c->cfg.ftrl_lambda1 = 1.0f; c->cfg.ftrl_beta = 1.0f; c->cfg.ftrl_lambda2 = 1.0f;
+    }
+    if (c->cfg.world <= 0) { c->cfg.world = 1; c->cfg.rank = 0; }
+    c->F = cfg->feature_cnt;
+    c->rowlen = cfg->model == LCTR_MODEL_FFM ? (size_t)cfg->field_cnt * cfg->factor_cnt : cfg->factor_cnt;
+    cudaDeviceProp prop;
+    LCTR_CUDA(cudaGetDeviceProperties(&prop, cfg->device));
+    c->sm_count = prop.multiProcessorCount;
+    LCTR_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    const size_t nv = c->F * c->rowlen;
+    const bool two = cfg->optimizer != LCTR_OPT_ADAGRAD;
+    int rc = 0;
+    rc |= dalloc(&c->W, c->F); rc |= dalloc(&c->V, nv);
+    rc |= dalloc(&c->gW, c->F); rc |= dalloc(&c->gV, nv);
+    rc |= dalloc(&c->s1W, c->F); rc |= dalloc(&c->s1V, nv);
+    if (two) { rc |= dalloc(&c->s2W, c->F); rc |= dalloc(&c->s2V, nv); }
+    rc |= dalloc(&c->touched, c->F + 512);
+    rc |= dalloc(&c->stats, (size_t)2 * kStatRing);
+    rc |= dalloc(&c->stat_partial, 2);
+    rc |= dalloc(&c->stat_done, 1);
+    if (rc) { lctr_destroy(c); return 1; }
+    LCTR_CUDA(cudaMallocHost((void**)&c->h_stats, 2 * sizeof(double)));
+    LCTR_CUDA(cudaMemsetAsync(c->W, 0, c->F * sizeof(float), c->stream));
+    LCTR_CUDA(cudaMemsetAsync(c->V, 0, nv * sizeof(float), c->stream));
+    LCTR_CUDA(cudaMemsetAsync(c->gW, 0, c->F * sizeof(float), c->stream));
+    LCTR_CUDA(cudaMemsetAsync(c->gV, 0, nv * sizeof(float), c->stream));
+    LCTR_CUDA(cudaMemsetAsync(c->s1W, 0, c->F * sizeof(float), c->stream));
+    LCTR_CUDA(cudaMemsetAsync(c->s1V, 0, nv * sizeof(float), c->stream));
+    if (two) {
+        LCTR_CUDA(cudaMemsetAsync(c->s2W, 0, c->F * sizeof(float), c->stream));
+        LCTR_CUDA(cudaMemsetAsync(c->s2V, 0, nv * sizeof(float), c->stream));
+    }
+    LCTR_CUDA(cudaMemsetAsync(c->touched, 0, c->F + 512, c->stream));
+    LCTR_CUDA(cudaMemsetAsync(c->stats, 0, sizeof(double) * 2 * kStatRing, c->stream));
+    LCTR_CUDA(cudaMemsetAsync(c->stat_partial, 0, sizeof(double) * 2, c->stream));
+    LCTR_CUDA(cudaMemsetAsync(c->stat_done, 0, sizeof(unsigned int), c->stream));
+    if (cfg->model == LCTR_MODEL_NFM) {
+        if (mlp_alloc(c)) { lctr_destroy(c); return 1; }
+    }
+    LCTR_CUDA(cudaStreamSynchronize(c->stream));
+    *out = c;
+    return 0;
+}
+
+int lctr_destroy(lctr_ctx* c) {
+    if (!c) return 0;
+    cudaSetDevice(c->cfg.device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    dfree(c->W); dfree(c->V); dfree(c->gW); dfree(c->gV); dfree(c->s1W); dfree(c->s1V); dfree(c->s2W); dfree(c->s2V);
+    dfree(c->touched); dfree(c->stats); dfree(c->stat_partial); dfree(c->stat_done);
+    for (auto& s : c->slots) {
+        dfree(s.row_ptr); dfree(s.fid); dfree(s.field); dfree(s.val); dfree(s.label); dfree(s.pred); dfree(s.sumvx);
+        dfree(s.wide);
+    }
+    mlp_free(c);
+    if (c->h_stats) cudaFreeHost(c->h_stats);
+    if (c->h_stage) cudaFreeHost(c->h_stage);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+    return 0;
+}
+
+int lctr_sync(lctr_ctx* c) {
+    LCTR_CHECK(c, "null ctx");
+    LCTR_CUDA(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int lctr_upload_params(lctr_ctx* c, const float* W, const float* V) {
+    LCTR_CHECK(c, "null ctx");
+    if (W) LCTR_CUDA(cudaMemcpyAsync(c->W, W, c->F * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    if (V) LCTR_CUDA(cudaMemcpyAsync(c->V, V, c->F * c->rowlen * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    LCTR_CUDA(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+int lctr_download_params(lctr_ctx* c, float* W, float* V) {
+    LCTR_CHECK(c, "null ctx");
+    if (W) LCTR_CUDA(cudaMemcpyAsync(W, c->W, c->F * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    if (V) LCTR_CUDA(cudaMemcpyAsync(V, c->V, c->F * c->rowlen * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    LCTR_CUDA(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+int lctr_download_opt_state(lctr_ctx* c, float* s1, float* s2) {
+    LCTR_CHECK(c, "null ctx");
+    const size_t nv = c->F * c->rowlen;
+    if (s1) {
+        LCTR_CUDA(cudaMemcpyAsync(s1, c->s1W, c->F * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+        LCTR_CUDA(cudaMemcpyAsync(s1 + c->F, c->s1V, nv * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    }
+    if (s2 && c->s2W) {
+        LCTR_CUDA(cudaMemcpyAsync(s2, c->s2W, c->F * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+        LCTR_CUDA(cudaMemcpyAsync(s2 + c->F, c->s2V, nv * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    }
+    LCTR_CUDA(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+int lctr_upload_opt_state(lctr_ctx* c, const float* s1, const float* s2) {
+    LCTR_CHECK(c, "null ctx");
+    const size_t nv = c->F * c->rowlen;
+    if (s1) {
+        LCTR_CUDA(cudaMemcpyAsync(c->s1W, s1, c->F * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+        LCTR_CUDA(cudaMemcpyAsync(c->s1V, s1 + c->F, nv * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    }
+    if (s2 && c->s2W) {
+        LCTR_CUDA(cudaMemcpyAsync(c->s2W, s2, c->F * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+        LCTR_CUDA(cudaMemcpyAsync(c->s2V, s2 + c->F, nv * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    }
+    LCTR_CUDA(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int lctr_upload_batch(lctr_ctx* c, int slot, int64_t rows, int64_t nnz, const int64_t* row_ptr, const uint32_t* fid,
+                      const uint16_t* field, const float* val, const int32_t* label) {
+    LCTR_CHECK(c, "null ctx");
+    LCTR_CHECK(slot >= 0 && slot < kNumSlots, "slot %d out of range", slot);
+    LCTR_CHECK(rows >= 0 && nnz >= 0 && row_ptr && (nnz == 0 || fid) && (rows == 0 || label), "upload_batch: null input");
+    LCTR_CHECK(c->cfg.model != LCTR_MODEL_FFM || field || nnz == 0, "upload_batch: FFM needs the field array");
+    Slot& s = c->slots[slot];
+    if (slot_reserve(c, s, rows, nnz)) return 1;
+    s.rows = rows; s.nnz = nnz;
+    s.has_val = val != nullptr;
+    s.has_field = field != nullptr;
+    LCTR_CUDA(cudaMemcpyAsync(s.row_ptr, row_ptr, (size_t)(rows + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, c->stream));
+    if (nnz) {
+        LCTR_CUDA(cudaMemcpyAsync(s.fid, fid, (size_t)nnz * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+        if (field) LCTR_CUDA(cudaMemcpyAsync(s.field, field, (size_t)nnz * sizeof(uint16_t), cudaMemcpyHostToDevice, c->stream));
+        if (val) LCTR_CUDA(cudaMemcpyAsync(s.val, val, (size_t)nnz * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    }
+    if (rows) {
+        // labels travel as int32 and are widened on device (the reference compares a `float target`)
+        int32_t* tmp = reinterpret_cast<int32_t*>(s.pred);  // pred is overwritten by the next forward anyway
+        LCTR_CUDA(cudaMemcpyAsync(tmp, label, (size_t)rows * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+        label_to_float_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, c->stream>>>(tmp, s.label, rows);
+        c->launches++;
+        LCTR_CUDA(cudaGetLastError());
+    }
+    return 0;
+}
+
+static int read_stats(lctr_ctx* c, uint64_t step, float* loss_sum, float* acc_cnt) {
+    if (!loss_sum && !acc_cnt) return 0;
+    LCTR_CUDA(cudaMemcpyAsync(c->h_stats, c->stats + 2 * (step % kStatRing), 2 * sizeof(double), cudaMemcpyDeviceToHost,
+                              c->stream));
+    LCTR_CUDA(cudaStreamSynchronize(c->stream));
+    if (loss_sum) *loss_sum = (float)c->h_stats[0];
+    if (acc_cnt) *acc_cnt = (float)c->h_stats[1];
+    return 0;
+}
+
+int lctr_train_step(lctr_ctx* c, int slot, int64_t rb, int64_t re, float* loss_sum, float* acc_cnt) {
+    LCTR_CHECK(c, "null ctx");
+    LCTR_CHECK(slot >= 0 && slot < kNumSlots, "slot %d out of range", slot);
+    Slot& s = c->slots[slot];
+    LCTR_CHECK(rb >= 0 && re <= s.rows && rb <= re, "train_step: rows [%lld,%lld) outside slot (%lld rows)",
+               (long long)rb, (long long)re, (long long)s.rows);
+    const uint64_t step = c->step;
+    int rc = 0;
+    switch (c->cfg.model) {
+        case LCTR_MODEL_FM:
+            rc = launch_fm_forward(c, s, rb, re, false, true) || launch_fm_backward(c, s, rb, re, false) ||
+                 launch_apply(c, re - rb);
+            break;
+        case LCTR_MODEL_FFM:
+            rc = launch_ffm_forward(c, s, rb, re, true) || launch_ffm_backward(c, s, rb, re) || launch_apply(c, re - rb);
+            break;
+        case LCTR_MODEL_NFM:
+            rc = mlp_reserve(c, re - rb) || launch_fm_forward(c, s, rb, re, true, false) ||
+                 launch_nfm_mlp(c, s, rb, re, re - rb) || launch_fm_backward(c, s, rb, re, true) ||
+                 launch_apply(c, re - rb);
+            break;
+    }
+    if (rc) return 1;
+    c->step++;
+    return read_stats(c, step, loss_sum, acc_cnt);
+}
+
+int lctr_train_batch(lctr_ctx* c, int64_t rows, int64_t nnz, const int64_t* row_ptr, const uint32_t* fid,
+                     const uint16_t* field, const float* val, const int32_t* label, float* loss_sum, float* acc_cnt) {
+    if (lctr_upload_batch(c, 0, rows, nnz, row_ptr, fid, field, val, label)) return 1;
+    return lctr_train_step(c, 0, 0, rows, loss_sum, acc_cnt);
+}
+
+int lctr_predict(lctr_ctx* c, int slot, int quirk_sumvx_slot, float* pctr) {
+    LCTR_CHECK(c, "null ctx");
+    LCTR_CHECK(slot >= 0 && slot < kNumSlots, "slot %d out of range", slot);
+    Slot& s = c->slots[slot];
+    int rc = 0;
+    if (c->cfg.model == LCTR_MODEL_FFM) {
+        rc = launch_ffm_forward(c, s, 0, s.rows, false);
+    } else if (c->cfg.model == LCTR_MODEL_FM) {
+        if (quirk_sumvx_slot >= 0) {
+            LCTR_CHECK(quirk_sumvx_slot < kNumSlots, "quirk slot out of range");
+            rc = launch_predict_quirk(c, s, c->slots[quirk_sumvx_slot]);
+        } else {
+            rc = launch_fm_forward(c, s, 0, s.rows, false, false);
+        }
+    } else {
+        set_error("lctr_predict: the reference ships no NFM predictor (main.cpp:230-233)");
+        return 1;
+    }
+    if (rc) return 1;
+    if (pctr) {
+        LCTR_CUDA(cudaMemcpyAsync(pctr, s.pred, (size_t)s.rows * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+        LCTR_CUDA(cudaStreamSynchronize(c->stream));
+    }
+    return 0;
+}
+
+int lctr_download_sumvx(lctr_ctx* c, int slot, float* out) {
+    LCTR_CHECK(c && out, "null argument");
+    LCTR_CHECK(slot >= 0 && slot < kNumSlots, "slot %d out of range", slot);
+    Slot& s = c->slots[slot];
+    LCTR_CHECK(s.sumvx, "model has no sumVX (FFM keeps it NULL, fm_predict.cpp:20)");
+    LCTR_CUDA(cudaMemcpyAsync(out, s.sumvx, (size_t)s.rows * c->cfg.factor_cnt * sizeof(float), cudaMemcpyDeviceToHost,
+                              c->stream));
+    LCTR_CUDA(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+int lctr_download_pred(lctr_ctx* c, int slot, float* out) {
+    LCTR_CHECK(c && out, "null argument");
+    LCTR_CHECK(slot >= 0 && slot < kNumSlots, "slot %d out of range", slot);
+    Slot& s = c->slots[slot];
+    LCTR_CUDA(cudaMemcpyAsync(out, s.pred, (size_t)s.rows * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    LCTR_CUDA(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int lctr_dense_grad_buffer(lctr_ctx* c, void** dev_ptr, size_t* n_floats) {
+    LCTR_CHECK(c && dev_ptr && n_floats, "null argument");
+    *dev_ptr = c->dense_grad;
+    *n_floats = c->dense_grad_n;
+    return 0;
+}
+
+int lctr_ipc_export(lctr_ctx* c, void* handles_out, size_t cap, size_t* bytes) {
+    (void)c; (void)handles_out; (void)cap; (void)bytes;
+    set_error("lctr_ipc_export: multi-GPU table sharding not built yet (DESIGN.md, row e)");
+    return 1;
+}
+int lctr_ipc_import(lctr_ctx* c, const void* all_handles, size_t bytes_per_rank) {
+    (void)c; (void)all_handles; (void)bytes_per_rank;
+    set_error("lctr_ipc_import: multi-GPU table sharding not built yet (DESIGN.md, row e)");
+    return 1;
+}
+
+int64_t lctr_launch_count(const lctr_ctx* c) { return c ? c->launches : 0; }
+void* lctr_stream(lctr_ctx* c) { return c ? (void*)c->stream : nullptr; }
+
+}  // extern "C"

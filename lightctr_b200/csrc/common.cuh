@@ -1,0 +1,174 @@
+// lightctr_b200/csrc/common.cuh -- shared device/host helpers for the sm_100a kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+
+#include "../../include/lightctr_b200.h"
+
+namespace lctr {
+
+void set_error(const char* fmt, ...);
+
+#define LCTR_CUDA(call)                                                                         \
+    do {                                                                                        \
+        cudaError_t _e = (call);                                                                \
+        if (_e != cudaSuccess) {                                                                \
+            ::lctr::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(_e)); \
+            return 1;                                                                           \
+        }                                                                                       \
+    } while (0)
+
+#define LCTR_CHECK(cond, ...)                  \
+    do {                                       \
+        if (!(cond)) {                         \
+            ::lctr::set_error(__VA_ARGS__);    \
+            return 1;                          \
+        }                                      \
+    } while (0)
+
+constexpr int kNumSlots = 4;
+constexpr int kStatRing = 64;
+constexpr unsigned kFull = 0xffffffffu;
+
+// One resident CSR batch / dataset (FM_Algo_Abst::dataSet + label, fm_algo_abst.h:156,170).
+struct Slot {
+    int64_t rows = 0, nnz = 0, cap_rows = 0, cap_nnz = 0;
+    int64_t* row_ptr = nullptr;  // rows+1
+    uint32_t* fid = nullptr;     // nnz
+    uint16_t* field = nullptr;   // nnz (FFM)
+    float* val = nullptr;        // nnz, or unused when !has_val (all 1.0f)
+    float* label = nullptr;      // rows, as float (the reference compares `float target`)
+    float* pred = nullptr;       // rows: sigmoid(pred) of the last forward
+    float* sumvx = nullptr;      // rows*k: FM_Algo_Abst::sumVX (fm_algo_abst.h:145)
+    float* wide = nullptr;       // rows (NFM: wide part)
+    bool has_val = false, has_field = false;
+};
+
+struct MlpLayer {
+    int in = 0, out = 0;
+    float *w = nullptr, *b = nullptr, *mask = nullptr;  // [out][in], [out], [out]
+    float *dw = nullptr, *db = nullptr;                 // views into the fused dense-grad buffer
+    float *acc_w = nullptr, *acc_b = nullptr;           // Adagrad state
+    float* act = nullptr;                               // [B][out] activations (post-activation for hidden layers)
+    float* delta = nullptr;                             // [B][out] dL/d(pre-activation)
+};
+
+}  // namespace lctr
+
+struct lctr_ctx {
+    lctr_cfg cfg;
+    cudaStream_t stream = nullptr;
+    size_t F = 0, rowlen = 0;  // rowlen = k (FM/NFM) or Fc*k (FFM)
+    // parameters, gradient accumulators (update_g layout: W part, V part), optimizer state
+    float *W = nullptr, *V = nullptr, *gW = nullptr, *gV = nullptr;
+    float *s1W = nullptr, *s1V = nullptr, *s2W = nullptr, *s2V = nullptr;
+    uint8_t* touched = nullptr;  // F bytes: 1 = fid received gradient this step
+    // per-step statistics ring: [kStatRing][2] doubles (loss sum, correct count) + scratch
+    double* stats = nullptr;
+    double* stat_partial = nullptr;     // [2] running accumulation of the current step
+    unsigned int* stat_done = nullptr;  // block-completion counter
+    double* h_stats = nullptr;          // pinned host mirror [2]
+    uint64_t step = 0;
+    size_t adam_iter = 0;
+    lctr::Slot slots[lctr::kNumSlots];
+    // MLP
+    int n_layers = 0;
+    lctr::MlpLayer layers[LCTR_MAX_LAYERS + 1];
+    float* dense_grad = nullptr;  // fused [dW0, db0, dW1, db1, ...]
+    size_t dense_grad_n = 0;
+    float *z = nullptr, *dz = nullptr;  // [B][k] NFM bi-interaction output and its gradient
+    float* mlp_out = nullptr;           // [B]
+    size_t mlp_cap_rows = 0;
+    int sm_count = 148;
+    int64_t launches = 0;
+    // pinned staging for lctr_train_batch (end-to-end path)
+    void* h_stage = nullptr;
+    size_t h_stage_bytes = 0;
+};
+
+namespace lctr {
+
+// ---------------------------------------------------------------------------------------------
+// device helpers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+    return v;
+}
+// vectorised no-return atomic add: one 16-byte RED per 4 floats (sm_90+: red.global.add.v4.f32)
+__device__ __forceinline__ void red_add_v4(float* addr, float4 v) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+                 : "memory");
+}
+__device__ __forceinline__ void red_add_f32(float* addr, float v) {
+    asm volatile("red.global.add.f32 [%0], %1;" ::"l"(addr), "f"(v) : "memory");
+}
+__device__ __forceinline__ float4 ldg_f4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+
+// Sigmoid::forward, util/activations.h:65-72 (clamps at +-16; accurate expf, no fast-math)
+__device__ __forceinline__ float ref_sigmoid(float x) {
+    if (x < -16.f) return 1e-7f;
+    if (x > 16.f) return 0.99999988f;  // (float)(1.0 - 1e-7)
+    return 1.0f / (1.0f + expf(-x));
+}
+// loss term + accuracy, train_fm_algo.cpp:93-98: y==1 ? -logf(p) : -log(1.0 - p) (double)
+__device__ __forceinline__ void loss_terms(float p, float y, double& loss, double& correct) {
+    loss = (y == 1.f) ? (double)(-logf(p)) : -log(1.0 - (double)p);
+    correct = ((p > 0.5f && y == 1.f) || (p < 0.5f && y == 0.f)) ? 1.0 : 0.0;
+}
+
+// Block-level accumulation of (loss, correct) into ctx statistics; the last block to finish publishes
+// the step totals into the ring slot and re-arms the accumulators (no memset launches between steps).
+__device__ __forceinline__ void publish_stats(double loss, double correct, double* partial, unsigned int* done,
+                                               double* out_slot, bool accumulate_out) {
+    __shared__ double sh[2][32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    loss = warp_sum_d(loss);
+    correct = warp_sum_d(correct);
+    if (lane == 0) { sh[0][wid] = loss; sh[1][wid] = correct; }
+    __syncthreads();
+    if (wid == 0) {
+        double a = lane < nw ? sh[0][lane] : 0.0, b = lane < nw ? sh[1][lane] : 0.0;
+        a = warp_sum_d(a);
+        b = warp_sum_d(b);
+        if (lane == 0) {
+            atomicAdd(&partial[0], a);
+            atomicAdd(&partial[1], b);
+            __threadfence();
+            unsigned int prev = atomicAdd(done, 1u);
+            if (prev == gridDim.x - 1) {
+                __threadfence();
+                double l = atomicAdd(&partial[0], 0.0), c = atomicAdd(&partial[1], 0.0);
+                if (accumulate_out) { out_slot[0] += l; out_slot[1] += c; }
+                else { out_slot[0] = l; out_slot[1] = c; }
+                partial[0] = 0.0; partial[1] = 0.0;
+                *done = 0u;
+                __threadfence();
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// kernel launchers (defined in the .cu files)
+// ---------------------------------------------------------------------------------------------
+int launch_fm_forward(lctr_ctx* c, Slot& s, int64_t rb, int64_t re, bool nfm, bool stats);
+int launch_fm_backward(lctr_ctx* c, Slot& s, int64_t rb, int64_t re, bool nfm);
+int launch_ffm_forward(lctr_ctx* c, Slot& s, int64_t rb, int64_t re, bool stats);
+int launch_ffm_backward(lctr_ctx* c, Slot& s, int64_t rb, int64_t re);
+int launch_apply(lctr_ctx* c, int64_t rows_in_step);
+int launch_predict_quirk(lctr_ctx* c, Slot& s, Slot& train);
+int mlp_alloc(lctr_ctx* c);
+int mlp_free(lctr_ctx* c);
+int mlp_reserve(lctr_ctx* c, int64_t rows);
+int launch_nfm_mlp(lctr_ctx* c, Slot& s, int64_t rb, int64_t re, int64_t rows_divisor);
+
+}  // namespace lctr

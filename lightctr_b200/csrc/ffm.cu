@@ -1,0 +1,243 @@
+// lightctr_b200/csrc/ffm.cu -- field-aware FM forward + backward fused per sample, sm_100a.
+//
+// Reference semantics: Train_FFM_Algo::batchGradCompute / accumWVGrad (train/train_ffm_algo.cpp:51-118):
+//     pred   = sum_i W[f_i] x_i + sum_{i<j} <V[f_i, fld_j], V[f_j, fld_i]> x_i x_j
+//     gV[f_i, fld_j] += x_i x_j d V[f_j, fld_i] + l2 V[f_i, fld_j]      (and symmetric), d = p - y,
+//     one l2 term PER PAIR (quirk); whole row skipped when d == 0 (:81-83).
+// The reference walks all n(n-1)/2 pairs.  Here the pair sum is factored through per-sample
+// field-pair sums  T[a][b] = sum_{j in field b} x_j R_j[a]   (R_j = the Fc*k-float row of f_j,
+// [a] = its k-slice for field a):
+//     sum_{i<j} ... = 1/2 ( sum_{a,b} <T[a][b], T[b][a]>  -  sum_i x_i^2 |R_i[fld_i]|^2 )
+//     gV[f_i][b]   = d x_i ( T[fld_i][b] - [b == fld_i] x_i R_i[fld_i] ) + l2 c_{i,b} R_i[b],
+//                    c_{i,b} = #(features of the sample in field b) - [b == fld_i]
+// which is algebraically identical (same terms, re-associated) and costs O(n Fc k) instead of
+// O(n^2 k) per sample.  Each embedding row is read as ONE contiguous Fc*k*4-byte segment
+// (624 B at Fc=39,k=4), fully coalesced across the CTA; T lives in shared memory with
+// thread-owned slots (no shared atomics); gradients leave as 16 B vector REDs that are
+// contiguous per row.  HBM-bound by the row gather: no tensor cores by design.
+#include <algorithm>
+#include <vector>
+
+#include "common.cuh"
+
+namespace lctr {
+
+template <int VEC>
+struct VT {
+    float a[VEC];
+};
+template <int VEC>
+__device__ __forceinline__ VT<VEC> vload(const float* p) {
+    VT<VEC> r;
+    if (VEC == 4) { float4 t = ldg_f4(p); r.a[0] = t.x; r.a[1 % VEC] = t.y; r.a[2 % VEC] = t.z; r.a[3 % VEC] = t.w; }
+    else if (VEC == 2) { float2 t = __ldg(reinterpret_cast<const float2*>(p)); r.a[0] = t.x; r.a[1 % VEC] = t.y; }
+    else r.a[0] = __ldg(p);
+    return r;
+}
+template <int VEC>
+__device__ __forceinline__ void vred(float* p, const VT<VEC>& v) {
+    if (VEC == 4) red_add_v4(p, make_float4(v.a[0], v.a[1 % VEC], v.a[2 % VEC], v.a[3 % VEC]));
+    else {
+#pragma unroll
+        for (int c = 0; c < VEC; c++) red_add_f32(p + c, v.a[c]);
+    }
+}
+
+constexpr int FFM_UNROLL = 4;
+
+// One CTA per sample; thread t < A owns slot t (VEC floats of the row; A = Fc*k/VEC).
+template <int VEC, bool HAS_VAL, bool TRAIN>
+__global__ void ffm_fused_kernel(const int64_t* __restrict__ row_ptr, const uint32_t* __restrict__ fid,
+                                 const uint16_t* __restrict__ field, const float* __restrict__ val,
+                                 const float* __restrict__ label, const float* __restrict__ W,
+                                 const float* __restrict__ V, int Fc, int k, float* __restrict__ pred,
+                                 float* __restrict__ gW, float* __restrict__ gV, uint8_t* __restrict__ touched,
+                                 float l2, int64_t rb, double* partial, unsigned int* done, double* out_slot,
+                                 int do_stats) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int A = Fc * k / VEC;   // slots per row
+    const int PPF = k / VEC;      // slots (parts) per field
+    VT<VEC>* S = reinterpret_cast<VT<VEC>*>(smem_raw);                       // S[col b][slot a] = T[a][b]
+    int* cnt = reinterpret_cast<int*>(smem_raw + (size_t)Fc * A * VEC * 4);  // features per field
+    float* red = reinterpret_cast<float*>(cnt + Fc);                         // [3][32] block reduction scratch + bcast
+    const int t = threadIdx.x;
+    const int64_t r = rb + blockIdx.x;
+    const int64_t b0 = row_ptr[r], e0 = row_ptr[r + 1];
+    const size_t rowlen = (size_t)Fc * k;
+    const bool own = t < A;
+    const int my_field = own ? t / PPF : -1, my_part = own ? t % PPF : 0;
+
+    for (int i = t; i < Fc * A; i += blockDim.x) {
+#pragma unroll
+        for (int c = 0; c < VEC; c++) S[i].a[c] = 0.f;
+    }
+    for (int i = t; i < Fc; i += blockDim.x) cnt[i] = 0;
+    __syncthreads();
+
+    // ---- phase 1: gather rows, accumulate T, wide sum, diagonal ---------------------------------
+    float wsum = 0.f, dsq = 0.f;
+    for (int64_t i = b0; i < e0; i += FFM_UNROLL) {
+        uint32_t f[FFM_UNROLL];
+        int fl[FFM_UNROLL];
+        float x[FFM_UNROLL];
+        VT<VEC> v[FFM_UNROLL];
+#pragma unroll
+        for (int u = 0; u < FFM_UNROLL; u++) {
+            const bool ok = i + u < e0;
+            f[u] = ok ? __ldg(fid + i + u) : 0u;
+            fl[u] = ok ? (int)__ldg(field + i + u) : 0;
+            x[u] = ok ? (HAS_VAL ? __ldg(val + i + u) : 1.f) : 0.f;
+            if (ok && own) v[u] = vload<VEC>(V + (size_t)f[u] * rowlen + (size_t)t * VEC);
+            else {
+#pragma unroll
+                for (int c = 0; c < VEC; c++) v[u].a[c] = 0.f;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < FFM_UNROLL; u++) {
+            if (i + u >= e0) break;
+            if (own) {
+                VT<VEC>& dst = S[fl[u] * A + t];
+#pragma unroll
+                for (int c = 0; c < VEC; c++) {
+                    const float tv = v[u].a[c] * x[u];
+                    dst.a[c] += tv;
+                    if (my_field == fl[u]) dsq += tv * tv;
+                }
+            }
+            if (t == 0) {
+                wsum += __ldg(W + f[u]) * x[u];  // fm_pred += W[fid] * X  (train_ffm_algo.cpp:60)
+                cnt[fl[u]] += 1;
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- phase 2: P = sum_{a,b} <T[a][b], T[b][a]> ------------------------------------------------
+    float P = 0.f;
+    if (own) {
+        for (int b = 0; b < Fc; b++) {
+            if (cnt[b] == 0) continue;
+            const VT<VEC> u1 = S[b * A + t];                           // T[my_field][b], my part
+            const VT<VEC> u2 = S[my_field * A + b * PPF + my_part];    // T[b][my_field], same part
+#pragma unroll
+            for (int c = 0; c < VEC; c++) P += u1.a[c] * u2.a[c];
+        }
+    }
+    // block reduce (P, dsq)
+    {
+        const int lane = t & 31, wid = t >> 5, nw = (blockDim.x + 31) >> 5;
+        float a = warp_sum(P), d2 = warp_sum(dsq);
+        if (lane == 0) { red[wid] = a; red[32 + wid] = d2; }
+        __syncthreads();
+        if (wid == 0) {
+            float aa = lane < nw ? red[lane] : 0.f, dd = lane < nw ? red[32 + lane] : 0.f;
+            aa = warp_sum(aa);
+            dd = warp_sum(dd);
+            if (lane == 0) {
+                const float fm_pred = (float)((double)wsum + 0.5 * ((double)aa - (double)dd));
+                const float p = ref_sigmoid(fm_pred);
+                pred[r] = p;
+                red[64] = p;
+            }
+        }
+        __syncthreads();
+    }
+    const float p = red[64];
+    double loss = 0.0, correct = 0.0;
+    if (TRAIN) {
+        const float y = label[r];
+        const float d = p - y;
+        if (d != 0.f) {  // train_ffm_algo.cpp:81-83: rows with pred == label contribute nothing at all
+            if (t == 0 && do_stats) loss_terms(p, y, loss, correct);
+            // ---- phase 3: gradients ------------------------------------------------------------------
+            const int my_cnt = own ? cnt[my_field] : 0;
+            for (int64_t i = b0; i < e0; i += FFM_UNROLL) {
+                uint32_t f[FFM_UNROLL];
+                int fl[FFM_UNROLL];
+                float x[FFM_UNROLL];
+                VT<VEC> v[FFM_UNROLL];
+#pragma unroll
+                for (int u = 0; u < FFM_UNROLL; u++) {
+                    const bool ok = i + u < e0;
+                    f[u] = ok ? __ldg(fid + i + u) : 0u;
+                    fl[u] = ok ? (int)__ldg(field + i + u) : 0;
+                    x[u] = ok ? (HAS_VAL ? __ldg(val + i + u) : 1.f) : 0.f;
+                    if (ok && own) v[u] = vload<VEC>(V + (size_t)f[u] * rowlen + (size_t)t * VEC);
+                    else {
+#pragma unroll
+                        for (int c = 0; c < VEC; c++) v[u].a[c] = 0.f;
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < FFM_UNROLL; u++) {
+                    if (i + u >= e0) break;
+                    if (own) {
+                        const int c_ib = my_cnt - (my_field == fl[u] ? 1 : 0);
+                        if (c_ib > 0) {
+                            const VT<VEC> tt = S[my_field * A + fl[u] * PPF + my_part];  // T[fld_i][my_field]
+                            VT<VEC> g;
+                            const float sx = d * x[u];
+                            const float lc = l2 * (float)c_ib;
+#pragma unroll
+                            for (int c = 0; c < VEC; c++) {
+                                float tv = tt.a[c];
+                                if (my_field == fl[u]) tv -= x[u] * v[u].a[c];
+                                g.a[c] = sx * tv + lc * v[u].a[c];
+                            }
+                            vred<VEC>(gV + (size_t)f[u] * rowlen + (size_t)t * VEC, g);
+                        }
+                    }
+                    if (t == 0) {
+                        red_add_f32(gW + f[u], d * x[u] + l2 * __ldg(W + f[u]));  // train_ffm_algo.cpp:98
+                        touched[f[u]] = 1;
+                    }
+                }
+            }
+        }
+    }
+    if (TRAIN && do_stats) publish_stats(loss, correct, partial, done, out_slot, false);
+}
+
+static int ffm_launch(lctr_ctx* c, Slot& s, int64_t rb, int64_t re, bool train, bool stats) {
+    const int k = (int)c->cfg.factor_cnt, Fc = (int)c->cfg.field_cnt;
+    const int64_t rows = re - rb;
+    if (rows <= 0) return 0;
+    LCTR_CHECK(s.has_field, "FFM batch uploaded without the field array");
+    const int vec = (k % 4 == 0) ? 4 : ((k % 2 == 0) ? 2 : 1);
+    const int A = Fc * k / vec;
+    LCTR_CHECK(A <= 1024, "FFM row of %d slots exceeds one CTA (Fc=%d k=%d)", A, Fc, k);
+    const int tpb = std::max(64, (A + 31) / 32 * 32);
+    const size_t smem = (size_t)Fc * A * vec * 4 + (size_t)Fc * 4 + 80 * 4;
+    LCTR_CHECK(smem <= 227 * 1024, "FFM field-pair tile needs %zu B shared memory (> 227 KB): Fc=%d k=%d", smem, Fc, k);
+    double* out_slot = c->stats + 2 * (c->step % kStatRing);
+#define FFM_GO(VECN, HV, TR)                                                                                          \
+    do {                                                                                                              \
+        auto kern = ffm_fused_kernel<VECN, HV, TR>;                                                                   \
+        LCTR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                \
+        kern<<<(unsigned)rows, tpb, smem, c->stream>>>(s.row_ptr, s.fid, s.field, s.val, s.label, c->W, c->V, Fc, k, \
+                                                       s.pred, c->gW, c->gV, c->touched, c->cfg.l2_reg, rb,          \
+                                                       c->stat_partial, c->stat_done, out_slot, stats ? 1 : 0);      \
+    } while (0)
+#define FFM_GO2(VECN)                                                                \
+    do {                                                                             \
+        if (s.has_val) { if (train) FFM_GO(VECN, true, true); else FFM_GO(VECN, true, false); } \
+        else { if (train) FFM_GO(VECN, false, true); else FFM_GO(VECN, false, false); }          \
+    } while (0)
+    if (vec == 4) FFM_GO2(4);
+    else if (vec == 2) FFM_GO2(2);
+    else FFM_GO2(1);
+#undef FFM_GO2
+#undef FFM_GO
+    c->launches++;
+    LCTR_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// forward+backward are one fused kernel; launch_ffm_backward is therefore a no-op kept for symmetry
+int launch_ffm_forward(lctr_ctx* c, Slot& s, int64_t rb, int64_t re, bool stats) {
+    return ffm_launch(c, s, rb, re, /*train=*/stats, stats);
+}
+int launch_ffm_backward(lctr_ctx*, Slot&, int64_t, int64_t) { return 0; }
+
+}  // namespace lctr
