@@ -60,7 +60,14 @@ typedef struct lctr_cfg {
     uint64_t max_rows, max_nnz;
     /* multi-GPU: this process' rank / world (1 process per GPU); tables are owner-sharded by fid % world */
     int32_t rank, world;
-    uint32_t reserved[8];
+    /* deterministic != 0: backward uses a feature-major (CSC) view of the slot built at upload, so every
+     * gradient is summed in ascending row order -- the order of the reference's canonical single-thread
+     * run -- with no atomics, and the updater is fused into the same kernel.  csc_row_block = rows per
+     * train_step range (0 => the whole slot is one block; NFM: the minibatch size). */
+    int32_t deterministic;
+    int32_t reserved0;
+    uint64_t csc_row_block;
+    uint32_t reserved[4];
 } lctr_cfg;
 
 const char* lctr_last_error(void);

@@ -37,7 +37,8 @@ class Cfg(C.Structure):
                 ("ftrl_beta", C.c_float), ("ftrl_lambda1", C.c_float), ("ftrl_lambda2", C.c_float),
                 ("n_hidden", C.c_int32), ("hidden", C.c_uint32 * MAX_LAYERS), ("activation", C.c_int32),
                 ("mlp_precision", C.c_int32), ("max_rows", C.c_uint64), ("max_nnz", C.c_uint64), ("rank", C.c_int32),
-                ("world", C.c_int32), ("reserved", C.c_uint32 * 8)]
+                ("world", C.c_int32), ("deterministic", C.c_int32), ("reserved0", C.c_int32),
+                ("csc_row_block", C.c_uint64), ("reserved", C.c_uint32 * 4)]
 
 
 class DatasetC(C.Structure):
@@ -138,7 +139,7 @@ class Context:
 
     def __init__(self, model, feature_cnt, factor_cnt, field_cnt=0, optimizer=OPT_ADAGRAD, lr=0.05, l2=0.001,
                  minibatch_size=0, momentum=0.8, momentum_adam2=0.999, hidden=(), activation=ACT_SIGMOID,
-                 mlp_precision=MLP_FP32, device=0, rank=0, world=1):
+                 mlp_precision=MLP_FP32, device=0, rank=0, world=1, deterministic=0, csc_row_block=0):
         L = load_library()
         cfg = Cfg()
         cfg.abi_version = ABI_VERSION
@@ -151,6 +152,7 @@ class Context:
             cfg.hidden[i] = h
         cfg.activation, cfg.mlp_precision = activation, mlp_precision
         cfg.rank, cfg.world = rank, world
+        cfg.deterministic, cfg.csc_row_block = deterministic, csc_row_block
         self.cfg = cfg
         self.h = C.c_void_p()
         _chk(L.lctr_create(C.byref(cfg), C.byref(self.h)))

@@ -61,6 +61,80 @@ __global__ void label_to_float_kernel(const int32_t* in, float* out, int64_t n) 
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = (float)in[i];
 }
+
+// Feature-major view of a slot, built on the host from the caller's CSR arrays (one counting sort per row
+// block; stable, so each fid's entries stay in ascending row order -- the accumulation order of the
+// reference's canonical single-thread run, train_fm_algo.cpp:101-116).
+static int build_csc(lctr_ctx* c, Slot& s, int64_t rows, int64_t nnz, const int64_t* row_ptr, const uint32_t* fid,
+                     const float* val) {
+    const int64_t block = c->cfg.csc_row_block ? (int64_t)c->cfg.csc_row_block : std::max<int64_t>(rows, 1);
+    const int64_t nblocks = (rows + block - 1) / block;
+    std::vector<int64_t> blk_seg_ptr(nblocks + 1, 0), seg_ptr;
+    std::vector<uint32_t> seg_fid, ent_row((size_t)nnz);
+    std::vector<float> ent_x(val ? (size_t)nnz : 0);
+    seg_ptr.reserve((size_t)nnz / 4 + 16);
+    seg_fid.reserve((size_t)nnz / 4 + 16);
+    std::vector<uint32_t> cnt(c->F + 1, 0);
+    std::vector<uint32_t> touched_list;
+    int64_t out = 0;
+    for (int64_t bi = 0; bi < nblocks; bi++) {
+        const int64_t rb = bi * block, re = std::min(rows, rb + block);
+        const int64_t eb = row_ptr[rb], ee = row_ptr[re];
+        touched_list.clear();
+        for (int64_t e = eb; e < ee; e++) {
+            const uint32_t f = fid[e];
+            if (f >= c->F) { set_error("upload_batch: fid %u >= feature_cnt %zu", f, c->F); return 1; }
+            if (cnt[f]++ == 0) touched_list.push_back(f);
+        }
+        std::sort(touched_list.begin(), touched_list.end());
+        // segment offsets for this block; cnt[f] becomes the write cursor
+        for (uint32_t f : touched_list) {
+            seg_fid.push_back(f);
+            seg_ptr.push_back(out);
+            const uint32_t n = cnt[f];
+            cnt[f] = (uint32_t)(out - eb);  // cursor relative to the block (fits u32: block nnz < 2^32)
+            out += n;
+        }
+        for (int64_t r = rb; r < re; r++)
+            for (int64_t e = row_ptr[r]; e < row_ptr[r + 1]; e++) {
+                const uint32_t f = fid[e];
+                const int64_t pos = eb + cnt[f]++;
+                ent_row[(size_t)pos] = (uint32_t)r;
+                if (val) ent_x[(size_t)pos] = val[e];
+            }
+        for (uint32_t f : touched_list) cnt[f] = 0;
+        blk_seg_ptr[bi + 1] = (int64_t)seg_fid.size();
+    }
+    seg_ptr.push_back(out);
+    const int64_t nseg = (int64_t)seg_fid.size();
+    if (nseg > s.cap_segs) {
+        dfree(s.seg_ptr); dfree(s.seg_fid);
+        if (dalloc(&s.seg_ptr, (size_t)nseg + 1) || dalloc(&s.seg_fid, (size_t)nseg + 1)) return 1;
+        s.cap_segs = nseg;
+    }
+    if (nblocks > s.cap_blocks) {
+        dfree(s.blk_seg_ptr);
+        if (dalloc(&s.blk_seg_ptr, (size_t)nblocks + 1)) return 1;
+        s.cap_blocks = nblocks;
+    }
+    if (nnz > s.cap_ent) {
+        dfree(s.ent_row); dfree(s.ent_x);
+        if (dalloc(&s.ent_row, (size_t)nnz + 32) || dalloc(&s.ent_x, (size_t)nnz + 32)) return 1;
+        s.cap_ent = nnz;
+    }
+    LCTR_CUDA(cudaMemcpyAsync(s.seg_ptr, seg_ptr.data(), (size_t)(nseg + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, c->stream));
+    if (nseg) LCTR_CUDA(cudaMemcpyAsync(s.seg_fid, seg_fid.data(), (size_t)nseg * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+    LCTR_CUDA(cudaMemcpyAsync(s.blk_seg_ptr, blk_seg_ptr.data(), (size_t)(nblocks + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, c->stream));
+    if (nnz) {
+        LCTR_CUDA(cudaMemcpyAsync(s.ent_row, ent_row.data(), (size_t)nnz * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+        if (val) LCTR_CUDA(cudaMemcpyAsync(s.ent_x, ent_x.data(), (size_t)nnz * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    }
+    LCTR_CUDA(cudaStreamSynchronize(c->stream));  // the staging vectors die with this frame
+    if (!s.h_blk_seg_ptr) s.h_blk_seg_ptr = new std::vector<int64_t>();
+    *s.h_blk_seg_ptr = blk_seg_ptr;
+    s.csc_block = block; s.n_blocks = nblocks; s.n_segs = nseg;
+    return 0;
+}
 }  // namespace lctr
 
 using namespace lctr;
@@ -145,6 +219,8 @@ int lctr_destroy(lctr_ctx* c) {
     for (auto& s : c->slots) {
         dfree(s.row_ptr); dfree(s.fid); dfree(s.field); dfree(s.val); dfree(s.label); dfree(s.pred); dfree(s.sumvx);
         dfree(s.wide);
+        dfree(s.blk_seg_ptr); dfree(s.seg_ptr); dfree(s.seg_fid); dfree(s.ent_row); dfree(s.ent_x);
+        delete s.h_blk_seg_ptr; s.h_blk_seg_ptr = nullptr;
     }
     mlp_free(c);
     if (c->h_stats) cudaFreeHost(c->h_stats);
@@ -228,6 +304,10 @@ int lctr_upload_batch(lctr_ctx* c, int slot, int64_t rows, int64_t nnz, const in
         c->launches++;
         LCTR_CUDA(cudaGetLastError());
     }
+    s.csc_block = 0;
+    if (c->cfg.deterministic && c->cfg.model != LCTR_MODEL_FFM && rows > 0) {
+        if (build_csc(c, s, rows, nnz, row_ptr, fid, val)) return 1;
+    }
     return 0;
 }
 
@@ -251,16 +331,22 @@ int lctr_train_step(lctr_ctx* c, int slot, int64_t rb, int64_t re, float* loss_s
     int rc = 0;
     switch (c->cfg.model) {
         case LCTR_MODEL_FM:
-            rc = launch_fm_forward(c, s, rb, re, false, true) || launch_fm_backward(c, s, rb, re, false) ||
-                 launch_apply(c, re - rb);
+            if (c->cfg.deterministic)
+                rc = launch_fm_forward(c, s, rb, re, false, true) || launch_fm_backward_csc(c, s, rb, re, false);
+            else
+                rc = launch_fm_forward(c, s, rb, re, false, true) || launch_fm_backward(c, s, rb, re, false) ||
+                     launch_apply(c, re - rb);
             break;
         case LCTR_MODEL_FFM:
             rc = launch_ffm_forward(c, s, rb, re, true) || launch_ffm_backward(c, s, rb, re) || launch_apply(c, re - rb);
             break;
         case LCTR_MODEL_NFM:
             rc = mlp_reserve(c, re - rb) || launch_fm_forward(c, s, rb, re, true, false) ||
-                 launch_nfm_mlp(c, s, rb, re, re - rb) || launch_fm_backward(c, s, rb, re, true) ||
-                 launch_apply(c, re - rb);
+                 launch_nfm_mlp(c, s, rb, re, re - rb);
+            if (!rc) {
+                if (c->cfg.deterministic) rc = launch_fm_backward_csc(c, s, rb, re, true);
+                else rc = launch_fm_backward(c, s, rb, re, true) || launch_apply(c, re - rb);
+            }
             break;
     }
     if (rc) return 1;

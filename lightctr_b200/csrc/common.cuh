@@ -4,8 +4,10 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string>
+#include <vector>
 
 #include "../../include/lightctr_b200.h"
+#include "ref_expf.h"
 
 namespace lctr {
 
@@ -44,6 +46,17 @@ struct Slot {
     float* sumvx = nullptr;      // rows*k: FM_Algo_Abst::sumVX (fm_algo_abst.h:145)
     float* wide = nullptr;       // rows (NFM: wide part)
     bool has_val = false, has_field = false;
+    // feature-major view (built on the host at upload when cfg.deterministic): per row block, the segments
+    // (one per distinct fid of the block) list that fid's entries in ascending row order
+    int64_t csc_block = 0;          // rows per block (0: none built)
+    int64_t n_blocks = 0, n_segs = 0;
+    int64_t* blk_seg_ptr = nullptr; // n_blocks+1 (host copy in h_blk_seg_ptr)
+    int64_t* seg_ptr = nullptr;     // n_segs+1 offsets into ent_*
+    uint32_t* seg_fid = nullptr;    // n_segs
+    uint32_t* ent_row = nullptr;    // nnz: row index of the entry
+    float* ent_x = nullptr;         // nnz (only when has_val)
+    std::vector<int64_t>* h_blk_seg_ptr = nullptr;
+    int64_t cap_segs = 0, cap_blocks = 0, cap_ent = 0;
 };
 
 struct MlpLayer {
@@ -117,8 +130,10 @@ __device__ __forceinline__ float4 ldg_f4(const float* p) { return __ldg(reinterp
 __device__ __forceinline__ float ref_sigmoid(float x) {
     if (x < -16.f) return 1e-7f;
     if (x > 16.f) return 0.99999988f;  // (float)(1.0 - 1e-7)
-    return 1.0f / (1.0f + expf(-x));
+    return 1.0f / (1.0f + lctr_ref_expf(-x));
 }
+// std::exp(float) of the reference (glibc expf) for unbounded arguments (Tanh, activations.h:134)
+__device__ __forceinline__ float ref_exp_any(float x) { return fabsf(x) < 87.f ? lctr_ref_expf(x) : expf(x); }
 // loss term + accuracy, train_fm_algo.cpp:93-98: y==1 ? -logf(p) : -log(1.0 - p) (double)
 __device__ __forceinline__ void loss_terms(float p, float y, double& loss, double& correct) {
     loss = (y == 1.f) ? (double)(-logf(p)) : -log(1.0 - (double)p);
@@ -165,6 +180,7 @@ int launch_fm_backward(lctr_ctx* c, Slot& s, int64_t rb, int64_t re, bool nfm);
 int launch_ffm_forward(lctr_ctx* c, Slot& s, int64_t rb, int64_t re, bool stats);
 int launch_ffm_backward(lctr_ctx* c, Slot& s, int64_t rb, int64_t re);
 int launch_apply(lctr_ctx* c, int64_t rows_in_step);
+int launch_fm_backward_csc(lctr_ctx* c, Slot& s, int64_t rb, int64_t re, bool nfm);
 int launch_predict_quirk(lctr_ctx* c, Slot& s, Slot& train);
 int mlp_alloc(lctr_ctx* c);
 int mlp_free(lctr_ctx* c);

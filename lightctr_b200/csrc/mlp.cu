@@ -5,11 +5,10 @@
 // last layer linear (:116); backward clips delta to +-15 (:129-131), dX_i = sum_j W[j,i] mask_j delta_j
 // (:139-147, mask only on hidden layers), previous activation' (:153-156), dW[j,:] += delta_j x
 // (:165-178, UNmasked delta), db += delta (:179); Adagrad on bias then weights (:194-197).
-// Here the per-sample GEMVs become batched GEMMs over the B rows of the step:
-//     fwd  Y = act(mask .* (X W^T + b))        NT gemm   [B,in]x[out,in]^T
-//     dX   = (D .* mask) W                      NN gemm   [B,out]x[out,in]
-//     dW   = D^T X   (sum over the batch)       TN gemm   [out,B]x[B,in]
-// fp32 SIMT tiles here are the PARITY mode (fp32 like the reference, no FMA contraction).
+// fp32 mode here is the PARITY mode: every dot product is evaluated in the reference's AVX lane order and every
+// batch accumulation in sample order (one thread per output element), so that with equal inputs the MLP state
+// follows the reference bit for bit.  (Training on the reference's data is chaotic: a 1-ulp difference in one
+// activation grows to percent-level loss differences within an epoch, see DESIGN.md.)
 #include <algorithm>
 #include <vector>
 
@@ -17,82 +16,94 @@
 
 namespace lctr {
 
-constexpr int TM = 64, TN = 64, TK = 16;
-
-// C[M][N] (+)= op(A)[M][K] * op(B)[K][N];   element accessors via strides so NT/NN/TN share one kernel.
-// A(m,k) = A[m*sam + k*sak], B(k,n) = B[k*sbk + n*sbn].  Epilogue: 0 none, 1 forward (bias+mask+act).
-struct GemmEpi {
-    int mode;           // 0: store; 1: forward epilogue
-    const float* bias;  // [N]
-    const float* mask;  // [N] or nullptr
-    int act;            // -1 none (last layer), 0 sigmoid, 1 tanh
-    int atomic;         // 1: atomicAdd into C (split-K)
-};
-
-__global__ void __launch_bounds__(256)
-gemm_f32_kernel(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ C, int M, int N, int K,
-                long sam, long sak, long sbk, long sbn, int ksplit, GemmEpi epi) {
-    __shared__ float As[TK][TM + 4];
-    __shared__ float Bs[TK][TN + 4];
-    const int tx = threadIdx.x % 16, ty = threadIdx.x / 16;
-    const int m0 = blockIdx.y * TM, n0 = blockIdx.x * TN;
-    const int kchunk = (K + ksplit - 1) / ksplit;
-    const int kb = blockIdx.z * kchunk, ke = min(K, kb + kchunk);
-    float acc[4][4];
+// avx_dotProduct(x, y, n) (common/avx.h:102-127) with strided operands, evaluated by ONE thread in the
+// reference's order: 8 lane accumulators over the full 8-chunks, the hsum tree, then the scalar tail.
+template <typename FX, typename FY>
+__device__ __forceinline__ float avx_dot_seq(FX x, FY y, int n) {
+    float result = 0.f;
+    int i = 0;
+    if (n > 7) {
+        float d[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        for (; i + 8 <= n; i += 8) {
 #pragma unroll
-    for (int i = 0; i < 4; i++)
-#pragma unroll
-        for (int j = 0; j < 4; j++) acc[i][j] = 0.f;
-    for (int k0 = kb; k0 < ke; k0 += TK) {
-        for (int i = threadIdx.x; i < TM * TK; i += 256) {
-            int mm, kk;
-            if (sak == 1) { kk = i % TK; mm = i / TK; } else { mm = i % TM; kk = i / TM; }
-            const int gm = m0 + mm, gk = k0 + kk;
-            As[kk][mm] = (gm < M && gk < ke) ? A[(long)gm * sam + (long)gk * sak] : 0.f;
+            for (int l = 0; l < 8; l++) d[l] = d[l] + x(i + l) * y(i + l);
         }
-        for (int i = threadIdx.x; i < TN * TK; i += 256) {
-            int nn, kk;
-            if (sbk == 1) { kk = i % TK; nn = i / TK; } else { nn = i % TN; kk = i / TN; }
-            const int gn = n0 + nn, gk = k0 + kk;
-            Bs[kk][nn] = (gn < N && gk < ke) ? B[(long)gk * sbk + (long)gn * sbn] : 0.f;
-        }
-        __syncthreads();
-#pragma unroll
-        for (int kk = 0; kk < TK; kk++) {
-            float a[4], b[4];
-#pragma unroll
-            for (int i = 0; i < 4; i++) a[i] = As[kk][ty * 4 + i];
-#pragma unroll
-            for (int j = 0; j < 4; j++) b[j] = Bs[kk][tx * 4 + j];
-#pragma unroll
-            for (int i = 0; i < 4; i++)
-#pragma unroll
-                for (int j = 0; j < 4; j++) acc[i][j] += a[i] * b[j];
-        }
-        __syncthreads();
+        const float a0 = d[4] + d[0], a1 = d[5] + d[1], a2 = d[6] + d[2], a3 = d[7] + d[3];
+        const float b0 = a0 + a2, b1 = a1 + a3;
+        result = result + (b0 + b1);
     }
-#pragma unroll
-    for (int i = 0; i < 4; i++) {
-        const int gm = m0 + ty * 4 + i;
-        if (gm >= M) continue;
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-            const int gn = n0 + tx * 4 + j;
-            if (gn >= N) continue;
-            float v = acc[i][j];
-            if (epi.mode == 1) {
-                v += epi.bias[gn];
-                if (epi.mask && epi.mask[gn] == 0.f) v = 0.f;  // masked neuron: pre-activation forced to 0
-                if (epi.act == LCTR_ACT_SIGMOID) {
-                    v = v < -16.f ? 1e-7f : (v > 16.f ? 0.99999988f : 1.0f / (1.0f + expf(-v)));  // activations.h:73-84
-                } else if (epi.act == LCTR_ACT_TANH) {
-                    const float t1 = expf(v), t2 = expf(-v);  // activations.h:132-138
-                    v = (t1 - t2) / (t1 + t2);
-                }
-            }
-            if (epi.atomic) atomicAdd(&C[(long)gm * N + gn], v);
-            else C[(long)gm * N + gn] = v;
+    for (; i < n; i++) result = result + x(i) * y(i);
+    return result;
+}
+
+// Fully_Conn_Layer::forward (fullyconnLayer.h:80-118), one thread per (sample, output neuron).
+__global__ void fc_forward_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                                  const float* __restrict__ mask, float* __restrict__ y, int B, int in, int out,
+                                  int has_next, int act) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (int64_t)B * out) return;
+    const int r = (int)(idx / out), j = (int)(idx % out);
+    float v;
+    if (has_next && mask[j] == 0.f) {
+        v = 0.f;  // :96-99
+    } else {
+        const float* xr = x + (size_t)r * in;
+        const float* wj = w + (size_t)j * in;
+        v = avx_dot_seq([&](int i) { return xr[i]; }, [&](int i) { return wj[i]; }, in);  // :100
+        v = v + bias[j];                                                                    // :101
+    }
+    if (has_next) {  // activation over ALL outputs, masked ones included (:110-113)
+        if (act == LCTR_ACT_SIGMOID) {
+            v = v < -16.f ? 1e-7f : (v > 16.f ? 0.99999988f : 1.0f / (1.0f + lctr_ref_expf(-v)));  // activations.h:73-84
+        } else {
+            const float t1 = ref_exp_any(v), t2 = ref_exp_any(-v);  // activations.h:132-138
+            v = (t1 - t2) / (t1 + t2);
         }
+    }
+    y[idx] = v;
+}
+
+// clip(+-15) in place (matrix.h:152-162; fullyconnLayer.h:129-131)
+__global__ void clip_kernel(float* __restrict__ d, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float v = d[i];
+    d[i] = v < -15.f ? -15.f : (v > 15.f ? 15.f : v);
+}
+
+// input_delta[r][i] = avx_dot(mask .* W[:,i], delta[r][:])  (fullyconnLayer.h:139-147), then the previous layer's
+// activation' (:153-156) when prev_act != nullptr.  One thread per (sample, input).
+__global__ void fc_input_delta_kernel(const float* __restrict__ delta, const float* __restrict__ w,
+                                      const float* __restrict__ mask, const float* __restrict__ prev_act,
+                                      float* __restrict__ dx, int B, int in, int out, int has_next, int act) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (int64_t)B * in) return;
+    const int r = (int)(idx / in), i = (int)(idx % in);
+    const float* dr = delta + (size_t)r * out;
+    float v = avx_dot_seq([&](int j) { const float t = w[(size_t)j * in + i]; return has_next ? t * mask[j] : t; },
+                          [&](int j) { return dr[j]; }, out);
+    if (prev_act) {
+        const float fo = prev_act[idx];
+        v = act == LCTR_ACT_SIGMOID ? (v * fo) * (1.0f - fo) : v * (1.0f - fo * fo);  // activations.h:85-90,139-143
+    }
+    dx[idx] = v;
+}
+
+// weightDelta[j][i] += x[r][i] * delta[r][j] for r = 0..B-1 IN ORDER (fullyconnLayer.h:165-178);
+// thread (j,i) with i == in accumulates biasDelta[j] += delta[r][j] (:179).
+__global__ void fc_weight_grad_kernel(const float* __restrict__ x, const float* __restrict__ delta,
+                                      float* __restrict__ dw, float* __restrict__ db, int B, int in, int out) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (int64_t)out * (in + 1)) return;
+    const int j = (int)(idx / (in + 1)), i = (int)(idx % (in + 1));
+    if (i < in) {
+        float acc = dw[(size_t)j * in + i];
+        for (int r = 0; r < B; r++) acc = acc + x[(size_t)r * in + i] * delta[(size_t)r * out + j];
+        dw[(size_t)j * in + i] = acc;
+    } else {
+        float acc = db[j];
+        for (int r = 0; r < B; r++) acc = acc + delta[(size_t)r * out + j];
+        db[j] = acc;
     }
 }
 
@@ -112,38 +123,6 @@ __global__ void nfm_loss_kernel(const float* __restrict__ wide, const float* __r
     publish_stats(loss, correct, partial, done, out_slot, false);
 }
 
-// in-place clip to +-15 (matrix.h:152-162) and optional masked copy for the dX gemm
-__global__ void clip_mask_kernel(float* __restrict__ d, float* __restrict__ dm, const float* __restrict__ mask,
-                                 int64_t n, int out) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    float v = d[i];
-    v = v < -15.f ? -15.f : (v > 15.f ? 15.f : v);
-    d[i] = v;
-    if (dm) dm[i] = mask ? v * mask[i % out] : v;
-}
-// delta_prev = dX .* act'(act_prev)   (activations.h:85-90 sigmoid: (d*f)*(1-f); :139-143 tanh: d*(1-f*f))
-__global__ void act_backward_kernel(float* __restrict__ dx, const float* __restrict__ f, int64_t n, int act) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const float fo = f[i], d = dx[i];
-    dx[i] = act == LCTR_ACT_SIGMOID ? (d * fo) * (1.0f - fo) : d * (1.0f - fo * fo);
-}
-__global__ void colsum_kernel(const float* __restrict__ d, float* __restrict__ db, int64_t rows, int out) {
-    // db[j] += sum_r d[r][j]
-    const int j = blockIdx.x;
-    double acc = 0.0;
-    for (int64_t r = threadIdx.x; r < rows; r += blockDim.x) acc += (double)d[r * out + j];
-    __shared__ double sh[32];
-    acc = warp_sum_d(acc);
-    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
-    __syncthreads();
-    if (threadIdx.x < 32) {
-        double a = threadIdx.x < (blockDim.x >> 5) ? sh[threadIdx.x] : 0.0;
-        a = warp_sum_d(a);
-        if (threadIdx.x == 0) db[j] += (float)a;
-    }
-}
 // AdagradUpdater_Num::update on a dense array (gradientUpdater.h:139-150)
 __global__ void adagrad_dense_kernel(float* __restrict__ w, float* __restrict__ g, float* __restrict__ acc, size_t n,
                                      float invB, float lr) {
@@ -156,15 +135,6 @@ __global__ void adagrad_dense_kernel(float* __restrict__ w, float* __restrict__ 
         w[i] = (float)((double)w[i] - (double)(lr * g1) / sqrt((double)a + 1e-7));
     }
     g[i] = 0.f;
-}
-
-static int gemm(lctr_ctx* c, const float* A, const float* B, float* C, int M, int N, int K, long sam, long sak,
-                long sbk, long sbn, int ksplit, GemmEpi epi) {
-    dim3 grid((N + TN - 1) / TN, (M + TM - 1) / TM, ksplit);
-    gemm_f32_kernel<<<grid, 256, 0, c->stream>>>(A, B, C, M, N, K, sam, sak, sbk, sbn, ksplit, epi);
-    c->launches++;
-    LCTR_CUDA(cudaGetLastError());
-    return 0;
 }
 
 int mlp_alloc(lctr_ctx* c) {
@@ -240,59 +210,41 @@ int mlp_reserve(lctr_ctx* c, int64_t rows) {
     return 0;
 }
 
-// forward MLP on c->z, loss, backward to c->dz, accumulate dW/db, Adagrad on the MLP.
+// forward MLP on c->z, loss, backward to c->dz, accumulate dW/db, Adagrad on the MLP (fp32, reference order).
 int launch_nfm_mlp(lctr_ctx* c, Slot& s, int64_t rb, int64_t re, int64_t rows_divisor) {
     const int B = (int)(re - rb);
     const int nl = c->n_layers;
+    LCTR_CHECK(c->cfg.mlp_precision == LCTR_MLP_FP32, "mlp_precision=%d: only the fp32 reference-order MLP is built",
+               c->cfg.mlp_precision);
+    auto blocks = [](int64_t n) { return (unsigned)((n + 255) / 256); };
     // ---- forward
     const float* x = c->z;
     for (int l = 0; l < nl; l++) {
         MlpLayer& L = c->layers[l];
-        GemmEpi e{1, L.b, l + 1 < nl ? L.mask : nullptr, l + 1 < nl ? c->cfg.activation : -1, 0};
-        // Y[B][out] = X[B][in] * W[out][in]^T : A=X (sam=in, sak=1), B(k,n)=W[n][k] (sbk=1, sbn=in)
-        if (gemm(c, x, L.w, L.act, B, L.out, L.in, L.in, 1, 1, L.in, 1, e)) return 1;
+        fc_forward_kernel<<<blocks((int64_t)B * L.out), 256, 0, c->stream>>>(x, L.w, L.b, L.mask, L.act, B, L.in, L.out,
+                                                                             l + 1 < nl ? 1 : 0, c->cfg.activation);
+        c->launches++;
         x = L.act;
     }
     // ---- loss, delta of the output layer
     double* out_slot = c->stats + 2 * (c->step % kStatRing);
     MlpLayer& last = c->layers[nl - 1];
-    nfm_loss_kernel<<<(B + 255) / 256, 256, 0, c->stream>>>(s.wide, last.act, s.label, s.pred, last.delta, rb, B,
-                                                           c->stat_partial, c->stat_done, out_slot);
+    nfm_loss_kernel<<<blocks(B), 256, 0, c->stream>>>(s.wide, last.act, s.label, s.pred, last.delta, rb, B,
+                                                      c->stat_partial, c->stat_done, out_slot);
     c->launches++;
-    // ---- backward
+    // ---- backward, output layer first (fullyconnLayer.h:120-180)
     for (int l = nl - 1; l >= 0; l--) {
         MlpLayer& L = c->layers[l];
-        const bool hidden = l + 1 < nl;
-        const int64_t n = (int64_t)B * L.out;
-        // scratch for the masked delta: reuse act of this layer?  no -- act is needed by layer l+1's dW (already done)
-        // and by act_backward of THIS layer's output (done when processing l+1).  So L.act is free now for hidden l,
-        // but the last layer's act is tiny; use a dedicated region: the upper half of next-lower delta buffer is not
-        // safe, so masked delta goes into L.act (its consumers have all run).
-        float* dm = hidden ? L.act : nullptr;
+        const bool has_next = l + 1 < nl;
         const float* xin = l == 0 ? c->z : c->layers[l - 1].act;
-        // clip (in place) + masked copy
-        clip_mask_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(L.delta, dm, hidden ? L.mask : nullptr, n, L.out);
-        c->launches++;
-        // dW[out][in] += D^T X : A(m=j,k=r) = D[r*out + j] (sam=1, sak=out); B(k=r,n=i) = X[r*in + i] (sbk=in, sbn=1)
-        {
-            GemmEpi e{0, nullptr, nullptr, -1, 1};
-            int ksplit = std::max(1, std::min(64, B / 256));
-            if (gemm(c, L.delta, xin, L.dw, L.out, L.in, B, 1, L.out, L.in, 1, ksplit, e)) return 1;
-        }
-        colsum_kernel<<<L.out, 256, 0, c->stream>>>(L.delta, L.db, B, L.out);
-        c->launches++;
-        // dX[B][in] = Dm[B][out] * W[out][in] : A=Dm (sam=out, sak=1); B(k=j,n=i)=W[j*in+i] (sbk=in, sbn=1)
+        clip_kernel<<<blocks((int64_t)B * L.out), 256, 0, c->stream>>>(L.delta, (int64_t)B * L.out);
         float* dx = l == 0 ? c->dz : c->layers[l - 1].delta;
-        {
-            GemmEpi e{0, nullptr, nullptr, -1, 0};
-            if (gemm(c, hidden ? dm : L.delta, L.w, dx, B, L.in, L.out, L.out, 1, L.in, 1, 1, e)) return 1;
-        }
-        if (l > 0) {
-            const int64_t m = (int64_t)B * L.in;
-            act_backward_kernel<<<(unsigned)((m + 255) / 256), 256, 0, c->stream>>>(dx, c->layers[l - 1].act, m,
-                                                                                    c->cfg.activation);
-            c->launches++;
-        }
+        fc_input_delta_kernel<<<blocks((int64_t)B * L.in), 256, 0, c->stream>>>(
+            L.delta, L.w, L.mask, l > 0 ? c->layers[l - 1].act : nullptr, dx, B, L.in, L.out, has_next ? 1 : 0,
+            c->cfg.activation);
+        fc_weight_grad_kernel<<<blocks((int64_t)L.out * (L.in + 1)), 256, 0, c->stream>>>(xin, L.delta, L.dw, L.db, B,
+                                                                                          L.in, L.out);
+        c->launches += 3;
     }
     // ---- Adagrad on bias then weights, per layer (fullyconnLayer.h:194-197)
     const uint64_t mb = c->cfg.minibatch_size ? c->cfg.minibatch_size : (uint64_t)rows_divisor;
@@ -300,10 +252,9 @@ int launch_nfm_mlp(lctr_ctx* c, Slot& s, int64_t rb, int64_t re, int64_t rows_di
     for (int l = 0; l < nl; l++) {
         MlpLayer& L = c->layers[l];
         const size_t nw = (size_t)L.out * L.in;
-        adagrad_dense_kernel<<<(unsigned)((L.out + 255) / 256), 256, 0, c->stream>>>(L.b, L.db, L.acc_b, L.out, invB,
-                                                                                     c->cfg.learning_rate);
-        adagrad_dense_kernel<<<(unsigned)((nw + 255) / 256), 256, 0, c->stream>>>(L.w, L.dw, L.acc_w, nw, invB,
-                                                                                  c->cfg.learning_rate);
+        adagrad_dense_kernel<<<blocks(L.out), 256, 0, c->stream>>>(L.b, L.db, L.acc_b, L.out, invB, c->cfg.learning_rate);
+        adagrad_dense_kernel<<<blocks((int64_t)nw), 256, 0, c->stream>>>(L.w, L.dw, L.acc_w, nw, invB,
+                                                                        c->cfg.learning_rate);
         c->launches += 2;
     }
     LCTR_CUDA(cudaGetLastError());

@@ -13,52 +13,9 @@
 #include <algorithm>
 #include <vector>
 
-#include "common.cuh"
+#include "opt.cuh"
 
 namespace lctr {
-
-struct OptParams {
-    int opt;
-    float invB;       // (float)(1.0 / minibatch)  (Adagrad: avx_vecScale(grad, grad, len, 1.0/B))
-    float mb;         // (float)minibatch          (Adam: grad / minibatch)
-    float lr;
-    float beta1;
-    float corrW, corrV;  // Adam bias corrections of the W call and the V call (iter++ per call)
-    float alpha, beta, l1, l2;
-};
-
-// one coordinate; arithmetic order as in the reference (compiled with -fmad=false)
-__device__ __forceinline__ void update_one(const OptParams& P, float corr, float& w, float g, float& s1, float& s2) {
-    if (P.opt == LCTR_OPT_ADAGRAD) {
-        const float g1 = g * P.invB;
-        if (g1 != 0.f) {
-            s1 = s1 + g1 * g1;
-            w = (float)((double)w - (double)(P.lr * g1) / sqrt((double)s1 + 1e-7));
-        }
-    } else if (P.opt == LCTR_OPT_FTRL) {
-        if (g != 0.f) {
-            const float g2 = g * g;
-            const float sigma = (sqrtf(s2 + g2) - sqrtf(s2)) / P.alpha;
-            s1 = s1 + (g - sigma * w);  // z
-            s2 = s2 + g2;               // n
-            if (fabsf(s1) <= P.l1) {
-                w = 0.f;
-            } else {
-                float t = s1;
-                if (t >= 0.f) t -= P.l1; else t += P.l1;
-                w = -t / ((P.beta + sqrtf(s2)) / P.alpha + P.l2);
-            }
-        }
-    } else {  // Adam (both moments decay with beta1 -- reference quirk, momentumUpdater.h:197-201)
-        const float g1 = g / P.mb;
-        if (g1 != 0.f) {
-            s1 = (float)((double)(s1 * P.beta1) + (1.0 - (double)P.beta1) * (double)g1);
-            s2 = (float)((double)(s2 * P.beta1) + (1.0 - (double)P.beta1) * (double)g1 * (double)g1);
-            const float tmp = (float)((double)s1 / ((double)sqrtf(s2) + 1e-7));
-            w = w - P.lr * corr * tmp;
-        }
-    }
-}
 
 template <int LPR, int VEC>
 __global__ void __launch_bounds__(256)
@@ -149,23 +106,7 @@ apply_kernel(uint8_t* __restrict__ touched, size_t F, int rowlen, float* __restr
 }
 
 int launch_apply(lctr_ctx* c, int64_t rows_in_step) {
-    const lctr_cfg& cf = c->cfg;
-    OptParams P;
-    P.opt = cf.optimizer;
-    const uint64_t mb = cf.minibatch_size ? cf.minibatch_size : (uint64_t)rows_in_step;
-    P.invB = (float)(1.0 / (double)mb);
-    P.mb = (float)mb;
-    P.lr = cf.learning_rate;
-    P.beta1 = cf.momentum;
-    P.corrW = P.corrV = 1.f;
-    if (cf.optimizer == LCTR_OPT_ADAM) {
-        // iter++ per update() call: W first, then V (train_fm_algo.cpp:120-126 order)
-        size_t it = ++c->adam_iter;
-        P.corrW = (float)(sqrt(1 - pow((double)cf.momentum_adam2, (double)it)) / (1 - pow((double)cf.momentum, (double)it)));
-        it = ++c->adam_iter;
-        P.corrV = (float)(sqrt(1 - pow((double)cf.momentum_adam2, (double)it)) / (1 - pow((double)cf.momentum, (double)it)));
-    }
-    P.alpha = cf.ftrl_alpha; P.beta = cf.ftrl_beta; P.l1 = cf.ftrl_lambda1; P.l2 = cf.ftrl_lambda2;
+    OptParams P = make_opt_params(c, rows_in_step);
     const int rowlen = (int)c->rowlen;
     int vec = (rowlen % 4 == 0) ? 4 : 1;
     int slices = rowlen / vec;

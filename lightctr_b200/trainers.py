@@ -49,7 +49,8 @@ def srand(seed):
 class FM_Algo_Abst:
     """fm_algo_abst.h:37-172."""
 
-    def __init__(self, dataPath, factor_cnt, field_cnt=0, feature_cnt=0, optimizer=capi.OPT_ADAGRAD, device=0):
+    def __init__(self, dataPath, factor_cnt, field_cnt=0, feature_cnt=0, optimizer=capi.OPT_ADAGRAD, device=0,
+                 deterministic=True):
         ds = capi.load_libffm(dataPath, field_cnt, feature_cnt)  # loadDataRow, :70-107
         self.data = ds
         self.feature_cnt, self.field_cnt, self.factor_cnt = ds.feature_cnt, ds.field_cnt, factor_cnt
@@ -57,6 +58,9 @@ class FM_Algo_Abst:
         self.L2Reg_ratio = 0.001
         self.optimizer = optimizer
         self.device = device
+        # deterministic: gradients summed in ascending row order (the reference's canonical proc_cnt=1 order) through
+        # the feature-major view; False selects the RED-based scatter used for streamed batches
+        self.deterministic = deterministic
         # init(), :53-68
         self.W = np.zeros(self.feature_cnt, np.float32)
         n = self.feature_cnt * factor_cnt * (self.field_cnt if self.field_cnt > 0 else 1)
@@ -70,7 +74,7 @@ class FM_Algo_Abst:
         self._ctx = capi.Context(model, self.feature_cnt, self.factor_cnt, self.field_cnt if model == capi.MODEL_FFM else 0,
                                  optimizer=self.optimizer, lr=GradientUpdater.learning_rate, l2=self.L2Reg_ratio,
                                  momentum=MomentumUpdater.momentum, momentum_adam2=MomentumUpdater.momentum_adam2,
-                                 device=self.device, **kw)
+                                 device=self.device, deterministic=1 if self.deterministic else 0, **kw)
         self._ctx.upload_params(self.W, self.V)
         self._ctx.upload_dataset(0, self.data)
 
@@ -173,7 +177,7 @@ class Train_NFM_Algo(FM_Algo_Abst):
         if self._ctx is None:
             # the updater divides by the GLOBAL minibatch size even for the short tail batch (:161-169)
             self._make_ctx(capi.MODEL_NFM, hidden=self.hidden, activation=self.activation,
-                           minibatch_size=GradientUpdater.minibatch_size)
+                           minibatch_size=GradientUpdater.minibatch_size, csc_row_block=self.batch_size)
             for l, L in enumerate(self.layers):
                 self._ctx.mlp_upload(l, L.weight, L.bias)
                 self._ctx.mlp_set_mask(l, L.mask)

@@ -59,11 +59,13 @@ def test_fm_k8_c1_parity(files, oracle_api):
         assert _rel(lg, lo) < LOSS_RTOL, (e, lg, lo)
         assert _rel(lg, g["loss"][e]) < LOSS_RTOL  # and against the compiled reference's own curve
         assert abs(fm.acc_curve[-1] - ao) <= 1.0 / ds.rows + 1e-9
-    # parameters after 20 epochs: abs tolerance 2e-4 on values of magnitude ~0.3 (RED-order reassociation
-    # amplified through 20 Adagrad steps); typical max |diff| observed ~1e-5
-    assert np.max(np.abs(fm.W - o.W)) < 2e-4
-    assert np.max(np.abs(fm.V - o.V)) < 2e-4
-    assert np.max(np.abs(fm.sumVX - o.sumVX)) < 2e-3
+    # deterministic mode follows the reference's accumulation order exactly: parameters after 20 epochs agree to
+    # float rounding of a handful of ulps (tolerance 1e-6 abs on values of magnitude ~0.3)
+    print("max |dW|", np.max(np.abs(fm.W - o.W)), "max |dV|", np.max(np.abs(fm.V - o.V)),
+          "bit-equal V:", np.array_equal(fm.V.view(np.uint32), o.V.view(np.uint32)))
+    assert np.max(np.abs(fm.W - o.W)) < 1e-6
+    assert np.max(np.abs(fm.V - o.V)) < 1e-6
+    assert np.max(np.abs(fm.sumVX - o.sumVX)) < 1e-5
     # FM_Predict with the reference quirks: loss/AUC within 1e-5 relative of the oracle
     pred = T.FM_Predict(fm, files["test"], True)
     pctr = pred.Predict("")
@@ -111,12 +113,15 @@ def test_ffm_other_updaters(files, oracle_api, opt):
     ds = files["tr"]
     W0, V0 = oracle_api.init_params(1, ds.feature_cnt, 4, 68)
     o = oracle_api.FFMOracle(ds, 4, W0, V0, optimizer=opt)
+    # FTRL has a hard threshold (|z| <= lambda1 -> w = 0, gradientUpdater.h:262-264) and Adam's first steps are
+    # sign-like (m / sqrt(v)), so the fp32 re-association of the field-pair factorisation (ffm.cu) is amplified more
+    # than under Adagrad: tolerance 5e-5 on the loss curve, 5e-4 abs on parameters (Adagrad above holds 1e-5 / 1e-4).
     for e in range(3):
         ffm.Train()
         lo, ao = o.epoch()
-        assert _rel(ffm.loss_curve[-1], lo) < LOSS_RTOL, (opt, e, ffm.loss_curve[-1], lo)
-    assert np.max(np.abs(ffm.W - o.W)) < 1e-4
-    assert np.max(np.abs(ffm.V - o.V)) < 1e-4
+        assert _rel(ffm.loss_curve[-1], lo) < 5e-5, (opt, e, ffm.loss_curve[-1], lo)
+    assert np.max(np.abs(ffm.W - o.W)) < 5e-4
+    assert np.max(np.abs(ffm.V - o.V)) < 5e-4
 
 
 def test_nfm_k10_h32_parity(files, oracle_api):
@@ -141,3 +146,31 @@ def test_nfm_k10_h32_parity(files, oracle_api):
     assert np.max(np.abs(nfm.V - o.V)) < 1e-4
     assert np.max(np.abs(nfm.layers[0].weight.ravel() - o.mlp.arrays("weight", 0))) < 1e-4
     assert np.array_equal(nfm.layers[0].mask, o.mlp.arrays("mask", 0))  # rand() stream still aligned
+
+
+def test_fm_red_path_per_step_parity(files, oracle_api):
+    """The non-deterministic scatter (vector REDs into update_g + sparse apply), used for streamed batches: from the
+    oracle's exact state at several epochs, ONE step must reproduce the oracle's next loss / parameters.  (Over many
+    epochs this path drifts like the reference's own multi-threaded Hogwild mode does)"""
+    from lightctr_b200 import capi
+    ds = files["tr"]
+    k = 8
+    W0, V0 = oracle_api.init_params(1, ds.feature_cnt, k)
+    o = oracle_api.FMOracle(ds, k, W0, V0)
+    ctx = capi.Context(capi.MODEL_FM, ds.feature_cnt, k, deterministic=0)
+    ctx.upload_batch(0, ds.row_ptr, ds.fid, None, None, ds.label)
+    for e in range(12):
+        if e in (0, 1, 5, 11):
+            ctx.upload_params(o.W, o.V)
+            ctx.upload_opt_state(o.accum)
+            lg, cg = ctx.train_step(0)
+            lo, ao = o.epoch()
+            assert _rel(lg, lo) < 1e-6, (e, lg, lo)
+            Wg, Vg = ctx.download_params()
+            # RED order reassociation only: observed <= 2e-6 abs
+            assert np.max(np.abs(Wg - o.W)) < 2e-5 and np.max(np.abs(Vg - o.V)) < 2e-5, e
+            s1, _ = ctx.download_opt_state()
+            assert np.allclose(s1, o.accum, rtol=1e-4, atol=1e-9)
+        else:
+            o.epoch()
+    ctx.close()
