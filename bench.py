@@ -1,0 +1,293 @@
+#!/usr/bin/env python
+"""bench.py -- the headline measurement (BASELINE.json metric) of the B200-native LightCTR hot path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload fm_c2|ffm_c3]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is one pass of the hot path (gather -> interaction -> loss -> scatter-add -> updater) over one batch of
+synthetic Criteo-shaped input.  N=1 workload = BASELINE.json configs[1]: FM k=16, 1M features, 39 fields,
+~77 nnz/row, batch 4096, Adagrad.  Prints ONE JSON line (rank 0).
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+WORKLOADS = {
+    # name: (model, k, F, batch, optimizer)
+    "fm_c2": dict(model="fm", k=16, F=1_000_000, batch=4096, opt="adagrad",
+                  desc="FM k=16, 1M synthetic Criteo-shape features (39 fields, ~77 nnz/row), batch 4096, Adagrad"),
+    "ffm_c3": dict(model="ffm", k=4, F=1_000_000, batch=8192, opt="ftrl",
+                   desc="FFM k=4, 39 fields, 1M features, batch 8192, FTRL"),
+    "ffm_c5": dict(model="ffm", k=8, F=10_000_000, batch=65536, opt="adagrad",
+                   desc="FFM k=8, 39 fields, 10M features, global batch 65536, Adagrad"),
+}
+N_FIELDS = 39
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, gpu_index=0, period_ms=100):
+        super().__init__(daemon=True)
+        self.q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+                  "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+                  "clocks_event_reasons.sw_power_cap")
+        self.gpu, self.period, self.samples, self.proc = gpu_index, period_ms, [], None
+        self.stop_flag = False
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.q,
+                                          "--format=csv,noheader,nounits", "-lms", str(self.period)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                if self.stop_flag:
+                    break
+                self.samples.append(line.strip())
+        except Exception:
+            pass
+
+    def finish(self):
+        self.stop_flag = True
+        if self.proc:
+            self.proc.terminate()
+        sm, mx, reasons = [], 0, set()
+        for s in self.samples:
+            p = [x.strip() for x in s.split(",")]
+            if len(p) < 8:
+                continue
+            try:
+                sm.append(float(p[1]))
+                mx = max(mx, float(p[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("hbm_gbs", 6650.0), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def make_batches(wl, n_batches, seed_offset=0):
+    from lightctr_b200.data import BASE_SEED, CriteoSynth
+    gen = CriteoSynth(wl["F"], seed=BASE_SEED + seed_offset, alpha=float(os.environ.get("LCTR_BENCH_ALPHA", "1.1")))
+    return [gen.batch(wl["batch"]) for _ in range(n_batches)]
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm / cpu_baseline: the reference's own Train() on the host cores
+# ------------------------------------------------------------------------------------------------
+def run_reference(wl, steps, warmup, budget_s=20.0):
+    """Times Train_FM_Algo / Train_FFM_Algo::Train() of the UNMODIFIED reference (oracle/_ref/libref.so) on one
+    synthetic batch written in its libffm text format; one epoch over the B-row file == one step."""
+    from lightctr_b200.data import write_libffm
+    from oracle import api
+    if not api.ref_available():
+        return None
+    rp, fid, fld, lab = make_batches(wl, 1)[0]
+    path = "/tmp/lctr_bench_%s_%d.txt" % (wl["model"], os.getpid())
+    write_libffm(path, rp, fid, fld, lab)
+    cores = int(api.ref().ref_hw_threads())
+    if wl["model"] == "fm":
+        t = api.RefTrainer("fm", path, wl["k"], seed=1, proc_cnt=0)
+    else:
+        t = api.RefTrainer("ffm", path, wl["k"], seed=1, proc_cnt=0, field_cnt=N_FIELDS)
+    rows = t.rows
+    t0 = time.time()
+    t.time_train(max(1, warmup))
+    per = (time.time() - t0) / max(1, warmup)
+    steps = max(1, min(steps, int(budget_s / max(per, 1e-6))))
+    secs = t.time_train(steps)
+    t.close()
+    os.unlink(path)
+    return dict(value=rows * steps / secs, cores=cores, steps=steps, ms_per_step=1e3 * secs / steps, rows=rows,
+                sample="%d epochs of Train() over one %d-row synthetic batch (%d features), all %d host threads"
+                       % (steps, rows, wl["F"], cores))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=None)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    wname = args.workload or ("fm_c2" if world == 1 else "ffm_c5")
+    wl = WORKLOADS[wname]
+    metric = "samples/sec (device-timed) %s train step on Criteo-shape" % wl["model"].upper()
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        r = run_reference(wl, args.steps, max(args.warmup, 1))
+        if r is None:
+            print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libref.so not built"}))
+            return 0
+        line = {"impl": "reference", "metric": metric, "value": r["value"], "unit": "samples/s", "n_gpus": args.gpus,
+                "steps": r["steps"], "warmup": max(args.warmup, 1), "ms_per_step": r["ms_per_step"],
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": wl["desc"]},
+                "cpu_baseline": {"value": r["value"], "unit": "samples/s", "cores": r["cores"], "kind": "reference",
+                                 "sample": r["sample"]},
+                "e2e": {"value": r["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return 0
+
+    import torch
+    from lightctr_b200 import build as lbuild
+    from lightctr_b200 import capi
+    lbuild.build()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the product has no CPU path)")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    if world > 1:
+        raise SystemExit("bench.py: multi-GPU path not built yet in this revision")
+
+    model = {"fm": capi.MODEL_FM, "ffm": capi.MODEL_FFM}[wl["model"]]
+    opt = {"adagrad": capi.OPT_ADAGRAD, "ftrl": capi.OPT_FTRL, "adam": capi.OPT_ADAM}[wl["opt"]]
+    F, k, B = wl["F"], wl["k"], wl["batch"]
+    Fc = N_FIELDS if wl["model"] == "ffm" else 0
+    ctx = capi.Context(model, F, k, Fc, optimizer=opt, device=local_rank, deterministic=0)
+    rng = np.random.default_rng(1234 + rank)
+    rowlen = k * max(Fc, 1)
+    V0 = (rng.standard_normal(F * rowlen, dtype=np.float32) * np.float32(1.0 / np.sqrt(k)))
+    ctx.upload_params(np.zeros(F, np.float32), V0)
+    del V0
+    NB = 8
+    batches = make_batches(wl, NB, seed_offset=rank)
+    # pinned host copies (the end-to-end arm copies from these every step)
+    pinned = []
+    for (rp, fid, fld, lab) in batches:
+        t_rp = torch.from_numpy(rp).pin_memory()
+        t_fid = torch.from_numpy(fid.astype(np.int32)).pin_memory()  # same bits as uint32
+        t_fld = torch.from_numpy(fld.astype(np.int16)).pin_memory()
+        t_lab = torch.from_numpy(lab).pin_memory()
+        pinned.append((t_rp, t_fid, t_fld, t_lab))
+    for i, (rp, fid, fld, lab) in enumerate(batches):
+        ctx.upload_batch(i, rp, fid, fld if Fc else None, None, lab)
+    nnz_mean = float(np.mean([len(b[1]) for b in batches]))
+    stream = torch.cuda.ExternalStream(ctx.stream())
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
+
+    do_flush = os.environ.get("LCTR_BENCH_NOFLUSH", "0") != "1"
+
+    def one_step(i, timed_events=None):
+        with torch.cuda.stream(stream):
+            if do_flush:
+                flush.zero_()
+            if timed_events is not None:
+                timed_events[0].record(stream)
+        ctx.train_step(i % NB, want_stats=False)
+        if timed_events is not None:
+            with torch.cuda.stream(stream):
+                timed_events[1].record(stream)
+
+    for i in range(max(args.warmup, 3)):
+        one_step(i)
+    ctx.sync()
+    ctx.profile(True)
+    ctx.profile_read(reset=True)
+    launches0 = ctx.launch_count()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    torch.cuda.synchronize()
+    t_wall0 = time.time()
+    for i in range(args.steps):
+        one_step(i, evs[i])
+    ctx.sync()
+    torch.cuda.synchronize()
+    t_wall = time.time() - t_wall0
+    launches = ctx.launch_count() - launches0
+    prof = ctx.profile_read(reset=True)
+    ctx.profile(False)
+    step_ms = [a.elapsed_time(b) for a, b in evs]
+    ms_per_step = float(np.mean(step_ms))
+    value = B / (ms_per_step * 1e-3)
+
+    # ---- end-to-end arm: host buffers in, loss out, every step (C-ABI lctr_train_batch) ------------------
+    h2d = 8 * (B + 1) + 4 * nnz_mean + 4 * B + (2 * nnz_mean if Fc else 0)
+    for i in range(3):
+        ctx.train_batch(*_host_arrays(pinned[i % NB], Fc))
+    ctx.sync()
+    t0 = time.time()
+    for i in range(args.steps):
+        ctx.train_batch(*_host_arrays(pinned[i % NB], Fc))
+    ctx.sync()
+    e2e_s = time.time() - t0
+    clocks = sampler.finish()
+    e2e_value = B * args.steps / e2e_s
+
+    # ---- roofline of the dominant kernel (algorithmic bytes per SURVEY.md 8d / DESIGN.md) -----------------
+    peak, peak_src = measured_peaks()
+    dom = max(prof.items(), key=lambda kv: kv[1][0]) if prof else (None, (0.0, 0))
+    n = nnz_mean / B
+    if wl["model"] == "fm":
+        bytes_per_sample = {"fm_forward": n * (4 * k + 12) + 8, "fm_backward_red": n * (4 * k + 12) + 8,
+                            "apply": None}
+    else:
+        bytes_per_sample = {"ffm_fused": n * (Fc * k * 4 + 12)}
+    roof = None
+    if dom[0] is not None:
+        ms, cnt = dom[1]
+        bps = bytes_per_sample.get(dom[0])
+        if bps is not None and cnt:
+            achieved = bps * B / (ms / cnt * 1e-3) / 1e9
+            roof = {"bound": "hbm", "kernel": dom[0], "achieved": achieved, "peak": peak, "unit": "GB/s",
+                    "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                    "algorithmic_bytes_per_launch": bps * B, "kernel_ms": ms / cnt}
+    kernels = {name: {"ms": v[0] / max(v[1], 1), "launches": v[1]} for name, v in prof.items()}
+    line = {"metric": metric, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": wl["desc"], "l2": "flushed between timed steps (256 MB write)", "batch": B,
+                       "nnz_per_row": n, "backward": "RED scatter + sparse apply (streamed batches)"},
+            "clocks": clocks, "gpu_launches": int(launches), "kernels_ms": kernels,
+            "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 16},
+            "roofline": roof, "wall_s_timed_region": t_wall}
+    if not args.no_cpu_baseline and rank == 0 and world == 1:
+        r = run_reference(wl, 50, 1, budget_s=15.0)
+        if r is not None:
+            line["cpu_baseline"] = {"value": r["value"], "unit": "samples/s", "cores": r["cores"], "kind": "reference",
+                                    "sample": r["sample"]}
+    if rank == 0:
+        print(json.dumps(line))
+    ctx.close()
+    return 0
+
+
+def _host_arrays(p, Fc):
+    t_rp, t_fid, t_fld, t_lab = p
+    return (t_rp.numpy(), t_fid.numpy().view(np.uint32), t_fld.numpy().view(np.uint16) if Fc else None, None,
+            t_lab.numpy())
+
+
+if __name__ == "__main__":
+    sys.exit(main())

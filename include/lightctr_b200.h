@@ -144,6 +144,12 @@ typedef struct lctr_dataset {
 int lctr_load_libffm(const char* path, uint64_t field_cnt_in, uint64_t feature_cnt_in, lctr_dataset** out);
 int lctr_free_dataset(lctr_dataset* d);
 
+/* per-kernel device timing for bench.py's roofline: when enabled, every launch on the ctx stream is bracketed by
+ * CUDA events; lctr_profile_read sums the elapsed ms and launch counts per kernel class
+ * (0 fm_forward, 1 fm_backward(RED), 2 sparse apply, 3 ffm_fused, 4 fm_backward(CSC)+update, 5 mlp). */
+int lctr_profile(lctr_ctx* ctx, int enable);
+int lctr_profile_read(lctr_ctx* ctx, double* ms, int64_t* counts, int n, int reset);
+
 /* introspection for tests / bench: number of kernels this library has launched on ctx so far */
 int64_t lctr_launch_count(const lctr_ctx* ctx);
 /* raw CUDA stream handle (cudaStream_t) of the ctx, for event timing on the launching stream */

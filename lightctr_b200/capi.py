@@ -25,7 +25,7 @@ SYMBOLS = [
     "lctr_download_params", "lctr_download_opt_state", "lctr_upload_opt_state", "lctr_upload_batch",
     "lctr_train_step", "lctr_train_batch", "lctr_predict", "lctr_download_sumvx", "lctr_download_pred",
     "lctr_mlp_upload", "lctr_mlp_download", "lctr_mlp_set_mask", "lctr_ipc_export", "lctr_ipc_import",
-    "lctr_dense_grad_buffer", "lctr_load_libffm", "lctr_free_dataset", "lctr_launch_count", "lctr_stream",
+    "lctr_dense_grad_buffer", "lctr_load_libffm", "lctr_free_dataset", "lctr_launch_count", "lctr_stream", "lctr_profile", "lctr_profile_read",
 ]
 
 
@@ -86,6 +86,8 @@ def load_library():
     L.lctr_launch_count.restype = C.c_int64
     L.lctr_stream.argtypes = [vp]
     L.lctr_stream.restype = vp
+    L.lctr_profile.argtypes = [vp, C.c_int]
+    L.lctr_profile_read.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.c_int, C.c_int]
     _lib = L
     return L
 
@@ -257,6 +259,17 @@ class Context:
     def mlp_set_mask(self, layer, mask):
         m = np.ascontiguousarray(mask, np.float32)
         _chk(self.L.lctr_mlp_set_mask(self.h, layer, m.ctypes.data))
+
+    PROF_NAMES = ["fm_forward", "fm_backward_red", "apply", "ffm_fused", "fm_backward_csc", "mlp", "", ""]
+
+    def profile(self, enable=True):
+        _chk(self.L.lctr_profile(self.h, 1 if enable else 0))
+
+    def profile_read(self, reset=True):
+        ms = (C.c_double * 8)()
+        cnt = (C.c_int64 * 8)()
+        _chk(self.L.lctr_profile_read(self.h, ms, cnt, 8, 1 if reset else 0))
+        return {self.PROF_NAMES[i]: (ms[i], cnt[i]) for i in range(8) if cnt[i] > 0}
 
     def launch_count(self):
         return self.L.lctr_launch_count(self.h)

@@ -183,6 +183,9 @@ int lctr_create(const lctr_cfg* cfg, lctr_ctx** out) {
     rc |= dalloc(&c->s1W, c->F); rc |= dalloc(&c->s1V, nv);
     if (two) { rc |= dalloc(&c->s2W, c->F); rc |= dalloc(&c->s2V, nv); }
     rc |= dalloc(&c->touched, c->F + 512);
+    rc |= dalloc(&c->touch_list, c->F + 32);
+    rc |= dalloc(&c->n_touch, 1);
+    rc |= dalloc(&c->apply_done, 1);
     rc |= dalloc(&c->stats, (size_t)2 * kStatRing);
     rc |= dalloc(&c->stat_partial, 2);
     rc |= dalloc(&c->stat_done, 1);
@@ -199,6 +202,8 @@ int lctr_create(const lctr_cfg* cfg, lctr_ctx** out) {
         LCTR_CUDA(cudaMemsetAsync(c->s2V, 0, nv * sizeof(float), c->stream));
     }
     LCTR_CUDA(cudaMemsetAsync(c->touched, 0, c->F + 512, c->stream));
+    LCTR_CUDA(cudaMemsetAsync(c->n_touch, 0, sizeof(unsigned int), c->stream));
+    LCTR_CUDA(cudaMemsetAsync(c->apply_done, 0, sizeof(unsigned int), c->stream));
     LCTR_CUDA(cudaMemsetAsync(c->stats, 0, sizeof(double) * 2 * kStatRing, c->stream));
     LCTR_CUDA(cudaMemsetAsync(c->stat_partial, 0, sizeof(double) * 2, c->stream));
     LCTR_CUDA(cudaMemsetAsync(c->stat_done, 0, sizeof(unsigned int), c->stream));
@@ -215,7 +220,7 @@ int lctr_destroy(lctr_ctx* c) {
     cudaSetDevice(c->cfg.device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     dfree(c->W); dfree(c->V); dfree(c->gW); dfree(c->gV); dfree(c->s1W); dfree(c->s1V); dfree(c->s2W); dfree(c->s2V);
-    dfree(c->touched); dfree(c->stats); dfree(c->stat_partial); dfree(c->stat_done);
+    dfree(c->touched); dfree(c->touch_list); dfree(c->n_touch); dfree(c->apply_done); dfree(c->stats); dfree(c->stat_partial); dfree(c->stat_done);
     for (auto& s : c->slots) {
         dfree(s.row_ptr); dfree(s.fid); dfree(s.field); dfree(s.val); dfree(s.label); dfree(s.pred); dfree(s.sumvx);
         dfree(s.wide);
@@ -421,6 +426,30 @@ int lctr_ipc_import(lctr_ctx* c, const void* all_handles, size_t bytes_per_rank)
     (void)c; (void)all_handles; (void)bytes_per_rank;
     set_error("lctr_ipc_import: multi-GPU table sharding not built yet (DESIGN.md, row e)");
     return 1;
+}
+
+int lctr_profile(lctr_ctx* c, int enable) {
+    LCTR_CHECK(c, "null ctx");
+    if (enable && !c->prof_ev) { c->prof_ev = new std::vector<cudaEvent_t>(); c->prof_id = new std::vector<int>(); }
+    c->profiling = enable ? 1 : 0;
+    return 0;
+}
+int lctr_profile_read(lctr_ctx* c, double* ms, int64_t* counts, int n, int reset) {
+    LCTR_CHECK(c && ms && counts, "null argument");
+    LCTR_CUDA(cudaStreamSynchronize(c->stream));
+    if (c->prof_ev) {
+        for (size_t i = 0; i < c->prof_id->size(); i++) {
+            float t = 0.f;
+            cudaEventElapsedTime(&t, (*c->prof_ev)[2 * i], (*c->prof_ev)[2 * i + 1]);
+            const int id = (*c->prof_id)[i];
+            if (id >= 0 && id < kNumProf) { c->prof_ms[id] += t; c->prof_cnt[id]++; }
+            cudaEventDestroy((*c->prof_ev)[2 * i]); cudaEventDestroy((*c->prof_ev)[2 * i + 1]);
+        }
+        c->prof_ev->clear(); c->prof_id->clear();
+    }
+    for (int i = 0; i < n && i < kNumProf; i++) { ms[i] = c->prof_ms[i]; counts[i] = c->prof_cnt[i]; }
+    if (reset) for (int i = 0; i < kNumProf; i++) { c->prof_ms[i] = 0; c->prof_cnt[i] = 0; }
+    return 0;
 }
 
 int64_t lctr_launch_count(const lctr_ctx* c) { return c ? c->launches : 0; }

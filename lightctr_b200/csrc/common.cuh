@@ -30,7 +30,9 @@ void set_error(const char* fmt, ...);
         }                                      \
     } while (0)
 
-constexpr int kNumSlots = 4;
+constexpr int kNumSlots = 8;
+constexpr int kNumProf = 8;  // per-kernel timing buckets
+enum { PROF_FM_FWD = 0, PROF_FM_BWD_RED = 1, PROF_APPLY = 2, PROF_FFM_FUSED = 3, PROF_FM_BWD_CSC = 4, PROF_MLP = 5 };
 constexpr int kStatRing = 64;
 constexpr unsigned kFull = 0xffffffffu;
 
@@ -78,6 +80,9 @@ struct lctr_ctx {
     float *W = nullptr, *V = nullptr, *gW = nullptr, *gV = nullptr;
     float *s1W = nullptr, *s1V = nullptr, *s2W = nullptr, *s2V = nullptr;
     uint8_t* touched = nullptr;  // F bytes: 1 = fid received gradient this step
+    uint32_t* touch_list = nullptr;      // compacted fids of the step (stage A of the sparse apply)
+    unsigned int* n_touch = nullptr;     // list length (device)
+    unsigned int* apply_done = nullptr;  // block-completion counter of stage B
     // per-step statistics ring: [kStatRing][2] doubles (loss sum, correct count) + scratch
     double* stats = nullptr;
     double* stat_partial = nullptr;     // [2] running accumulation of the current step
@@ -96,6 +101,12 @@ struct lctr_ctx {
     size_t mlp_cap_rows = 0;
     int sm_count = 148;
     int64_t launches = 0;
+    // optional per-kernel timing (lctr_profile): events bracket every launch on the ctx stream
+    int profiling = 0;
+    std::vector<cudaEvent_t>* prof_ev = nullptr;   // flat list of (start, stop) pairs
+    std::vector<int>* prof_id = nullptr;
+    double prof_ms[lctr::kNumProf] = {0};
+    int64_t prof_cnt[lctr::kNumProf] = {0};
     // pinned staging for lctr_train_batch (end-to-end path)
     void* h_stage = nullptr;
     size_t h_stage_bytes = 0;
@@ -175,6 +186,20 @@ __device__ __forceinline__ void publish_stats(double loss, double correct, doubl
 // ---------------------------------------------------------------------------------------------
 // kernel launchers (defined in the .cu files)
 // ---------------------------------------------------------------------------------------------
+// RAII bracket: records a (start, stop) event pair around one launch when profiling is on
+struct ProfScope {
+    lctr_ctx* c; int id; cudaEvent_t a = nullptr, b = nullptr;
+    ProfScope(lctr_ctx* c_, int id_) : c(c_), id(id_) {
+        if (!c->profiling) return;
+        cudaEventCreate(&a); cudaEventCreate(&b);
+        cudaEventRecord(a, c->stream);
+    }
+    ~ProfScope() {
+        if (!a) return;
+        cudaEventRecord(b, c->stream);
+        c->prof_ev->push_back(a); c->prof_ev->push_back(b); c->prof_id->push_back(id);
+    }
+};
 int launch_fm_forward(lctr_ctx* c, Slot& s, int64_t rb, int64_t re, bool nfm, bool stats);
 int launch_fm_backward(lctr_ctx* c, Slot& s, int64_t rb, int64_t re, bool nfm);
 int launch_ffm_forward(lctr_ctx* c, Slot& s, int64_t rb, int64_t re, bool stats);

@@ -211,6 +211,7 @@ static int ffm_launch(lctr_ctx* c, Slot& s, int64_t rb, int64_t re, bool train, 
     const size_t smem = (size_t)Fc * A * vec * 4 + (size_t)Fc * 4 + 80 * 4;
     LCTR_CHECK(smem <= 227 * 1024, "FFM field-pair tile needs %zu B shared memory (> 227 KB): Fc=%d k=%d", smem, Fc, k);
     double* out_slot = c->stats + 2 * (c->step % kStatRing);
+    ProfScope prof(c, PROF_FFM_FUSED);
 #define FFM_GO(VECN, HV, TR)                                                                                          \
     do {                                                                                                              \
         auto kern = ffm_fused_kernel<VECN, HV, TR>;                                                                   \

@@ -10,6 +10,8 @@
 // with one coalesced 128 B load and redistributed by shuffle.  All gathers of a 32-entry chunk are
 // issued before any is consumed (LPR independent 16 B loads in flight per lane).  Interaction sums
 // are reduced with xor-shuffles.  HBM/L2-bound integer+fp32 work: no tensor cores here by design.
+#include <stdlib.h>
+
 #include "opt.cuh"
 
 namespace lctr {
@@ -34,100 +36,137 @@ __device__ __forceinline__ Vec<VEC> load_row(const float* p, bool active) {
 // ------------------------------------------------------------------------------------------------
 // forward -- arithmetic in the reference's own order
 // ------------------------------------------------------------------------------------------------
-// avx_dotProduct(x, x, k) of common/avx.h:102-127 evaluated across the LR lanes of one sample group:
-// lane c holds p = x_c*x_c.  Full 8-chunks are accumulated lane-wise (d_l = p_l + p_{l+8} + ...), then
-// the hsum tree (d_i + d_{i+4}; a_0 + a_2, a_1 + a_3; b_0 + b_1), then the scalar tail in order.
-// Result valid in lane c == 0 of the group.  All 32 lanes must call this.
-template <int LR>
-__device__ __forceinline__ float avx_dot_lanes(float p, int k, int c) {
-    const int nfull = k >> 3;
+// avx_dotProduct(t, t, K) (common/avx.h:102-127) on K register-resident values, in the reference's order:
+// 8 lane accumulators over the full 8-chunks, the hsum tree, then the scalar tail.
+template <int K>
+__device__ __forceinline__ float avx_dot_regs(const float (&t)[K]) {
     float result = 0.f;
-    if (nfull > 0) {
-        float d = p;
-        if (LR > 8) {
-            for (int m = 1; m < nfull; m++) {
-                const float o = __shfl_down_sync(kFull, p, 8 * m, LR);
-                d = d + o;
-            }
-        }
-        float a = d + __shfl_down_sync(kFull, d, 4, LR);
-        float b = a + __shfl_down_sync(kFull, a, 2, LR);
-        result = b + __shfl_down_sync(kFull, b, 1, LR);
+    constexpr int NFULL = K / 8;
+    if (NFULL > 0) {
+        float d[8];
+#pragma unroll
+        for (int l = 0; l < 8; l++) d[l] = t[l] * t[l];
+#pragma unroll
+        for (int m = 1; m < NFULL; m++)
+#pragma unroll
+            for (int l = 0; l < 8; l++) d[l] = d[l] + t[8 * m + l] * t[8 * m + l];
+        const float a0 = d[4] + d[0], a1 = d[5] + d[1], a2 = d[6] + d[2], a3 = d[7] + d[3];
+        const float b0 = a0 + a2, b1 = a1 + a3;
+        result = b0 + b1;
     }
-    for (int t = nfull * 8; t < k; t++) {
-        const float o = __shfl_sync(kFull, p, t, LR);
-        result = result + o;
-    }
-    (void)c;
+#pragma unroll
+    for (int i = NFULL * 8; i < K; i++) result = result + t[i] * t[i];
     return result;
 }
 
-// One sample per group of LR lanes (LR = next power of two >= k); lane c of the group owns factor c and
-// walks the sample's features IN ORDER, so sumVX[c], the bi-interaction z[c] and -- on lane 0 -- the
-// float/double fm_pred chain of train_fm_algo.cpp:69-84 are evaluated exactly as the reference does.
-// The LR gathers of a chunk are all issued before the first is consumed.
-template <int LR, bool HAS_VAL, bool NFM>
+// Forward, two phases per warp (= one sample):
+//   phase 1 (order-free, wide): lane j owns feature j of the current block of NB features: it gathers the whole
+//     V row (K floats, K/4 x 16 B loads, all in flight at once), forms t = V*x, its avx-ordered self dot product
+//     entirely in registers (no shuffles) and W*x, and parks {t[0..K), dot, w*x} in the warp's shared-memory tile.
+//   phase 2 (in-order, light): the tile is read back transposed -- lane c accumulates sumVX[c] (and NFM's z[c])
+//     over the features IN ORDER, every lane replays the scalar fm_pred chain -- so the per-sample arithmetic
+//     sequence is exactly train_fm_algo.cpp:69-84.  (fm_pred -= 0.5*dot is formed in double there and rounded
+//     to float; 0.5*dot is exact and a single double add/sub rounded to float equals the float operation
+//     [53 >= 2*24+2 bits: innocuous double rounding], so the chain runs in fp32, bit-identically.)
+template <int K, bool HAS_VAL, bool NFM>
 __global__ void __launch_bounds__(256)
 fm_forward_kernel(const int64_t* __restrict__ row_ptr, const uint32_t* __restrict__ fid,
                   const float* __restrict__ val, const float* __restrict__ label, const float* __restrict__ W,
-                  const float* __restrict__ V, int k, float* __restrict__ pred, float* __restrict__ sumvx,
+                  const float* __restrict__ V, float* __restrict__ pred, float* __restrict__ sumvx,
                   float* __restrict__ z_out, float* __restrict__ wide_out, int64_t rb, int64_t re, double* partial,
                   unsigned int* done, double* out_slot, int do_stats) {
-    constexpr int RPW = 32 / LR;
-    const int lane = threadIdx.x & 31;
-    const int c = lane % LR, grp = lane / LR;
-    const int64_t r = rb + ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * RPW + grp;
-    const bool rv = r < re, act = c < k;
-    const int64_t b = rv ? row_ptr[r] : 0;
-    const int n = rv ? (int)(row_ptr[r + 1] - b) : 0;
-    int nmax = n;
+    constexpr int STR = K + 4;     // tile row: t[0..K), dot, w*x, pad (16 B aligned, conflict-free strides)
+    constexpr int NB = 64;         // features per pass (two 32-lane gathers in flight)
+    extern __shared__ __align__(16) float fwd_smem[];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    float* tile = fwd_smem + (size_t)wid * NB * STR;
+    const int64_t r = rb + (int64_t)blockIdx.x * (blockDim.x >> 5) + wid;
+    double loss = 0.0, correct = 0.0;
+    if (r < re) {
+        const int64_t b = row_ptr[r];
+        const int n = (int)(row_ptr[r + 1] - b);
+        float s = 0.f, z = 0.f, fm = 0.f;
+        for (int base = 0; base < n; base += NB) {
+            // ---- phase 1
+            float t[2][K], wx[2];
+            bool ok[2];
 #pragma unroll
-    for (int o = LR; o < 32; o <<= 1) nmax = max(nmax, __shfl_xor_sync(kFull, nmax, o));
-    float s = 0.f, z = 0.f, fm = 0.f;
-    for (int base = 0; base < nmax; base += LR) {
-        const int cnt = n - base;  // entries of this chunk that exist for my group (may be <= 0)
-        const uint32_t my_f = c < cnt ? __ldg(fid + b + base + c) : 0u;
-        const float my_x = HAS_VAL ? (c < cnt ? __ldg(val + b + base + c) : 0.f) : 1.f;
-        float v[LR], w[LR];
+            for (int u = 0; u < 2; u++) {
+                const int i = base + u * 32 + lane;
+                ok[u] = i < n;
+                const uint32_t f = ok[u] ? __ldg(fid + b + i) : 0u;
+                const float x = HAS_VAL ? (ok[u] ? __ldg(val + b + i) : 0.f) : 1.f;
+                const float* row = V + (size_t)f * K;
+                if (K % 4 == 0) {
 #pragma unroll
-        for (int j = 0; j < LR; j++) {
-            const uint32_t f = __shfl_sync(kFull, my_f, j, LR);
-            const bool ok = j < cnt;
-            v[j] = (ok && act) ? __ldg(V + (size_t)f * k + c) : 0.f;
-            w[j] = (ok && c == 0) ? __ldg(W + f) : 0.f;
-        }
+                    for (int q = 0; q < K / 4; q++) {
+                        const float4 v4 = ldg_f4(row + 4 * q);
+                        t[u][4 * q] = v4.x; t[u][4 * q + 1] = v4.y; t[u][4 * q + 2] = v4.z; t[u][4 * q + 3] = v4.w;
+                    }
+                } else {
 #pragma unroll
-        for (int j = 0; j < LR; j++) {
-            if (j >= nmax - base) break;  // warp-uniform
-            const bool ok = j < cnt;
-            const float x = __shfl_sync(kFull, my_x, j, LR);
-            const float t = v[j] * x;                    // avx_vecScale(V, tmp, X)      train_fm_algo.cpp:76
-            s = s + t;                                   // sumVX += tmp                 :77
-            if (NFM) {
-                z = z + t * (t * -0.5f);                 // train_nfm_algo.cpp:87-91
-                if (ok) fm = fm + w[j] * x;              // wide part                    train_nfm_algo.cpp:83
-            } else {
-                const float dot = avx_dot_lanes<LR>(t * t, k, c);                      // :78
-                if (ok) {
-                    fm = fm + w[j] * x;                                                // fm_pred += W[fid] * X  :74
-                    fm = (float)((double)fm - 0.5 * (double)dot);                      // fm_pred -= 0.5 * dot   :78
+                    for (int q = 0; q < K; q++) t[u][q] = __ldg(row + q);
+                }
+                wx[u] = __ldg(W + f) * x;                       // W[fid] * X             train_fm_algo.cpp:74
+                if (HAS_VAL) {
+#pragma unroll
+                    for (int q = 0; q < K; q++) t[u][q] = t[u][q] * x;   // avx_vecScale(V, tmp, X)   :76
                 }
             }
+#pragma unroll
+            for (int u = 0; u < 2; u++) {
+                if (!ok[u]) continue;
+                float* dst = tile + (size_t)(u * 32 + lane) * STR;
+                if (K % 4 == 0) {
+#pragma unroll
+                    for (int q = 0; q < K / 4; q++)
+                        *reinterpret_cast<float4*>(dst + 4 * q) = make_float4(t[u][4 * q], t[u][4 * q + 1], t[u][4 * q + 2], t[u][4 * q + 3]);
+                } else {
+#pragma unroll
+                    for (int q = 0; q < K; q++) dst[q] = t[u][q];
+                }
+                dst[K] = NFM ? 0.f : avx_dot_regs<K>(t[u]);     // dot(tmp, tmp)          :78
+                dst[K + 1] = wx[u];
+            }
+            __syncwarp();
+            // ---- phase 2: features base .. base+cnt in order
+            const int cnt = min(NB, n - base);
+            const int col = lane < K ? lane : 0;
+#pragma unroll 4
+            for (int j = 0; j < cnt; j++) {
+                const float* src = tile + (size_t)j * STR;
+                const float tj = src[col];
+                const float dot = src[K], w1 = src[K + 1];
+                s = s + tj;                                     // sumVX += tmp           :77
+                if (NFM) {
+                    z = z + tj * (tj * -0.5f);                  // train_nfm_algo.cpp:87-91
+                    fm = fm + w1;                               // wide part              train_nfm_algo.cpp:83
+                } else {
+                    fm = fm + w1;                               // fm_pred += W[fid] * X  :74
+                    fm = fm - 0.5f * dot;                       // fm_pred -= 0.5 * dot   :78
+                }
+            }
+            __syncwarp();
         }
-    }
-    double loss = 0.0, correct = 0.0;
-    if (rv && act) sumvx[(size_t)r * k + c] = s;
-    if (NFM) {
-        // z = z + sumVX * (sumVX * 0.5)    (train_nfm_algo.cpp:93-94)
-        if (rv && act) z_out[(size_t)(r - rb) * k + c] = z + s * (s * 0.5f);
-        if (rv && c == 0) wide_out[r] = fm;
-    } else {
-        const float dot = avx_dot_lanes<LR>(act ? s * s : 0.f, k, c);
-        if (rv && c == 0) {
-            fm = (float)((double)fm + 0.5 * (double)dot);  // :82
-            const float p = ref_sigmoid(fm);               // :84
-            pred[r] = p;
-            if (do_stats) loss_terms(p, label[r], loss, correct);
+        if (lane < K) sumvx[(size_t)r * K + lane] = s;
+        if (NFM) {
+            // z = z + sumVX * (sumVX * 0.5)    (train_nfm_algo.cpp:93-94)
+            if (lane < K) z_out[(size_t)(r - rb) * K + lane] = z + s * (s * 0.5f);
+            if (lane == 0) wide_out[r] = fm;
+        } else {
+            // avx_dotProduct(sumVX, sumVX, K) across lanes 0..K-1 in the reference's order, via the tile
+            if (lane < K) tile[lane] = s;
+            __syncwarp();
+            if (lane == 0) {
+                float sv[K];
+#pragma unroll
+                for (int q = 0; q < K; q++) sv[q] = tile[q];
+                const float dot = avx_dot_regs<K>(sv);
+                fm = (float)((double)fm + 0.5 * (double)dot);  // :82
+                const float pr = ref_sigmoid(fm);              // :84
+                pred[r] = pr;
+                if (do_stats) loss_terms(pr, label[r], loss, correct);
+            }
         }
     }
     if (!NFM && do_stats) publish_stats(loss, correct, partial, done, out_slot, false);
@@ -254,37 +293,43 @@ static bool pick_shape(int k, Shape& sh) {
         }                                                                               \
     } while (0)
 
-template <int LR>
-static void fwd_go(lctr_ctx* c, Slot& s, bool nfm, unsigned grid, int k, int64_t rb, int64_t re, double* out_slot,
-                   int stats) {
-#define FWD_ARGS s.row_ptr, s.fid, s.val, s.label, c->W, c->V, k, s.pred, s.sumvx, c->z, s.wide, rb, re, \
-                 c->stat_partial, c->stat_done, out_slot, stats
-    if (s.has_val) {
-        if (nfm) fm_forward_kernel<LR, true, true><<<grid, 256, 0, c->stream>>>(FWD_ARGS);
-        else fm_forward_kernel<LR, true, false><<<grid, 256, 0, c->stream>>>(FWD_ARGS);
-    } else {
-        if (nfm) fm_forward_kernel<LR, false, true><<<grid, 256, 0, c->stream>>>(FWD_ARGS);
-        else fm_forward_kernel<LR, false, false><<<grid, 256, 0, c->stream>>>(FWD_ARGS);
-    }
-#undef FWD_ARGS
+template <int K>
+static int fwd_go(lctr_ctx* c, Slot& s, bool nfm, int64_t rb, int64_t re, double* out_slot, int stats) {
+    const unsigned grid = (unsigned)((re - rb + 7) / 8);
+    const size_t smem = (size_t)8 * 64 * (K + 4) * sizeof(float);
+#define FWD_GO(HV, NF)                                                                                         \
+    do {                                                                                                       \
+        auto kern = fm_forward_kernel<K, HV, NF>;                                                              \
+        if (smem > 48 * 1024) LCTR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        kern<<<grid, 256, smem, c->stream>>>(s.row_ptr, s.fid, s.val, s.label, c->W, c->V, s.pred, s.sumvx, c->z, \
+                                             s.wide, rb, re, c->stat_partial, c->stat_done, out_slot, stats);  \
+    } while (0)
+    if (s.has_val) { if (nfm) FWD_GO(true, true); else FWD_GO(true, false); }
+    else { if (nfm) FWD_GO(false, true); else FWD_GO(false, false); }
+#undef FWD_GO
+    return 0;
 }
 
 int launch_fm_forward(lctr_ctx* c, Slot& s, int64_t rb, int64_t re, bool nfm, bool stats) {
     const int k = (int)c->cfg.factor_cnt;
-    LCTR_CHECK(k <= 32, "factor_cnt=%d unsupported by the in-order forward (need k <= 32)", k);
     const int64_t rows = re - rb;
     if (rows <= 0) return 0;
-    int lr = 4;
-    while (lr < k) lr <<= 1;
-    const int rows_per_cta = 8 * (32 / lr);
-    const unsigned grid = (unsigned)((rows + rows_per_cta - 1) / rows_per_cta);
     double* out_slot = c->stats + 2 * (c->step % kStatRing);
-    switch (lr) {
-        case 4: fwd_go<4>(c, s, nfm, grid, k, rb, re, out_slot, stats ? 1 : 0); break;
-        case 8: fwd_go<8>(c, s, nfm, grid, k, rb, re, out_slot, stats ? 1 : 0); break;
-        case 16: fwd_go<16>(c, s, nfm, grid, k, rb, re, out_slot, stats ? 1 : 0); break;
-        default: fwd_go<32>(c, s, nfm, grid, k, rb, re, out_slot, stats ? 1 : 0); break;
+    const int st = stats ? 1 : 0;
+    ProfScope prof(c, PROF_FM_FWD);
+    int rc = 0;
+    static const int dbg_repeat = getenv("LCTR_DBG_FWD_REPEAT") ? atoi(getenv("LCTR_DBG_FWD_REPEAT")) : 1;
+    for (int rep = 0; rep < dbg_repeat && !rc; rep++)
+    switch (k) {  // the factor count is a compile-time constant of the kernel (register-resident rows)
+#define FWD_CASE(KK) case KK: rc = fwd_go<KK>(c, s, nfm, rb, re, out_slot, st); break;
+        FWD_CASE(1) FWD_CASE(2) FWD_CASE(3) FWD_CASE(4) FWD_CASE(5) FWD_CASE(6) FWD_CASE(7) FWD_CASE(8)
+        FWD_CASE(10) FWD_CASE(12) FWD_CASE(16) FWD_CASE(20) FWD_CASE(24) FWD_CASE(32)
+#undef FWD_CASE
+        default:
+            set_error("factor_cnt=%d is not instantiated (built: 1-8, 10, 12, 16, 20, 24, 32)", k);
+            return 1;
     }
+    if (rc) return 1;
     c->launches++;
     LCTR_CUDA(cudaGetLastError());
     return 0;
@@ -297,6 +342,7 @@ int launch_fm_backward(lctr_ctx* c, Slot& s, int64_t rb, int64_t re, bool nfm) {
     const int64_t rows = re - rb;
     if (rows <= 0) return 0;
     const unsigned grid = (unsigned)((rows + 7) / 8);
+    ProfScope prof(c, PROF_FM_BWD_RED);
     FM_DISPATCH(fm_backward_kernel, s.row_ptr, s.fid, s.val, s.label, c->W, c->V, k, s.pred, s.sumvx, c->dz, c->gW,
                 c->gV, c->touched, c->cfg.l2_reg, rb, re);
     c->launches++;
@@ -410,6 +456,7 @@ int launch_fm_backward_csc(lctr_ctx* c, Slot& s, int64_t rb, int64_t re, bool nf
     while (lr < k) lr <<= 1;
     const int segs_per_cta = 8 * (32 / lr);
     const unsigned grid = (unsigned)((se - sb + segs_per_cta - 1) / segs_per_cta);
+    ProfScope prof(c, PROF_FM_BWD_CSC);
     switch (lr) {
         case 4: bwd_csc_go<4>(c, s, nfm, grid, k, sb, se, rb, P); break;
         case 8: bwd_csc_go<8>(c, s, nfm, grid, k, sb, se, rb, P); break;

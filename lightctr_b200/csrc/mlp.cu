@@ -217,6 +217,7 @@ int launch_nfm_mlp(lctr_ctx* c, Slot& s, int64_t rb, int64_t re, int64_t rows_di
     LCTR_CHECK(c->cfg.mlp_precision == LCTR_MLP_FP32, "mlp_precision=%d: only the fp32 reference-order MLP is built",
                c->cfg.mlp_precision);
     auto blocks = [](int64_t n) { return (unsigned)((n + 255) / 256); };
+    ProfScope prof(c, PROF_MLP);
     // ---- forward
     const float* x = c->z;
     for (int l = 0; l < nl; l++) {

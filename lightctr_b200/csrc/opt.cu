@@ -17,18 +17,17 @@
 
 namespace lctr {
 
-template <int LPR, int VEC>
+// Stage A: scan the touched byte map (16 marks per lane, 512 per warp tile), clear it, and append the set
+// positions to a global list of fids (one warp-aggregated atomicAdd per non-empty tile).  Decoupling the
+// scan from the update balances the update work: the small-vocabulary fields at the low end of the id
+// space are dense (every mark set) while the tail is ~5 % dense.
 __global__ void __launch_bounds__(256)
-apply_kernel(uint8_t* __restrict__ touched, size_t F, int rowlen, float* __restrict__ W, float* __restrict__ V,
-             float* __restrict__ gW, float* __restrict__ gV, float* __restrict__ s1W, float* __restrict__ s1V,
-             float* __restrict__ s2W, float* __restrict__ s2V, OptParams P) {
-    constexpr int G = 32 / LPR;
+compact_touched_kernel(uint8_t* __restrict__ touched, size_t F, uint32_t* __restrict__ list,
+                       unsigned int* __restrict__ n_list) {
     const int lane = threadIdx.x & 31;
-    const int q = lane % LPR, g = lane / LPR;
     const size_t warp = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const size_t nwarps = (size_t)gridDim.x * (blockDim.x >> 5);
-    const size_t ntiles = (F + 511) / 512;  // 512 marks per warp-tile (16 B per lane)
-    const bool two_state = P.opt != LCTR_OPT_ADAGRAD;
+    const size_t ntiles = (F + 511) / 512;
     for (size_t tile = warp; tile < ntiles; tile += nwarps) {
         const size_t base = tile * 512 + (size_t)lane * 16;
         uint4 m = make_uint4(0, 0, 0, 0);
@@ -41,7 +40,6 @@ apply_kernel(uint8_t* __restrict__ touched, size_t F, int rowlen, float* __restr
         }
         const bool any = (m.x | m.y | m.z | m.w) != 0;
         if (!__any_sync(kFull, any)) continue;
-        // 16-bit mask of set marks of this lane
         unsigned bits = 0;
         {
             const unsigned wv[4] = {m.x, m.y, m.z, m.w};
@@ -51,93 +49,180 @@ apply_kernel(uint8_t* __restrict__ touched, size_t F, int rowlen, float* __restr
                 for (int b = 0; b < 4; b++)
                     if ((wv[i] >> (8 * b)) & 0xffu) bits |= 1u << (i * 4 + b);
         }
-        if (any) {  // clear the marks (memset(grad) analogue)
+        if (any) {  // clear the marks (memset(grad) analogue, gradientUpdater.h:149)
             if (base + 16 <= F) *reinterpret_cast<uint4*>(touched + base) = make_uint4(0, 0, 0, 0);
             else for (int i = 0; i < 16 && base + i < F; i++) touched[base + i] = 0;
         }
-        while (__any_sync(kFull, bits != 0)) {
-            // every lane pops one fid
-            const bool has = bits != 0;
-            const int bit = has ? __ffs(bits) - 1 : 0;
-            if (has) bits &= bits - 1;
-            const size_t my_f = base + bit;
-            const unsigned havemask = __ballot_sync(kFull, has);
-            // process the up-to-32 popped fids, G rows at a time
-            for (int j = 0; j < 32; j += G) {
-                if (((havemask >> j) & ((G == 32) ? 0xffffffffu : ((1u << G) - 1u))) == 0) continue;
-                const int src = j + g;
-                const size_t f = __shfl_sync(kFull, (unsigned long long)my_f, src);
-                const bool ok = (havemask >> src) & 1u;
-                if (!ok) continue;
-                if (q == 0) {
-                    float w = W[f], s1 = s1W[f], s2 = two_state ? s2W[f] : 0.f;
-                    update_one(P, P.corrW, w, gW[f], s1, s2);
-                    W[f] = w; s1W[f] = s1; gW[f] = 0.f;
-                    if (two_state) s2W[f] = s2;
+        const int mycnt = __popc(bits);
+        int incl = mycnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(kFull, incl, o);
+            if (lane >= o) incl += t;
+        }
+        const int total = __shfl_sync(kFull, incl, 31);
+        unsigned int gbase = 0;
+        if (lane == 31) gbase = atomicAdd(n_list, (unsigned int)total);
+        gbase = __shfl_sync(kFull, gbase, 31);
+        unsigned int pos = gbase + (unsigned int)(incl - mycnt);
+        while (bits) {
+            const int bit = __ffs(bits) - 1;
+            bits &= bits - 1;
+            list[pos++] = (uint32_t)(base + bit);
+        }
+    }
+}
+
+// Stage B: walk the list G*U rows at a time.  Slice = VEC contiguous floats of a row; a row has rowlen/VEC
+// slices spread over LPR lanes, SPL slices per lane (slice index = q + i*LPR).  ALL loads of a batch
+// (gradient, weight, state of U rows per lane group) are issued before the first update is computed, so one
+// HBM/L2 round trip covers 32/LPR*U rows.  The last block re-arms the list counter.
+template <int LPR, int VEC, int SPL, int U>
+__global__ void __launch_bounds__(256)
+apply_kernel(const uint32_t* __restrict__ list, unsigned int* __restrict__ n_list, unsigned int* __restrict__ done,
+             int rowlen, float* __restrict__ W, float* __restrict__ V,
+             float* __restrict__ gW, float* __restrict__ gV, float* __restrict__ s1W, float* __restrict__ s1V,
+             float* __restrict__ s2W, float* __restrict__ s2V, OptParams P) {
+    constexpr int G = 32 / LPR;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int q = lane % LPR, g = lane / LPR;
+    const unsigned warp = blockIdx.x * (blockDim.x >> 5) + wid;
+    const unsigned nwarps = gridDim.x * (blockDim.x >> 5);
+    const bool two_state = P.opt != LCTR_OPT_ADAGRAD;
+    const int slices = rowlen / VEC;
+    const unsigned total = *reinterpret_cast<volatile unsigned int*>(n_list);
+    {
+        for (unsigned b0 = warp * (G * U); b0 < total; b0 += nwarps * (G * U)) {
+            size_t f[U];
+            bool ok[U];
+            float gw_[U], w_[U], a_[U], b_[U];
+            float gv[U][SPL][VEC], wv[U][SPL][VEC], s1[U][SPL][VEC], s2[U][SPL][VEC];
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                const unsigned idx = b0 + u * G + g;
+                ok[u] = idx < total;
+                f[u] = ok[u] ? __ldg(list + idx) : 0;
+                if (ok[u] && q == 0) {
+                    gw_[u] = gW[f[u]]; w_[u] = W[f[u]]; a_[u] = s1W[f[u]];
+                    b_[u] = two_state ? s2W[f[u]] : 0.f;
                 }
-                const size_t ro = f * (size_t)rowlen;
-                for (int o = q * VEC; o < rowlen; o += LPR * VEC) {
+                const size_t ro = f[u] * (size_t)rowlen;
+#pragma unroll
+                for (int i = 0; i < SPL; i++) {
+                    const int sl = q + i * LPR;
+                    const bool on = ok[u] && sl < slices;
+                    const size_t o = ro + (size_t)sl * VEC;
                     if (VEC == 4) {
-                        float4 gv = *reinterpret_cast<float4*>(gV + ro + o);
-                        if (gv.x == 0.f && gv.y == 0.f && gv.z == 0.f && gv.w == 0.f) continue;  // untouched slice (FFM)
-                        float4 wv = *reinterpret_cast<float4*>(V + ro + o);
-                        float4 a = *reinterpret_cast<float4*>(s1V + ro + o);
-                        float4 b2 = two_state ? *reinterpret_cast<float4*>(s2V + ro + o) : make_float4(0, 0, 0, 0);
-                        update_one(P, P.corrV, wv.x, gv.x, a.x, b2.x);
-                        update_one(P, P.corrV, wv.y, gv.y, a.y, b2.y);
-                        update_one(P, P.corrV, wv.z, gv.z, a.z, b2.z);
-                        update_one(P, P.corrV, wv.w, gv.w, a.w, b2.w);
-                        *reinterpret_cast<float4*>(V + ro + o) = wv;
-                        *reinterpret_cast<float4*>(s1V + ro + o) = a;
-                        if (two_state) *reinterpret_cast<float4*>(s2V + ro + o) = b2;
-                        *reinterpret_cast<float4*>(gV + ro + o) = make_float4(0, 0, 0, 0);
+                        float4 t0 = make_float4(0, 0, 0, 0), t1 = t0, t2 = t0, t3 = t0;
+                        if (on) {
+                            t0 = *reinterpret_cast<const float4*>(gV + o);
+                            t1 = *reinterpret_cast<const float4*>(V + o);
+                            t2 = *reinterpret_cast<const float4*>(s1V + o);
+                            if (two_state) t3 = *reinterpret_cast<const float4*>(s2V + o);
+                        }
+                        gv[u][i][0] = t0.x; gv[u][i][1 % VEC] = t0.y; gv[u][i][2 % VEC] = t0.z; gv[u][i][3 % VEC] = t0.w;
+                        wv[u][i][0] = t1.x; wv[u][i][1 % VEC] = t1.y; wv[u][i][2 % VEC] = t1.z; wv[u][i][3 % VEC] = t1.w;
+                        s1[u][i][0] = t2.x; s1[u][i][1 % VEC] = t2.y; s1[u][i][2 % VEC] = t2.z; s1[u][i][3 % VEC] = t2.w;
+                        s2[u][i][0] = t3.x; s2[u][i][1 % VEC] = t3.y; s2[u][i][2 % VEC] = t3.z; s2[u][i][3 % VEC] = t3.w;
                     } else {
-                        const float gv = gV[ro + o];
-                        if (gv == 0.f) continue;
-                        float wv = V[ro + o], a = s1V[ro + o], b2 = two_state ? s2V[ro + o] : 0.f;
-                        update_one(P, P.corrV, wv, gv, a, b2);
-                        V[ro + o] = wv; s1V[ro + o] = a; gV[ro + o] = 0.f;
-                        if (two_state) s2V[ro + o] = b2;
+                        gv[u][i][0] = on ? gV[o] : 0.f;
+                        wv[u][i][0] = on ? V[o] : 0.f;
+                        s1[u][i][0] = on ? s1V[o] : 0.f;
+                        s2[u][i][0] = (on && two_state) ? s2V[o] : 0.f;
+                    }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                if (!ok[u]) continue;
+                if (q == 0) {
+                    float w = w_[u], a = a_[u], b2 = b_[u];
+                    update_one(P, P.corrW, w, gw_[u], a, b2);
+                    W[f[u]] = w; s1W[f[u]] = a; gW[f[u]] = 0.f;
+                    if (two_state) s2W[f[u]] = b2;
+                }
+                const size_t ro = f[u] * (size_t)rowlen;
+#pragma unroll
+                for (int i = 0; i < SPL; i++) {
+                    const int sl = q + i * LPR;
+                    if (sl >= slices) continue;
+                    bool nz = false;
+#pragma unroll
+                    for (int cc = 0; cc < VEC; cc++) nz |= gv[u][i][cc] != 0.f;
+                    if (!nz) continue;  // untouched slice (FFM: field absent from every row of the batch)
+#pragma unroll
+                    for (int cc = 0; cc < VEC; cc++) update_one(P, P.corrV, wv[u][i][cc], gv[u][i][cc], s1[u][i][cc], s2[u][i][cc]);
+                    const size_t o = ro + (size_t)sl * VEC;
+                    if (VEC == 4) {
+                        *reinterpret_cast<float4*>(V + o) = make_float4(wv[u][i][0], wv[u][i][1 % VEC], wv[u][i][2 % VEC], wv[u][i][3 % VEC]);
+                        *reinterpret_cast<float4*>(s1V + o) = make_float4(s1[u][i][0], s1[u][i][1 % VEC], s1[u][i][2 % VEC], s1[u][i][3 % VEC]);
+                        if (two_state) *reinterpret_cast<float4*>(s2V + o) = make_float4(s2[u][i][0], s2[u][i][1 % VEC], s2[u][i][2 % VEC], s2[u][i][3 % VEC]);
+                        *reinterpret_cast<float4*>(gV + o) = make_float4(0, 0, 0, 0);
+                    } else {
+                        V[o] = wv[u][i][0]; s1V[o] = s1[u][i][0]; gV[o] = 0.f;
+                        if (two_state) s2V[o] = s2[u][i][0];
                     }
                 }
             }
         }
+    }
+    // re-arm the list for the next step once every block has consumed it
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(done, 1u) == gridDim.x - 1) { *n_list = 0u; *done = 0u; __threadfence(); }
     }
 }
 
 int launch_apply(lctr_ctx* c, int64_t rows_in_step) {
     OptParams P = make_opt_params(c, rows_in_step);
     const int rowlen = (int)c->rowlen;
-    int vec = (rowlen % 4 == 0) ? 4 : 1;
-    int slices = rowlen / vec;
+    const int vec = (rowlen % 4 == 0) ? 4 : 1;
+    const int slices = rowlen / vec;
     int lpr = 1;
     while (lpr < slices && lpr < 32) lpr <<= 1;
+    const int spl = (slices + lpr - 1) / lpr;
+    LCTR_CHECK(spl <= 4, "row of %d floats is too long for the sparse apply kernel (max %d)", rowlen, 4 * 32 * vec);
     const size_t ntiles = (c->F + 511) / 512;
-    unsigned grid = (unsigned)std::min<size_t>((ntiles + 7) / 8, (size_t)c->sm_count * 8);
-    if (grid == 0) grid = 1;
-#define APPLY_CASE(L, VV) \
-    apply_kernel<L, VV><<<grid, 256, 0, c->stream>>>(c->touched, c->F, rowlen, c->W, c->V, c->gW, c->gV, c->s1W, \
-                                                     c->s1V, c->s2W, c->s2V, P)
+    unsigned grid_a = (unsigned)std::min<size_t>((ntiles + 7) / 8, (size_t)c->sm_count * 8);
+    if (grid_a == 0) grid_a = 1;
+    const unsigned grid = (unsigned)c->sm_count * 2;
+    ProfScope prof(c, PROF_APPLY);
+    compact_touched_kernel<<<grid_a, 256, 0, c->stream>>>(c->touched, c->F, c->touch_list, c->n_touch);
+    c->launches++;
+#define APPLY_ARGS c->touch_list, c->n_touch, c->apply_done, rowlen, c->W, c->V, c->gW, c->gV, c->s1W, c->s1V, c->s2W, c->s2V, P
+#define APPLY_CASE(L, VV, S, UU) apply_kernel<L, VV, S, UU><<<grid, 256, 0, c->stream>>>(APPLY_ARGS)
     if (vec == 4) {
         switch (lpr) {
-            case 1: APPLY_CASE(1, 4); break;
-            case 2: APPLY_CASE(2, 4); break;
-            case 4: APPLY_CASE(4, 4); break;
-            case 8: APPLY_CASE(8, 4); break;
-            case 16: APPLY_CASE(16, 4); break;
-            default: APPLY_CASE(32, 4); break;
+            case 1: APPLY_CASE(1, 4, 1, 4); break;
+            case 2: APPLY_CASE(2, 4, 1, 4); break;
+            case 4: APPLY_CASE(4, 4, 1, 4); break;
+            case 8: APPLY_CASE(8, 4, 1, 4); break;
+            case 16: APPLY_CASE(16, 4, 1, 4); break;
+            default:
+                if (spl == 1) APPLY_CASE(32, 4, 1, 4);
+                else if (spl == 2) APPLY_CASE(32, 4, 2, 2);
+                else if (spl == 3) APPLY_CASE(32, 4, 3, 1);
+                else APPLY_CASE(32, 4, 4, 1);
+                break;
         }
     } else {
         switch (lpr) {
-            case 1: APPLY_CASE(1, 1); break;
-            case 2: APPLY_CASE(2, 1); break;
-            case 4: APPLY_CASE(4, 1); break;
-            case 8: APPLY_CASE(8, 1); break;
-            case 16: APPLY_CASE(16, 1); break;
-            default: APPLY_CASE(32, 1); break;
+            case 1: APPLY_CASE(1, 1, 1, 4); break;
+            case 2: APPLY_CASE(2, 1, 1, 4); break;
+            case 4: APPLY_CASE(4, 1, 1, 4); break;
+            case 8: APPLY_CASE(8, 1, 1, 4); break;
+            case 16: APPLY_CASE(16, 1, 1, 4); break;
+            default:
+                if (spl == 1) APPLY_CASE(32, 1, 1, 4);
+                else if (spl == 2) APPLY_CASE(32, 1, 2, 2);
+                else if (spl == 3) APPLY_CASE(32, 1, 3, 1);
+                else APPLY_CASE(32, 1, 4, 1);
+                break;
         }
     }
 #undef APPLY_CASE
+#undef APPLY_ARGS
     c->launches++;
     LCTR_CUDA(cudaGetLastError());
     return 0;

@@ -1,0 +1,407 @@
+// lightctr_b200/host/lightctr_gpu.h -- C++ host shims with the reference's trainer class surface.
+//
+// Drop-in for the FM / FFM / NFM hot path of cnkuangshi/LightCTR: same class names, constructor
+// signatures, public members and call sequence as
+//     FM_Algo_Abst        LightCTR/fm_algo_abst.h:37-172
+//     Train_FM_Algo       LightCTR/train/train_fm_algo.h:21-58
+//     Train_FFM_Algo      LightCTR/train/train_ffm_algo.h:22-66
+//     Train_NFM_Algo      LightCTR/train/train_nfm_algo.h:18-77
+//     FM_Predict          LightCTR/predict/fm_predict.h:17-39
+//     GradientUpdater / MomentumUpdater statics   LightCTR/util/gradientUpdater.h:36-42, main.cpp:64-73
+// but every Train()/Predict() lowers to the C ABI of include/lightctr_b200.h (CUDA, sm_100a).  A caller
+// such as the reference's main.cpp:144-162,228-253 compiles unchanged against this header inside
+// `namespace lightctr_b200`.  Error behaviour follows the reference: print + exit(1)
+// (fm_algo_abst.h:79-82).  Host-side randomness uses libc rand() in the reference's call order
+// (util/random.h:21-58,82), so srand(seed) reproduces its initialisation bit for bit.
+#ifndef LIGHTCTR_GPU_H
+#define LIGHTCTR_GPU_H
+
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <fstream>
+#include <iomanip>
+#include <iostream>
+#include <string>
+#include <vector>
+
+#include "../../include/lightctr_b200.h"
+
+namespace lightctr_b200 {
+
+// ---- util/gradientUpdater.h:36-42, util/momentumUpdater.h: process-global hyper-parameters ----------------
+struct GradientUpdater {
+    static size_t __global_minibatch_size;
+    static float __global_learning_rate;
+    static float __global_ema_rate;
+    static float __global_sparse_rate;
+    static float __global_lambdaL2, __global_lambdaL1;
+    static bool __global_bTraining;
+};
+struct MomentumUpdater {
+    static float __global_momentum;
+    static float __global_momentum_adam2;
+};
+// Define once in the application (the reference does the same in main.cpp:64-73):
+#define LIGHTCTR_B200_DEFINE_GLOBALS                                                   \
+    size_t lightctr_b200::GradientUpdater::__global_minibatch_size(50);                \
+    float lightctr_b200::GradientUpdater::__global_learning_rate(0.05);                \
+    float lightctr_b200::GradientUpdater::__global_ema_rate(0.99);                     \
+    float lightctr_b200::GradientUpdater::__global_sparse_rate(0.8);                   \
+    float lightctr_b200::GradientUpdater::__global_lambdaL2(0.001f);                   \
+    float lightctr_b200::GradientUpdater::__global_lambdaL1(1e-5);                     \
+    float lightctr_b200::MomentumUpdater::__global_momentum(0.8);                      \
+    float lightctr_b200::MomentumUpdater::__global_momentum_adam2(0.999);              \
+    bool lightctr_b200::GradientUpdater::__global_bTraining(true);
+
+// ---- util/random.h:21-58,82 ------------------------------------------------------------------------------
+inline double UniformNumRand() { return static_cast<double>(rand()) / (static_cast<double>(RAND_MAX) + 1.0); }
+inline double UniformNumRand2() { return (static_cast<double>(rand()) + 1.0) / (static_cast<double>(RAND_MAX) + 2.0); }
+inline double GaussRand() {
+    static double V1, V2, S;
+    static int phase = 0;
+    double X;
+    if (phase == 0) {
+        do {
+            V1 = 2.0 * UniformNumRand2() - 1.0;
+            V2 = 2.0 * UniformNumRand2() - 1.0;
+            S = V1 * V1 + V2 * V2;
+        } while (S >= 1.0 || S == 0.0);
+        X = V1 * sqrt(-2.0 * log(S) / S);
+    } else {
+        X = V2 * sqrt(-2.0 * log(S) / S);
+    }
+    phase = 1 - phase;
+    return X;
+}
+inline bool SampleBinary(double p) { return UniformNumRand() < p; }
+
+inline void lctr_die(const char* what) {
+    std::cout << what << ": " << lctr_last_error() << std::endl;
+    exit(1);
+}
+#define LCTR_OK(call) do { if ((call) != 0) ::lightctr_b200::lctr_die(#call); } while (0)
+
+struct FMFeature {  // fm_algo_abst.h:29-35
+    size_t first;   // feature id
+    float second;   // value
+    size_t field;
+    FMFeature(size_t _first, float _second, size_t _field) : first(_first), second(_second), field(_field) {}
+};
+
+class FM_Algo_Abst {
+public:
+    FM_Algo_Abst(std::string _dataPath, size_t _factor_cnt, size_t _field_cnt = 0, size_t _feature_cnt = 0)
+        : feature_cnt(_feature_cnt), field_cnt(_field_cnt), factor_cnt(_factor_cnt) {
+        proc_cnt = 1;  // kept for source compatibility (fm_algo_abst.h:42); parallelism lives on the device
+        loadDataRow(_dataPath);
+        init();
+    }
+    virtual ~FM_Algo_Abst() {
+        delete[] W;
+        delete[] V;
+        delete[] sumVX;
+        if (ds) lctr_free_dataset(ds);
+        if (ctx) lctr_destroy(ctx);
+    }
+    void init() {  // fm_algo_abst.h:53-68
+        W = new float[feature_cnt];
+        memset(W, 0, sizeof(float) * feature_cnt);
+        size_t memsize = feature_cnt * factor_cnt;
+        if (field_cnt > 0) memsize = feature_cnt * field_cnt * factor_cnt;
+        V = new float[memsize];
+        const float scale = 1.0 / sqrt(factor_cnt);
+        for (size_t i = 0; i < memsize; i++) V[i] = GaussRand() * scale;
+        sumVX = NULL;
+    }
+    void loadDataRow(std::string dataPath) {  // fm_algo_abst.h:70-107 (parser lives in the library, bit-exact)
+        if (lctr_load_libffm(dataPath.c_str(), field_cnt, feature_cnt, &ds) != 0) {
+            std::cout << "open file error!" << std::endl;
+            exit(1);
+        }
+        feature_cnt = ds->feature_cnt;
+        field_cnt = ds->field_cnt;
+        dataRow_cnt = (size_t)ds->rows;
+        dataSet.clear();  // the AoS view the reference exposes publicly (fm_algo_abst.h:156)
+        dataSet.resize(dataRow_cnt);
+        for (size_t r = 0; r < dataRow_cnt; r++)
+            for (int64_t e = ds->row_ptr[r]; e < ds->row_ptr[r + 1]; e++)
+                dataSet[r].emplace_back(FMFeature(ds->fid[e], ds->val[e], ds->field[e]));
+        label.assign(ds->label, ds->label + ds->label_cnt);
+    }
+    void saveModel(size_t epoch) {  // fm_algo_abst.h:109-135
+        char buffer[1024];
+        snprintf(buffer, 1024, "%d", (int)epoch);
+        std::string filename = buffer;
+        std::ofstream md("./output/model_epoch_" + filename + ".txt");
+        if (!md.is_open()) {
+            std::cout << "save model open file error" << std::endl;
+            exit(1);
+        }
+        for (size_t fid = 0; fid < feature_cnt; fid++)
+            if (W[fid] != 0) md << fid << ":" << W[fid] << " ";
+        md << std::endl;
+        for (size_t fid = 0; fid < feature_cnt; fid++) {
+            md << fid << ":";
+            for (size_t f = 0; f < factor_cnt; f++) md << *getV(fid, f) << " ";
+            md << std::endl;
+        }
+        md.close();
+    }
+    virtual void Train() = 0;
+
+    float L2Reg_ratio;
+    float* W;
+    size_t feature_cnt, proc_cnt, field_cnt, factor_cnt;
+    size_t dataRow_cnt;
+    float *V, *sumVX;
+    inline float* getV(size_t fid, size_t facid) const { return &V[fid * factor_cnt + facid]; }
+    inline float* getV_field(size_t fid, size_t fieldid, size_t facid) const {
+        return &V[fid * field_cnt * factor_cnt + fieldid * factor_cnt + facid];
+    }
+    inline float* getSumVX(size_t rid, size_t facid) const { return &sumVX[rid * factor_cnt + facid]; }
+    std::vector<std::vector<FMFeature> > dataSet;
+    std::vector<int> label;
+
+    // ---- device side ---------------------------------------------------------------------------------------
+    lctr_ctx* ctx = nullptr;
+    lctr_dataset* ds = nullptr;
+    int updater = LCTR_OPT_ADAGRAD;  // the reference's `AdagradUpdater_Num updater;` member (fm_algo_abst.h:166)
+    int deterministic = 1;           // ascending-row accumulation (== the reference's canonical proc_cnt=1 order)
+
+protected:
+    float __loss;
+    float __accuracy;
+    void make_ctx(int model, size_t minibatch, size_t csc_block, int n_hidden = 0, const uint32_t* hidden = nullptr) {
+        lctr_cfg cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.abi_version = LCTR_ABI_VERSION;
+        cfg.model = model;
+        cfg.optimizer = updater;
+        cfg.feature_cnt = feature_cnt;
+        cfg.field_cnt = model == LCTR_MODEL_FFM ? (uint32_t)field_cnt : 0;
+        cfg.factor_cnt = (uint32_t)factor_cnt;
+        cfg.learning_rate = GradientUpdater::__global_learning_rate;
+        cfg.l2_reg = L2Reg_ratio;
+        cfg.minibatch_size = minibatch;
+        cfg.momentum = MomentumUpdater::__global_momentum;
+        cfg.momentum_adam2 = MomentumUpdater::__global_momentum_adam2;
+        cfg.n_hidden = n_hidden;
+        for (int i = 0; i < n_hidden; i++) cfg.hidden[i] = hidden[i];
+        cfg.activation = LCTR_ACT_SIGMOID;
+        cfg.deterministic = deterministic;
+        cfg.csc_row_block = csc_block;
+        LCTR_OK(lctr_create(&cfg, &ctx));
+        LCTR_OK(lctr_upload_params(ctx, W, V));
+        bool ones = true;
+        for (int64_t e = 0; e < ds->nnz && ones; e++) ones = ds->val[e] == 1.0f;
+        LCTR_OK(lctr_upload_batch(ctx, 0, ds->rows, ds->nnz, ds->row_ptr, ds->fid, ds->field, ones ? nullptr : ds->val,
+                                  ds->label));
+        LCTR_OK(lctr_sync(ctx));
+    }
+};
+
+class Train_FM_Algo : public FM_Algo_Abst {
+public:
+    Train_FM_Algo(std::string _dataPath, size_t _epoch_cnt, size_t _factor_cnt)
+        : FM_Algo_Abst(_dataPath, _factor_cnt), epoch_cnt(_epoch_cnt) {
+        if (feature_cnt == 0) { std::cout << "assert(feature_cnt != 0)" << std::endl; exit(1); }
+        L2Reg_ratio = 0.001f;  // train_fm_algo.cpp:13
+        sumVX = new float[dataRow_cnt * factor_cnt];
+        memset(sumVX, 0, sizeof(float) * dataRow_cnt * factor_cnt);
+    }
+    void Train() {  // train_fm_algo.cpp:35-61
+        GradientUpdater::__global_bTraining = true;
+        GradientUpdater::__global_minibatch_size = dataRow_cnt;
+        if (!ctx) make_ctx(LCTR_MODEL_FM, 0, 0);
+        for (size_t i = 0; i < epoch_cnt; i++) {
+            LCTR_OK(lctr_train_step(ctx, 0, 0, (int64_t)dataRow_cnt, &__loss, &__accuracy));
+            printf("Epoch %zu Train Loss = %f Accuracy = %f\n", i, __loss, __accuracy / dataRow_cnt);
+        }
+        LCTR_OK(lctr_download_params(ctx, W, V));  // FM_Predict / saveModel read these (fm_predict.cpp:25-32)
+        LCTR_OK(lctr_download_sumvx(ctx, 0, sumVX));
+        GradientUpdater::__global_bTraining = false;
+    }
+    float last_loss() const { return __loss; }
+
+private:
+    size_t epoch_cnt;
+};
+
+class Train_FFM_Algo : public FM_Algo_Abst {
+public:
+    Train_FFM_Algo(std::string _dataPath, size_t _epoch_cnt, size_t _factor_cnt, size_t _field_cnt)
+        : FM_Algo_Abst(_dataPath, _factor_cnt, _field_cnt), epoch(_epoch_cnt) {
+        L2Reg_ratio = 0.001f;
+        printf("Training FFM\n");
+    }
+    void Train() {  // train_ffm_algo.cpp:23-49
+        GradientUpdater::__global_bTraining = true;
+        GradientUpdater::__global_minibatch_size = dataRow_cnt;
+        if (!ctx) make_ctx(LCTR_MODEL_FFM, 0, 0);
+        for (size_t i = 0; i < epoch; i++) {
+            LCTR_OK(lctr_train_step(ctx, 0, 0, (int64_t)dataRow_cnt, &__loss, &__accuracy));
+            printf("Epoch %zu Train Loss = %f Accuracy = %f\n", i, __loss, __accuracy / dataRow_cnt);
+        }
+        LCTR_OK(lctr_download_params(ctx, W, V));
+        GradientUpdater::__global_bTraining = false;
+    }
+    float last_loss() const { return __loss; }
+
+private:
+    size_t epoch;
+};
+
+// Host shadow of Fully_Conn_Layer (train/layer/fullyconnLayer.h:36-61,194-206): initial values and the dropout
+// mask come from the reference's rand() stream in the reference's order; the arithmetic runs on the device.
+struct Fully_Conn_Layer_Host {
+    size_t in, out;
+    std::vector<float> weight, bias, mask;
+    Fully_Conn_Layer_Host(size_t _in, size_t _out) : in(_in), out(_out), weight(_in * _out), bias(_out, 0.f), mask(_out) {
+        for (size_t i = 0; i < out; i++) {
+            mask[i] = SampleBinary(GradientUpdater::__global_sparse_rate) ? 1. : 0.;
+            for (size_t j = 0; j < in; j++) weight[i * in + j] = UniformNumRand() - 0.5f;
+        }
+    }
+    void resample() {
+        for (size_t i = 0; i < out; i++) mask[i] = SampleBinary(GradientUpdater::__global_sparse_rate) ? 1. : 0.;
+    }
+};
+
+class Train_NFM_Algo : public FM_Algo_Abst {
+public:
+    Train_NFM_Algo(std::string _dataPath, size_t _epoch_cnt, size_t _factor_cnt, size_t _hidden_layer_size)
+        : FM_Algo_Abst(_dataPath, _factor_cnt), epoch(_epoch_cnt), hidden_layer_size(_hidden_layer_size) {
+        L2Reg_ratio = 0.001f;
+        batch_size = GradientUpdater::__global_minibatch_size;  // train_nfm_algo.cpp:13
+        sumVX = new float[dataRow_cnt * factor_cnt];
+        memset(sumVX, 0, sizeof(float) * dataRow_cnt * factor_cnt);
+        layers.emplace_back(factor_cnt, hidden_layer_size);  // :21-27
+        layers.emplace_back(hidden_layer_size, 1);
+    }
+    void Train() {  // train_nfm_algo.cpp:30-54
+        GradientUpdater::__global_bTraining = true;
+        if (!ctx) {
+            uint32_t hidden[1] = {(uint32_t)hidden_layer_size};
+            make_ctx(LCTR_MODEL_NFM, GradientUpdater::__global_minibatch_size, batch_size, 1, hidden);
+            for (size_t l = 0; l < layers.size(); l++) {
+                LCTR_OK(lctr_mlp_upload(ctx, (int)l, layers[l].weight.data(), layers[l].bias.data()));
+                LCTR_OK(lctr_mlp_set_mask(ctx, (int)l, layers[l].mask.data()));
+            }
+        }
+        for (size_t i = 0; i < epoch; i++) {
+            loss = 0;
+            accuracy = 0;
+            const size_t minibatch_epoch = (dataRow_cnt + batch_size - 1) / batch_size;
+            for (size_t p = 0; p < minibatch_epoch; p++) {
+                const size_t start_pos = p * batch_size;
+                float l = 0, c = 0;
+                LCTR_OK(lctr_train_step(ctx, 0, (int64_t)start_pos, (int64_t)std::min(start_pos + batch_size, dataRow_cnt), &l, &c));
+                loss += l;
+                accuracy += (size_t)c;
+                for (size_t li = 0; li < layers.size(); li++) {  // applyBatchGradient re-draws the masks
+                    layers[li].resample();
+                    LCTR_OK(lctr_mlp_set_mask(ctx, (int)li, layers[li].mask.data()));
+                }
+            }
+            printf("Epoch %zu loss = %f accuracy = %f\n", i, loss, 1.0 * accuracy / dataRow_cnt);
+        }
+        LCTR_OK(lctr_download_params(ctx, W, V));
+        LCTR_OK(lctr_download_sumvx(ctx, 0, sumVX));
+        for (size_t l = 0; l < layers.size(); l++)
+            LCTR_OK(lctr_mlp_download(ctx, (int)l, layers[l].weight.data(), layers[l].bias.data()));
+        GradientUpdater::__global_bTraining = false;
+    }
+    float last_loss() const { return loss; }
+    std::vector<Fully_Conn_Layer_Host> layers;
+
+private:
+    size_t epoch, batch_size, hidden_layer_size;
+    float loss;
+    size_t accuracy;
+};
+
+// predict/fm_predict.{h,cpp}.  The reference's loader drops the first feature of every test row and every fid
+// >= the training feature_cnt (:117-126); its FM branch adds 0.5*|sumVX_train[rid]|^2 of the TRAINING row with the
+// same index (:27-32).  Both quirks are reproduced (quirks = false gives the mathematically intended predictor).
+class FM_Predict {
+public:
+    FM_Predict(FM_Algo_Abst* p, std::string _testDataPath, bool with_valid_label, bool quirks = true)
+        : fm(p), quirks_(quirks) {
+        (void)with_valid_label;
+        lctr_dataset* t = nullptr;
+        if (lctr_load_libffm(_testDataPath.c_str(), 0, 0, &t) != 0) {
+            std::cout << "open file error!" << std::endl;
+            exit(1);
+        }
+        row_ptr.push_back(0);
+        for (int64_t r = 0; r < t->rows; r++) {
+            const size_t before = fid.size();
+            for (int64_t e = t->row_ptr[r] + (quirks ? 1 : 0); e < t->row_ptr[r + 1]; e++) {
+                if (t->fid[e] < fm->feature_cnt) {
+                    fid.push_back(t->fid[e]); field.push_back(t->field[e]); val.push_back(t->val[e]);
+                }
+            }
+            if (fid.size() == before) continue;
+            row_ptr.push_back((int64_t)fid.size());
+            test_label.push_back(t->label[quirks ? (int64_t)test_label.size() : r]);
+        }
+        test_dataRow_cnt = row_ptr.size() - 1;
+        lctr_free_dataset(t);
+    }
+    void Predict(std::string savePath) {  // fm_predict.cpp:12-90
+        ans.resize(test_dataRow_cnt);
+        LCTR_OK(lctr_upload_batch(fm->ctx, 1, (int64_t)test_dataRow_cnt, (int64_t)fid.size(), row_ptr.data(), fid.data(),
+                                  field.data(), val.data(), test_label.data()));
+        const bool is_ffm = fm->sumVX == NULL;
+        LCTR_OK(lctr_predict(fm->ctx, 1, (quirks_ && !is_ffm) ? 0 : -1, ans.data()));
+        float loss = 0;
+        int correct = 0;
+        for (size_t i = 0; i < test_label.size(); i++) {
+            loss += (int)test_label[i] == 1 ? -log(ans[i]) : -log(1.0 - ans[i]);
+            if (ans[i] > 0.5 && test_label[i] == 1) correct++;
+            else if (ans[i] < 0.5 && test_label[i] == 0) correct++;
+        }
+        std::cout << "total log likelihood = " << loss << " correct = " << std::setprecision(5)
+                  << (float)correct / test_dataRow_cnt;
+        printf(" auc = %.4f\n", Auc());
+        if (savePath != "") {
+            std::ofstream md(savePath);
+            if (!md.is_open()) { std::cout << "save model open file error" << std::endl; exit(0); }
+            for (auto v : ans) md << v << std::endl;
+            md.close();
+        }
+    }
+    std::vector<float> ans;
+
+private:
+    float Auc() {  // util/evaluator.h:51-104
+        const size_t kHashLen = (1 << 24) - 1;
+        std::vector<int> PosNum(kHashLen + 1, 0), NegNum(kHashLen + 1, 0);
+        for (size_t i = 0; i < ans.size(); i++) {
+            size_t index = ans[i] * kHashLen;
+            if (test_label[i] == 1) PosNum[index]++; else NegNum[index]++;
+        }
+        float totPos = 0.0, totNeg = 0.0, totPosPrev = 0.0, totNegPrev = 0.0, auc = 0.0;
+        for (int64_t idx = kHashLen; idx >= 0; --idx) {
+            totPosPrev = totPos; totNegPrev = totNeg;
+            totPos += PosNum[idx]; totNeg += NegNum[idx];
+            auc += (totNeg > totNegPrev ? (totNeg - totNegPrev) : (totNegPrev - totNeg)) * (totPos + totPosPrev) / 2.0;
+        }
+        if (totPos > 0.0 && totNeg > 0.0) return auc / totPos / totNeg;
+        return 0.0;
+    }
+    FM_Algo_Abst* fm;
+    bool quirks_;
+    size_t test_dataRow_cnt;
+    std::vector<int64_t> row_ptr;
+    std::vector<uint32_t> fid;
+    std::vector<uint16_t> field;
+    std::vector<float> val;
+    std::vector<int32_t> test_label;
+};
+
+}  // namespace lightctr_b200
+#endif

@@ -1,0 +1,82 @@
+"""The C++ host shims (lightctr_b200/host/lightctr_gpu.h) driven by a main.cpp-style program: same class names and
+call sequence as the reference's own driver (main.cpp:144-162,228-253), lowered to the C ABI.  Output is compared
+with the CPU oracle epoch by epoch."""
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+from golden_util import load_csr, write_libffm
+
+pytestmark = pytest.mark.gpu
+HOST = os.path.join(ROOT, "lightctr_b200", "host")
+LIBDIR = os.path.join(ROOT, "lightctr_b200", "lib")
+
+
+@pytest.fixture(scope="module")
+def exe(tmp_path_factory):
+    from lightctr_b200 import build as lbuild
+    lbuild.build()
+    out = str(tmp_path_factory.mktemp("bin") / "main_example")
+    subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++11", os.path.join(HOST, "main_example.cpp"), "-L" + LIBDIR,
+                           "-llightctr_b200", "-Wl,-rpath," + LIBDIR, "-L/usr/local/cuda/lib64",
+                           "-Wl,-rpath,/usr/local/cuda/lib64", "-o", out])
+    return out
+
+
+@pytest.fixture(scope="module")
+def files(tmp_path_factory):
+    d = tmp_path_factory.mktemp("hostdata")
+    tr, te = load_csr("train_sparse_csr.npz", field_cnt=68), load_csr("test_sparse_csr.npz", field_cnt=68)
+    ptr, pte = str(d / "train.csv"), str(d / "test.csv")
+    write_libffm(tr, ptr)
+    te.fid = np.insert(te.fid, te.row_ptr[:-1], 0).astype(np.uint32)
+    te.field = np.insert(te.field, te.row_ptr[:-1], 0).astype(np.uint32)
+    te.val = np.insert(te.val, te.row_ptr[:-1], 1.0).astype(np.float32)
+    te.row_ptr = te.row_ptr + np.arange(te.rows + 1)
+    write_libffm(te, pte)
+    return dict(train=ptr, test=pte, tr=tr, dir=str(d))
+
+
+def _losses(text, key):
+    return [float(x) for x in re.findall(key + r" = ([0-9.eE+-]+)", text)]
+
+
+def test_cxx_fm_driver(exe, files, oracle_api):
+    out = os.path.join(files["dir"], "fm.bin")
+    text = subprocess.check_output([exe, "fm", files["train"], files["test"], "5", "8", "0", "1", out], text=True)
+    got = _losses(text, "Train Loss")
+    ds = files["tr"]
+    W0, V0 = oracle_api.init_params(1, ds.feature_cnt, 8)
+    o = oracle_api.FMOracle(ds, 8, W0, V0)
+    want = [o.epoch()[0] for _ in range(5)]
+    assert len(got) == 5
+    for g, w in zip(got, want):
+        assert abs(g - w) <= 1e-5 * abs(w), (got, want)
+    raw = np.fromfile(out, np.float32)
+    F = ds.feature_cnt
+    assert np.max(np.abs(raw[:F] - o.W)) < 1e-6 and np.max(np.abs(raw[F:] - o.V)) < 1e-6
+    assert "total log likelihood" in text and "auc" in text
+
+
+def test_cxx_ffm_driver(exe, files, oracle_api):
+    text = subprocess.check_output([exe, "ffm", files["train"], files["test"], "2", "4", "68", "1"], text=True)
+    got = _losses(text, "Train Loss")
+    ds = files["tr"]
+    W0, V0 = oracle_api.init_params(1, ds.feature_cnt, 4, 68)
+    o = oracle_api.FFMOracle(ds, 4, W0, V0)
+    want = [o.epoch()[0] for _ in range(2)]
+    for g, w in zip(got, want):
+        assert abs(g - w) <= 1e-5 * abs(w), (got, want)
+
+
+def test_cxx_nfm_driver(exe, files, oracle_api):
+    text = subprocess.check_output([exe, "nfm", files["train"], files["test"], "2", "10", "32", "1"], text=True)
+    got = _losses(text, "loss")
+    o = oracle_api.NFMOracle(files["tr"], 10, 32, seed=1)
+    want = [o.epoch()[0] for _ in range(2)]
+    for g, w in zip(got, want):
+        assert abs(g - w) <= 1e-5 * abs(w), (got, want)
