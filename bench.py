@@ -234,12 +234,22 @@ def main():
 
     # ---- end-to-end arm: host buffers in, loss out, every step (C-ABI lctr_train_batch) ------------------
     h2d = 8 * (B + 1) + 4 * nnz_mean + 4 * B + (2 * nnz_mean if Fc else 0)
+    # every step: H2D of that step's CSR batch from pinned host memory, the train step, D2H of (loss, acc); the
+    # copy of batch i+1 overlaps the kernels of batch i (lctr_train_batch_async / lctr_wait, two batches in flight)
+    host = [_host_arrays(p, Fc) for p in pinned]
     for i in range(3):
-        ctx.train_batch(*_host_arrays(pinned[i % NB], Fc))
+        ctx.train_batch(*host[i % NB])
     ctx.sync()
+    torch.cuda.synchronize()
     t0 = time.time()
+    prev = None
+    e2e_loss = 0.0
     for i in range(args.steps):
-        ctx.train_batch(*_host_arrays(pinned[i % NB], Fc))
+        t = ctx.train_batch_async(*host[i % NB])
+        if prev is not None:
+            e2e_loss += ctx.wait(prev)[0]
+        prev = t
+    e2e_loss += ctx.wait(prev)[0]
     ctx.sync()
     e2e_s = time.time() - t0
     clocks = sampler.finish()

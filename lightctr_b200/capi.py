@@ -23,7 +23,7 @@ ABI_VERSION = 1
 SYMBOLS = [
     "lctr_last_error", "lctr_abi_version", "lctr_create", "lctr_destroy", "lctr_sync", "lctr_upload_params",
     "lctr_download_params", "lctr_download_opt_state", "lctr_upload_opt_state", "lctr_upload_batch",
-    "lctr_train_step", "lctr_train_batch", "lctr_predict", "lctr_download_sumvx", "lctr_download_pred",
+    "lctr_train_step", "lctr_train_batch", "lctr_train_batch_async", "lctr_wait", "lctr_predict", "lctr_download_sumvx", "lctr_download_pred",
     "lctr_mlp_upload", "lctr_mlp_download", "lctr_mlp_set_mask", "lctr_ipc_export", "lctr_ipc_import",
     "lctr_dense_grad_buffer", "lctr_load_libffm", "lctr_free_dataset", "lctr_launch_count", "lctr_stream", "lctr_profile", "lctr_profile_read",
 ]
@@ -71,6 +71,8 @@ def load_library():
     L.lctr_upload_batch.argtypes = [vp, C.c_int, i64, i64, vp, vp, vp, vp, vp]
     L.lctr_train_step.argtypes = [vp, C.c_int, i64, i64, C.POINTER(C.c_float), C.POINTER(C.c_float)]
     L.lctr_train_batch.argtypes = [vp, i64, i64, vp, vp, vp, vp, vp, C.POINTER(C.c_float), C.POINTER(C.c_float)]
+    L.lctr_train_batch_async.argtypes = [vp, i64, i64, vp, vp, vp, vp, vp, C.POINTER(C.c_uint64)]
+    L.lctr_wait.argtypes = [vp, C.c_uint64, C.POINTER(C.c_float), C.POINTER(C.c_float)]
     L.lctr_predict.argtypes = [vp, C.c_int, C.c_int, f32p]
     L.lctr_download_sumvx.argtypes = [vp, C.c_int, f32p]
     L.lctr_download_pred.argtypes = [vp, C.c_int, f32p]
@@ -229,6 +231,17 @@ class Context:
         loss, acc = C.c_float(), C.c_float()
         _chk(self.L.lctr_train_batch(self.h, len(row_ptr) - 1, len(fid), _p(row_ptr), _p(fid), _p(field), _p(val),
                                      _p(label), C.byref(loss), C.byref(acc)))
+        return loss.value, acc.value
+
+    def train_batch_async(self, row_ptr, fid, field, val, label):
+        t = C.c_uint64()
+        _chk(self.L.lctr_train_batch_async(self.h, len(row_ptr) - 1, len(fid), _p(row_ptr), _p(fid), _p(field), _p(val),
+                                           _p(label), C.byref(t)))
+        return t.value
+
+    def wait(self, ticket):
+        loss, acc = C.c_float(), C.c_float()
+        _chk(self.L.lctr_wait(self.h, ticket, C.byref(loss), C.byref(acc)))
         return loss.value, acc.value
 
     def predict(self, slot, quirk_sumvx_slot=-1):

@@ -229,7 +229,12 @@ int lctr_destroy(lctr_ctx* c) {
     }
     mlp_free(c);
     if (c->h_stats) cudaFreeHost(c->h_stats);
-    if (c->h_stage) cudaFreeHost(c->h_stage);
+    if (c->h_stat_ring) cudaFreeHost(c->h_stat_ring);
+    if (c->copy_stream) {
+        for (int i = 0; i < 2; i++) { cudaEventDestroy(c->ev_copied[i]); cudaEventDestroy(c->ev_computed[i]); }
+        for (int i = 0; i < kStatRing; i++) cudaEventDestroy(c->ev_stat[i]);
+        cudaStreamDestroy(c->copy_stream);
+    }
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
     return 0;
@@ -284,36 +289,47 @@ int lctr_upload_opt_state(lctr_ctx* c, const float* s1, const float* s2) {
     return 0;
 }
 
-int lctr_upload_batch(lctr_ctx* c, int slot, int64_t rows, int64_t nnz, const int64_t* row_ptr, const uint32_t* fid,
-                      const uint16_t* field, const float* val, const int32_t* label) {
+static int upload_batch_on(lctr_ctx* c, cudaStream_t st, int slot, int64_t rows, int64_t nnz, const int64_t* row_ptr,
+                           const uint32_t* fid, const uint16_t* field, const float* val, const int32_t* label) {
     LCTR_CHECK(c, "null ctx");
     LCTR_CHECK(slot >= 0 && slot < kNumSlots, "slot %d out of range", slot);
     LCTR_CHECK(rows >= 0 && nnz >= 0 && row_ptr && (nnz == 0 || fid) && (rows == 0 || label), "upload_batch: null input");
     LCTR_CHECK(c->cfg.model != LCTR_MODEL_FFM || field || nnz == 0, "upload_batch: FFM needs the field array");
     Slot& s = c->slots[slot];
-    if (slot_reserve(c, s, rows, nnz)) return 1;
+    if (rows > s.cap_rows || nnz > s.cap_nnz) {
+        LCTR_CUDA(cudaStreamSynchronize(c->stream));  // buffers about to be reallocated may still be in use
+        if (slot_reserve(c, s, rows, nnz)) return 1;
+        LCTR_CUDA(cudaStreamSynchronize(c->stream));
+    }
     s.rows = rows; s.nnz = nnz;
     s.has_val = val != nullptr;
     s.has_field = field != nullptr;
-    LCTR_CUDA(cudaMemcpyAsync(s.row_ptr, row_ptr, (size_t)(rows + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, c->stream));
+    LCTR_CUDA(cudaMemcpyAsync(s.row_ptr, row_ptr, (size_t)(rows + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, st));
     if (nnz) {
-        LCTR_CUDA(cudaMemcpyAsync(s.fid, fid, (size_t)nnz * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
-        if (field) LCTR_CUDA(cudaMemcpyAsync(s.field, field, (size_t)nnz * sizeof(uint16_t), cudaMemcpyHostToDevice, c->stream));
-        if (val) LCTR_CUDA(cudaMemcpyAsync(s.val, val, (size_t)nnz * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+        LCTR_CUDA(cudaMemcpyAsync(s.fid, fid, (size_t)nnz * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+        if (field) LCTR_CUDA(cudaMemcpyAsync(s.field, field, (size_t)nnz * sizeof(uint16_t), cudaMemcpyHostToDevice, st));
+        if (val) LCTR_CUDA(cudaMemcpyAsync(s.val, val, (size_t)nnz * sizeof(float), cudaMemcpyHostToDevice, st));
     }
     if (rows) {
         // labels travel as int32 and are widened on device (the reference compares a `float target`)
         int32_t* tmp = reinterpret_cast<int32_t*>(s.pred);  // pred is overwritten by the next forward anyway
-        LCTR_CUDA(cudaMemcpyAsync(tmp, label, (size_t)rows * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
-        label_to_float_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, c->stream>>>(tmp, s.label, rows);
+        LCTR_CUDA(cudaMemcpyAsync(tmp, label, (size_t)rows * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+        label_to_float_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>(tmp, s.label, rows);
         c->launches++;
         LCTR_CUDA(cudaGetLastError());
     }
     s.csc_block = 0;
     if (c->cfg.deterministic && c->cfg.model != LCTR_MODEL_FFM && rows > 0) {
+        LCTR_CUDA(cudaStreamSynchronize(st));
         if (build_csc(c, s, rows, nnz, row_ptr, fid, val)) return 1;
     }
     return 0;
+}
+
+int lctr_upload_batch(lctr_ctx* c, int slot, int64_t rows, int64_t nnz, const int64_t* row_ptr, const uint32_t* fid,
+                      const uint16_t* field, const float* val, const int32_t* label) {
+    LCTR_CHECK(c, "null ctx");
+    return upload_batch_on(c, c->stream, slot, rows, nnz, row_ptr, fid, field, val, label);
 }
 
 static int read_stats(lctr_ctx* c, uint64_t step, float* loss_sum, float* acc_cnt) {
@@ -363,6 +379,55 @@ int lctr_train_batch(lctr_ctx* c, int64_t rows, int64_t nnz, const int64_t* row_
                      const uint16_t* field, const float* val, const int32_t* label, float* loss_sum, float* acc_cnt) {
     if (lctr_upload_batch(c, 0, rows, nnz, row_ptr, fid, field, val, label)) return 1;
     return lctr_train_step(c, 0, 0, rows, loss_sum, acc_cnt);
+}
+
+// ---- streamed training: copy stream + compute stream, two pipeline slots -------------------------------------
+static int pipe_init(lctr_ctx* c) {
+    if (c->copy_stream) return 0;
+    LCTR_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; i++) {
+        LCTR_CUDA(cudaEventCreateWithFlags(&c->ev_copied[i], cudaEventDisableTiming));
+        LCTR_CUDA(cudaEventCreateWithFlags(&c->ev_computed[i], cudaEventDisableTiming));
+    }
+    for (int i = 0; i < kStatRing; i++) LCTR_CUDA(cudaEventCreateWithFlags(&c->ev_stat[i], cudaEventDisableTiming));
+    LCTR_CUDA(cudaMallocHost((void**)&c->h_stat_ring, sizeof(double) * 2 * kStatRing));
+    return 0;
+}
+
+int lctr_train_batch_async(lctr_ctx* c, int64_t rows, int64_t nnz, const int64_t* row_ptr, const uint32_t* fid,
+                           const uint16_t* field, const float* val, const int32_t* label, uint64_t* ticket) {
+    LCTR_CHECK(c && ticket, "null argument");
+    LCTR_CHECK(!c->cfg.deterministic, "streamed batches use the RED scatter path (cfg.deterministic must be 0)");
+    if (pipe_init(c)) return 1;
+    LCTR_CHECK(c->pipe_issued - c->pipe_waited < 2, "more than 2 streamed batches outstanding: call lctr_wait first");
+    const int p = (int)(c->pipe_issued & 1);
+    const int slot = kNumSlots - 2 + p;
+    // the copy may only overwrite the slot once the step that last used it has finished
+    if (c->pipe_issued >= 2) LCTR_CUDA(cudaStreamWaitEvent(c->copy_stream, c->ev_computed[p], 0));
+    if (upload_batch_on(c, c->copy_stream, slot, rows, nnz, row_ptr, fid, field, val, label)) return 1;
+    LCTR_CUDA(cudaEventRecord(c->ev_copied[p], c->copy_stream));
+    LCTR_CUDA(cudaStreamWaitEvent(c->stream, c->ev_copied[p], 0));
+    const uint64_t step = c->step;
+    if (lctr_train_step(c, slot, 0, rows, nullptr, nullptr)) return 1;
+    LCTR_CUDA(cudaEventRecord(c->ev_computed[p], c->stream));
+    const int ri = (int)(step % kStatRing);
+    LCTR_CUDA(cudaMemcpyAsync(c->h_stat_ring + 2 * ri, c->stats + 2 * ri, 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    LCTR_CUDA(cudaEventRecord(c->ev_stat[ri], c->stream));
+    *ticket = step;
+    c->pipe_issued++;
+    return 0;
+}
+
+int lctr_wait(lctr_ctx* c, uint64_t ticket, float* loss_sum, float* acc_cnt) {
+    LCTR_CHECK(c && c->copy_stream, "lctr_wait: no streamed batch was issued");
+    LCTR_CHECK(ticket < c->step && c->step - ticket <= (uint64_t)kStatRing, "lctr_wait: ticket %llu is not outstanding",
+               (unsigned long long)ticket);
+    const int ri = (int)(ticket % kStatRing);
+    LCTR_CUDA(cudaEventSynchronize(c->ev_stat[ri]));
+    if (loss_sum) *loss_sum = (float)c->h_stat_ring[2 * ri];
+    if (acc_cnt) *acc_cnt = (float)c->h_stat_ring[2 * ri + 1];
+    if (c->pipe_waited < c->pipe_issued) c->pipe_waited++;
+    return 0;
 }
 
 int lctr_predict(lctr_ctx* c, int slot, int quirk_sumvx_slot, float* pctr) {

@@ -107,9 +107,12 @@ struct lctr_ctx {
     std::vector<int>* prof_id = nullptr;
     double prof_ms[lctr::kNumProf] = {0};
     int64_t prof_cnt[lctr::kNumProf] = {0};
-    // pinned staging for lctr_train_batch (end-to-end path)
-    void* h_stage = nullptr;
-    size_t h_stage_bytes = 0;
+    // streamed training pipeline (lctr_train_batch_async): copy stream, per-slot events, pinned result ring
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_computed[2] = {nullptr, nullptr};
+    cudaEvent_t ev_stat[lctr::kStatRing] = {nullptr};
+    double* h_stat_ring = nullptr;
+    uint64_t pipe_issued = 0, pipe_waited = 0;
 };
 
 namespace lctr {

@@ -174,3 +174,43 @@ def test_fm_red_path_per_step_parity(files, oracle_api):
         else:
             o.epoch()
     ctx.close()
+
+
+def test_streamed_async_matches_sync(oracle_api):
+    """lctr_train_batch_async / lctr_wait (copy of batch i+1 overlapping step i) must give the same per-step results
+    as the synchronous lctr_train_batch on the same sequence of batches (RED summation order aside: 1e-6)."""
+    from lightctr_b200 import capi
+    from lightctr_b200.data import CriteoSynth
+    F, k, B = 20000, 16, 512
+    gen = CriteoSynth(F, seed=7)
+    batches = [gen.batch(B) for _ in range(6)]
+    rng = np.random.default_rng(3)
+    V0 = (rng.standard_normal(F * k) / 4).astype(np.float32)
+    res = []
+    for mode in ("sync", "async"):
+        ctx = capi.Context(capi.MODEL_FM, F, k, deterministic=0)
+        ctx.upload_params(np.zeros(F, np.float32), V0)
+        out = []
+        if mode == "sync":
+            for rp, fid, fld, lab in batches:
+                out.append(ctx.train_batch(rp, fid, None, None, lab))
+        else:
+            prev = None
+            for rp, fid, fld, lab in batches:
+                t = ctx.train_batch_async(rp, fid, None, None, lab)
+                if prev is not None:
+                    out.append(ctx.wait(prev))
+                prev = t
+            out.append(ctx.wait(prev))
+        W, V = ctx.download_params()
+        res.append((out, W, V))
+        ctx.close()
+    for (la, ca), (lb, cb) in zip(res[0][0], res[1][0]):
+        assert _rel(la, lb) < 1e-6 and ca == cb
+    assert np.max(np.abs(res[0][2] - res[1][2])) < 1e-5
+    # and the first step against the oracle
+    rp, fid, fld, lab = batches[0]
+    ds = oracle_api.Dataset(rp, fid, fld.astype(np.uint32), np.ones(len(fid), np.float32), lab, F, 0)
+    o = oracle_api.FMOracle(ds, k, np.zeros(F, np.float32), V0)
+    lo, _ = o.epoch()
+    assert _rel(res[0][0][0][0], lo) < 1e-6
