@@ -143,7 +143,8 @@ class Context:
 
     def __init__(self, model, feature_cnt, factor_cnt, field_cnt=0, optimizer=OPT_ADAGRAD, lr=0.05, l2=0.001,
                  minibatch_size=0, momentum=0.8, momentum_adam2=0.999, hidden=(), activation=ACT_SIGMOID,
-                 mlp_precision=MLP_FP32, device=0, rank=0, world=1, deterministic=0, csc_row_block=0):
+                 mlp_precision=MLP_FP32, device=0, rank=0, world=1, deterministic=0, csc_row_block=0, max_rows=0,
+                 max_nnz=0):
         L = load_library()
         cfg = Cfg()
         cfg.abi_version = ABI_VERSION
@@ -157,6 +158,7 @@ class Context:
         cfg.activation, cfg.mlp_precision = activation, mlp_precision
         cfg.rank, cfg.world = rank, world
         cfg.deterministic, cfg.csc_row_block = deterministic, csc_row_block
+        cfg.max_rows, cfg.max_nnz = max_rows, max_nnz
         self.cfg = cfg
         self.h = C.c_void_p()
         _chk(L.lctr_create(C.byref(cfg), C.byref(self.h)))
@@ -283,6 +285,17 @@ class Context:
         cnt = (C.c_int64 * 8)()
         _chk(self.L.lctr_profile_read(self.h, ms, cnt, 8, 1 if reset else 0))
         return {self.PROF_NAMES[i]: (ms[i], cnt[i]) for i in range(8) if cnt[i] > 0}
+
+    def ipc_export(self):
+        n = C.c_size_t()
+        _chk(self.L.lctr_ipc_export(self.h, None, 0, C.byref(n)))
+        buf = C.create_string_buffer(n.value)
+        _chk(self.L.lctr_ipc_export(self.h, buf, n.value, C.byref(n)))
+        return buf.raw
+
+    def ipc_import(self, all_blobs, bytes_per_rank):
+        buf = C.create_string_buffer(all_blobs, len(all_blobs))
+        _chk(self.L.lctr_ipc_import(self.h, buf, bytes_per_rank))
 
     def launch_count(self):
         return self.L.lctr_launch_count(self.h)

@@ -170,20 +170,24 @@ int lctr_create(const lctr_cfg* cfg, lctr_ctx** out) {
     }
     if (c->cfg.world <= 0) { c->cfg.world = 1; c->cfg.rank = 0; }
     c->F = cfg->feature_cnt;
+    c->Fl = (c->F + (size_t)c->cfg.world - 1) / (size_t)c->cfg.world;
+    LCTR_CHECK(c->cfg.world == 1 || !cfg->deterministic, "lctr_create: deterministic mode is single-GPU only");
+    LCTR_CHECK(c->cfg.world == 1 || cfg->model != LCTR_MODEL_NFM, "lctr_create: multi-GPU NFM is not built");
     c->rowlen = cfg->model == LCTR_MODEL_FFM ? (size_t)cfg->field_cnt * cfg->factor_cnt : cfg->factor_cnt;
     cudaDeviceProp prop;
     LCTR_CUDA(cudaGetDeviceProperties(&prop, cfg->device));
     c->sm_count = prop.multiProcessorCount;
     LCTR_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-    const size_t nv = c->F * c->rowlen;
+    const size_t FL = c->Fl;
+    const size_t nv = FL * c->rowlen;
     const bool two = cfg->optimizer != LCTR_OPT_ADAGRAD;
     int rc = 0;
-    rc |= dalloc(&c->W, c->F); rc |= dalloc(&c->V, nv);
-    rc |= dalloc(&c->gW, c->F); rc |= dalloc(&c->gV, nv);
-    rc |= dalloc(&c->s1W, c->F); rc |= dalloc(&c->s1V, nv);
-    if (two) { rc |= dalloc(&c->s2W, c->F); rc |= dalloc(&c->s2V, nv); }
-    rc |= dalloc(&c->touched, c->F + 512);
-    rc |= dalloc(&c->touch_list, c->F + 32);
+    rc |= dalloc(&c->W, FL); rc |= dalloc(&c->V, nv);
+    rc |= dalloc(&c->gW, FL); rc |= dalloc(&c->gV, nv);
+    rc |= dalloc(&c->s1W, FL); rc |= dalloc(&c->s1V, nv);
+    if (two) { rc |= dalloc(&c->s2W, FL); rc |= dalloc(&c->s2V, nv); }
+    rc |= dalloc(&c->touched, FL + 512);
+    rc |= dalloc(&c->touch_list, FL + 32);
     rc |= dalloc(&c->n_touch, 1);
     rc |= dalloc(&c->apply_done, 1);
     rc |= dalloc(&c->stats, (size_t)2 * kStatRing);
@@ -191,17 +195,22 @@ int lctr_create(const lctr_cfg* cfg, lctr_ctx** out) {
     rc |= dalloc(&c->stat_done, 1);
     if (rc) { lctr_destroy(c); return 1; }
     LCTR_CUDA(cudaMallocHost((void**)&c->h_stats, 2 * sizeof(double)));
-    LCTR_CUDA(cudaMemsetAsync(c->W, 0, c->F * sizeof(float), c->stream));
+    LCTR_CUDA(cudaMemsetAsync(c->W, 0, FL * sizeof(float), c->stream));
     LCTR_CUDA(cudaMemsetAsync(c->V, 0, nv * sizeof(float), c->stream));
-    LCTR_CUDA(cudaMemsetAsync(c->gW, 0, c->F * sizeof(float), c->stream));
+    LCTR_CUDA(cudaMemsetAsync(c->gW, 0, FL * sizeof(float), c->stream));
     LCTR_CUDA(cudaMemsetAsync(c->gV, 0, nv * sizeof(float), c->stream));
-    LCTR_CUDA(cudaMemsetAsync(c->s1W, 0, c->F * sizeof(float), c->stream));
+    LCTR_CUDA(cudaMemsetAsync(c->s1W, 0, FL * sizeof(float), c->stream));
     LCTR_CUDA(cudaMemsetAsync(c->s1V, 0, nv * sizeof(float), c->stream));
     if (two) {
-        LCTR_CUDA(cudaMemsetAsync(c->s2W, 0, c->F * sizeof(float), c->stream));
+        LCTR_CUDA(cudaMemsetAsync(c->s2W, 0, FL * sizeof(float), c->stream));
         LCTR_CUDA(cudaMemsetAsync(c->s2V, 0, nv * sizeof(float), c->stream));
     }
-    LCTR_CUDA(cudaMemsetAsync(c->touched, 0, c->F + 512, c->stream));
+    LCTR_CUDA(cudaMemsetAsync(c->touched, 0, FL + 512, c->stream));
+    if (c->cfg.world > 1) {
+        if (dist_alloc(c)) { lctr_destroy(c); return 1; }
+    } else {
+        c->cW = c->W; c->cV = c->V; c->cgW = c->gW; c->cgV = c->gV;
+    }
     LCTR_CUDA(cudaMemsetAsync(c->n_touch, 0, sizeof(unsigned int), c->stream));
     LCTR_CUDA(cudaMemsetAsync(c->apply_done, 0, sizeof(unsigned int), c->stream));
     LCTR_CUDA(cudaMemsetAsync(c->stats, 0, sizeof(double) * 2 * kStatRing, c->stream));
@@ -228,6 +237,7 @@ int lctr_destroy(lctr_ctx* c) {
         delete s.h_blk_seg_ptr; s.h_blk_seg_ptr = nullptr;
     }
     mlp_free(c);
+    dist_free(c);
     if (c->h_stats) cudaFreeHost(c->h_stats);
     if (c->h_stat_ring) cudaFreeHost(c->h_stat_ring);
     if (c->copy_stream) {
@@ -246,22 +256,54 @@ int lctr_sync(lctr_ctx* c) {
     return 0;
 }
 
+// world > 1: W / V are the FULL (global) arrays; each rank keeps / returns only the rows it owns (fid % world == rank)
 int lctr_upload_params(lctr_ctx* c, const float* W, const float* V) {
     LCTR_CHECK(c, "null ctx");
-    if (W) LCTR_CUDA(cudaMemcpyAsync(c->W, W, c->F * sizeof(float), cudaMemcpyHostToDevice, c->stream));
-    if (V) LCTR_CUDA(cudaMemcpyAsync(c->V, V, c->F * c->rowlen * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    const int R = c->cfg.world, me = c->cfg.rank;
+    if (R == 1) {
+        if (W) LCTR_CUDA(cudaMemcpyAsync(c->W, W, c->F * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+        if (V) LCTR_CUDA(cudaMemcpyAsync(c->V, V, c->F * c->rowlen * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    } else {
+        std::vector<float> w, v;
+        if (W) {
+            w.assign(c->Fl, 0.f);
+            for (size_t f = (size_t)me, l = 0; f < c->F; f += R, l++) w[l] = W[f];
+            LCTR_CUDA(cudaMemcpyAsync(c->W, w.data(), c->Fl * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+        }
+        if (V) {
+            v.assign(c->Fl * c->rowlen, 0.f);
+            for (size_t f = (size_t)me, l = 0; f < c->F; f += R, l++)
+                memcpy(&v[l * c->rowlen], V + f * c->rowlen, c->rowlen * sizeof(float));
+            LCTR_CUDA(cudaMemcpyAsync(c->V, v.data(), v.size() * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+        }
+        LCTR_CUDA(cudaStreamSynchronize(c->stream));
+        return 0;
+    }
     LCTR_CUDA(cudaStreamSynchronize(c->stream));
     return 0;
 }
 int lctr_download_params(lctr_ctx* c, float* W, float* V) {
     LCTR_CHECK(c, "null ctx");
-    if (W) LCTR_CUDA(cudaMemcpyAsync(W, c->W, c->F * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
-    if (V) LCTR_CUDA(cudaMemcpyAsync(V, c->V, c->F * c->rowlen * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    const int R = c->cfg.world, me = c->cfg.rank;
+    if (R == 1) {
+        if (W) LCTR_CUDA(cudaMemcpyAsync(W, c->W, c->F * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+        if (V) LCTR_CUDA(cudaMemcpyAsync(V, c->V, c->F * c->rowlen * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+        LCTR_CUDA(cudaStreamSynchronize(c->stream));
+        return 0;
+    }
+    std::vector<float> w(c->Fl), v(c->Fl * c->rowlen);
+    LCTR_CUDA(cudaMemcpyAsync(w.data(), c->W, w.size() * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    LCTR_CUDA(cudaMemcpyAsync(v.data(), c->V, v.size() * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
     LCTR_CUDA(cudaStreamSynchronize(c->stream));
+    for (size_t f = (size_t)me, l = 0; f < c->F; f += R, l++) {
+        if (W) W[f] = w[l];
+        if (V) memcpy(V + f * c->rowlen, &v[l * c->rowlen], c->rowlen * sizeof(float));
+    }
     return 0;
 }
 int lctr_download_opt_state(lctr_ctx* c, float* s1, float* s2) {
     LCTR_CHECK(c, "null ctx");
+    LCTR_CHECK(c->cfg.world == 1, "optimizer-state transfer is single-GPU only");
     const size_t nv = c->F * c->rowlen;
     if (s1) {
         LCTR_CUDA(cudaMemcpyAsync(s1, c->s1W, c->F * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
@@ -352,14 +394,20 @@ int lctr_train_step(lctr_ctx* c, int slot, int64_t rb, int64_t re, float* loss_s
     int rc = 0;
     switch (c->cfg.model) {
         case LCTR_MODEL_FM:
-            if (c->cfg.deterministic)
+            if (c->cfg.world > 1)
+                rc = dist_pre_step(c, s, rb, re) || launch_fm_forward(c, s, rb, re, false, true) ||
+                     launch_fm_backward(c, s, rb, re, false) || dist_post_step(c, re - rb);
+            else if (c->cfg.deterministic)
                 rc = launch_fm_forward(c, s, rb, re, false, true) || launch_fm_backward_csc(c, s, rb, re, false);
             else
                 rc = launch_fm_forward(c, s, rb, re, false, true) || launch_fm_backward(c, s, rb, re, false) ||
                      launch_apply(c, re - rb);
             break;
         case LCTR_MODEL_FFM:
-            rc = launch_ffm_forward(c, s, rb, re, true) || launch_ffm_backward(c, s, rb, re) || launch_apply(c, re - rb);
+            if (c->cfg.world > 1)
+                rc = dist_pre_step(c, s, rb, re) || launch_ffm_forward(c, s, rb, re, true) || dist_post_step(c, re - rb);
+            else
+                rc = launch_ffm_forward(c, s, rb, re, true) || launch_ffm_backward(c, s, rb, re) || launch_apply(c, re - rb);
             break;
         case LCTR_MODEL_NFM:
             rc = mlp_reserve(c, re - rb) || launch_fm_forward(c, s, rb, re, true, false) ||
@@ -480,17 +528,6 @@ int lctr_dense_grad_buffer(lctr_ctx* c, void** dev_ptr, size_t* n_floats) {
     *dev_ptr = c->dense_grad;
     *n_floats = c->dense_grad_n;
     return 0;
-}
-
-int lctr_ipc_export(lctr_ctx* c, void* handles_out, size_t cap, size_t* bytes) {
-    (void)c; (void)handles_out; (void)cap; (void)bytes;
-    set_error("lctr_ipc_export: multi-GPU table sharding not built yet (DESIGN.md, row e)");
-    return 1;
-}
-int lctr_ipc_import(lctr_ctx* c, const void* all_handles, size_t bytes_per_rank) {
-    (void)c; (void)all_handles; (void)bytes_per_rank;
-    set_error("lctr_ipc_import: multi-GPU table sharding not built yet (DESIGN.md, row e)");
-    return 1;
 }
 
 int lctr_profile(lctr_ctx* c, int enable) {

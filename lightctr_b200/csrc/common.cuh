@@ -72,14 +72,20 @@ struct MlpLayer {
 
 }  // namespace lctr
 
+namespace lctr { struct DistState; }
 struct lctr_ctx {
     lctr_cfg cfg;
     cudaStream_t stream = nullptr;
     size_t F = 0, rowlen = 0;  // rowlen = k (FM/NFM) or Fc*k (FFM)
+    size_t Fl = 0;             // rows of this rank's table shard (== F when world == 1)
     // parameters, gradient accumulators (update_g layout: W part, V part), optimizer state
     float *W = nullptr, *V = nullptr, *gW = nullptr, *gV = nullptr;
     float *s1W = nullptr, *s1V = nullptr, *s2W = nullptr, *s2V = nullptr;
-    uint8_t* touched = nullptr;  // F bytes: 1 = fid received gradient this step
+    uint8_t* touched = nullptr;  // Fl bytes: 1 = fid (shard-local index) received gradient this step
+    // compute view used by the forward/backward kernels, indexed by GLOBAL fid: aliases of the arrays above when
+    // world == 1; in multi-GPU mode a full-size local cache of the rows pulled this step + local gradient buffers
+    float *cW = nullptr, *cV = nullptr, *cgW = nullptr, *cgV = nullptr;
+    lctr::DistState* dist = nullptr;
     uint32_t* touch_list = nullptr;      // compacted fids of the step (stage A of the sparse apply)
     unsigned int* n_touch = nullptr;     // list length (device)
     unsigned int* apply_done = nullptr;  // block-completion counter of stage B
@@ -210,6 +216,12 @@ int launch_ffm_backward(lctr_ctx* c, Slot& s, int64_t rb, int64_t re);
 int launch_apply(lctr_ctx* c, int64_t rows_in_step);
 int launch_fm_backward_csc(lctr_ctx* c, Slot& s, int64_t rb, int64_t re, bool nfm);
 int launch_predict_quirk(lctr_ctx* c, Slot& s, Slot& train);
+// multi-GPU (dist.cu)
+int dist_alloc(lctr_ctx* c);
+int dist_free(lctr_ctx* c);
+int dist_pre_step(lctr_ctx* c, Slot& s, int64_t rb, int64_t re);   // unique ids of the batch + pull their rows
+int dist_post_step(lctr_ctx* c, int64_t rows_divisor);             // push gradients, owner-side merge + update
+__global__ void compact_touched_kernel(uint8_t* touched, size_t F, uint32_t* list, unsigned int* n_list);
 int mlp_alloc(lctr_ctx* c);
 int mlp_free(lctr_ctx* c);
 int mlp_reserve(lctr_ctx* c, int64_t rows);

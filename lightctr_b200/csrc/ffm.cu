@@ -190,7 +190,7 @@ __global__ void ffm_fused_kernel(const int64_t* __restrict__ row_ptr, const uint
                     }
                     if (t == 0) {
                         red_add_f32(gW + f[u], d * x[u] + l2 * __ldg(W + f[u]));  // train_ffm_algo.cpp:98
-                        touched[f[u]] = 1;
+                        if (touched) touched[f[u]] = 1;
                     }
                 }
             }
@@ -216,8 +216,8 @@ static int ffm_launch(lctr_ctx* c, Slot& s, int64_t rb, int64_t re, bool train, 
     do {                                                                                                              \
         auto kern = ffm_fused_kernel<VECN, HV, TR>;                                                                   \
         LCTR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                \
-        kern<<<(unsigned)rows, tpb, smem, c->stream>>>(s.row_ptr, s.fid, s.field, s.val, s.label, c->W, c->V, Fc, k, \
-                                                       s.pred, c->gW, c->gV, c->touched, c->cfg.l2_reg, rb,          \
+        kern<<<(unsigned)rows, tpb, smem, c->stream>>>(s.row_ptr, s.fid, s.field, s.val, s.label, c->cW, c->cV, Fc, k, \
+                                                       s.pred, c->cgW, c->cgV, c->cfg.world > 1 ? nullptr : c->touched, c->cfg.l2_reg, rb, \
                                                        c->stat_partial, c->stat_done, out_slot, stats ? 1 : 0);      \
     } while (0)
 #define FFM_GO2(VECN)                                                                \

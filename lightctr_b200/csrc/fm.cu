@@ -231,7 +231,7 @@ fm_backward_kernel(const int64_t* __restrict__ row_ptr, const uint32_t* __restri
             }
             if (q == 0) {
                 red_add_f32(gW + ff[j], gw);  // *update_W(fid) += gradW  (:109)
-                touched[ff[j]] = 1;
+                if (touched) touched[ff[j]] = 1;
             }
         }
     }
@@ -301,7 +301,7 @@ static int fwd_go(lctr_ctx* c, Slot& s, bool nfm, int64_t rb, int64_t re, double
     do {                                                                                                       \
         auto kern = fm_forward_kernel<K, HV, NF>;                                                              \
         if (smem > 48 * 1024) LCTR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        kern<<<grid, 256, smem, c->stream>>>(s.row_ptr, s.fid, s.val, s.label, c->W, c->V, s.pred, s.sumvx, c->z, \
+        kern<<<grid, 256, smem, c->stream>>>(s.row_ptr, s.fid, s.val, s.label, c->cW, c->cV, s.pred, s.sumvx, c->z, \
                                              s.wide, rb, re, c->stat_partial, c->stat_done, out_slot, stats);  \
     } while (0)
     if (s.has_val) { if (nfm) FWD_GO(true, true); else FWD_GO(true, false); }
@@ -343,8 +343,8 @@ int launch_fm_backward(lctr_ctx* c, Slot& s, int64_t rb, int64_t re, bool nfm) {
     if (rows <= 0) return 0;
     const unsigned grid = (unsigned)((rows + 7) / 8);
     ProfScope prof(c, PROF_FM_BWD_RED);
-    FM_DISPATCH(fm_backward_kernel, s.row_ptr, s.fid, s.val, s.label, c->W, c->V, k, s.pred, s.sumvx, c->dz, c->gW,
-                c->gV, c->touched, c->cfg.l2_reg, rb, re);
+    FM_DISPATCH(fm_backward_kernel, s.row_ptr, s.fid, s.val, s.label, c->cW, c->cV, k, s.pred, s.sumvx, c->dz, c->cgW,
+                c->cgV, c->cfg.world > 1 ? nullptr : c->touched, c->cfg.l2_reg, rb, re);
     c->launches++;
     LCTR_CUDA(cudaGetLastError());
     return 0;
@@ -471,7 +471,7 @@ int launch_fm_backward_csc(lctr_ctx* c, Slot& s, int64_t rb, int64_t re, bool nf
 int launch_predict_quirk(lctr_ctx* c, Slot& s, Slot& train) {
     if (s.rows <= 0) return 0;
     const unsigned grid = (unsigned)((s.rows + 7) / 8);
-    fm_predict_quirk_kernel<<<grid, 256, 0, c->stream>>>(s.row_ptr, s.fid, s.has_val ? s.val : nullptr, c->W, c->V,
+    fm_predict_quirk_kernel<<<grid, 256, 0, c->stream>>>(s.row_ptr, s.fid, s.has_val ? s.val : nullptr, c->cW, c->cV,
                                                          (int)c->cfg.factor_cnt, train.sumvx, train.rows, s.pred,
                                                          s.rows);
     c->launches++;

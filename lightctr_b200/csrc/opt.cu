@@ -183,12 +183,12 @@ int launch_apply(lctr_ctx* c, int64_t rows_in_step) {
     while (lpr < slices && lpr < 32) lpr <<= 1;
     const int spl = (slices + lpr - 1) / lpr;
     LCTR_CHECK(spl <= 4, "row of %d floats is too long for the sparse apply kernel (max %d)", rowlen, 4 * 32 * vec);
-    const size_t ntiles = (c->F + 511) / 512;
+    const size_t ntiles = (c->Fl + 511) / 512;
     unsigned grid_a = (unsigned)std::min<size_t>((ntiles + 7) / 8, (size_t)c->sm_count * 8);
     if (grid_a == 0) grid_a = 1;
     const unsigned grid = (unsigned)c->sm_count * 2;
     ProfScope prof(c, PROF_APPLY);
-    compact_touched_kernel<<<grid_a, 256, 0, c->stream>>>(c->touched, c->F, c->touch_list, c->n_touch);
+    compact_touched_kernel<<<grid_a, 256, 0, c->stream>>>(c->touched, c->Fl, c->touch_list, c->n_touch);
     c->launches++;
 #define APPLY_ARGS c->touch_list, c->n_touch, c->apply_done, rowlen, c->W, c->V, c->gW, c->gV, c->s1W, c->s1V, c->s2W, c->s2V, P
 #define APPLY_CASE(L, VV, S, UU) apply_kernel<L, VV, S, UU><<<grid, 256, 0, c->stream>>>(APPLY_ARGS)
