@@ -135,7 +135,7 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    wname = args.workload or ("fm_c2" if world == 1 else "ffm_c5")
+    wname = args.workload or "fm_c2"
     wl = WORKLOADS[wname]
     metric = "samples/sec (device-timed) %s train step on Criteo-shape" % wl["model"].upper()
 
@@ -167,19 +167,22 @@ def main():
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    if world > 1:
-        raise SystemExit("bench.py: multi-GPU path not built yet in this revision")
-
     model = {"fm": capi.MODEL_FM, "ffm": capi.MODEL_FFM}[wl["model"]]
     opt = {"adagrad": capi.OPT_ADAGRAD, "ftrl": capi.OPT_FTRL, "adam": capi.OPT_ADAM}[wl["opt"]]
     F, k, B = wl["F"], wl["k"], wl["batch"]
     Fc = N_FIELDS if wl["model"] == "ffm" else 0
-    ctx = capi.Context(model, F, k, Fc, optimizer=opt, device=local_rank, deterministic=0)
-    rng = np.random.default_rng(1234 + rank)
+    # weak scaling: every rank trains its own batch of B rows per step (global batch world*B, the updater divides by
+    # it); W / V / updater state are owner-sharded over the ranks and exchanged per batch (csrc/dist.cu)
+    ctx = capi.Context(model, F, k, Fc, optimizer=opt, device=local_rank, deterministic=0, rank=rank, world=world,
+                       minibatch_size=(world * B if world > 1 else 0), max_nnz=B * 160)
+    rng = np.random.default_rng(1234)
     rowlen = k * max(Fc, 1)
     V0 = (rng.standard_normal(F * rowlen, dtype=np.float32) * np.float32(1.0 / np.sqrt(k)))
     ctx.upload_params(np.zeros(F, np.float32), V0)
     del V0
+    if world > 1:
+        from lightctr_b200 import dist as ldist
+        ldist.connect(ctx)
     NB = 8
     batches = make_batches(wl, NB, seed_offset=rank)
     # pinned host copies (the end-to-end arm copies from these every step)
@@ -219,18 +222,26 @@ def main():
     sampler = ClockSampler(local_rank)
     sampler.start()
     torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
     t_wall0 = time.time()
     for i in range(args.steps):
         one_step(i, evs[i])
     ctx.sync()
     torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
     t_wall = time.time() - t_wall0
     launches = ctx.launch_count() - launches0
     prof = ctx.profile_read(reset=True)
     ctx.profile(False)
     step_ms = [a.elapsed_time(b) for a, b in evs]
     ms_per_step = float(np.mean(step_ms))
-    value = B / (ms_per_step * 1e-3)
+    if world > 1:  # device time, max over ranks
+        t = torch.tensor([ms_per_step], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_per_step = float(t[0])
+    value = world * B / (ms_per_step * 1e-3)
 
     # ---- end-to-end arm: host buffers in, loss out, every step (C-ABI lctr_train_batch) ------------------
     h2d = 8 * (B + 1) + 4 * nnz_mean + 4 * B + (2 * nnz_mean if Fc else 0)
@@ -241,6 +252,8 @@ def main():
         ctx.wait(ctx.train_batch_async(*host[i % NB]))
     ctx.sync()
     torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
     t0 = time.time()
     prev = None
     e2e_loss = 0.0
@@ -252,12 +265,17 @@ def main():
     e2e_loss += ctx.wait(prev)[0]
     ctx.sync()
     e2e_s = time.time() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t[0])
     clocks = sampler.finish()
-    e2e_value = B * args.steps / e2e_s
+    e2e_value = world * B * args.steps / e2e_s
 
     # ---- roofline of the dominant kernel (algorithmic bytes per SURVEY.md 8d / DESIGN.md) -----------------
     peak, peak_src = measured_peaks()
-    dom = max(prof.items(), key=lambda kv: kv[1][0]) if prof else (None, (0.0, 0))
+    compute = {kk: vv for kk, vv in prof.items() if not kk.startswith("dist_")}
+    dom = max(compute.items(), key=lambda kv: kv[1][0]) if compute else (None, (0.0, 0))
     n = nnz_mean / B
     if wl["model"] == "fm":
         bytes_per_sample = {"fm_forward": n * (4 * k + 12) + 8, "fm_backward_red": n * (4 * k + 12) + 8,
@@ -277,8 +295,11 @@ def main():
     line = {"metric": metric, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": wl["desc"], "l2": "flushed between timed steps (256 MB write)", "batch": B,
-                       "nnz_per_row": n, "backward": "RED scatter + sparse apply (streamed batches)"},
+            "config": {"workload": wl["desc"], "l2": "flushed between timed steps (256 MB write)", "batch_per_gpu": B,
+                       "global_batch": world * B, "nnz_per_row": n,
+                       "backward": "RED scatter + sparse apply (streamed batches)",
+                       "parallelism": "1 GPU" if world == 1 else
+                       "dp%d rows + owner-sharded tables (fid mod %d), unique-id pull/push over NVLink peer memory" % (world, world)},
             "clocks": clocks, "gpu_launches": int(launches), "kernels_ms": kernels,
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 16},
             "roofline": roof, "wall_s_timed_region": t_wall}
@@ -289,7 +310,11 @@ def main():
                                     "sample": r["sample"]}
     if rank == 0:
         print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
     ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
     return 0
 
 

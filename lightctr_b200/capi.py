@@ -275,16 +275,17 @@ class Context:
         m = np.ascontiguousarray(mask, np.float32)
         _chk(self.L.lctr_mlp_set_mask(self.h, layer, m.ctypes.data))
 
-    PROF_NAMES = ["fm_forward", "fm_backward_red", "apply", "ffm_fused", "fm_backward_csc", "mlp", "", ""]
+    PROF_NAMES = ["fm_forward", "fm_backward_red", "apply", "ffm_fused", "fm_backward_csc", "mlp", "dist_mark", "dist_compact",
+                  "dist_pull", "dist_push", "dist_barrier0", "dist_merge", "dist_barrier1", "", "", ""]
 
     def profile(self, enable=True):
         _chk(self.L.lctr_profile(self.h, 1 if enable else 0))
 
     def profile_read(self, reset=True):
-        ms = (C.c_double * 8)()
-        cnt = (C.c_int64 * 8)()
-        _chk(self.L.lctr_profile_read(self.h, ms, cnt, 8, 1 if reset else 0))
-        return {self.PROF_NAMES[i]: (ms[i], cnt[i]) for i in range(8) if cnt[i] > 0}
+        ms = (C.c_double * 16)()
+        cnt = (C.c_int64 * 16)()
+        _chk(self.L.lctr_profile_read(self.h, ms, cnt, 16, 1 if reset else 0))
+        return {self.PROF_NAMES[i]: (ms[i], cnt[i]) for i in range(16) if cnt[i] > 0}
 
     def ipc_export(self):
         n = C.c_size_t()

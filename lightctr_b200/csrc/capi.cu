@@ -234,6 +234,7 @@ int lctr_destroy(lctr_ctx* c) {
         dfree(s.row_ptr); dfree(s.fid); dfree(s.field); dfree(s.val); dfree(s.label); dfree(s.pred); dfree(s.sumvx);
         dfree(s.wide);
         dfree(s.blk_seg_ptr); dfree(s.seg_ptr); dfree(s.seg_fid); dfree(s.ent_row); dfree(s.ent_x);
+        dfree(s.uniq); dfree(s.n_uniq);
         delete s.h_blk_seg_ptr; s.h_blk_seg_ptr = nullptr;
     }
     mlp_free(c);
@@ -360,6 +361,7 @@ static int upload_batch_on(lctr_ctx* c, cudaStream_t st, int slot, int64_t rows,
         c->launches++;
         LCTR_CUDA(cudaGetLastError());
     }
+    if (c->cfg.world > 1 && dist_build_uniq(c, s, st)) return 1;
     s.csc_block = 0;
     if (c->cfg.deterministic && c->cfg.model != LCTR_MODEL_FFM && rows > 0) {
         LCTR_CUDA(cudaStreamSynchronize(st));

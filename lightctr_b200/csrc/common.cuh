@@ -31,8 +31,8 @@ void set_error(const char* fmt, ...);
     } while (0)
 
 constexpr int kNumSlots = 8;
-constexpr int kNumProf = 8;  // per-kernel timing buckets
-enum { PROF_FM_FWD = 0, PROF_FM_BWD_RED = 1, PROF_APPLY = 2, PROF_FFM_FUSED = 3, PROF_FM_BWD_CSC = 4, PROF_MLP = 5 };
+constexpr int kNumProf = 16;  // per-kernel timing buckets
+enum { PROF_FM_FWD = 0, PROF_FM_BWD_RED = 1, PROF_APPLY = 2, PROF_FFM_FUSED = 3, PROF_FM_BWD_CSC = 4, PROF_MLP = 5, PROF_DIST_MARK = 6, PROF_DIST_COMPACT = 7, PROF_DIST_PULL = 8, PROF_DIST_PUSH = 9, PROF_DIST_BAR0 = 10, PROF_DIST_MERGE = 11, PROF_DIST_BAR1 = 12 };
 constexpr int kStatRing = 64;
 constexpr unsigned kFull = 0xffffffffu;
 
@@ -59,6 +59,11 @@ struct Slot {
     float* ent_x = nullptr;         // nnz (only when has_val)
     std::vector<int64_t>* h_blk_seg_ptr = nullptr;
     int64_t cap_segs = 0, cap_blocks = 0, cap_ent = 0;
+    // multi-GPU: unique fids of the whole slot (the pull/push key set), built once at upload on the upload stream
+    uint32_t* uniq = nullptr;
+    unsigned int* n_uniq = nullptr;
+    int64_t cap_uniq = 0;
+    bool uniq_valid = false;
 };
 
 struct MlpLayer {
@@ -219,6 +224,7 @@ int launch_predict_quirk(lctr_ctx* c, Slot& s, Slot& train);
 // multi-GPU (dist.cu)
 int dist_alloc(lctr_ctx* c);
 int dist_free(lctr_ctx* c);
+int dist_build_uniq(lctr_ctx* c, Slot& s, cudaStream_t st);        // per-slot key set, at upload
 int dist_pre_step(lctr_ctx* c, Slot& s, int64_t rb, int64_t re);   // unique ids of the batch + pull their rows
 int dist_post_step(lctr_ctx* c, int64_t rows_divisor);             // push gradients, owner-side merge + update
 __global__ void compact_touched_kernel(uint8_t* touched, size_t F, uint32_t* list, unsigned int* n_list);

@@ -21,6 +21,9 @@
 //   8 apply     the single-GPU sparse updater on the shard               (opt.cu, unchanged)
 //   9 barrier   updated rows visible before anybody's next pull
 // NVLink carries each unique row once per rank and direction (vs. once per occurrence for naive peer gathers).
+#include <stdlib.h>
+#include <string.h>
+
 #include <algorithm>
 #include <vector>
 
@@ -36,10 +39,17 @@ struct PeerPtrs {
     unsigned char* mail[kMaxWorld];
     unsigned long long* bar[kMaxWorld];
 };
+struct PeerPtrs2 {  // second set (update_g shards + touched maps), kept in device memory
+    float* gW[kMaxWorld];
+    float* gV[kMaxWorld];
+    uint8_t* touched[kMaxWorld];
+    unsigned long long* bar[kMaxWorld];
+};
 
 struct DistState {
     int rank = 0, world = 1, shift = 0;
-    uint8_t* mark = nullptr;        // F bytes (global fid)
+    uint8_t* mark = nullptr;        // F bytes (global fid), per-step fallback on the compute stream
+    uint8_t* mark_up = nullptr;     // F bytes, used by uploads (their own stream)
     uint32_t* uniq = nullptr;       // unique fids of my batch
     unsigned int* n_uniq = nullptr;
     unsigned int* push_cnt = nullptr;  // [world] records written per destination this step
@@ -49,8 +59,15 @@ struct DistState {
     unsigned long long* bar = nullptr; // [2][world] epoch words written by peers
     size_t rec_floats = 0, rec_cap = 0, region_bytes = 0;
     PeerPtrs peers;                 // device pointers valid in THIS process
-    void* opened[kMaxWorld][4] = {{nullptr}};
+    PeerPtrs2 peers2;
+    PeerPtrs2* d_peers2 = nullptr;  // device copy
+    void* opened[kMaxWorld][7] = {{nullptr}};
     bool imported = false;
+    bool use_mailbox = false;       // LCTR_DIST_PUSH=mailbox selects the record/merge variant
+    bool bar1_pending = false;      // barrier 1 has been signalled but not yet waited for
+    const uint32_t* cur_uniq = nullptr;       // key set of the step in flight (slot-owned or the per-step list)
+    unsigned int* cur_n = nullptr;
+    bool cur_dynamic = false;
     unsigned long long epoch = 0;
 };
 
@@ -119,6 +136,76 @@ push_kernel(const uint32_t* __restrict__ uniq, const unsigned int* __restrict__ 
             gsrc[i] = 0.f;
         }
     }
+    __threadfence_system();
+}
+
+// push variant without mailboxes: each unique row's gradient is added straight into the OWNER's update_g with vector
+// REDs through the peer mapping (NVLink forwards the atomics) and the owner's touched byte is set with a peer store.
+// G rows per warp step; the local update_g row is zeroed on the way.  One RED row per unique id per rank.
+__global__ void __launch_bounds__(256)
+push_red_kernel(const uint32_t* __restrict__ uniq, const unsigned int* __restrict__ n_uniq, float* const* __restrict__ pgW,
+                float* const* __restrict__ pgV, uint8_t* const* __restrict__ ptouched, int shift, unsigned mask, int rowlen,
+                float* __restrict__ cgW, float* __restrict__ cgV) {
+    const unsigned n = *n_uniq;
+    const int lane = threadIdx.x & 31;
+    const unsigned warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const unsigned nwarps = gridDim.x * (blockDim.x >> 5);
+    const int vec = (rowlen % 4 == 0) ? 4 : 1;
+    const int slices = rowlen / vec;
+    int lpr = 1;
+    while (lpr < slices && lpr < 32) lpr <<= 1;
+    const int G = 32 / lpr, q = lane % lpr, g = lane / lpr;
+    for (unsigned b0 = warp * G; b0 < n; b0 += nwarps * G) {
+        const unsigned idx = b0 + g;
+        if (idx >= n) continue;
+        const uint32_t f = uniq[idx];
+        const unsigned o = f & mask;
+        const size_t l = f >> shift;
+        float* src = cgV + (size_t)f * rowlen;
+        float* dst = pgV[o] + l * (size_t)rowlen;
+        if (vec == 4) {
+            for (int sl = q; sl < slices; sl += lpr) {
+                const float4 v = *reinterpret_cast<const float4*>(src + 4 * sl);
+                *reinterpret_cast<float4*>(src + 4 * sl) = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (v.x != 0.f || v.y != 0.f || v.z != 0.f || v.w != 0.f) red_add_v4(dst + 4 * sl, v);
+            }
+        } else {
+            for (int sl = q; sl < slices; sl += lpr) {
+                const float v = src[sl];
+                src[sl] = 0.f;
+                if (v != 0.f) red_add_f32(dst + sl, v);
+            }
+        }
+        if (q == 0) {
+            red_add_f32(pgW[o] + l, cgW[f]);
+            cgW[f] = 0.f;
+            ptouched[o][l] = 1;
+        }
+    }
+    __threadfence_system();
+}
+
+__global__ void reset_counter_kernel(unsigned int* n) { *n = 0; }
+
+// barrier split in two so that rank-local work can sit between signalling and waiting
+__global__ void rank_arrive_kernel(unsigned long long* const* __restrict__ pbar, int me, int world, int which,
+                                   unsigned long long epoch) {
+    const int d = threadIdx.x;
+    __threadfence_system();
+    if (d < world) {
+        volatile unsigned long long* theirs = pbar[d] + (size_t)which * kMaxWorld + me;
+        *theirs = epoch;
+    }
+    __threadfence_system();
+}
+__global__ void rank_wait_kernel(unsigned long long* const* __restrict__ pbar, int me, int world, int which,
+                                 unsigned long long epoch) {
+    const int d = threadIdx.x;
+    if (d < world) {
+        volatile unsigned long long* mine = pbar[me] + (size_t)which * kMaxWorld + d;
+        while (*mine < epoch) { __nanosleep(32); }
+    }
+    __syncthreads();
     __threadfence_system();
 }
 
@@ -201,6 +288,8 @@ int dist_alloc(lctr_ctx* c) {
     LCTR_CUDA(cudaMemsetAsync(c->cgV, 0, nv * sizeof(float), c->stream));
     LCTR_CUDA(cudaMalloc((void**)&d->mark, c->F + 512));
     LCTR_CUDA(cudaMemsetAsync(d->mark, 0, c->F + 512, c->stream));
+    LCTR_CUDA(cudaMalloc((void**)&d->mark_up, c->F + 512));
+    LCTR_CUDA(cudaMemsetAsync(d->mark_up, 0, c->F + 512, c->stream));
     const size_t cap = c->cfg.max_nnz ? std::min<size_t>(c->cfg.max_nnz, c->F) : c->F;
     LCTR_CUDA(cudaMalloc((void**)&d->uniq, (c->F + 32) * sizeof(uint32_t)));
     LCTR_CUDA(cudaMalloc((void**)&d->n_uniq, sizeof(unsigned int)));
@@ -219,6 +308,12 @@ int dist_alloc(lctr_ctx* c) {
     memset(&d->peers, 0, sizeof(d->peers));
     d->peers.W[d->rank] = c->W; d->peers.V[d->rank] = c->V;
     d->peers.mail[d->rank] = d->mailbox; d->peers.bar[d->rank] = d->bar;
+    memset(&d->peers2, 0, sizeof(d->peers2));
+    d->peers2.gW[d->rank] = c->gW; d->peers2.gV[d->rank] = c->gV; d->peers2.touched[d->rank] = c->touched;
+    d->peers2.bar[d->rank] = d->bar;
+    LCTR_CUDA(cudaMalloc((void**)&d->d_peers2, sizeof(PeerPtrs2)));
+    const char* pm = getenv("LCTR_DIST_PUSH");
+    d->use_mailbox = pm && strcmp(pm, "mailbox") == 0;
     return 0;
 }
 
@@ -226,11 +321,12 @@ int dist_free(lctr_ctx* c) {
     DistState* d = c->dist;
     if (!d) return 0;
     for (int r = 0; r < d->world; r++)
-        for (int j = 0; j < 4; j++)
+        for (int j = 0; j < 7; j++)
             if (d->opened[r][j]) cudaIpcCloseMemHandle(d->opened[r][j]);
+    if (d->d_peers2) cudaFree(d->d_peers2);
     if (c->cW) cudaFree(c->cW); if (c->cV) cudaFree(c->cV); if (c->cgW) cudaFree(c->cgW); if (c->cgV) cudaFree(c->cgV);
     c->cW = c->cV = c->cgW = c->cgV = nullptr;
-    cudaFree(d->mark); cudaFree(d->uniq); cudaFree(d->n_uniq); cudaFree(d->push_cnt); cudaFree(d->scratch_done);
+    cudaFree(d->mark); cudaFree(d->mark_up); cudaFree(d->uniq); cudaFree(d->n_uniq); cudaFree(d->push_cnt); cudaFree(d->scratch_done);
     cudaFree(d->mailbox); cudaFree(d->bar);
     delete d;
     c->dist = nullptr;
@@ -245,29 +341,69 @@ static int barrier(lctr_ctx* c, int which) {
     return 0;
 }
 
+// key set of a whole slot (its unique fids), computed once per upload on the upload stream: mark + compact depend
+// only on the batch, not on the parameters, so for streamed batches they overlap the previous step's kernels
+int dist_build_uniq(lctr_ctx* c, Slot& s, cudaStream_t st) {
+    DistState* d = c->dist;
+    s.uniq_valid = false;
+    if (!d || s.nnz == 0) return 0;
+    const int64_t need = std::min<int64_t>(s.nnz, (int64_t)c->F);
+    if (need > s.cap_uniq) {
+        LCTR_CUDA(cudaStreamSynchronize(c->stream));
+        if (s.uniq) cudaFree(s.uniq);
+        if (!s.n_uniq) LCTR_CUDA(cudaMalloc((void**)&s.n_uniq, sizeof(unsigned int)));
+        const int64_t cap = std::max<int64_t>(need, s.cap_uniq + s.cap_uniq / 2);
+        LCTR_CUDA(cudaMalloc((void**)&s.uniq, (size_t)(cap + 32) * sizeof(uint32_t)));
+        s.cap_uniq = cap;
+    }
+    // a private mark map per upload stream would be needed if two uploads ran concurrently; uploads are serialised
+    // on their stream, and the per-step fallback below uses the same map only on the compute stream when no slot
+    // list exists, so one map suffices
+    LCTR_CUDA(cudaMemsetAsync(s.n_uniq, 0, sizeof(unsigned int), st));
+    const unsigned mg = (unsigned)std::min<int64_t>((s.nnz + 255) / 256, (int64_t)c->sm_count * 8);
+    mark_kernel<<<std::max(mg, 1u), 256, 0, st>>>(s.fid, 0, s.nnz, d->mark_up);
+    const size_t ntiles = (c->F + 511) / 512;
+    const unsigned cg = (unsigned)std::min<size_t>((ntiles + 7) / 8, (size_t)c->sm_count * 8);
+    compact_touched_kernel<<<std::max(cg, 1u), 256, 0, st>>>(d->mark_up, c->F, s.uniq, s.n_uniq);
+    c->launches += 2;
+    LCTR_CUDA(cudaGetLastError());
+    s.uniq_valid = true;
+    return 0;
+}
+
 int dist_pre_step(lctr_ctx* c, Slot& s, int64_t rb, int64_t re) {
     DistState* d = c->dist;
     LCTR_CHECK(d->imported, "multi-GPU step before lctr_ipc_import");
-    const int64_t eb_rows = re - rb;
-    if (eb_rows <= 0) return 0;
-    // entry range of the row range lives on the device; mark over the whole slot when the step covers it, else a
-    // conservative host copy of the two row_ptr values
-    int64_t rp[2];
-    if (rb == 0 && re == s.rows) { rp[0] = 0; rp[1] = s.nnz; }
-    else {
+    if (re - rb <= 0) return 0;
+    const unsigned mask = (unsigned)d->world - 1;
+    if (s.uniq_valid && rb == 0 && re == s.rows) {
+        d->cur_uniq = s.uniq; d->cur_n = s.n_uniq; d->cur_dynamic = false;
+    } else {
+        // a sub-range of the slot: build the key set of just these rows on the compute stream
+        int64_t rp[2];
         LCTR_CUDA(cudaMemcpyAsync(&rp[0], s.row_ptr + rb, sizeof(int64_t), cudaMemcpyDeviceToHost, c->stream));
         LCTR_CUDA(cudaMemcpyAsync(&rp[1], s.row_ptr + re, sizeof(int64_t), cudaMemcpyDeviceToHost, c->stream));
         LCTR_CUDA(cudaStreamSynchronize(c->stream));
+        const unsigned mg = (unsigned)std::min<int64_t>((rp[1] - rp[0] + 255) / 256, (int64_t)c->sm_count * 8);
+        { ProfScope prof(c, PROF_DIST_MARK);
+        mark_kernel<<<std::max(mg, 1u), 256, 0, c->stream>>>(s.fid, rp[0], rp[1], d->mark); }
+        const size_t ntiles = (c->F + 511) / 512;
+        const unsigned cg = (unsigned)std::min<size_t>((ntiles + 7) / 8, (size_t)c->sm_count * 8);
+        { ProfScope prof(c, PROF_DIST_COMPACT);
+        compact_touched_kernel<<<std::max(cg, 1u), 256, 0, c->stream>>>(d->mark, c->F, d->uniq, d->n_uniq); }
+        c->launches += 2;
+        d->cur_uniq = d->uniq; d->cur_n = d->n_uniq; d->cur_dynamic = true;
     }
-    const unsigned mg = (unsigned)std::min<int64_t>((rp[1] - rp[0] + 255) / 256, (int64_t)c->sm_count * 8);
-    mark_kernel<<<std::max(mg, 1u), 256, 0, c->stream>>>(s.fid, rp[0], rp[1], d->mark);
-    const size_t ntiles = (c->F + 511) / 512;
-    const unsigned cg = (unsigned)std::min<size_t>((ntiles + 7) / 8, (size_t)c->sm_count * 8);
-    compact_touched_kernel<<<std::max(cg, 1u), 256, 0, c->stream>>>(d->mark, c->F, d->uniq, d->n_uniq);
-    const unsigned mask = (unsigned)d->world - 1;
-    pull_kernel<<<c->sm_count * 4, 256, 0, c->stream>>>(d->uniq, d->n_uniq, d->peers, d->shift, mask, (int)c->rowlen,
-                                                        c->cW, c->cV);
-    c->launches += 3;
+    if (d->bar1_pending) {  // every owner's update of the previous step must be visible before the pull
+        ProfScope prof(c, PROF_DIST_BAR1);
+        rank_wait_kernel<<<1, 32, 0, c->stream>>>(d->d_peers2->bar, d->rank, d->world, 1, d->epoch);
+        c->launches++;
+        d->bar1_pending = false;
+    }
+    { ProfScope prof(c, PROF_DIST_PULL);
+    pull_kernel<<<c->sm_count * 4, 256, 0, c->stream>>>(d->cur_uniq, d->cur_n, d->peers, d->shift, mask, (int)c->rowlen,
+                                                        c->cW, c->cV); }
+    c->launches++;
     LCTR_CUDA(cudaGetLastError());
     return 0;
 }
@@ -275,19 +411,36 @@ int dist_pre_step(lctr_ctx* c, Slot& s, int64_t rb, int64_t re) {
 int dist_post_step(lctr_ctx* c, int64_t rows_divisor) {
     DistState* d = c->dist;
     const unsigned mask = (unsigned)d->world - 1;
-    push_kernel<<<c->sm_count * 4, 256, 0, c->stream>>>(d->uniq, d->n_uniq, d->peers, d->rank, d->shift, mask,
-                                                        (int)c->rowlen, (int)d->rec_floats, d->region_bytes,
-                                                        (unsigned)d->rec_cap, c->cgW, c->cgV, d->push_cnt);
-    push_counts_kernel<<<1, 32, 0, c->stream>>>(d->peers, d->rank, d->world, d->region_bytes, (unsigned)d->rec_cap,
-                                                d->push_cnt, d->n_uniq);
-    c->launches += 2;
     d->epoch++;
-    if (barrier(c, 0)) return 1;
-    merge_kernel<<<c->sm_count * 4, 256, 0, c->stream>>>(d->mailbox, d->world, d->region_bytes, (int)d->rec_floats,
-                                                         (int)c->rowlen, d->shift, c->gW, c->gV, c->touched);
-    c->launches++;
+    if (d->use_mailbox) {
+        { ProfScope prof(c, PROF_DIST_PUSH);
+        push_kernel<<<c->sm_count * 4, 256, 0, c->stream>>>(d->cur_uniq, d->cur_n, d->peers, d->rank, d->shift, mask,
+                                                            (int)c->rowlen, (int)d->rec_floats, d->region_bytes,
+                                                            (unsigned)d->rec_cap, c->cgW, c->cgV, d->push_cnt);
+        push_counts_kernel<<<1, 32, 0, c->stream>>>(d->peers, d->rank, d->world, d->region_bytes, (unsigned)d->rec_cap,
+                                                    d->push_cnt, d->cur_dynamic ? d->cur_n : d->scratch_done); }
+        c->launches += 2;
+        { ProfScope prof(c, PROF_DIST_BAR0);
+        if (barrier(c, 0)) return 1; }
+        { ProfScope prof(c, PROF_DIST_MERGE);
+        merge_kernel<<<c->sm_count * 4, 256, 0, c->stream>>>(d->mailbox, d->world, d->region_bytes, (int)d->rec_floats,
+                                                             (int)c->rowlen, d->shift, c->gW, c->gV, c->touched); }
+        c->launches++;
+    } else {
+        { ProfScope prof(c, PROF_DIST_PUSH);
+        push_red_kernel<<<c->sm_count * 4, 256, 0, c->stream>>>(d->cur_uniq, d->cur_n, d->d_peers2->gW, d->d_peers2->gV,
+                                                                d->d_peers2->touched, d->shift, mask, (int)c->rowlen,
+                                                                c->cgW, c->cgV);
+        if (d->cur_dynamic) { reset_counter_kernel<<<1, 1, 0, c->stream>>>(d->cur_n); c->launches++; } }
+        c->launches++;
+        { ProfScope prof(c, PROF_DIST_BAR0);
+        if (barrier(c, 0)) return 1; }
+    }
     if (launch_apply(c, rows_divisor)) return 1;
-    if (barrier(c, 1)) return 1;
+    // barrier 1 is split: signal now, wait at the start of the next step after its rank-local mark + compact
+    rank_arrive_kernel<<<1, 32, 0, c->stream>>>(d->d_peers2->bar, d->rank, d->world, 1, d->epoch);
+    c->launches++;
+    d->bar1_pending = true;
     LCTR_CUDA(cudaGetLastError());
     return 0;
 }
@@ -298,11 +451,11 @@ using namespace lctr;
 
 extern "C" {
 
-// handles exported per rank, in this order: W shard, V shard, mailbox, barrier words
+// handles exported per rank, in this order: W, V shards, mailbox, barrier words, update_g W, V shards, touched map
 int lctr_ipc_export(lctr_ctx* c, void* handles_out, size_t cap, size_t* bytes) {
     LCTR_CHECK(c && bytes, "null argument");
     LCTR_CHECK(c->dist, "lctr_ipc_export: ctx was created with world == 1");
-    const size_t need = 4 * sizeof(cudaIpcMemHandle_t);
+    const size_t need = 7 * sizeof(cudaIpcMemHandle_t);
     *bytes = need;
     if (!handles_out) return 0;
     LCTR_CHECK(cap >= need, "lctr_ipc_export: need %zu bytes", need);
@@ -312,19 +465,22 @@ int lctr_ipc_export(lctr_ctx* c, void* handles_out, size_t cap, size_t* bytes) {
     LCTR_CUDA(cudaIpcGetMemHandle(&h[1], c->V));
     LCTR_CUDA(cudaIpcGetMemHandle(&h[2], c->dist->mailbox));
     LCTR_CUDA(cudaIpcGetMemHandle(&h[3], c->dist->bar));
+    LCTR_CUDA(cudaIpcGetMemHandle(&h[4], c->gW));
+    LCTR_CUDA(cudaIpcGetMemHandle(&h[5], c->gV));
+    LCTR_CUDA(cudaIpcGetMemHandle(&h[6], c->touched));
     return 0;
 }
 
 int lctr_ipc_import(lctr_ctx* c, const void* all_handles, size_t bytes_per_rank) {
     LCTR_CHECK(c && all_handles, "null argument");
     LCTR_CHECK(c->dist, "lctr_ipc_import: ctx was created with world == 1");
-    LCTR_CHECK(bytes_per_rank == 4 * sizeof(cudaIpcMemHandle_t), "lctr_ipc_import: bytes_per_rank %zu", bytes_per_rank);
+    LCTR_CHECK(bytes_per_rank == 7 * sizeof(cudaIpcMemHandle_t), "lctr_ipc_import: bytes_per_rank %zu", bytes_per_rank);
     DistState* d = c->dist;
     const unsigned char* base = reinterpret_cast<const unsigned char*>(all_handles);
     for (int r = 0; r < d->world; r++) {
         if (r == d->rank) continue;
         const cudaIpcMemHandle_t* h = reinterpret_cast<const cudaIpcMemHandle_t*>(base + (size_t)r * bytes_per_rank);
-        for (int j = 0; j < 4; j++) {
+        for (int j = 0; j < 7; j++) {
             cudaIpcMemHandle_t hh;
             memcpy(&hh, &h[j], sizeof(hh));
             LCTR_CUDA(cudaIpcOpenMemHandle(&d->opened[r][j], hh, cudaIpcMemLazyEnablePeerAccess));
@@ -333,7 +489,12 @@ int lctr_ipc_import(lctr_ctx* c, const void* all_handles, size_t bytes_per_rank)
         d->peers.V[r] = (float*)d->opened[r][1];
         d->peers.mail[r] = (unsigned char*)d->opened[r][2];
         d->peers.bar[r] = (unsigned long long*)d->opened[r][3];
+        d->peers2.gW[r] = (float*)d->opened[r][4];
+        d->peers2.gV[r] = (float*)d->opened[r][5];
+        d->peers2.touched[r] = (uint8_t*)d->opened[r][6];
+        d->peers2.bar[r] = d->peers.bar[r];
     }
+    LCTR_CUDA(cudaMemcpy(d->d_peers2, &d->peers2, sizeof(PeerPtrs2), cudaMemcpyHostToDevice));
     d->imported = true;
     return 0;
 }
