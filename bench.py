@@ -173,7 +173,9 @@ def main():
     Fc = N_FIELDS if wl["model"] == "ffm" else 0
     # weak scaling: every rank trains its own batch of B rows per step (global batch world*B, the updater divides by
     # it); W / V / updater state are owner-sharded over the ranks and exchanged per batch (csrc/dist.cu)
-    ctx = capi.Context(model, F, k, Fc, optimizer=opt, device=local_rank, deterministic=0, rank=rank, world=world,
+    # backward strategy: feature-grouped on the device (csc.cu) where it is built, else the RED scatter
+    det = 2 if (world == 1 and wl["model"] == "fm" and os.environ.get("LCTR_BENCH_BACKWARD", "grouped") == "grouped") else 0
+    ctx = capi.Context(model, F, k, Fc, optimizer=opt, device=local_rank, deterministic=det, rank=rank, world=world,
                        minibatch_size=(world * B if world > 1 else 0), max_nnz=B * 160)
     rng = np.random.default_rng(1234)
     rowlen = k * max(Fc, 1)
@@ -279,7 +281,7 @@ def main():
     n = nnz_mean / B
     if wl["model"] == "fm":
         bytes_per_sample = {"fm_forward": n * (4 * k + 12) + 8, "fm_backward_red": n * (4 * k + 12) + 8,
-                            "apply": None}
+                            "fm_backward_csc": n * (4 * k + 12) + 8, "apply": None}
     else:
         bytes_per_sample = {"ffm_fused": n * (Fc * k * 4 + 12)}
     roof = None
@@ -297,7 +299,8 @@ def main():
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": wl["desc"], "l2": "flushed between timed steps (256 MB write)", "batch_per_gpu": B,
                        "global_batch": world * B, "nnz_per_row": n,
-                       "backward": "RED scatter + sparse apply (streamed batches)",
+                       "backward": ("feature-grouped on device + fused updater (csc.cu)" if det == 2
+                                    else "RED scatter + sparse apply"),
                        "parallelism": "1 GPU" if world == 1 else
                        "dp%d rows + owner-sharded tables (fid mod %d), unique-id pull/push over NVLink peer memory" % (world, world)},
             "clocks": clocks, "gpu_launches": int(launches), "kernels_ms": kernels,

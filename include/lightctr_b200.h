@@ -60,10 +60,14 @@ typedef struct lctr_cfg {
     uint64_t max_rows, max_nnz;
     /* multi-GPU: this process' rank / world (1 process per GPU); tables are owner-sharded by fid % world */
     int32_t rank, world;
-    /* deterministic != 0: backward uses a feature-major (CSC) view of the slot built at upload, so every
-     * gradient is summed in ascending row order -- the order of the reference's canonical single-thread
-     * run -- with no atomics, and the updater is fused into the same kernel.  csc_row_block = rows per
-     * train_step range (0 => the whole slot is one block; NFM: the minibatch size). */
+    /* Backward scatter-add strategy (FM / NFM; FFM always uses REDs):
+     *  0  vector REDs into update_g + sparse apply (sum order arbitrary, like the reference's Hogwild threads);
+     *  1  feature-major (CSC) view of the slot built on the HOST at upload: every gradient is summed in ascending
+     *     row order -- the order of the reference's canonical single-thread run -- no atomics, updater fused.
+     *     csc_row_block = rows per train_step range (0 => whole slot; NFM: the minibatch size);
+     *  2  the same view built on the DEVICE at upload (overlaps the previous step); entries of a feature arrive in
+     *     arbitrary order and are accumulated in double precision, so the fp32 result is order-independent.
+     *     Whole-slot steps only, FM with k in {4, 8, 16, 32}.  Default for streamed batches. */
     int32_t deterministic;
     int32_t reserved0;
     uint64_t csc_row_block;

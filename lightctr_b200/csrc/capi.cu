@@ -171,7 +171,8 @@ int lctr_create(const lctr_cfg* cfg, lctr_ctx** out) {
     if (c->cfg.world <= 0) { c->cfg.world = 1; c->cfg.rank = 0; }
     c->F = cfg->feature_cnt;
     c->Fl = (c->F + (size_t)c->cfg.world - 1) / (size_t)c->cfg.world;
-    LCTR_CHECK(c->cfg.world == 1 || !cfg->deterministic, "lctr_create: deterministic mode is single-GPU only");
+    LCTR_CHECK(c->cfg.world == 1 || !cfg->deterministic, "lctr_create: deterministic modes are single-GPU only");
+    LCTR_CHECK(cfg->deterministic >= 0 && cfg->deterministic <= 2, "lctr_create: deterministic must be 0, 1 or 2");
     LCTR_CHECK(c->cfg.world == 1 || cfg->model != LCTR_MODEL_NFM, "lctr_create: multi-GPU NFM is not built");
     c->rowlen = cfg->model == LCTR_MODEL_FFM ? (size_t)cfg->field_cnt * cfg->factor_cnt : cfg->factor_cnt;
     cudaDeviceProp prop;
@@ -234,11 +235,12 @@ int lctr_destroy(lctr_ctx* c) {
         dfree(s.row_ptr); dfree(s.fid); dfree(s.field); dfree(s.val); dfree(s.label); dfree(s.pred); dfree(s.sumvx);
         dfree(s.wide);
         dfree(s.blk_seg_ptr); dfree(s.seg_ptr); dfree(s.seg_fid); dfree(s.ent_row); dfree(s.ent_x);
-        dfree(s.uniq); dfree(s.n_uniq);
+        dfree(s.uniq); dfree(s.n_uniq); dfree(s.short_list); dfree(s.long_list); dfree(s.csc_totals); dfree(s.csc_acc); dfree(s.csc_arrived);
         delete s.h_blk_seg_ptr; s.h_blk_seg_ptr = nullptr;
     }
     mlp_free(c);
     dist_free(c);
+    csc_scratch_free(c);
     if (c->h_stats) cudaFreeHost(c->h_stats);
     if (c->h_stat_ring) cudaFreeHost(c->h_stat_ring);
     if (c->copy_stream) {
@@ -363,7 +365,11 @@ static int upload_batch_on(lctr_ctx* c, cudaStream_t st, int slot, int64_t rows,
     }
     if (c->cfg.world > 1 && dist_build_uniq(c, s, st)) return 1;
     s.csc_block = 0;
-    if (c->cfg.deterministic && c->cfg.model != LCTR_MODEL_FFM && rows > 0) {
+    s.dev_csc = false;
+    if (c->cfg.deterministic == 2 && rows > 0 && c->cfg.world == 1) {
+        LCTR_CHECK(csc_device_supported(c), "cfg.deterministic=2 (device-grouped backward) needs FM with k in {4,8,16,32}");
+        if (csc_build_device(c, s, st)) return 1;
+    } else if (c->cfg.deterministic == 1 && c->cfg.model != LCTR_MODEL_FFM && rows > 0) {
         LCTR_CUDA(cudaStreamSynchronize(st));
         if (build_csc(c, s, rows, nnz, row_ptr, fid, val)) return 1;
     }
@@ -399,6 +405,8 @@ int lctr_train_step(lctr_ctx* c, int slot, int64_t rb, int64_t re, float* loss_s
             if (c->cfg.world > 1)
                 rc = dist_pre_step(c, s, rb, re) || launch_fm_forward(c, s, rb, re, false, true) ||
                      launch_fm_backward(c, s, rb, re, false) || dist_post_step(c, re - rb);
+            else if (c->cfg.deterministic == 2)
+                rc = launch_fm_forward(c, s, rb, re, false, true) || launch_fm_backward_devcsc(c, s, rb, re);
             else if (c->cfg.deterministic)
                 rc = launch_fm_forward(c, s, rb, re, false, true) || launch_fm_backward_csc(c, s, rb, re, false);
             else
@@ -415,7 +423,7 @@ int lctr_train_step(lctr_ctx* c, int slot, int64_t rb, int64_t re, float* loss_s
             rc = mlp_reserve(c, re - rb) || launch_fm_forward(c, s, rb, re, true, false) ||
                  launch_nfm_mlp(c, s, rb, re, re - rb);
             if (!rc) {
-                if (c->cfg.deterministic) rc = launch_fm_backward_csc(c, s, rb, re, true);
+                if (c->cfg.deterministic == 1) rc = launch_fm_backward_csc(c, s, rb, re, true);
                 else rc = launch_fm_backward(c, s, rb, re, true) || launch_apply(c, re - rb);
             }
             break;
@@ -447,7 +455,7 @@ static int pipe_init(lctr_ctx* c) {
 int lctr_train_batch_async(lctr_ctx* c, int64_t rows, int64_t nnz, const int64_t* row_ptr, const uint32_t* fid,
                            const uint16_t* field, const float* val, const int32_t* label, uint64_t* ticket) {
     LCTR_CHECK(c && ticket, "null argument");
-    LCTR_CHECK(!c->cfg.deterministic, "streamed batches use the RED scatter path (cfg.deterministic must be 0)");
+    LCTR_CHECK(c->cfg.deterministic != 1, "streamed batches need cfg.deterministic 0 (RED scatter) or 2 (device grouping)");
     if (pipe_init(c)) return 1;
     LCTR_CHECK(c->pipe_issued - c->pipe_waited < 2, "more than 2 streamed batches outstanding: call lctr_wait first");
     const int p = (int)(c->pipe_issued & 1);

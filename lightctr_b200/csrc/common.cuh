@@ -59,6 +59,13 @@ struct Slot {
     float* ent_x = nullptr;         // nnz (only when has_val)
     std::vector<int64_t>* h_blk_seg_ptr = nullptr;
     int64_t cap_segs = 0, cap_blocks = 0, cap_ent = 0;
+    // device-built feature-major view (cfg.deterministic == 2): work lists of short / long segments and
+    // totals[4] = {nnz, n_segs, n_short, n_long} (device)
+    bool dev_csc = false;
+    uint32_t *short_list = nullptr, *long_list = nullptr;  // long_list holds uint2 {segment, first entry} tasks
+    double* csc_acc = nullptr;            // meeting point of multi-task segments
+    unsigned int* csc_arrived = nullptr;
+    unsigned int* csc_totals = nullptr;
     // multi-GPU: unique fids of the whole slot (the pull/push key set), built once at upload on the upload stream
     uint32_t* uniq = nullptr;
     unsigned int* n_uniq = nullptr;
@@ -112,6 +119,7 @@ struct lctr_ctx {
     size_t mlp_cap_rows = 0;
     int sm_count = 148;
     int64_t launches = 0;
+    void* csc_scratch = nullptr;  // csc.cu: dense count / offset arrays of the device-side grouping
     // optional per-kernel timing (lctr_profile): events bracket every launch on the ctx stream
     int profiling = 0;
     std::vector<cudaEvent_t>* prof_ev = nullptr;   // flat list of (start, stop) pairs
@@ -220,6 +228,11 @@ int launch_ffm_forward(lctr_ctx* c, Slot& s, int64_t rb, int64_t re, bool stats)
 int launch_ffm_backward(lctr_ctx* c, Slot& s, int64_t rb, int64_t re);
 int launch_apply(lctr_ctx* c, int64_t rows_in_step);
 int launch_fm_backward_csc(lctr_ctx* c, Slot& s, int64_t rb, int64_t re, bool nfm);
+// csc.cu: feature-major view built on the device at upload + atomic-free backward with fused updater
+int csc_build_device(lctr_ctx* c, Slot& s, cudaStream_t st);
+int launch_fm_backward_devcsc(lctr_ctx* c, Slot& s, int64_t rb, int64_t re);
+bool csc_device_supported(const lctr_ctx* c);
+void csc_scratch_free(lctr_ctx* c);
 int launch_predict_quirk(lctr_ctx* c, Slot& s, Slot& train);
 // multi-GPU (dist.cu)
 int dist_alloc(lctr_ctx* c);
