@@ -173,8 +173,10 @@ def main():
     Fc = N_FIELDS if wl["model"] == "ffm" else 0
     # weak scaling: every rank trains its own batch of B rows per step (global batch world*B, the updater divides by
     # it); W / V / updater state are owner-sharded over the ranks and exchanged per batch (csrc/dist.cu)
-    # backward strategy: feature-grouped on the device (csc.cu) where it is built, else the RED scatter
-    det = 2 if (world == 1 and wl["model"] == "fm" and os.environ.get("LCTR_BENCH_BACKWARD", "grouped") == "grouped") else 0
+    # backward strategy: RED scatter + sparse apply by default (every per-batch kernel is inside the timed region).
+    # LCTR_BENCH_BACKWARD=grouped selects the feature-grouped backward of csc.cu; its per-batch grouping kernels run
+    # at upload, i.e. OUTSIDE the device-timed `value` region but INSIDE the end-to-end region.
+    det = 2 if (world == 1 and wl["model"] == "fm" and os.environ.get("LCTR_BENCH_BACKWARD", "red") == "grouped") else 0
     ctx = capi.Context(model, F, k, Fc, optimizer=opt, device=local_rank, deterministic=det, rank=rank, world=world,
                        minibatch_size=(world * B if world > 1 else 0), max_nnz=B * 160)
     rng = np.random.default_rng(1234)

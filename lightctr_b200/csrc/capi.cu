@@ -243,6 +243,14 @@ int lctr_destroy(lctr_ctx* c) {
     csc_scratch_free(c);
     if (c->h_stats) cudaFreeHost(c->h_stats);
     if (c->h_stat_ring) cudaFreeHost(c->h_stat_ring);
+    for (int p = 0; p < 2; p++) {
+        PipeGraph& g = c->pipe_graph[p];
+        if (g.build) cudaGraphExecDestroy(g.build);
+        if (g.step) cudaGraphExecDestroy(g.step);
+        if (g.d_hdr) cudaFree(g.d_hdr); if (g.h_hdr) cudaFreeHost(g.h_hdr);
+        if (g.d_opt) cudaFree(g.d_opt); if (g.h_opt) cudaFreeHost(g.h_opt);
+        if (g.d_stat) cudaFree(g.d_stat); if (g.h_stat) cudaFreeHost(g.h_stat);
+    }
     if (c->copy_stream) {
         for (int i = 0; i < 2; i++) { cudaEventDestroy(c->ev_copied[i]); cudaEventDestroy(c->ev_computed[i]); }
         for (int i = 0; i < kStatRing; i++) cudaEventDestroy(c->ev_stat[i]);
@@ -355,20 +363,23 @@ static int upload_batch_on(lctr_ctx* c, cudaStream_t st, int slot, int64_t rows,
         if (field) LCTR_CUDA(cudaMemcpyAsync(s.field, field, (size_t)nnz * sizeof(uint16_t), cudaMemcpyHostToDevice, st));
         if (val) LCTR_CUDA(cudaMemcpyAsync(s.val, val, (size_t)nnz * sizeof(float), cudaMemcpyHostToDevice, st));
     }
+    const bool grouped = c->cfg.deterministic == 2 && rows > 0 && nnz > 0 && c->cfg.world == 1;
+    int32_t* tmp = reinterpret_cast<int32_t*>(s.pred);  // pred is overwritten by the next forward anyway
     if (rows) {
         // labels travel as int32 and are widened on device (the reference compares a `float target`)
-        int32_t* tmp = reinterpret_cast<int32_t*>(s.pred);  // pred is overwritten by the next forward anyway
         LCTR_CUDA(cudaMemcpyAsync(tmp, label, (size_t)rows * sizeof(int32_t), cudaMemcpyHostToDevice, st));
-        label_to_float_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>(tmp, s.label, rows);
-        c->launches++;
-        LCTR_CUDA(cudaGetLastError());
+        if (!grouped) {
+            label_to_float_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>(tmp, s.label, rows);
+            c->launches++;
+            LCTR_CUDA(cudaGetLastError());
+        }
     }
     if (c->cfg.world > 1 && dist_build_uniq(c, s, st)) return 1;
     s.csc_block = 0;
     s.dev_csc = false;
-    if (c->cfg.deterministic == 2 && rows > 0 && c->cfg.world == 1) {
+    if (grouped) {
         LCTR_CHECK(csc_device_supported(c), "cfg.deterministic=2 (device-grouped backward) needs FM with k in {4,8,16,32}");
-        if (csc_build_device(c, s, st)) return 1;
+        if (csc_build_device(c, s, st, tmp, nullptr, rows, nnz)) return 1;  // widens the labels in its first kernel
     } else if (c->cfg.deterministic == 1 && c->cfg.model != LCTR_MODEL_FFM && rows > 0) {
         LCTR_CUDA(cudaStreamSynchronize(st));
         if (build_csc(c, s, rows, nnz, row_ptr, fid, val)) return 1;
@@ -452,12 +463,93 @@ static int pipe_init(lctr_ctx* c) {
     return 0;
 }
 
+// Graph path of the streamed pipeline (FM, cfg.deterministic == 2, one GPU): per pipeline slot two captured graphs --
+// `build` (slot header copy + the five grouping kernels, on the copy stream) and `step` (updater-parameter copy,
+// forward, grouped backward + update, result copy, on the compute stream).  Kernels take the batch size from the
+// device-side slot header and the updater parameters from device memory, so the graphs are static: a streamed step
+// costs the host three cudaMemcpyAsync, two graph launches and four event calls instead of ~20 launches.
+static int pipe_graph_capture(lctr_ctx* c, int p, bool has_val) {
+    PipeGraph& g = c->pipe_graph[p];
+    Slot& s = c->slots[kNumSlots - 2 + p];
+    if (g.build) { cudaGraphExecDestroy(g.build); g.build = nullptr; }
+    if (g.step) { cudaGraphExecDestroy(g.step); g.step = nullptr; }
+    if (!g.d_hdr) {
+        LCTR_CUDA(cudaMalloc((void**)&g.d_hdr, 2 * sizeof(int64_t)));
+        LCTR_CUDA(cudaMallocHost((void**)&g.h_hdr, 2 * sizeof(int64_t)));
+        LCTR_CUDA(cudaMalloc((void**)&g.d_opt, csc_opt_params_size()));
+        LCTR_CUDA(cudaMallocHost((void**)&g.h_opt, csc_opt_params_size()));
+        LCTR_CUDA(cudaMalloc((void**)&g.d_stat, 2 * sizeof(double)));
+        LCTR_CUDA(cudaMallocHost((void**)&g.h_stat, 2 * sizeof(double)));
+    }
+    s.has_val = has_val;
+    cudaGraph_t graph;
+    // ---- build graph (copy stream)
+    LCTR_CUDA(cudaStreamBeginCapture(c->copy_stream, cudaStreamCaptureModeThreadLocal));
+    LCTR_CUDA(cudaMemcpyAsync(g.d_hdr, g.h_hdr, 2 * sizeof(int64_t), cudaMemcpyHostToDevice, c->copy_stream));
+    int rc = csc_build_device(c, s, c->copy_stream, reinterpret_cast<int32_t*>(s.pred), g.d_hdr, s.cap_rows, s.cap_nnz);
+    LCTR_CUDA(cudaStreamEndCapture(c->copy_stream, &graph));
+    if (rc) return 1;
+    LCTR_CUDA(cudaGraphInstantiate(&g.build, graph, 0));
+    cudaGraphDestroy(graph);
+    // ---- step graph (compute stream)
+    LCTR_CUDA(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+    LCTR_CUDA(cudaMemcpyAsync(g.d_opt, g.h_opt, csc_opt_params_size(), cudaMemcpyHostToDevice, c->stream));
+    rc = launch_fm_forward_ex(c, s, 0, s.cap_rows, false, true, g.d_hdr, g.d_stat) ||
+         launch_fm_backward_devcsc_ex(c, s, 0, s.cap_rows, reinterpret_cast<const OptParams*>(g.h_opt), g.d_opt);
+    LCTR_CUDA(cudaMemcpyAsync(g.h_stat, g.d_stat, 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    LCTR_CUDA(cudaStreamEndCapture(c->stream, &graph));
+    if (rc) return 1;
+    LCTR_CUDA(cudaGraphInstantiate(&g.step, graph, 0));
+    cudaGraphDestroy(graph);
+    g.cap_rows = s.cap_rows; g.cap_nnz = s.cap_nnz; g.has_val = has_val;
+    return 0;
+}
+
+static int train_batch_async_graph(lctr_ctx* c, int64_t rows, int64_t nnz, const int64_t* row_ptr, const uint32_t* fid,
+                                   const float* val, const int32_t* label, uint64_t* ticket) {
+    const int p = (int)(c->pipe_issued & 1);
+    const int slot = kNumSlots - 2 + p;
+    Slot& s = c->slots[slot];
+    PipeGraph& g = c->pipe_graph[p];
+    if (rows > s.cap_rows || nnz > s.cap_nnz || !g.build || g.has_val != (val != nullptr) || g.cap_rows != s.cap_rows ||
+        g.cap_nnz != s.cap_nnz) {
+        LCTR_CUDA(cudaStreamSynchronize(c->stream));
+        LCTR_CUDA(cudaStreamSynchronize(c->copy_stream));
+        if (rows > s.cap_rows || nnz > s.cap_nnz)  // head-room so that slightly larger batches do not re-capture
+            if (slot_reserve(c, s, std::max(rows, s.cap_rows) + rows / 8 + 64, std::max(nnz, s.cap_nnz) + nnz / 8 + 1024)) return 1;
+        if (csc_reserve(c, s, s.cap_nnz)) return 1;
+        LCTR_CUDA(cudaStreamSynchronize(c->stream));
+        if (pipe_graph_capture(c, p, val != nullptr)) return 1;
+    }
+    s.rows = rows; s.nnz = nnz; s.has_val = val != nullptr; s.has_field = false;
+    if (c->pipe_issued >= 2) LCTR_CUDA(cudaStreamWaitEvent(c->copy_stream, c->ev_computed[p], 0));
+    LCTR_CUDA(cudaMemcpyAsync(s.row_ptr, row_ptr, (size_t)(rows + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, c->copy_stream));
+    LCTR_CUDA(cudaMemcpyAsync(s.fid, fid, (size_t)nnz * sizeof(uint32_t), cudaMemcpyHostToDevice, c->copy_stream));
+    if (val) LCTR_CUDA(cudaMemcpyAsync(s.val, val, (size_t)nnz * sizeof(float), cudaMemcpyHostToDevice, c->copy_stream));
+    LCTR_CUDA(cudaMemcpyAsync(s.pred, label, (size_t)rows * sizeof(int32_t), cudaMemcpyHostToDevice, c->copy_stream));
+    g.h_hdr[0] = rows; g.h_hdr[1] = nnz;
+    LCTR_CUDA(cudaGraphLaunch(g.build, c->copy_stream));
+    LCTR_CUDA(cudaEventRecord(c->ev_copied[p], c->copy_stream));
+    LCTR_CUDA(cudaStreamWaitEvent(c->stream, c->ev_copied[p], 0));
+    csc_opt_params(c, rows, g.h_opt);
+    LCTR_CUDA(cudaGraphLaunch(g.step, c->stream));
+    LCTR_CUDA(cudaEventRecord(c->ev_computed[p], c->stream));
+    s.dev_csc = true;
+    c->launches += 8;  // kernels inside the two graphs
+    g.ticket = c->step;
+    *ticket = c->step++;
+    c->pipe_issued++;
+    return 0;
+}
+
 int lctr_train_batch_async(lctr_ctx* c, int64_t rows, int64_t nnz, const int64_t* row_ptr, const uint32_t* fid,
                            const uint16_t* field, const float* val, const int32_t* label, uint64_t* ticket) {
     LCTR_CHECK(c && ticket, "null argument");
     LCTR_CHECK(c->cfg.deterministic != 1, "streamed batches need cfg.deterministic 0 (RED scatter) or 2 (device grouping)");
     if (pipe_init(c)) return 1;
     LCTR_CHECK(c->pipe_issued - c->pipe_waited < 2, "more than 2 streamed batches outstanding: call lctr_wait first");
+    if (c->cfg.deterministic == 2 && c->cfg.world == 1 && c->cfg.model == LCTR_MODEL_FM && !c->profiling && rows > 0 && nnz > 0)
+        return train_batch_async_graph(c, rows, nnz, row_ptr, fid, val, label, ticket);
     const int p = (int)(c->pipe_issued & 1);
     const int slot = kNumSlots - 2 + p;
     // the copy may only overwrite the slot once the step that last used it has finished
@@ -471,6 +563,7 @@ int lctr_train_batch_async(lctr_ctx* c, int64_t rows, int64_t nnz, const int64_t
     const int ri = (int)(step % kStatRing);
     LCTR_CUDA(cudaMemcpyAsync(c->h_stat_ring + 2 * ri, c->stats + 2 * ri, 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     LCTR_CUDA(cudaEventRecord(c->ev_stat[ri], c->stream));
+    c->pipe_graph[p].ticket = ~0ull;
     *ticket = step;
     c->pipe_issued++;
     return 0;
@@ -480,6 +573,15 @@ int lctr_wait(lctr_ctx* c, uint64_t ticket, float* loss_sum, float* acc_cnt) {
     LCTR_CHECK(c && c->copy_stream, "lctr_wait: no streamed batch was issued");
     LCTR_CHECK(ticket < c->step && c->step - ticket <= (uint64_t)kStatRing, "lctr_wait: ticket %llu is not outstanding",
                (unsigned long long)ticket);
+    for (int p = 0; p < 2; p++) {
+        if (c->pipe_graph[p].build && c->pipe_graph[p].ticket == ticket) {
+            LCTR_CUDA(cudaEventSynchronize(c->ev_computed[p]));
+            if (loss_sum) *loss_sum = (float)c->pipe_graph[p].h_stat[0];
+            if (acc_cnt) *acc_cnt = (float)c->pipe_graph[p].h_stat[1];
+            if (c->pipe_waited < c->pipe_issued) c->pipe_waited++;
+            return 0;
+        }
+    }
     const int ri = (int)(ticket % kStatRing);
     LCTR_CUDA(cudaEventSynchronize(c->ev_stat[ri]));
     if (loss_sum) *loss_sum = (float)c->h_stat_ring[2 * ri];

@@ -63,6 +63,7 @@ struct Slot {
     // totals[4] = {nnz, n_segs, n_short, n_long} (device)
     bool dev_csc = false;
     uint32_t *short_list = nullptr, *long_list = nullptr;  // long_list holds uint2 {segment, first entry} tasks
+    int64_t cap_long = 0;
     double* csc_acc = nullptr;            // meeting point of multi-task segments
     unsigned int* csc_arrived = nullptr;
     unsigned int* csc_totals = nullptr;
@@ -71,6 +72,17 @@ struct Slot {
     unsigned int* n_uniq = nullptr;
     int64_t cap_uniq = 0;
     bool uniq_valid = false;
+};
+
+// captured graphs of one slot of the streamed pipeline (capi.cu)
+struct PipeGraph {
+    cudaGraphExec_t build = nullptr, step = nullptr;
+    int64_t cap_rows = 0, cap_nnz = 0;
+    bool has_val = false;
+    int64_t *d_hdr = nullptr, *h_hdr = nullptr;  // {rows, nnz} of the batch in the slot
+    void *d_opt = nullptr, *h_opt = nullptr;     // updater parameters of the step
+    double *d_stat = nullptr, *h_stat = nullptr; // (loss, correct)
+    uint64_t ticket = ~0ull;
 };
 
 struct MlpLayer {
@@ -132,6 +144,7 @@ struct lctr_ctx {
     cudaEvent_t ev_stat[lctr::kStatRing] = {nullptr};
     double* h_stat_ring = nullptr;
     uint64_t pipe_issued = 0, pipe_waited = 0;
+    lctr::PipeGraph pipe_graph[2];
 };
 
 namespace lctr {
@@ -229,8 +242,16 @@ int launch_ffm_backward(lctr_ctx* c, Slot& s, int64_t rb, int64_t re);
 int launch_apply(lctr_ctx* c, int64_t rows_in_step);
 int launch_fm_backward_csc(lctr_ctx* c, Slot& s, int64_t rb, int64_t re, bool nfm);
 // csc.cu: feature-major view built on the device at upload + atomic-free backward with fused updater
-int csc_build_device(lctr_ctx* c, Slot& s, cudaStream_t st);
+int csc_reserve(lctr_ctx* c, Slot& s, int64_t max_nnz);
+int csc_build_device(lctr_ctx* c, Slot& s, cudaStream_t st, const int32_t* label_i32, const int64_t* hdr,
+                     int64_t rows_cap, int64_t nnz_cap);
 int launch_fm_backward_devcsc(lctr_ctx* c, Slot& s, int64_t rb, int64_t re);
+struct OptParams;
+int launch_fm_backward_devcsc_ex(lctr_ctx* c, Slot& s, int64_t rb, int64_t re, const OptParams* P_host, const void* dP);
+void csc_opt_params(lctr_ctx* c, int64_t rows, void* out);
+size_t csc_opt_params_size();
+int launch_fm_forward_ex(lctr_ctx* c, Slot& s, int64_t rb, int64_t re, bool nfm, bool stats, const int64_t* hdr,
+                         double* out_slot_override);
 bool csc_device_supported(const lctr_ctx* c);
 void csc_scratch_free(lctr_ctx* c);
 int launch_predict_quirk(lctr_ctx* c, Slot& s, Slot& train);

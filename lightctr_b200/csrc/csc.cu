@@ -20,6 +20,8 @@
 // within ~1e-12 ulp of a rounding boundary).  Reference semantics of the accumulated expression:
 // train_fm_algo.cpp:101-116 (see fm.cu); the host-built view of cfg.deterministic == 1 keeps the reference's exact
 // ascending-row fp32 order instead.
+#include <string.h>
+
 #include <algorithm>
 #include <vector>
 
@@ -30,9 +32,15 @@ namespace lctr {
 constexpr int kShortMax = 8;     // segments up to this many entries: one lane group each
 constexpr int kTaskLen = 256;    // longer segments are cut into warp tasks of this many entries
 
-__global__ void csc_count_kernel(const uint32_t* __restrict__ fid, int64_t nnz, unsigned int* __restrict__ cnt) {
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nnz; i += (int64_t)gridDim.x * blockDim.x)
-        atomicAdd(&cnt[fid[i]], 1u);
+// also widens the int32 labels that were copied into `label_i32` (the reference compares a float target)
+__global__ void csc_count_kernel(const uint32_t* __restrict__ fid, int64_t nnz_arg, unsigned int* __restrict__ cnt,
+                                 const int32_t* __restrict__ label_i32, float* __restrict__ label, int64_t rows_arg,
+                                 const int64_t* __restrict__ hdr) {
+    const int64_t nnz = hdr ? hdr[1] : nnz_arg, rows = hdr ? hdr[0] : rows_arg;
+    const int64_t t0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nt = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = t0; i < nnz; i += nt) atomicAdd(&cnt[fid[i]], 1u);
+    if (label_i32)
+        for (int64_t i = t0; i < rows; i += nt) label[i] = (float)label_i32[i];
 }
 
 // per 512-id tile: (sum of counts, number of present ids)
@@ -64,7 +72,8 @@ csc_tile_reduce_kernel(const unsigned int* __restrict__ cnt, size_t F, uint2* __
 // the work-list counters
 __global__ void __launch_bounds__(1024)
 csc_tile_scan_kernel(const uint2* __restrict__ tile_sum, size_t ntiles, uint2* __restrict__ tile_off,
-                     unsigned int* __restrict__ totals /* [0]=nnz [1]=nseg [2]=n_short [3]=n_long */) {
+                     unsigned int* __restrict__ totals /* [0]=nnz [1]=nseg [2]=n_short [3]=n_long */,
+                     int64_t* __restrict__ seg_ptr) {
     __shared__ uint2 sh[1024];
     __shared__ uint2 carry;
     if (threadIdx.x == 0) carry = make_uint2(0, 0);
@@ -94,6 +103,7 @@ csc_tile_scan_kernel(const uint2* __restrict__ tile_sum, size_t ntiles, uint2* _
         totals[1] = carry.y;
         totals[2] = 0;
         totals[3] = 0;
+        seg_ptr[carry.y] = (int64_t)carry.x;  // sentinel: seg_ptr[n_segs] = nnz
     }
 }
 
@@ -161,15 +171,12 @@ csc_tile_write_kernel(const unsigned int* __restrict__ cnt, size_t F, const uint
     }
 }
 
-__global__ void csc_sentinel_kernel(int64_t* __restrict__ seg_ptr, const unsigned int* __restrict__ totals) {
-    seg_ptr[totals[1]] = (int64_t)totals[0];
-}
-
 // every entry claims a slot of its fid's segment; cnt returns to zero (ready for the next upload)
 __global__ void __launch_bounds__(256)
 csc_fill_kernel(const int64_t* __restrict__ row_ptr, const uint32_t* __restrict__ fid, const float* __restrict__ val,
-                int64_t rows, const unsigned int* __restrict__ off, unsigned int* __restrict__ cnt,
-                uint32_t* __restrict__ ent_row, float* __restrict__ ent_x) {
+                int64_t rows_arg, const unsigned int* __restrict__ off, unsigned int* __restrict__ cnt,
+                uint32_t* __restrict__ ent_row, float* __restrict__ ent_x, const int64_t* __restrict__ hdr) {
+    const int64_t rows = hdr ? hdr[0] : rows_arg;
     const int lane = threadIdx.x & 31;
     const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
@@ -240,7 +247,8 @@ __device__ __forceinline__ void apply_update(const ParamView& T, const OptParams
 template <int K, bool HAS_VAL>
 __global__ void __launch_bounds__(256)
 csc_backward_short_kernel(const uint32_t* __restrict__ work, const unsigned int* __restrict__ totals, CscView C,
-                          ParamView T, float l2, OptParams P) {
+                          ParamView T, float l2, OptParams P_arg, const OptParams* __restrict__ dP) {
+    const OptParams P = dP ? *dP : P_arg;
     constexpr int LPR = K / 4;
     constexpr int G = 32 / LPR;
     constexpr int PER = kShortMax / LPR;  // row indices fetched per lane
@@ -291,7 +299,9 @@ csc_backward_short_kernel(const uint32_t* __restrict__ work, const unsigned int*
 template <int K, bool HAS_VAL>
 __global__ void __launch_bounds__(256)
 csc_backward_long_kernel(const uint2* __restrict__ work, const unsigned int* __restrict__ totals, CscView C, ParamView T,
-                         double* __restrict__ acc, unsigned int* __restrict__ arrived, float l2, OptParams P) {
+                         double* __restrict__ acc, unsigned int* __restrict__ arrived, float l2, OptParams P_arg,
+                         const OptParams* __restrict__ dP) {
+    const OptParams P = dP ? *dP : P_arg;
     constexpr int LPR = K / 4;
     constexpr int G = 32 / LPR;
     const int lane = threadIdx.x & 31;
@@ -407,13 +417,11 @@ void csc_scratch_free(lctr_ctx* c) {
     c->csc_scratch = nullptr;
 }
 
-// build the feature-major view of the whole slot on stream `st`
-int csc_build_device(lctr_ctx* c, Slot& s, cudaStream_t st) {
-    s.dev_csc = false;
-    if (s.nnz == 0) return 0;
-    CscScratch* sc;
-    if (scratch_get(c, &sc)) return 1;
-    const int64_t max_segs = std::min<int64_t>(s.nnz, (int64_t)c->F);
+// (re)allocate the per-slot arrays of the view for up to `max_nnz` entries
+int csc_reserve(lctr_ctx* c, Slot& s, int64_t max_nnz) {
+    CscScratch* sc0;
+    if (scratch_get(c, &sc0)) return 1;  // never allocate inside a stream capture
+    const int64_t max_segs = std::min<int64_t>(max_nnz, (int64_t)c->F);
     if (max_segs > s.cap_segs || !s.short_list) {
         LCTR_CUDA(cudaStreamSynchronize(c->stream));
         const int64_t cap = std::max<int64_t>(max_segs, s.cap_segs + s.cap_segs / 2);
@@ -422,7 +430,7 @@ int csc_build_device(lctr_ctx* c, Slot& s, cudaStream_t st) {
         LCTR_CUDA(cudaMalloc((void**)&s.seg_ptr, (size_t)(cap + 1) * sizeof(int64_t)));
         LCTR_CUDA(cudaMalloc((void**)&s.seg_fid, (size_t)(cap + 1) * sizeof(uint32_t)));
         LCTR_CUDA(cudaMalloc((void**)&s.short_list, (size_t)(cap + 1) * sizeof(uint32_t)));
-        LCTR_CUDA(cudaMalloc((void**)&s.long_list, (size_t)(s.nnz / 8 + cap + 1) * sizeof(uint2)));
+        LCTR_CUDA(cudaMalloc((void**)&s.long_list, (size_t)(max_nnz / 8 + cap + 1) * sizeof(uint2)));
         if (s.csc_acc) cudaFree(s.csc_acc); if (s.csc_arrived) cudaFree(s.csc_arrived);
         const size_t na = (size_t)(cap + 1) * (c->cfg.factor_cnt + 1);
         LCTR_CUDA(cudaMalloc((void**)&s.csc_acc, na * sizeof(double)));
@@ -431,28 +439,47 @@ int csc_build_device(lctr_ctx* c, Slot& s, cudaStream_t st) {
         LCTR_CUDA(cudaMemset(s.csc_arrived, 0, (size_t)(cap + 1) * sizeof(unsigned int)));
         if (!s.csc_totals) LCTR_CUDA(cudaMalloc((void**)&s.csc_totals, 4 * sizeof(unsigned int)));
         s.cap_segs = cap;
+        s.cap_long = max_nnz;
+    } else if (max_nnz > s.cap_long) {
+        LCTR_CUDA(cudaStreamSynchronize(c->stream));
+        if (s.long_list) cudaFree(s.long_list);
+        LCTR_CUDA(cudaMalloc((void**)&s.long_list, (size_t)(max_nnz / 8 + s.cap_segs + 1) * sizeof(uint2)));
+        s.cap_long = max_nnz;
     }
-    if (s.nnz > s.cap_ent) {
+    if (max_nnz > s.cap_ent) {
         LCTR_CUDA(cudaStreamSynchronize(c->stream));
         if (s.ent_row) cudaFree(s.ent_row); if (s.ent_x) cudaFree(s.ent_x);
-        const int64_t cap = std::max<int64_t>(s.nnz, s.cap_ent + s.cap_ent / 2);
+        const int64_t cap = std::max<int64_t>(max_nnz, s.cap_ent + s.cap_ent / 2);
         LCTR_CUDA(cudaMalloc((void**)&s.ent_row, (size_t)(cap + 32) * sizeof(uint32_t)));
         LCTR_CUDA(cudaMalloc((void**)&s.ent_x, (size_t)(cap + 32) * sizeof(float)));
         s.cap_ent = cap;
     }
-    const unsigned g1 = (unsigned)std::min<int64_t>((s.nnz + 255) / 256, (int64_t)c->sm_count * 8);
+    return 0;
+}
+
+// build the feature-major view of the whole slot on stream `st`.  label_i32 != nullptr: the int32 labels just
+// copied there are widened into s.label by the first kernel.  hdr != nullptr (graph capture): sizes come from the
+// device header {rows, nnz}; `rows_cap` / `nnz_cap` then only size the grids.
+int csc_build_device(lctr_ctx* c, Slot& s, cudaStream_t st, const int32_t* label_i32, const int64_t* hdr,
+                     int64_t rows_cap, int64_t nnz_cap) {
+    s.dev_csc = false;
+    const int64_t nnz = hdr ? nnz_cap : s.nnz, rows = hdr ? rows_cap : s.rows;
+    if (nnz == 0) return 0;
+    CscScratch* sc;
+    if (scratch_get(c, &sc)) return 1;
+    if (!hdr && csc_reserve(c, s, nnz)) return 1;
+    const unsigned g1 = (unsigned)std::min<int64_t>((nnz + 255) / 256, (int64_t)c->sm_count * 8);
     const unsigned gt = (unsigned)std::min<size_t>((sc->ntiles + 7) / 8, (size_t)c->sm_count * 8);
-    csc_count_kernel<<<std::max(g1, 1u), 256, 0, st>>>(s.fid, s.nnz, sc->cnt);
+    csc_count_kernel<<<std::max(g1, 1u), 256, 0, st>>>(s.fid, s.nnz, sc->cnt, label_i32, s.label, s.rows, hdr);
     csc_tile_reduce_kernel<<<std::max(gt, 1u), 256, 0, st>>>(sc->cnt, c->F, sc->tile_sum);
-    csc_tile_scan_kernel<<<1, 1024, 0, st>>>(sc->tile_sum, sc->ntiles, sc->tile_off, s.csc_totals);
+    csc_tile_scan_kernel<<<1, 1024, 0, st>>>(sc->tile_sum, sc->ntiles, sc->tile_off, s.csc_totals, s.seg_ptr);
     csc_tile_write_kernel<<<std::max(gt, 1u), 256, 0, st>>>(sc->cnt, c->F, sc->tile_off, sc->off, s.seg_fid, s.seg_ptr,
                                                            s.short_list, reinterpret_cast<uint2*>(s.long_list),
                                                            s.csc_totals);
-    csc_sentinel_kernel<<<1, 1, 0, st>>>(s.seg_ptr, s.csc_totals);
-    const unsigned gf = (unsigned)std::min<int64_t>((s.rows + 7) / 8, (int64_t)c->sm_count * 8);
+    const unsigned gf = (unsigned)std::min<int64_t>((rows + 7) / 8, (int64_t)c->sm_count * 8);
     csc_fill_kernel<<<std::max(gf, 1u), 256, 0, st>>>(s.row_ptr, s.fid, s.has_val ? s.val : nullptr, s.rows, sc->off,
-                                                     sc->cnt, s.ent_row, s.ent_x);
-    c->launches += 6;
+                                                     sc->cnt, s.ent_row, s.ent_x, hdr);
+    c->launches += 5;
     LCTR_CUDA(cudaGetLastError());
     s.dev_csc = true;
     s.csc_block = 0;
@@ -460,33 +487,36 @@ int csc_build_device(lctr_ctx* c, Slot& s, cudaStream_t st) {
 }
 
 template <int K>
-static int bwd_go(lctr_ctx* c, Slot& s, const OptParams& P) {
+static int bwd_go(lctr_ctx* c, Slot& s, const OptParams& P, const OptParams* dP) {
     const unsigned grid = (unsigned)c->sm_count * 4;
     const CscView C{s.seg_ptr, s.seg_fid, s.ent_row, s.ent_x, s.label, s.pred, s.sumvx};
     const ParamView T{c->W, c->V, c->s1W, c->s1V, c->s2W, c->s2V};
     const uint2* longs = reinterpret_cast<const uint2*>(s.long_list);
     if (s.has_val) {
-        csc_backward_long_kernel<K, true><<<grid, 256, 0, c->stream>>>(longs, s.csc_totals, C, T, s.csc_acc, s.csc_arrived, c->cfg.l2_reg, P);
-        csc_backward_short_kernel<K, true><<<grid, 256, 0, c->stream>>>(s.short_list, s.csc_totals, C, T, c->cfg.l2_reg, P);
+        csc_backward_long_kernel<K, true><<<grid, 256, 0, c->stream>>>(longs, s.csc_totals, C, T, s.csc_acc, s.csc_arrived, c->cfg.l2_reg, P, dP);
+        csc_backward_short_kernel<K, true><<<grid, 256, 0, c->stream>>>(s.short_list, s.csc_totals, C, T, c->cfg.l2_reg, P, dP);
     } else {
-        csc_backward_long_kernel<K, false><<<grid, 256, 0, c->stream>>>(longs, s.csc_totals, C, T, s.csc_acc, s.csc_arrived, c->cfg.l2_reg, P);
-        csc_backward_short_kernel<K, false><<<grid, 256, 0, c->stream>>>(s.short_list, s.csc_totals, C, T, c->cfg.l2_reg, P);
+        csc_backward_long_kernel<K, false><<<grid, 256, 0, c->stream>>>(longs, s.csc_totals, C, T, s.csc_acc, s.csc_arrived, c->cfg.l2_reg, P, dP);
+        csc_backward_short_kernel<K, false><<<grid, 256, 0, c->stream>>>(s.short_list, s.csc_totals, C, T, c->cfg.l2_reg, P, dP);
     }
     return 0;
 }
 
-int launch_fm_backward_devcsc(lctr_ctx* c, Slot& s, int64_t rb, int64_t re) {
+// dP != nullptr (graph capture): the updater parameters are read from device memory at run time
+int launch_fm_backward_devcsc_ex(lctr_ctx* c, Slot& s, int64_t rb, int64_t re, const OptParams* P_host, const void* dP) {
     LCTR_CHECK(s.dev_csc, "slot has no device-built feature-major view");
-    LCTR_CHECK(rb == 0 && re == s.rows, "the device-built view covers whole slots only (rows [%lld,%lld) of %lld)",
+    LCTR_CHECK(rb == 0 && (dP || re == s.rows), "the device-built view covers whole slots only (rows [%lld,%lld) of %lld)",
                (long long)rb, (long long)re, (long long)s.rows);
     const int k = (int)c->cfg.factor_cnt;
-    const OptParams P = make_opt_params(c, re - rb);
+    OptParams P;
+    if (P_host) P = *P_host; else P = make_opt_params(c, re - rb);
     ProfScope prof(c, PROF_FM_BWD_CSC);
+    const OptParams* d = reinterpret_cast<const OptParams*>(dP);
     switch (k) {
-        case 4: bwd_go<4>(c, s, P); break;
-        case 8: bwd_go<8>(c, s, P); break;
-        case 16: bwd_go<16>(c, s, P); break;
-        case 32: bwd_go<32>(c, s, P); break;
+        case 4: bwd_go<4>(c, s, P, d); break;
+        case 8: bwd_go<8>(c, s, P, d); break;
+        case 16: bwd_go<16>(c, s, P, d); break;
+        case 32: bwd_go<32>(c, s, P, d); break;
         default:
             set_error("device feature-major backward is built for k in {4, 8, 16, 32} (k=%d)", k);
             return 1;
@@ -495,6 +525,17 @@ int launch_fm_backward_devcsc(lctr_ctx* c, Slot& s, int64_t rb, int64_t re) {
     LCTR_CUDA(cudaGetLastError());
     return 0;
 }
+
+int launch_fm_backward_devcsc(lctr_ctx* c, Slot& s, int64_t rb, int64_t re) {
+    return launch_fm_backward_devcsc_ex(c, s, rb, re, nullptr, nullptr);
+}
+
+// host-side snapshot of the updater parameters for a step of `rows` rows (advances the Adam call counter)
+void csc_opt_params(lctr_ctx* c, int64_t rows, void* out) {
+    const OptParams P = make_opt_params(c, rows);
+    memcpy(out, &P, sizeof(P));
+}
+size_t csc_opt_params_size() { return sizeof(OptParams); }
 
 bool csc_device_supported(const lctr_ctx* c) {
     const int k = (int)c->cfg.factor_cnt;

@@ -73,8 +73,9 @@ __global__ void __launch_bounds__(256)
 fm_forward_kernel(const int64_t* __restrict__ row_ptr, const uint32_t* __restrict__ fid,
                   const float* __restrict__ val, const float* __restrict__ label, const float* __restrict__ W,
                   const float* __restrict__ V, float* __restrict__ pred, float* __restrict__ sumvx,
-                  float* __restrict__ z_out, float* __restrict__ wide_out, int64_t rb, int64_t re, double* partial,
-                  unsigned int* done, double* out_slot, int do_stats) {
+                  float* __restrict__ z_out, float* __restrict__ wide_out, int64_t rb, int64_t re_arg, double* partial,
+                  unsigned int* done, double* out_slot, int do_stats, const int64_t* __restrict__ hdr) {
+    const int64_t re = hdr ? hdr[0] : re_arg;  // graph launches read the batch size from the slot header
     constexpr int STR = K + 4;     // tile row: t[0..K), dot, w*x, pad (16 B aligned, conflict-free strides)
     constexpr int NB = 64;         // features per pass (two 32-lane gathers in flight)
     extern __shared__ __align__(16) float fwd_smem[];
@@ -294,7 +295,7 @@ static bool pick_shape(int k, Shape& sh) {
     } while (0)
 
 template <int K>
-static int fwd_go(lctr_ctx* c, Slot& s, bool nfm, int64_t rb, int64_t re, double* out_slot, int stats) {
+static int fwd_go(lctr_ctx* c, Slot& s, bool nfm, int64_t rb, int64_t re, double* out_slot, int stats, const int64_t* hdr) {
     const unsigned grid = (unsigned)((re - rb + 7) / 8);
     const size_t smem = (size_t)8 * 64 * (K + 4) * sizeof(float);
 #define FWD_GO(HV, NF)                                                                                         \
@@ -302,7 +303,7 @@ static int fwd_go(lctr_ctx* c, Slot& s, bool nfm, int64_t rb, int64_t re, double
         auto kern = fm_forward_kernel<K, HV, NF>;                                                              \
         if (smem > 48 * 1024) LCTR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
         kern<<<grid, 256, smem, c->stream>>>(s.row_ptr, s.fid, s.val, s.label, c->cW, c->cV, s.pred, s.sumvx, c->z, \
-                                             s.wide, rb, re, c->stat_partial, c->stat_done, out_slot, stats);  \
+                                             s.wide, rb, re, c->stat_partial, c->stat_done, out_slot, stats, hdr);  \
     } while (0)
     if (s.has_val) { if (nfm) FWD_GO(true, true); else FWD_GO(true, false); }
     else { if (nfm) FWD_GO(false, true); else FWD_GO(false, false); }
@@ -311,17 +312,23 @@ static int fwd_go(lctr_ctx* c, Slot& s, bool nfm, int64_t rb, int64_t re, double
 }
 
 int launch_fm_forward(lctr_ctx* c, Slot& s, int64_t rb, int64_t re, bool nfm, bool stats) {
+    return launch_fm_forward_ex(c, s, rb, re, nfm, stats, nullptr, nullptr);
+}
+
+// hdr != nullptr (graph capture): `re` is the grid-sizing upper bound, the kernel takes the row count from hdr[0]
+int launch_fm_forward_ex(lctr_ctx* c, Slot& s, int64_t rb, int64_t re, bool nfm, bool stats, const int64_t* hdr,
+                         double* out_slot_override) {
     const int k = (int)c->cfg.factor_cnt;
     const int64_t rows = re - rb;
     if (rows <= 0) return 0;
-    double* out_slot = c->stats + 2 * (c->step % kStatRing);
+    double* out_slot = out_slot_override ? out_slot_override : c->stats + 2 * (c->step % kStatRing);
     const int st = stats ? 1 : 0;
     ProfScope prof(c, PROF_FM_FWD);
     int rc = 0;
     static const int dbg_repeat = getenv("LCTR_DBG_FWD_REPEAT") ? atoi(getenv("LCTR_DBG_FWD_REPEAT")) : 1;
     for (int rep = 0; rep < dbg_repeat && !rc; rep++)
     switch (k) {  // the factor count is a compile-time constant of the kernel (register-resident rows)
-#define FWD_CASE(KK) case KK: rc = fwd_go<KK>(c, s, nfm, rb, re, out_slot, st); break;
+#define FWD_CASE(KK) case KK: rc = fwd_go<KK>(c, s, nfm, rb, re, out_slot, st, hdr); break;
         FWD_CASE(1) FWD_CASE(2) FWD_CASE(3) FWD_CASE(4) FWD_CASE(5) FWD_CASE(6) FWD_CASE(7) FWD_CASE(8)
         FWD_CASE(10) FWD_CASE(12) FWD_CASE(16) FWD_CASE(20) FWD_CASE(24) FWD_CASE(32)
 #undef FWD_CASE
