@@ -15,6 +15,8 @@
 // (624 B at Fc=39,k=4), fully coalesced across the CTA; T lives in shared memory with
 // thread-owned slots (no shared atomics); gradients leave as 16 B vector REDs that are
 // contiguous per row.  HBM-bound by the row gather: no tensor cores by design.
+#include <stdlib.h>
+
 #include <algorithm>
 #include <vector>
 
@@ -45,8 +47,19 @@ __device__ __forceinline__ void vred(float* p, const VT<VEC>& v) {
 
 constexpr int FFM_UNROLL = 4;
 
+// TMA bulk reduce-add of a contiguous fp32 segment from shared to global memory (one request per embedding row
+// instead of Fc*k/4 vector REDs): cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32
+__device__ __forceinline__ void bulk_reduce_add_f32(float* gdst, const float* ssrc, uint32_t bytes) {
+    const uint32_t saddr = (uint32_t)__cvta_generic_to_shared(ssrc);
+    asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;"
+                 :: "l"(gdst), "r"(saddr), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
 // One CTA per sample; thread t < A owns slot t (VEC floats of the row; A = Fc*k/VEC).
-template <int VEC, bool HAS_VAL, bool TRAIN>
+template <int VEC, bool HAS_VAL, bool TRAIN, bool BULK>
 __global__ void ffm_fused_kernel(const int64_t* __restrict__ row_ptr, const uint32_t* __restrict__ fid,
                                  const uint16_t* __restrict__ field, const float* __restrict__ val,
                                  const float* __restrict__ label, const float* __restrict__ W,
@@ -60,6 +73,8 @@ __global__ void ffm_fused_kernel(const int64_t* __restrict__ row_ptr, const uint
     VT<VEC>* S = reinterpret_cast<VT<VEC>*>(smem_raw);                       // S[col b][slot a] = T[a][b]
     int* cnt = reinterpret_cast<int*>(smem_raw + (size_t)Fc * A * VEC * 4);  // features per field
     float* red = reinterpret_cast<float*>(cnt + Fc);                         // [3][32] block reduction scratch + bcast
+    // BULK: FFM_UNROLL staging rows (A slots each, 16 B aligned) for the TMA reduce of the gradient rows
+    VT<VEC>* stage = reinterpret_cast<VT<VEC>*>(smem_raw + (((size_t)Fc * A * VEC * 4 + (size_t)Fc * 4 + 80 * 4 + 15) / 16) * 16);
     const int t = threadIdx.x;
     const int64_t r = rb + blockIdx.x;
     const int64_t b0 = row_ptr[r], e0 = row_ptr[r + 1];
@@ -169,14 +184,20 @@ __global__ void ffm_fused_kernel(const int64_t* __restrict__ row_ptr, const uint
                         for (int c = 0; c < VEC; c++) v[u].a[c] = 0.f;
                     }
                 }
+                if (BULK) {  // staging rows of the previous iteration must have been read by the TMA
+                    if (t == 0) bulk_wait_read_all();
+                    __syncthreads();
+                }
 #pragma unroll
                 for (int u = 0; u < FFM_UNROLL; u++) {
                     if (i + u >= e0) break;
                     if (own) {
                         const int c_ib = my_cnt - (my_field == fl[u] ? 1 : 0);
+                        VT<VEC> g;
+#pragma unroll
+                        for (int c = 0; c < VEC; c++) g.a[c] = 0.f;
                         if (c_ib > 0) {
                             const VT<VEC> tt = S[my_field * A + fl[u] * PPF + my_part];  // T[fld_i][my_field]
-                            VT<VEC> g;
                             const float sx = d * x[u];
                             const float lc = l2 * (float)c_ib;
 #pragma unroll
@@ -185,14 +206,31 @@ __global__ void ffm_fused_kernel(const int64_t* __restrict__ row_ptr, const uint
                                 if (my_field == fl[u]) tv -= x[u] * v[u].a[c];
                                 g.a[c] = sx * tv + lc * v[u].a[c];
                             }
-                            vred<VEC>(gV + (size_t)f[u] * rowlen + (size_t)t * VEC, g);
+                            if (!BULK) vred<VEC>(gV + (size_t)f[u] * rowlen + (size_t)t * VEC, g);
                         }
+                        if (BULK) stage[u * A + t] = g;
                     }
                     if (t == 0) {
                         red_add_f32(gW + f[u], d * x[u] + l2 * __ldg(W + f[u]));  // train_ffm_algo.cpp:98
                         if (touched) touched[f[u]] = 1;
                     }
                 }
+                if (BULK) {
+                    fence_proxy_async_smem();
+                    __syncthreads();
+                    if (t == 0) {
+#pragma unroll
+                        for (int u = 0; u < FFM_UNROLL; u++)
+                            if (i + u < e0)
+                                bulk_reduce_add_f32(gV + (size_t)f[u] * rowlen, reinterpret_cast<const float*>(stage + u * A),
+                                                    (uint32_t)(rowlen * sizeof(float)));
+                        bulk_commit();
+                    }
+                }
+            }
+            if (BULK) {
+                if (t == 0) bulk_wait_read_all();
+                __syncthreads();
             }
         }
     }
@@ -208,13 +246,18 @@ static int ffm_launch(lctr_ctx* c, Slot& s, int64_t rb, int64_t re, bool train, 
     const int A = Fc * k / vec;
     LCTR_CHECK(A <= 1024, "FFM row of %d slots exceeds one CTA (Fc=%d k=%d)", A, Fc, k);
     const int tpb = std::max(64, (A + 31) / 32 * 32);
-    const size_t smem = (size_t)Fc * A * vec * 4 + (size_t)Fc * 4 + 80 * 4;
+    // TMA bulk reduce-add of whole gradient rows is built but off by default: measured 554 us vs 532 us for the vector
+    // REDs on C3 -- both hit the same L2 reduction rate (~0.75 TB/s of fp32 adds), see profiles/README.md
+    static const bool use_bulk = getenv("LCTR_FFM_BULK") && atoi(getenv("LCTR_FFM_BULK")) == 1;
+    const bool bulk = use_bulk && train && vec == 4 && (Fc * k * 4) % 16 == 0;
+    const size_t smem = ((size_t)Fc * A * vec * 4 + (size_t)Fc * 4 + 80 * 4 + 15) / 16 * 16 +
+                        (bulk ? (size_t)FFM_UNROLL * A * vec * 4 : 0);
     LCTR_CHECK(smem <= 227 * 1024, "FFM field-pair tile needs %zu B shared memory (> 227 KB): Fc=%d k=%d", smem, Fc, k);
     double* out_slot = c->stats + 2 * (c->step % kStatRing);
     ProfScope prof(c, PROF_FFM_FUSED);
 #define FFM_GO(VECN, HV, TR)                                                                                          \
     do {                                                                                                              \
-        auto kern = ffm_fused_kernel<VECN, HV, TR>;                                                                   \
+        auto kern = bulk ? ffm_fused_kernel<VECN, HV, TR, (VECN == 4) && TR> : ffm_fused_kernel<VECN, HV, TR, false>; \
         LCTR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                \
         kern<<<(unsigned)rows, tpb, smem, c->stream>>>(s.row_ptr, s.fid, s.field, s.val, s.label, c->cW, c->cV, Fc, k, \
                                                        s.pred, c->cgW, c->cgV, c->cfg.world > 1 ? nullptr : c->touched, c->cfg.l2_reg, rb, \

@@ -44,17 +44,18 @@ def _launch(world, out, extra, timeout=600):
     assert all(p.returncode == 0 for p in procs), "\n".join(logs)
 
 
-def _oracle_global(oracle_api, world, F, k, rows, steps):
+def _oracle_global(oracle_api, world, F, k, rows, steps, model="fm"):
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import dist_worker
 
     class A:
         pass
     a = A()
-    a.F, a.k, a.rows, a.steps, a.model = F, k, rows, steps, "fm"
+    a.F, a.k, a.rows, a.steps, a.model = F, k, rows, steps, model
     per_rank = [dist_worker.make_problem(a, r) for r in range(world)]
     W, V = per_rank[0][1].copy(), per_rank[0][2].copy()
-    accum = np.zeros(F * (k + 1), np.float32)
+    Fc = 39 if model == "ffm" else 0
+    accum = np.zeros(F * (k * max(Fc, 1) + 1), np.float32)
     stats = []
     for s in range(steps):
         rps, fids, flds, labs, off = [np.zeros(1, np.int64)], [], [], [], 0
@@ -64,11 +65,17 @@ def _oracle_global(oracle_api, world, F, k, rows, steps):
             off += rp[-1]
             fids.append(fid); flds.append(fld); labs.append(lab)
         ds = oracle_api.Dataset(np.concatenate(rps), np.concatenate(fids), np.concatenate(flds).astype(np.uint32),
-                                np.ones(off, np.float32), np.concatenate(labs), F, 0)
-        o = oracle_api.FMOracle(ds, k, W, V)
-        o.accum[:] = accum
-        loss, acc = o.epoch()
-        W, V, accum = o.W.copy(), o.V.copy(), o.accum.copy()
+                                np.ones(off, np.float32), np.concatenate(labs), F, Fc)
+        if model == "ffm":
+            o = oracle_api.FFMOracle(ds, k, W, V)
+            o.s1[:] = accum
+            loss, acc = o.epoch()
+            W, V, accum = o.W.copy(), o.V.copy(), o.s1.copy()
+        else:
+            o = oracle_api.FMOracle(ds, k, W, V)
+            o.accum[:] = accum
+            loss, acc = o.epoch()
+            W, V, accum = o.W.copy(), o.V.copy(), o.accum.copy()
         stats.append((loss, acc * ds.rows))
     return W, V, stats
 
@@ -112,3 +119,12 @@ def test_cuda_two_ranks_one_device(oracle_api, tmp_path):
     _launch(2, str(tmp_path), ["--mode", "gpu", "--same-device", "--F", str(F), "--k", str(k), "--rows", str(rows),
                                "--steps", str(steps)], timeout=900)
     _check(str(tmp_path), 2, F, k, _oracle_global(oracle_api, 2, F, k, rows, steps), 2e-5)
+
+
+@pytest.mark.gpu
+def test_cuda_two_ranks_ffm(oracle_api, tmp_path):
+    """FFM (39 fields, k=4) over 2 ranks: rows of Fc*k floats travel through the same pull / push kernels."""
+    F, k, rows, steps = 6000, 4, 128, 2
+    _launch(2, str(tmp_path), ["--mode", "gpu", "--same-device", "--model", "ffm", "--F", str(F), "--k", str(k),
+                               "--rows", str(rows), "--steps", str(steps)], timeout=900)
+    _check(str(tmp_path), 2, F, k, _oracle_global(oracle_api, 2, F, k, rows, steps, model="ffm"), 5e-5)
