@@ -28,8 +28,10 @@ WORKLOADS = {
                   desc="FM k=16, 1M synthetic Criteo-shape features (39 fields, ~77 nnz/row), batch 4096, Adagrad"),
     "ffm_c3": dict(model="ffm", k=4, F=1_000_000, batch=8192, opt="ftrl",
                    desc="FFM k=4, 39 fields, 1M features, batch 8192, FTRL"),
-    "ffm_c5": dict(model="ffm", k=8, F=10_000_000, batch=65536, opt="adagrad",
-                   desc="FFM k=8, 39 fields, 10M features, global batch 65536, Adagrad"),
+    "nfm_c4": dict(model="nfm", k=16, F=1_000_000, batch=16384, opt="adagrad", hidden=[256, 128, 64], nb=4,
+                   desc="NFM k=16 + MLP [256,128,64] (fp32 reference-order MLP), 1M features, batch 16384, Adagrad"),
+    "ffm_c5": dict(model="ffm", k=8, F=10_000_000, batch=65536, opt="adagrad", nb=2,
+                   desc="FFM k=8, 39 fields, 10M features, batch 65536 per GPU, Adagrad"),
 }
 N_FIELDS = 39
 
@@ -96,6 +98,31 @@ def make_batches(wl, n_batches, seed_offset=0):
 # reference arm / cpu_baseline: the reference's own Train() on the host cores
 # ------------------------------------------------------------------------------------------------
 def run_reference(wl, steps, warmup, budget_s=20.0):
+    if wl["model"] == "nfm":
+        return run_port_nfm(wl, budget_s)
+    return _run_reference(wl, steps, warmup, budget_s)
+
+
+def run_port_nfm(wl, budget_s):
+    """The reference's NFM takes ONE hidden layer (train_nfm_algo.h:21); the [256,128,64] chain of config C4 is a
+    Fully_Conn_Layer chain only the oracle port can instantiate, so this arm is kind="port", single-threaded."""
+    from oracle import api
+    rp, fid, fld, lab = make_batches(wl, 1)[0]
+    sub = min(wl["batch"], 1024)  # bounded sample: the first `sub` rows of the batch as one minibatch
+    nz = rp[sub]
+    ds = api.Dataset(rp[:sub + 1], fid[:nz], fld[:nz].astype(np.uint32), np.ones(nz, np.float32), lab[:sub], wl["F"], 0)
+    o = api.NFMOracle(ds, wl["k"], wl["hidden"], seed=1, batch_size=sub, minibatch=sub)
+    t0 = time.time()
+    n = 0
+    while time.time() - t0 < budget_s and n < 50:
+        o.epoch()
+        n += 1
+    secs = time.time() - t0
+    return dict(value=sub * n / secs, cores=1, steps=n, ms_per_step=1e3 * secs / n, rows=sub, kind="port",
+                sample="%d minibatch steps of %d rows (first rows of one synthetic batch), oracle C port, 1 thread" % (n, sub))
+
+
+def _run_reference(wl, steps, warmup, budget_s=20.0):
     """Times Train_FM_Algo / Train_FFM_Algo::Train() of the UNMODIFIED reference (oracle/_ref/libref.so) on one
     synthetic batch written in its libffm text format; one epoch over the B-row file == one step."""
     from lightctr_b200.data import write_libffm
@@ -150,8 +177,8 @@ def main():
                 "steps": r["steps"], "warmup": max(args.warmup, 1), "ms_per_step": r["ms_per_step"],
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": wl["desc"]},
-                "cpu_baseline": {"value": r["value"], "unit": "samples/s", "cores": r["cores"], "kind": "reference",
-                                 "sample": r["sample"]},
+                "cpu_baseline": {"value": r["value"], "unit": "samples/s", "cores": r["cores"],
+                                 "kind": r.get("kind", "reference"), "sample": r["sample"]},
                 "e2e": {"value": r["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
         return 0
@@ -167,7 +194,7 @@ def main():
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    model = {"fm": capi.MODEL_FM, "ffm": capi.MODEL_FFM}[wl["model"]]
+    model = {"fm": capi.MODEL_FM, "ffm": capi.MODEL_FFM, "nfm": capi.MODEL_NFM}[wl["model"]]
     opt = {"adagrad": capi.OPT_ADAGRAD, "ftrl": capi.OPT_FTRL, "adam": capi.OPT_ADAM}[wl["opt"]]
     F, k, B = wl["F"], wl["k"], wl["batch"]
     Fc = N_FIELDS if wl["model"] == "ffm" else 0
@@ -178,16 +205,17 @@ def main():
     # at upload, i.e. OUTSIDE the device-timed `value` region but INSIDE the end-to-end region.
     det = 2 if (world == 1 and wl["model"] == "fm" and os.environ.get("LCTR_BENCH_BACKWARD", "red") == "grouped") else 0
     ctx = capi.Context(model, F, k, Fc, optimizer=opt, device=local_rank, deterministic=det, rank=rank, world=world,
-                       minibatch_size=(world * B if world > 1 else 0), max_nnz=B * 160)
-    rng = np.random.default_rng(1234)
-    rowlen = k * max(Fc, 1)
-    V0 = (rng.standard_normal(F * rowlen, dtype=np.float32) * np.float32(1.0 / np.sqrt(k)))
-    ctx.upload_params(np.zeros(F, np.float32), V0)
-    del V0
+                       minibatch_size=(world * B if world > 1 else 0), max_nnz=B * 120, hidden=wl.get("hidden", ()))
+    if wl["model"] == "nfm":  # FC chain initialised like fullyconnLayer.h:48-54 (U(-0.5,0.5), bias 0), masks all-ones
+        rng0 = np.random.default_rng(99)
+        dims = [k] + list(wl["hidden"]) + [1]
+        for li in range(len(dims) - 1):
+            ctx.mlp_upload(li, (rng0.random((dims[li + 1], dims[li]), dtype=np.float32) - 0.5), np.zeros(dims[li + 1], np.float32))
+    ctx.fill_params(1234, float(1.0 / np.sqrt(k)))  # random-init weights (W = 0, V ~ N(0,1)/sqrt(k)), on the device
     if world > 1:
         from lightctr_b200 import dist as ldist
         ldist.connect(ctx)
-    NB = 8
+    NB = wl.get("nb", 8)
     batches = make_batches(wl, NB, seed_offset=rank)
     # pinned host copies (the end-to-end arm copies from these every step)
     pinned = []
@@ -281,9 +309,9 @@ def main():
     compute = {kk: vv for kk, vv in prof.items() if not kk.startswith("dist_")}
     dom = max(compute.items(), key=lambda kv: kv[1][0]) if compute else (None, (0.0, 0))
     n = nnz_mean / B
-    if wl["model"] == "fm":
+    if wl["model"] in ("fm", "nfm"):
         bytes_per_sample = {"fm_forward": n * (4 * k + 12) + 8, "fm_backward_red": n * (4 * k + 12) + 8,
-                            "fm_backward_csc": n * (4 * k + 12) + 8, "apply": None}
+                            "fm_backward_csc": n * (4 * k + 12) + 8, "apply": None, "mlp": None}
     else:
         bytes_per_sample = {"ffm_fused": n * (Fc * k * 4 + 12)}
     roof = None
@@ -311,8 +339,8 @@ def main():
     if not args.no_cpu_baseline and rank == 0 and world == 1:
         r = run_reference(wl, 50, 1, budget_s=15.0)
         if r is not None:
-            line["cpu_baseline"] = {"value": r["value"], "unit": "samples/s", "cores": r["cores"], "kind": "reference",
-                                    "sample": r["sample"]}
+            line["cpu_baseline"] = {"value": r["value"], "unit": "samples/s", "cores": r["cores"],
+                                    "kind": r.get("kind", "reference"), "sample": r["sample"]}
     if rank == 0:
         print(json.dumps(line))
     if world > 1:

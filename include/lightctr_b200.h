@@ -86,6 +86,9 @@ int lctr_sync(lctr_ctx* ctx);
 /* V layout == reference: FM/NFM V[fid*k + f] (fm_algo_abst.h:146-148); FFM V[fid*Fc*k + field*k + f] (:149-151) */
 int lctr_upload_params(lctr_ctx* ctx, const float* W, const float* V);
 int lctr_download_params(lctr_ctx* ctx, float* W, float* V);
+/* synthetic initialisation on the device: W = 0, V ~ scale * N(0,1) (hash of the global element index; independent
+ * of the sharding).  Used by bench.py for tables too large to stage through host memory. */
+int lctr_fill_params(lctr_ctx* ctx, uint64_t seed, float scale);
 /* optimizer state: s1 = adagrad accum | ftrl z | adam m ; s2 = ftrl n | adam v ; each F + |V| floats, W part first
  * (same concatenation as update_g, train_fm_algo.h:52-57).  NULL pointers are skipped. */
 int lctr_download_opt_state(lctr_ctx* ctx, float* s1, float* s2);

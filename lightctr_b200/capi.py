@@ -22,7 +22,7 @@ ABI_VERSION = 1
 # every symbol include/lightctr_b200.h declares (tests check the .so exports each of them)
 SYMBOLS = [
     "lctr_last_error", "lctr_abi_version", "lctr_create", "lctr_destroy", "lctr_sync", "lctr_upload_params",
-    "lctr_download_params", "lctr_download_opt_state", "lctr_upload_opt_state", "lctr_upload_batch",
+    "lctr_download_params", "lctr_fill_params", "lctr_download_opt_state", "lctr_upload_opt_state", "lctr_upload_batch",
     "lctr_train_step", "lctr_train_batch", "lctr_train_batch_async", "lctr_wait", "lctr_predict", "lctr_download_sumvx", "lctr_download_pred",
     "lctr_mlp_upload", "lctr_mlp_download", "lctr_mlp_set_mask", "lctr_ipc_export", "lctr_ipc_import",
     "lctr_dense_grad_buffer", "lctr_load_libffm", "lctr_free_dataset", "lctr_launch_count", "lctr_stream", "lctr_profile", "lctr_profile_read",
@@ -66,6 +66,7 @@ def load_library():
     L.lctr_sync.argtypes = [vp]
     L.lctr_upload_params.argtypes = [vp, f32p, f32p]
     L.lctr_download_params.argtypes = [vp, f32p, f32p]
+    L.lctr_fill_params.argtypes = [vp, C.c_uint64, C.c_float]
     L.lctr_download_opt_state.argtypes = [vp, f32p, f32p]
     L.lctr_upload_opt_state.argtypes = [vp, f32p, f32p]
     L.lctr_upload_batch.argtypes = [vp, C.c_int, i64, i64, vp, vp, vp, vp, vp]
@@ -185,6 +186,9 @@ class Context:
         W = None if W is None else np.ascontiguousarray(W, np.float32)
         V = None if V is None else np.ascontiguousarray(V, np.float32)
         _chk(self.L.lctr_upload_params(self.h, _p(W), _p(V)))
+
+    def fill_params(self, seed, scale):
+        _chk(self.L.lctr_fill_params(self.h, seed, scale))
 
     def download_params(self):
         W = np.empty(self.F, np.float32)

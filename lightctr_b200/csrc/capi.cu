@@ -62,6 +62,23 @@ __global__ void label_to_float_kernel(const int32_t* in, float* out, int64_t n) 
     if (i < n) out[i] = (float)in[i];
 }
 
+// synthetic initialisation on the device (bench only): W = 0, V[f][j] = scale * N(0,1) from a counter-based hash of
+// the GLOBAL element index, so the values do not depend on how the table is sharded
+__global__ void fill_params_kernel(float* __restrict__ W, float* __restrict__ V, size_t Fl, size_t rowlen, int rank,
+                                   int world, unsigned long long seed, float scale) {
+    const size_t n = Fl * rowlen;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t l = i / rowlen, j = i % rowlen;
+        const unsigned long long g = ((unsigned long long)(l * world + rank)) * rowlen + j;
+        unsigned long long h = g * 0x9E3779B97F4A7C15ull + seed;
+        h ^= h >> 33; h *= 0xff51afd7ed558ccdull; h ^= h >> 33; h *= 0xc4ceb9fe1a85ec53ull; h ^= h >> 33;
+        const float u1 = ((unsigned)(h & 0xffffffu) + 1u) * (1.0f / 16777217.0f);
+        const float u2 = (unsigned)((h >> 24) & 0xffffffu) * (1.0f / 16777216.0f);
+        V[i] = scale * sqrtf(-2.0f * logf(u1)) * cosf(6.2831853f * u2);
+        if (j == 0) W[l] = 0.f;
+    }
+}
+
 // Feature-major view of a slot, built on the host from the caller's CSR arrays (one counting sort per row
 // block; stable, so each fid's entries stay in ascending row order -- the accumulation order of the
 // reference's canonical single-thread run, train_fm_algo.cpp:101-116).
@@ -310,6 +327,15 @@ int lctr_download_params(lctr_ctx* c, float* W, float* V) {
         if (W) W[f] = w[l];
         if (V) memcpy(V + f * c->rowlen, &v[l * c->rowlen], c->rowlen * sizeof(float));
     }
+    return 0;
+}
+int lctr_fill_params(lctr_ctx* c, uint64_t seed, float scale) {
+    LCTR_CHECK(c, "null ctx");
+    fill_params_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(c->W, c->V, c->Fl, c->rowlen, c->cfg.rank, c->cfg.world,
+                                                               (unsigned long long)seed, scale);
+    c->launches++;
+    LCTR_CUDA(cudaGetLastError());
+    LCTR_CUDA(cudaStreamSynchronize(c->stream));
     return 0;
 }
 int lctr_download_opt_state(lctr_ctx* c, float* s1, float* s2) {

@@ -298,8 +298,10 @@ int dist_alloc(lctr_ctx* c) {
     LCTR_CUDA(cudaMemsetAsync(d->n_uniq, 0, sizeof(unsigned int), c->stream));
     LCTR_CUDA(cudaMemsetAsync(d->push_cnt, 0, kMaxWorld * sizeof(unsigned int), c->stream));
     LCTR_CUDA(cudaMemsetAsync(d->scratch_done, 0, sizeof(unsigned int), c->stream));
+    const char* pm0 = getenv("LCTR_DIST_PUSH");
+    d->use_mailbox = pm0 && strcmp(pm0, "mailbox") == 0;
     d->rec_floats = ((2 + c->rowlen) + 3) / 4 * 4;
-    d->rec_cap = cap;  // records one source may send to one owner per step (<= its unique ids)
+    d->rec_cap = d->use_mailbox ? cap : 0;  // records one source may send to one owner per step (<= its unique ids)
     d->region_bytes = (64 + d->rec_cap * d->rec_floats * sizeof(float) + 255) / 256 * 256;
     LCTR_CUDA(cudaMalloc((void**)&d->mailbox, d->region_bytes * R));
     LCTR_CUDA(cudaMemsetAsync(d->mailbox, 0, d->region_bytes * R, c->stream));

@@ -294,13 +294,146 @@ static bool pick_shape(int k, Shape& sh) {
         }                                                                               \
     } while (0)
 
+// Coalesced variant for K % 8 == 0: LPR = K/4 lanes cover one V row with float4 loads (a 64 B row is ONE request of two
+// fully used sectors instead of four scattered 16 B requests), so a warp gathers G = 32/LPR rows per load instruction.
+// The avx-ordered self dot runs across the LPR lanes (chunk sums, then the hsum tree), the shared tile is
+// FACTOR-major -- T[c][j], rows K and K+1 hold dot and w*x -- so that the in-order scan of phase 2 reads four
+// features per LDS.128.  Same expression sequence as fm_forward_kernel; ~3x fewer LSU wavefronts per sample.
+template <int K, bool HAS_VAL, bool NFM>
+__global__ void __launch_bounds__(256)
+fm_forward_coalesced_kernel(const int64_t* __restrict__ row_ptr, const uint32_t* __restrict__ fid,
+                            const float* __restrict__ val, const float* __restrict__ label, const float* __restrict__ W,
+                            const float* __restrict__ V, float* __restrict__ pred, float* __restrict__ sumvx,
+                            float* __restrict__ z_out, float* __restrict__ wide_out, int64_t rb, int64_t re_arg,
+                            double* partial, unsigned int* done, double* out_slot, int do_stats,
+                            const int64_t* __restrict__ hdr) {
+    static_assert(K % 8 == 0 && K <= 32, "coalesced forward: K in {8, 16, 24, 32}");
+    const int64_t re = hdr ? hdr[0] : re_arg;
+    constexpr int LPR = K / 4 >= 8 ? 8 : (K / 4 >= 4 ? 4 : 2);  // lanes per row (power of two >= K/4 for K=24 -> 8)
+    constexpr int G = 32 / LPR;         // rows per gather instruction
+    constexpr int NB = 64;              // features per pass
+    constexpr int NIT = NB / G;         // gather iterations per pass
+    constexpr int TS = NB + 4;          // tile row stride in floats (16 B aligned, conflict-free LDS.128)
+    constexpr int NFULL = K / 8;
+    extern __shared__ __align__(16) float fwd_smem[];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    float* tile = fwd_smem + (size_t)wid * (K + 2) * TS;
+    const int q = lane % LPR, g = lane / LPR;
+    const bool qa = 4 * q < K;          // K = 24: lanes q = 6,7 idle
+    const int64_t r = rb + (int64_t)blockIdx.x * (blockDim.x >> 5) + wid;
+    double loss = 0.0, correct = 0.0;
+    if (r < re) {
+        const int64_t b = row_ptr[r];
+        const int n = (int)(row_ptr[r + 1] - b);
+        float s = 0.f, z = 0.f, fm = 0.f;
+        for (int base = 0; base < n; base += NB) {
+            // ---- phase 1: columns of this pass (2 coalesced loads), then NIT gathers of G rows each
+            const int i0 = base + lane, i1 = base + 32 + lane;
+            const uint32_t f0 = i0 < n ? __ldg(fid + b + i0) : 0u, f1 = i1 < n ? __ldg(fid + b + i1) : 0u;
+            const float x0 = HAS_VAL ? (i0 < n ? __ldg(val + b + i0) : 0.f) : 1.f;
+            const float x1 = HAS_VAL ? (i1 < n ? __ldg(val + b + i1) : 0.f) : 1.f;
+            float4 v[NIT];
+            float wv[NIT], xv[NIT];
+#pragma unroll
+            for (int it = 0; it < NIT; it++) {
+                const int j = it * G + g;  // feature index within the pass
+                const uint32_t f = __shfl_sync(kFull, j < 32 ? f0 : f1, j & 31);
+                xv[it] = HAS_VAL ? __shfl_sync(kFull, j < 32 ? x0 : x1, j & 31) : 1.f;
+                v[it] = qa ? ldg_f4(V + (size_t)f * K + 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);  // f = 0 beyond n: masked
+                wv[it] = q == 0 ? __ldg(W + f) : 0.f;
+            }
+#pragma unroll
+            for (int it = 0; it < NIT; it++) {
+                const int j = it * G + g;
+                const bool ok = base + j < n;
+                float t[4] = {v[it].x, v[it].y, v[it].z, v[it].w};
+                if (HAS_VAL) {
+#pragma unroll
+                    for (int c = 0; c < 4; c++) t[c] = t[c] * xv[it];          // avx_vecScale(V, tmp, X)  :76
+                }
+                if (!ok) { t[0] = t[1] = t[2] = t[3] = 0.f; }
+                float dot = 0.f;
+                if (!NFM) {
+                    // avx_dotProduct(tmp, tmp, K): lane q holds elements 4q..4q+3; chunk m = q/2, position (q%2)*4+c
+                    float d[4];
+#pragma unroll
+                    for (int c = 0; c < 4; c++) d[c] = t[c] * t[c];
+                    float p[4] = {d[0], d[1], d[2], d[3]};
+#pragma unroll
+                    for (int m = 1; m < NFULL; m++)
+#pragma unroll
+                        for (int c = 0; c < 4; c++) d[c] = d[c] + __shfl_down_sync(kFull, p[c], 2 * m, LPR);
+                    float a[4];
+#pragma unroll
+                    for (int c = 0; c < 4; c++) a[c] = d[c] + __shfl_down_sync(kFull, d[c], 1, LPR);  // d_i + d_{i+4}
+                    dot = (a[0] + a[2]) + (a[1] + a[3]);
+                }
+                if (ok && qa) {
+#pragma unroll
+                    for (int c = 0; c < 4; c++) tile[(4 * q + c) * TS + j] = t[c];
+                }
+                if (ok && q == 0) {
+                    tile[K * TS + j] = dot;                                  // dot(tmp, tmp)            :78
+                    tile[(K + 1) * TS + j] = wv[it] * xv[it];                // W[fid] * X               :74
+                }
+            }
+            __syncwarp();
+            // ---- phase 2: features base .. base+cnt in order, four per LDS.128
+            const int cnt = min(NB, n - base);
+            const int col = lane < K ? lane : 0;
+            for (int j0 = 0; j0 < cnt; j0 += 4) {
+                const float4 t4 = *reinterpret_cast<const float4*>(tile + col * TS + j0);
+                const float4 d4 = *reinterpret_cast<const float4*>(tile + K * TS + j0);
+                const float4 w4 = *reinterpret_cast<const float4*>(tile + (K + 1) * TS + j0);
+                const float tt[4] = {t4.x, t4.y, t4.z, t4.w}, dd[4] = {d4.x, d4.y, d4.z, d4.w}, ww[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    if (j0 + u < cnt) {
+                        s = s + tt[u];                                      // sumVX += tmp             :77
+                        if (NFM) {
+                            z = z + tt[u] * (tt[u] * -0.5f);                // train_nfm_algo.cpp:87-91
+                            fm = fm + ww[u];
+                        } else {
+                            fm = fm + ww[u];                                // fm_pred += W[fid] * X    :74
+                            fm = fm - 0.5f * dd[u];                         // fm_pred -= 0.5 * dot     :78
+                        }
+                    }
+                }
+            }
+            __syncwarp();
+        }
+        if (lane < K) sumvx[(size_t)r * K + lane] = s;
+        if (NFM) {
+            if (lane < K) z_out[(size_t)(r - rb) * K + lane] = z + s * (s * 0.5f);
+            if (lane == 0) wide_out[r] = fm;
+        } else {
+            if (lane < K) tile[lane] = s;
+            __syncwarp();
+            if (lane == 0) {
+                float sv[K];
+#pragma unroll
+                for (int c = 0; c < K; c++) sv[c] = tile[c];
+                const float dot = avx_dot_regs<K>(sv);
+                fm = (float)((double)fm + 0.5 * (double)dot);  // :82
+                const float pr = ref_sigmoid(fm);              // :84
+                pred[r] = pr;
+                if (do_stats) loss_terms(pr, label[r], loss, correct);
+            }
+        }
+    }
+    if (!NFM && do_stats) publish_stats(loss, correct, partial, done, out_slot, false);
+}
+
 template <int K>
 static int fwd_go(lctr_ctx* c, Slot& s, bool nfm, int64_t rb, int64_t re, double* out_slot, int stats, const int64_t* hdr) {
     const unsigned grid = (unsigned)((re - rb + 7) / 8);
-    const size_t smem = (size_t)8 * 64 * (K + 4) * sizeof(float);
+    constexpr bool kCoalesced = (K % 8 == 0) && K <= 32;
+    static const bool want_coalesced = !(getenv("LCTR_FWD_COALESCED") && atoi(getenv("LCTR_FWD_COALESCED")) == 0);
+    const bool co = kCoalesced && want_coalesced;
+    const size_t smem = co ? (size_t)8 * (K + 2) * 68 * sizeof(float) : (size_t)8 * 64 * (K + 4) * sizeof(float);
 #define FWD_GO(HV, NF)                                                                                         \
     do {                                                                                                       \
-        auto kern = fm_forward_kernel<K, HV, NF>;                                                              \
+        auto kern = co ? fm_forward_coalesced_kernel<kCoalesced ? K : 8, HV, NF> : fm_forward_kernel<K, HV, NF>; \
         if (smem > 48 * 1024) LCTR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
         kern<<<grid, 256, smem, c->stream>>>(s.row_ptr, s.fid, s.val, s.label, c->cW, c->cV, s.pred, s.sumvx, c->z, \
                                              s.wide, rb, re, c->stat_partial, c->stat_done, out_slot, stats, hdr);  \
