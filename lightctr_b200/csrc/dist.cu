@@ -77,7 +77,11 @@ __global__ void mark_kernel(const uint32_t* __restrict__ fid, int64_t b, int64_t
         mark[fid[i]] = 1;
 }
 
-// each unique row is read ONCE from its owner (peer or local shard) into the local cache; G rows per warp step
+// each unique row is read ONCE from its owner (peer or local shard) into the local cache.  LPR lanes cover a row with
+// 16 B loads (slices q, q+LPR, ...: up to kMaxSl per lane), G = 32/LPR rows per warp step, and kPullU steps are kept in
+// flight before the first store so that one NVLink round trip covers G*kPullU rows.
+constexpr int kMaxSl = 4;
+constexpr int kPullU = 4;
 __global__ void __launch_bounds__(256)
 pull_kernel(const uint32_t* __restrict__ uniq, const unsigned int* __restrict__ n_uniq, PeerPtrs P, int shift,
             unsigned mask, int rowlen, float* __restrict__ cW, float* __restrict__ cV) {
@@ -90,7 +94,41 @@ pull_kernel(const uint32_t* __restrict__ uniq, const unsigned int* __restrict__ 
     int lpr = 1;
     while (lpr < slices && lpr < 32) lpr <<= 1;
     const int G = 32 / lpr, q = lane % lpr, g = lane / lpr;
-    for (unsigned b0 = warp * G; b0 < n; b0 += nwarps * G) {
+    if (vec == 4 && slices <= lpr * kMaxSl) {
+        for (unsigned b0 = warp * (G * kPullU); b0 < n; b0 += nwarps * (G * kPullU)) {
+            uint32_t f[kPullU];
+            float4 v[kPullU][kMaxSl];
+            float w[kPullU];
+#pragma unroll
+            for (int u = 0; u < kPullU; u++) {
+                const unsigned idx = b0 + u * G + g;
+                f[u] = idx < n ? uniq[idx] : 0xffffffffu;
+                if (f[u] == 0xffffffffu) continue;
+                const unsigned o = f[u] & mask;
+                const size_t l = f[u] >> shift;
+                const float* src = P.V[o] + l * (size_t)rowlen;
+#pragma unroll
+                for (int i = 0; i < kMaxSl; i++) {
+                    const int sl = q + i * lpr;
+                    if (sl < slices) v[u][i] = *reinterpret_cast<const float4*>(src + 4 * sl);
+                }
+                if (q == 0) w[u] = P.W[o][l];
+            }
+#pragma unroll
+            for (int u = 0; u < kPullU; u++) {
+                if (f[u] == 0xffffffffu) continue;
+                float* dst = cV + (size_t)f[u] * rowlen;
+#pragma unroll
+                for (int i = 0; i < kMaxSl; i++) {
+                    const int sl = q + i * lpr;
+                    if (sl < slices) *reinterpret_cast<float4*>(dst + 4 * sl) = v[u][i];
+                }
+                if (q == 0) cW[f[u]] = w[u];
+            }
+        }
+        return;
+    }
+    for (unsigned b0 = warp * G; b0 < n; b0 += nwarps * G) {  // generic fallback (odd row lengths)
         const unsigned idx = b0 + g;
         if (idx >= n) continue;
         const uint32_t f = uniq[idx];
@@ -98,43 +136,61 @@ pull_kernel(const uint32_t* __restrict__ uniq, const unsigned int* __restrict__ 
         const size_t l = f >> shift;
         const float* src = P.V[o] + l * (size_t)rowlen;
         float* dst = cV + (size_t)f * rowlen;
-        if (vec == 4) {
-            for (int sl = q; sl < slices; sl += lpr)
-                *reinterpret_cast<float4*>(dst + 4 * sl) = *reinterpret_cast<const float4*>(src + 4 * sl);
-        } else {
-            for (int sl = q; sl < slices; sl += lpr) dst[sl] = src[sl];
-        }
+        for (int sl = q * vec; sl < rowlen; sl += lpr * vec)
+            for (int c = 0; c < vec; c++) dst[sl + c] = src[sl + c];
         if (q == 0) cW[f] = P.W[o][l];
     }
 }
 
-// record layout (floats): [0] fid bits, [1] gW, [2 .. 2+rowlen) gV ; records are padded to a multiple of 4 floats
+// record layout (floats): [0] fid bits, [1] gW, [2 .. 2+rowlen) gV ; records are padded to a multiple of 4 floats.
+// Slots are reserved per CTA chunk of kPushChunk records: a shared histogram over the <= 8 destinations, ONE global
+// atomicAdd per destination per chunk (the per-record atomics of a naive version serialise on 8 counters), ranks by
+// a short scan over the chunk; then each warp copies its records with the row stores fully coalesced.
+constexpr int kPushChunk = 64;
 __global__ void __launch_bounds__(256)
 push_kernel(const uint32_t* __restrict__ uniq, const unsigned int* __restrict__ n_uniq, PeerPtrs P, int me, int shift,
             unsigned mask, int rowlen, int rec_floats, size_t region_bytes, unsigned rec_cap,
             float* __restrict__ cgW, float* __restrict__ cgV, unsigned int* __restrict__ push_cnt) {
+    __shared__ uint32_t s_f[kPushChunk];
+    __shared__ unsigned s_slot[kPushChunk];
+    __shared__ unsigned s_hist[kMaxWorld], s_base[kMaxWorld];
     const unsigned n = *n_uniq;
-    const int lane = threadIdx.x & 31;
-    const unsigned warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const unsigned nwarps = gridDim.x * (blockDim.x >> 5);
-    for (unsigned idx = warp; idx < n; idx += nwarps) {  // one warp per record: row stores are contiguous
-        const uint32_t f = uniq[idx];
-        const unsigned o = f & mask;
-        unsigned slot = 0;
-        if (lane == 0) slot = atomicAdd(&push_cnt[o], 1u);
-        slot = __shfl_sync(kFull, slot, 0);
-        if (slot >= rec_cap) continue;  // capacity is sized from max_nnz; overflow is reported by the host
-        float* rec = reinterpret_cast<float*>(P.mail[o] + (size_t)me * region_bytes + 64) + (size_t)slot * rec_floats;
-        float* gsrc = cgV + (size_t)f * rowlen;
-        if (lane == 0) {
-            rec[0] = __uint_as_float(f);
-            rec[1] = cgW[f];
-            cgW[f] = 0.f;
+    const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
+    for (unsigned c0 = blockIdx.x * kPushChunk; c0 < n; c0 += gridDim.x * kPushChunk) {
+        if (t < kMaxWorld) s_hist[t] = 0;
+        __syncthreads();
+        uint32_t f = 0xffffffffu;
+        if (t < kPushChunk && c0 + t < n) { f = uniq[c0 + t]; atomicAdd(&s_hist[f & mask], 1u); }
+        if (t < kPushChunk) s_f[t] = f;
+        __syncthreads();
+        if (t < kMaxWorld && s_hist[t]) s_base[t] = atomicAdd(&push_cnt[t], s_hist[t]);
+        __syncthreads();
+        if (t < kPushChunk && f != 0xffffffffu) {
+            const unsigned o = f & mask;
+            unsigned rank = 0;
+            for (int j = 0; j < t; j++) rank += (s_f[j] != 0xffffffffu && (s_f[j] & mask) == o) ? 1u : 0u;
+            s_slot[t] = s_base[o] + rank;
         }
-        for (int i = lane; i < rowlen; i += 32) {
-            rec[2 + i] = gsrc[i];
-            gsrc[i] = 0.f;
+        __syncthreads();
+        for (int rI = wid; rI < kPushChunk; rI += (int)(blockDim.x >> 5)) {
+            const uint32_t ff = s_f[rI];
+            if (ff == 0xffffffffu) continue;
+            const unsigned slot = s_slot[rI];
+            if (slot >= rec_cap) continue;
+            const unsigned o = ff & mask;
+            float* rec = reinterpret_cast<float*>(P.mail[o] + (size_t)me * region_bytes + 64) + (size_t)slot * rec_floats;
+            float* gsrc = cgV + (size_t)ff * rowlen;
+            if (lane == 0) {
+                rec[0] = __uint_as_float(ff);
+                rec[1] = cgW[ff];
+                cgW[ff] = 0.f;
+            }
+            for (int i = lane; i < rowlen; i += 32) {
+                rec[2 + i] = gsrc[i];
+                gsrc[i] = 0.f;
+            }
         }
+        __syncthreads();
     }
     __threadfence_system();
 }
@@ -298,10 +354,13 @@ int dist_alloc(lctr_ctx* c) {
     LCTR_CUDA(cudaMemsetAsync(d->n_uniq, 0, sizeof(unsigned int), c->stream));
     LCTR_CUDA(cudaMemsetAsync(d->push_cnt, 0, kMaxWorld * sizeof(unsigned int), c->stream));
     LCTR_CUDA(cudaMemsetAsync(d->scratch_done, 0, sizeof(unsigned int), c->stream));
+    // push variant: narrow rows (FM) go straight into the owner's update_g with peer REDs; wide rows (FFM) are cheaper
+    // as plain peer stores into a mailbox + owner-side merge (measured on C5: 12.8 vs 14.2 ms per step)
     const char* pm0 = getenv("LCTR_DIST_PUSH");
-    d->use_mailbox = pm0 && strcmp(pm0, "mailbox") == 0;
+    d->use_mailbox = pm0 ? strcmp(pm0, "mailbox") == 0 : c->rowlen >= 64;
     d->rec_floats = ((2 + c->rowlen) + 3) / 4 * 4;
-    d->rec_cap = d->use_mailbox ? cap : 0;  // records one source may send to one owner per step (<= its unique ids)
+    // records one source may send to one owner per step: at most the owner's shard size (distinct fids)
+    d->rec_cap = d->use_mailbox ? std::min<size_t>(cap, c->Fl) : 0;
     d->region_bytes = (64 + d->rec_cap * d->rec_floats * sizeof(float) + 255) / 256 * 256;
     LCTR_CUDA(cudaMalloc((void**)&d->mailbox, d->region_bytes * R));
     LCTR_CUDA(cudaMemsetAsync(d->mailbox, 0, d->region_bytes * R, c->stream));
@@ -314,8 +373,6 @@ int dist_alloc(lctr_ctx* c) {
     d->peers2.gW[d->rank] = c->gW; d->peers2.gV[d->rank] = c->gV; d->peers2.touched[d->rank] = c->touched;
     d->peers2.bar[d->rank] = d->bar;
     LCTR_CUDA(cudaMalloc((void**)&d->d_peers2, sizeof(PeerPtrs2)));
-    const char* pm = getenv("LCTR_DIST_PUSH");
-    d->use_mailbox = pm && strcmp(pm, "mailbox") == 0;
     return 0;
 }
 
