@@ -29,7 +29,7 @@ WORKLOADS = {
     "ffm_c3": dict(model="ffm", k=4, F=1_000_000, batch=8192, opt="ftrl",
                    desc="FFM k=4, 39 fields, 1M features, batch 8192, FTRL"),
     "nfm_c4": dict(model="nfm", k=16, F=1_000_000, batch=16384, opt="adagrad", hidden=[256, 128, 64], nb=4,
-                   desc="NFM k=16 + MLP [256,128,64] (fp32 reference-order MLP), 1M features, batch 16384, Adagrad"),
+                   desc="NFM k=16 + MLP [256,128,64], 1M features, batch 16384, Adagrad"),
     "ffm_c5": dict(model="ffm", k=8, F=10_000_000, batch=65536, opt="adagrad", nb=2,
                    desc="FFM k=8, 39 fields, 10M features, batch 65536 per GPU, Adagrad"),
 }
@@ -86,6 +86,15 @@ def measured_peaks():
         d = json.load(open(p))
         return d.get("hbm_gbs", 6650.0), "measured (MEASURED_PEAKS.json)"
     return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def measured_tensor_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        if "bf16_tflops" in d:
+            return d["bf16_tflops"], "measured burst cuBLAS bf16 (MEASURED_PEAKS.json)"
+    return 1600.0, "fallback (B200_PROFILING.md)"
 
 
 def make_batches(wl, n_batches, seed_offset=0):
@@ -204,8 +213,11 @@ def main():
     # LCTR_BENCH_BACKWARD=grouped selects the feature-grouped backward of csc.cu; its per-batch grouping kernels run
     # at upload, i.e. OUTSIDE the device-timed `value` region but INSIDE the end-to-end region.
     det = 2 if (world == 1 and wl["model"] == "fm" and os.environ.get("LCTR_BENCH_BACKWARD", "red") == "grouped") else 0
+    # NFM dense layers: bf16 tensor-core mode (config C4) unless LCTR_BENCH_MLP=fp32 asks for the reference-order fp32 MLP
+    mlp_bf16 = wl["model"] == "nfm" and os.environ.get("LCTR_BENCH_MLP", "bf16") == "bf16"
     ctx = capi.Context(model, F, k, Fc, optimizer=opt, device=local_rank, deterministic=det, rank=rank, world=world,
-                       minibatch_size=(world * B if world > 1 else 0), max_nnz=B * 120, hidden=wl.get("hidden", ()))
+                       minibatch_size=(world * B if world > 1 else 0), max_nnz=B * 120, hidden=wl.get("hidden", ()),
+                       mlp_precision=capi.MLP_BF16 if mlp_bf16 else capi.MLP_FP32)
     if wl["model"] == "nfm":  # FC chain initialised like fullyconnLayer.h:48-54 (U(-0.5,0.5), bias 0), masks all-ones
         rng0 = np.random.default_rng(99)
         dims = [k] + list(wl["hidden"]) + [1]
@@ -323,12 +335,23 @@ def main():
             roof = {"bound": "hbm", "kernel": dom[0], "achieved": achieved, "peak": peak, "unit": "GB/s",
                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": bps * B, "kernel_ms": ms / cnt}
+    if dom[0] == "mlp" and cnt:  # dense layers: fwd + dX + dW = 6 flops per weight per sample
+        dims = [k] + list(wl["hidden"]) + [1]
+        flops = 6.0 * sum(dims[i] * dims[i + 1] for i in range(len(dims) - 1)) * B
+        tpeak, tsrc = measured_tensor_peak()
+        achieved = flops / (ms / cnt * 1e-3) / 1e12
+        roof = {"bound": "tensor", "kernel": "mlp (nfm_mlp_fused_kernel + dense Adagrad)", "achieved": achieved, "peak": tpeak,
+                "unit": "TFLOP/s", "frac": achieved / tpeak, "traffic": None, "peak_source": tsrc,
+                "algorithmic_flops_per_launch": flops, "kernel_ms": ms / cnt}
     kernels = {name: {"ms": v[0] / max(v[1], 1), "launches": v[1]} for name, v in prof.items()}
     line = {"metric": metric, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "vs_baseline": None, "dtype": "bf16 dense layers (fp32 accumulate, fp32 masters) + f32 embeddings" if mlp_bf16 else "f32",
+            "data": "synthetic",
             "config": {"workload": wl["desc"], "l2": "flushed between timed steps (256 MB write)", "batch_per_gpu": B,
                        "global_batch": world * B, "nnz_per_row": n,
+                       **({"mlp": "bf16 mma, fused fwd+bwd per 128-sample tile" if mlp_bf16 else "fp32 reference-order"}
+                          if wl["model"] == "nfm" else {}),
                        "backward": ("feature-grouped on device + fused updater (csc.cu)" if det == 2
                                     else "RED scatter + sparse apply"),
                        "parallelism": "1 GPU" if world == 1 else

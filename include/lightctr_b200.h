@@ -136,6 +136,10 @@ int lctr_download_pred(lctr_ctx* ctx, int slot, float* pred);
 int lctr_mlp_upload(lctr_ctx* ctx, int layer, const float* weight, const float* bias);
 int lctr_mlp_download(lctr_ctx* ctx, int layer, float* weight, float* bias);
 int lctr_mlp_set_mask(lctr_ctx* ctx, int layer, const float* mask);
+/* Fully_Conn_Layer::weightDelta / biasDelta (fullyconnLayer.h:165-179) as they stand in the fused dense-gradient
+ * buffer; zero after a step unless the process runs with LCTR_MLP_SKIP_UPDATE=1 (test hook: gradients are left in
+ * place and the Adagrad update of the dense layers is skipped). */
+int lctr_mlp_download_grad(lctr_ctx* ctx, int layer, float* dweight, float* dbias);
 
 /* ---- multi-GPU (replaces distribut/ring_collect.h + pull.h/push.h) ------------ */
 /* Exchange of CUDA IPC handles is done by the caller's process group (torch.distributed / MPI):

@@ -24,7 +24,7 @@ SYMBOLS = [
     "lctr_last_error", "lctr_abi_version", "lctr_create", "lctr_destroy", "lctr_sync", "lctr_upload_params",
     "lctr_download_params", "lctr_fill_params", "lctr_download_opt_state", "lctr_upload_opt_state", "lctr_upload_batch",
     "lctr_train_step", "lctr_train_batch", "lctr_train_batch_async", "lctr_wait", "lctr_predict", "lctr_download_sumvx", "lctr_download_pred",
-    "lctr_mlp_upload", "lctr_mlp_download", "lctr_mlp_set_mask", "lctr_ipc_export", "lctr_ipc_import",
+    "lctr_mlp_upload", "lctr_mlp_download", "lctr_mlp_set_mask", "lctr_mlp_download_grad", "lctr_ipc_export", "lctr_ipc_import",
     "lctr_dense_grad_buffer", "lctr_load_libffm", "lctr_free_dataset", "lctr_launch_count", "lctr_stream", "lctr_profile", "lctr_profile_read",
 ]
 
@@ -80,6 +80,7 @@ def load_library():
     L.lctr_mlp_upload.argtypes = [vp, C.c_int, f32p, f32p]
     L.lctr_mlp_download.argtypes = [vp, C.c_int, f32p, f32p]
     L.lctr_mlp_set_mask.argtypes = [vp, C.c_int, f32p]
+    L.lctr_mlp_download_grad.argtypes = [vp, C.c_int, f32p, f32p]
     L.lctr_ipc_export.argtypes = [vp, vp, C.c_size_t, C.POINTER(C.c_size_t)]
     L.lctr_ipc_import.argtypes = [vp, vp, C.c_size_t]
     L.lctr_dense_grad_buffer.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_size_t)]
@@ -273,6 +274,11 @@ class Context:
     def mlp_download(self, layer, n_in, n_out):
         w, b = np.empty(n_in * n_out, np.float32), np.empty(n_out, np.float32)
         _chk(self.L.lctr_mlp_download(self.h, layer, w.ctypes.data, b.ctypes.data))
+        return w, b
+
+    def mlp_download_grad(self, layer, n_in, n_out):
+        w, b = np.empty(n_in * n_out, np.float32), np.empty(n_out, np.float32)
+        _chk(self.L.lctr_mlp_download_grad(self.h, layer, w.ctypes.data, b.ctypes.data))
         return w, b
 
     def mlp_set_mask(self, layer, mask):

@@ -92,6 +92,7 @@ struct MlpLayer {
     float *acc_w = nullptr, *acc_b = nullptr;           // Adagrad state
     float* act = nullptr;                               // [B][out] activations (post-activation for hidden layers)
     float* delta = nullptr;                             // [B][out] dL/d(pre-activation)
+    void* w16 = nullptr;                                // bf16 copy of w (tensor-core mode, hidden layers)
 };
 
 }  // namespace lctr
@@ -129,6 +130,10 @@ struct lctr_ctx {
     float *z = nullptr, *dz = nullptr;  // [B][k] NFM bi-interaction output and its gradient
     float* mlp_out = nullptr;           // [B]
     size_t mlp_cap_rows = 0;
+    int mlp_tm = 0;             // bf16 mode: samples per CTA tile (128 or 64)
+    size_t mlp_smem = 0;        // bf16 mode: dynamic shared memory per CTA
+    int mlp_has_mask = 0;       // any dropout mask entry == 0
+    int mlp_skip_update = 0;    // LCTR_MLP_SKIP_UPDATE=1: leave the dense gradients in place (tests read them)
     int sm_count = 148;
     int64_t launches = 0;
     void* csc_scratch = nullptr;  // csc.cu: dense count / offset arrays of the device-side grouping
@@ -265,6 +270,9 @@ __global__ void compact_touched_kernel(uint8_t* touched, size_t F, uint32_t* lis
 int mlp_alloc(lctr_ctx* c);
 int mlp_free(lctr_ctx* c);
 int mlp_reserve(lctr_ctx* c, int64_t rows);
+int mlp_bf16_prepare(lctr_ctx* c);
+int mlp_bf16_refresh(lctr_ctx* c, int layer);
+int launch_nfm_mlp_bf16(lctr_ctx* c, Slot& s, int64_t rb, int64_t re, int64_t rows_divisor);
 int launch_nfm_mlp(lctr_ctx* c, Slot& s, int64_t rb, int64_t re, int64_t rows_divisor);
 
 }  // namespace lctr

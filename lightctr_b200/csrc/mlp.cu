@@ -173,6 +173,9 @@ int mlp_alloc(lctr_ctx* c) {
         L.dw = c->dense_grad + off; off += nw;   // registerGradient order: weightDelta then biasDelta (fullyconnLayer.h:69-75)
         L.db = c->dense_grad + off; off += L.out;
     }
+    const char* sk = getenv("LCTR_MLP_SKIP_UPDATE");
+    c->mlp_skip_update = sk && sk[0] == '1';
+    if (cf.mlp_precision == LCTR_MLP_BF16) return mlp_bf16_prepare(c);
     return 0;
 }
 
@@ -181,7 +184,7 @@ int mlp_free(lctr_ctx* c) {
         MlpLayer& L = c->layers[l];
         if (L.w) cudaFree(L.w); if (L.b) cudaFree(L.b); if (L.mask) cudaFree(L.mask);
         if (L.acc_w) cudaFree(L.acc_w); if (L.acc_b) cudaFree(L.acc_b);
-        if (L.act) cudaFree(L.act); if (L.delta) cudaFree(L.delta);
+        if (L.act) cudaFree(L.act); if (L.delta) cudaFree(L.delta); if (L.w16) cudaFree(L.w16);
         L = MlpLayer();
     }
     if (c->dense_grad) cudaFree(c->dense_grad);
@@ -200,7 +203,7 @@ int mlp_reserve(lctr_ctx* c, int64_t rows) {
     LCTR_CUDA(cudaMalloc((void**)&c->z, cap * k * sizeof(float)));
     LCTR_CUDA(cudaMalloc((void**)&c->dz, cap * k * sizeof(float)));
     LCTR_CUDA(cudaMalloc((void**)&c->mlp_out, cap * sizeof(float)));
-    for (int l = 0; l < c->n_layers; l++) {
+    for (int l = 0; l < c->n_layers && c->cfg.mlp_precision == LCTR_MLP_FP32; l++) {  // bf16 mode keeps activations on chip
         MlpLayer& L = c->layers[l];
         if (L.act) cudaFree(L.act); if (L.delta) cudaFree(L.delta);
         LCTR_CUDA(cudaMalloc((void**)&L.act, cap * L.out * sizeof(float)));
@@ -214,8 +217,8 @@ int mlp_reserve(lctr_ctx* c, int64_t rows) {
 int launch_nfm_mlp(lctr_ctx* c, Slot& s, int64_t rb, int64_t re, int64_t rows_divisor) {
     const int B = (int)(re - rb);
     const int nl = c->n_layers;
-    LCTR_CHECK(c->cfg.mlp_precision == LCTR_MLP_FP32, "mlp_precision=%d: only the fp32 reference-order MLP is built",
-               c->cfg.mlp_precision);
+    if (c->cfg.mlp_precision == LCTR_MLP_BF16) return launch_nfm_mlp_bf16(c, s, rb, re, rows_divisor);
+    LCTR_CHECK(c->cfg.mlp_precision == LCTR_MLP_FP32, "mlp_precision=%d unknown", c->cfg.mlp_precision);
     auto blocks = [](int64_t n) { return (unsigned)((n + 255) / 256); };
     ProfScope prof(c, PROF_MLP);
     // ---- forward
@@ -271,6 +274,15 @@ int lctr_mlp_upload(lctr_ctx* c, int layer, const float* weight, const float* bi
     MlpLayer& L = c->layers[layer];
     if (weight) LCTR_CUDA(cudaMemcpyAsync(L.w, weight, (size_t)L.out * L.in * sizeof(float), cudaMemcpyHostToDevice, c->stream));
     if (bias) LCTR_CUDA(cudaMemcpyAsync(L.b, bias, (size_t)L.out * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    if (weight && mlp_bf16_refresh(c, layer)) return 1;
+    LCTR_CUDA(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+int lctr_mlp_download_grad(lctr_ctx* c, int layer, float* dweight, float* dbias) {
+    LCTR_CHECK(c && layer >= 0 && layer < c->n_layers, "mlp layer %d out of range", layer);
+    MlpLayer& L = c->layers[layer];
+    if (dweight) LCTR_CUDA(cudaMemcpyAsync(dweight, L.dw, (size_t)L.out * L.in * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    if (dbias) LCTR_CUDA(cudaMemcpyAsync(dbias, L.db, (size_t)L.out * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
     LCTR_CUDA(cudaStreamSynchronize(c->stream));
     return 0;
 }
@@ -287,6 +299,7 @@ int lctr_mlp_set_mask(lctr_ctx* c, int layer, const float* mask) {
     MlpLayer& L = c->layers[layer];
     LCTR_CUDA(cudaMemcpyAsync(L.mask, mask, (size_t)L.out * sizeof(float), cudaMemcpyHostToDevice, c->stream));
     LCTR_CUDA(cudaStreamSynchronize(c->stream));
+    for (int j = 0; j < L.out; j++) if (mask[j] == 0.f) c->mlp_has_mask = 1;  // sticky: the masked code path stays on
     return 0;
 }
 }
