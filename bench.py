@@ -167,12 +167,18 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--batch", type=int, default=0, help="override the workload's rows per GPU per step (sweeps; "
+                    "the headline configs are the defaults)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     wname = args.workload or "fm_c2"
-    wl = WORKLOADS[wname]
+    wl = dict(WORKLOADS[wname])
+    if args.batch:
+        wl["desc"] = wl["desc"].replace("batch %d" % wl["batch"], "batch %d (--batch override)" % args.batch)
+        wl["batch"] = args.batch
+        wl["nb"] = min(wl.get("nb", 8), max(2, (1 << 21) // args.batch))
     metric = "samples/sec (device-timed) %s train step on Criteo-shape" % wl["model"].upper()
 
     if args.impl == "reference":
@@ -212,7 +218,13 @@ def main():
     # backward strategy: RED scatter + sparse apply by default (every per-batch kernel is inside the timed region).
     # LCTR_BENCH_BACKWARD=grouped selects the feature-grouped backward of csc.cu; its per-batch grouping kernels run
     # at upload, i.e. OUTSIDE the device-timed `value` region but INSIDE the end-to-end region.
-    det = 2 if (world == 1 and wl["model"] == "fm" and os.environ.get("LCTR_BENCH_BACKWARD", "red") == "grouped") else 0
+    # For FFM, grouped selects the atomic-free step of ffm_grouped.cu; its grouping kernels are then rebuilt INSIDE every
+    # timed step (LCTR_CSC_IN_STEP=1), so `value` pays for them.  Measured r01: RED path 13.6M (C3) / 9.9M (C5)
+    # samples/s vs grouped 9.1M / 8.2M, so RED stays the default.
+    bw_default = "red"
+    det = 2 if (world == 1 and wl["model"] in ("fm", "ffm") and os.environ.get("LCTR_BENCH_BACKWARD", bw_default) == "grouped") else 0
+    if det == 2 and wl["model"] == "ffm":
+        os.environ["LCTR_CSC_IN_STEP"] = "1"
     # NFM dense layers: bf16 tensor-core mode (config C4) unless LCTR_BENCH_MLP=fp32 asks for the reference-order fp32 MLP
     mlp_bf16 = wl["model"] == "nfm" and os.environ.get("LCTR_BENCH_MLP", "bf16") == "bf16"
     ctx = capi.Context(model, F, k, Fc, optimizer=opt, device=local_rank, deterministic=det, rank=rank, world=world,
@@ -325,7 +337,10 @@ def main():
         bytes_per_sample = {"fm_forward": n * (4 * k + 12) + 8, "fm_backward_red": n * (4 * k + 12) + 8,
                             "fm_backward_csc": n * (4 * k + 12) + 8, "apply": None, "mlp": None}
     else:
-        bytes_per_sample = {"ffm_fused": n * (Fc * k * 4 + 12)}
+        # fused: one row gather per entry (+ the sample's Fc x Fc x k tile written once in grouped mode);
+        # grouped backward: one contiguous tile row per entry
+        bytes_per_sample = {"ffm_fused": n * (Fc * k * 4 + 12) + (Fc * Fc * k * 4 if det == 2 else 0),
+                            "fm_backward_csc": n * (Fc * k * 4 + 10)}
     roof = None
     if dom[0] is not None:
         ms, cnt = dom[1]
@@ -352,8 +367,9 @@ def main():
                        "global_batch": world * B, "nnz_per_row": n,
                        **({"mlp": "bf16 mma, fused fwd+bwd per 128-sample tile" if mlp_bf16 else "fp32 reference-order"}
                           if wl["model"] == "nfm" else {}),
-                       "backward": ("feature-grouped on device + fused updater (csc.cu)" if det == 2
-                                    else "RED scatter + sparse apply"),
+                       "backward": (("feature-grouped on device + fused updater (csc.cu)" if wl["model"] == "fm" else
+                                     "feature-grouped, atomic-free, fused updater (ffm_grouped.cu); grouping kernels inside the timed step")
+                                    if det == 2 else "RED scatter + sparse apply"),
                        "parallelism": "1 GPU" if world == 1 else
                        "dp%d rows + owner-sharded tables (fid mod %d), unique-id pull/push over NVLink peer memory" % (world, world)},
             "clocks": clocks, "gpu_launches": int(launches), "kernels_ms": kernels,

@@ -286,7 +286,7 @@ class Context:
         _chk(self.L.lctr_mlp_set_mask(self.h, layer, m.ctypes.data))
 
     PROF_NAMES = ["fm_forward", "fm_backward_red", "apply", "ffm_fused", "fm_backward_csc", "mlp", "dist_mark", "dist_compact",
-                  "dist_pull", "dist_push", "dist_barrier0", "dist_merge", "dist_barrier1", "", "", ""]
+                  "dist_pull", "dist_push", "dist_barrier0", "dist_merge", "dist_barrier1", "csc_build", "", ""]
 
     def profile(self, enable=True):
         _chk(self.L.lctr_profile(self.h, 1 if enable else 0))

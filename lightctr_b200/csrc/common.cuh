@@ -32,7 +32,7 @@ void set_error(const char* fmt, ...);
 
 constexpr int kNumSlots = 8;
 constexpr int kNumProf = 16;  // per-kernel timing buckets
-enum { PROF_FM_FWD = 0, PROF_FM_BWD_RED = 1, PROF_APPLY = 2, PROF_FFM_FUSED = 3, PROF_FM_BWD_CSC = 4, PROF_MLP = 5, PROF_DIST_MARK = 6, PROF_DIST_COMPACT = 7, PROF_DIST_PULL = 8, PROF_DIST_PUSH = 9, PROF_DIST_BAR0 = 10, PROF_DIST_MERGE = 11, PROF_DIST_BAR1 = 12 };
+enum { PROF_FM_FWD = 0, PROF_FM_BWD_RED = 1, PROF_APPLY = 2, PROF_FFM_FUSED = 3, PROF_FM_BWD_CSC = 4, PROF_MLP = 5, PROF_DIST_MARK = 6, PROF_DIST_COMPACT = 7, PROF_DIST_PULL = 8, PROF_DIST_PUSH = 9, PROF_DIST_BAR0 = 10, PROF_DIST_MERGE = 11, PROF_DIST_BAR1 = 12, PROF_CSC_BUILD = 13 };
 constexpr int kStatRing = 64;
 constexpr unsigned kFull = 0xffffffffu;
 
@@ -57,6 +57,7 @@ struct Slot {
     uint32_t* seg_fid = nullptr;    // n_segs
     uint32_t* ent_row = nullptr;    // nnz: row index of the entry
     float* ent_x = nullptr;         // nnz (only when has_val)
+    uint16_t* ent_field = nullptr;  // nnz (FFM, device-built view only)
     std::vector<int64_t>* h_blk_seg_ptr = nullptr;
     int64_t cap_segs = 0, cap_blocks = 0, cap_ent = 0;
     // device-built feature-major view (cfg.deterministic == 2): work lists of short / long segments and
@@ -130,6 +131,10 @@ struct lctr_ctx {
     float *z = nullptr, *dz = nullptr;  // [B][k] NFM bi-interaction output and its gradient
     float* mlp_out = nullptr;           // [B]
     size_t mlp_cap_rows = 0;
+    int csc_in_step = 0;        // LCTR_CSC_IN_STEP=1: rebuild the feature-major view inside every train step (bench)
+    float* ffm_T = nullptr;     // FFM grouped step: per-sample field-pair tiles [rows][Fc][Fc][k]
+    uint16_t* ffm_cnt = nullptr; // [rows][Fc] features per field
+    size_t ffm_T_rows = 0;
     int mlp_tm = 0;             // bf16 mode: samples per CTA tile (128 or 64)
     size_t mlp_smem = 0;        // bf16 mode: dynamic shared memory per CTA
     int mlp_has_mask = 0;       // any dropout mask entry == 0
@@ -270,6 +275,11 @@ __global__ void compact_touched_kernel(uint8_t* touched, size_t F, uint32_t* lis
 int mlp_alloc(lctr_ctx* c);
 int mlp_free(lctr_ctx* c);
 int mlp_reserve(lctr_ctx* c, int64_t rows);
+bool ffm_grouped_supported(const lctr_ctx* c);
+int ffm_grouped_reserve(lctr_ctx* c, int64_t rows);
+void ffm_grouped_free(lctr_ctx* c);
+int launch_ffm_forward_tiles(lctr_ctx* c, Slot& s, int64_t rb, int64_t re);
+int launch_ffm_backward_grouped(lctr_ctx* c, Slot& s, int64_t rb, int64_t re);
 int mlp_bf16_prepare(lctr_ctx* c);
 int mlp_bf16_refresh(lctr_ctx* c, int layer);
 int launch_nfm_mlp_bf16(lctr_ctx* c, Slot& s, int64_t rb, int64_t re, int64_t rows_divisor);

@@ -175,7 +175,8 @@ csc_tile_write_kernel(const unsigned int* __restrict__ cnt, size_t F, const uint
 __global__ void __launch_bounds__(256)
 csc_fill_kernel(const int64_t* __restrict__ row_ptr, const uint32_t* __restrict__ fid, const float* __restrict__ val,
                 int64_t rows_arg, const unsigned int* __restrict__ off, unsigned int* __restrict__ cnt,
-                uint32_t* __restrict__ ent_row, float* __restrict__ ent_x, const int64_t* __restrict__ hdr) {
+                uint32_t* __restrict__ ent_row, float* __restrict__ ent_x, const int64_t* __restrict__ hdr,
+                const uint16_t* __restrict__ field, uint16_t* __restrict__ ent_field) {
     const int64_t rows = hdr ? hdr[0] : rows_arg;
     const int lane = threadIdx.x & 31;
     const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -188,6 +189,7 @@ csc_fill_kernel(const int64_t* __restrict__ row_ptr, const uint32_t* __restrict_
             const unsigned pos = off[f] + left - 1u;
             ent_row[pos] = (uint32_t)r;
             if (val) ent_x[pos] = val[i];
+            if (field) ent_field[pos] = field[i];  // FFM: the entry's field travels with it
         }
     }
 }
@@ -432,7 +434,8 @@ int csc_reserve(lctr_ctx* c, Slot& s, int64_t max_nnz) {
         LCTR_CUDA(cudaMalloc((void**)&s.short_list, (size_t)(cap + 1) * sizeof(uint32_t)));
         LCTR_CUDA(cudaMalloc((void**)&s.long_list, (size_t)(max_nnz / 8 + cap + 1) * sizeof(uint2)));
         if (s.csc_acc) cudaFree(s.csc_acc); if (s.csc_arrived) cudaFree(s.csc_arrived);
-        const size_t na = (size_t)(cap + 1) * (c->cfg.factor_cnt + 1);
+        // FM: per-segment double accumulators; FFM meets in update_g instead (ffm_grouped.cu)
+        const size_t na = c->cfg.model == LCTR_MODEL_FFM ? 8 : (size_t)(cap + 1) * (c->cfg.factor_cnt + 1);
         LCTR_CUDA(cudaMalloc((void**)&s.csc_acc, na * sizeof(double)));
         LCTR_CUDA(cudaMalloc((void**)&s.csc_arrived, (size_t)(cap + 1) * sizeof(unsigned int)));
         LCTR_CUDA(cudaMemset(s.csc_acc, 0, na * sizeof(double)));
@@ -448,10 +451,12 @@ int csc_reserve(lctr_ctx* c, Slot& s, int64_t max_nnz) {
     }
     if (max_nnz > s.cap_ent) {
         LCTR_CUDA(cudaStreamSynchronize(c->stream));
-        if (s.ent_row) cudaFree(s.ent_row); if (s.ent_x) cudaFree(s.ent_x);
+        if (s.ent_row) cudaFree(s.ent_row); if (s.ent_x) cudaFree(s.ent_x); if (s.ent_field) cudaFree(s.ent_field);
+        s.ent_field = nullptr;
         const int64_t cap = std::max<int64_t>(max_nnz, s.cap_ent + s.cap_ent / 2);
         LCTR_CUDA(cudaMalloc((void**)&s.ent_row, (size_t)(cap + 32) * sizeof(uint32_t)));
         LCTR_CUDA(cudaMalloc((void**)&s.ent_x, (size_t)(cap + 32) * sizeof(float)));
+        if (c->cfg.model == LCTR_MODEL_FFM) LCTR_CUDA(cudaMalloc((void**)&s.ent_field, (size_t)(cap + 32) * sizeof(uint16_t)));
         s.cap_ent = cap;
     }
     return 0;
@@ -478,7 +483,8 @@ int csc_build_device(lctr_ctx* c, Slot& s, cudaStream_t st, const int32_t* label
                                                            s.csc_totals);
     const unsigned gf = (unsigned)std::min<int64_t>((rows + 7) / 8, (int64_t)c->sm_count * 8);
     csc_fill_kernel<<<std::max(gf, 1u), 256, 0, st>>>(s.row_ptr, s.fid, s.has_val ? s.val : nullptr, s.rows, sc->off,
-                                                     sc->cnt, s.ent_row, s.ent_x, hdr);
+                                                     sc->cnt, s.ent_row, s.ent_x, hdr,
+                                                     s.has_field ? s.field : nullptr, s.ent_field);
     c->launches += 5;
     LCTR_CUDA(cudaGetLastError());
     s.dev_csc = true;
@@ -539,6 +545,7 @@ size_t csc_opt_params_size() { return sizeof(OptParams); }
 
 bool csc_device_supported(const lctr_ctx* c) {
     const int k = (int)c->cfg.factor_cnt;
+    if (c->cfg.model == LCTR_MODEL_FFM) return ffm_grouped_supported(c);
     return c->cfg.model == LCTR_MODEL_FM && (k == 4 || k == 8 || k == 16 || k == 32);
 }
 

@@ -45,7 +45,9 @@ __device__ __forceinline__ void vred(float* p, const VT<VEC>& v) {
     }
 }
 
-constexpr int FFM_UNROLL = 4;
+constexpr int FFM_UNROLL = 4;      // gradient phase: entries per group
+constexpr int FFM_GATHER_U = 16;   // forward gather: rows in flight per CTA
+constexpr int kFfmStage = 256;     // entries staged in shared memory per chunk
 
 // TMA bulk reduce-add of a contiguous fp32 segment from shared to global memory (one request per embedding row
 // instead of Fc*k/4 vector REDs): cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32
@@ -59,22 +61,28 @@ __device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bu
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // One CTA per sample; thread t < A owns slot t (VEC floats of the row; A = Fc*k/VEC).
-template <int VEC, bool HAS_VAL, bool TRAIN, bool BULK>
+// GROUPED (with TRAIN): the gradient phase is replaced by storing the sample's field-pair tile T (as [a][b][k], so that
+// {T[a][b]}_b -- what an entry of field a needs -- is one contiguous row) and its per-field counts; the feature-grouped
+// backward of ffm_grouped.cu consumes them.
+template <int VEC, bool HAS_VAL, bool TRAIN, bool BULK, bool GROUPED = false>
 __global__ void ffm_fused_kernel(const int64_t* __restrict__ row_ptr, const uint32_t* __restrict__ fid,
                                  const uint16_t* __restrict__ field, const float* __restrict__ val,
                                  const float* __restrict__ label, const float* __restrict__ W,
                                  const float* __restrict__ V, int Fc, int k, float* __restrict__ pred,
                                  float* __restrict__ gW, float* __restrict__ gV, uint8_t* __restrict__ touched,
                                  float l2, int64_t rb, double* partial, unsigned int* done, double* out_slot,
-                                 int do_stats) {
+                                 int do_stats, float* __restrict__ Tbuf, uint16_t* __restrict__ cntbuf) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int A = Fc * k / VEC;   // slots per row
     const int PPF = k / VEC;      // slots (parts) per field
     VT<VEC>* S = reinterpret_cast<VT<VEC>*>(smem_raw);                       // S[col b][slot a] = T[a][b]
     int* cnt = reinterpret_cast<int*>(smem_raw + (size_t)Fc * A * VEC * 4);  // features per field
     float* red = reinterpret_cast<float*>(cnt + Fc);                         // [3][32] block reduction scratch + bcast
+    uint32_t* st_f = reinterpret_cast<uint32_t*>(red + 80);                  // staged entries of the sample
+    float* st_x = reinterpret_cast<float*>(st_f + kFfmStage);
+    uint16_t* st_fl = reinterpret_cast<uint16_t*>(st_x + kFfmStage);
     // BULK: FFM_UNROLL staging rows (A slots each, 16 B aligned) for the TMA reduce of the gradient rows
-    VT<VEC>* stage = reinterpret_cast<VT<VEC>*>(smem_raw + (((size_t)Fc * A * VEC * 4 + (size_t)Fc * 4 + 80 * 4 + 15) / 16) * 16);
+    VT<VEC>* stage = reinterpret_cast<VT<VEC>*>(smem_raw + (((size_t)Fc * A * VEC * 4 + (size_t)Fc * 4 + 80 * 4 + (size_t)kFfmStage * 10 + 15) / 16) * 16);
     const int t = threadIdx.x;
     const int64_t r = rb + blockIdx.x;
     const int64_t b0 = row_ptr[r], e0 = row_ptr[r + 1];
@@ -90,39 +98,50 @@ __global__ void ffm_fused_kernel(const int64_t* __restrict__ row_ptr, const uint
     __syncthreads();
 
     // ---- phase 1: gather rows, accumulate T, wide sum, diagonal ---------------------------------
+    // The sample's (fid, field, x) triples are staged in shared memory with one coalesced load per kFfmStage entries, so
+    // that the row gathers of FFM_GATHER_U entries can be issued back to back (FFM_GATHER_U * Fc*k*4 bytes in flight per
+    // CTA) instead of waiting on a dependent index load per group.
     float wsum = 0.f, dsq = 0.f;
-    for (int64_t i = b0; i < e0; i += FFM_UNROLL) {
-        uint32_t f[FFM_UNROLL];
-        int fl[FFM_UNROLL];
-        float x[FFM_UNROLL];
-        VT<VEC> v[FFM_UNROLL];
-#pragma unroll
-        for (int u = 0; u < FFM_UNROLL; u++) {
-            const bool ok = i + u < e0;
-            f[u] = ok ? __ldg(fid + i + u) : 0u;
-            fl[u] = ok ? (int)__ldg(field + i + u) : 0;
-            x[u] = ok ? (HAS_VAL ? __ldg(val + i + u) : 1.f) : 0.f;
-            if (ok && own) v[u] = vload<VEC>(V + (size_t)f[u] * rowlen + (size_t)t * VEC);
-            else {
-#pragma unroll
-                for (int c = 0; c < VEC; c++) v[u].a[c] = 0.f;
-            }
+    for (int64_t c0 = b0; c0 < e0; c0 += kFfmStage) {
+        const int nst = (int)min((int64_t)kFfmStage, e0 - c0);
+        __syncthreads();  // previous chunk fully consumed
+        for (int i = t; i < nst; i += blockDim.x) {
+            st_f[i] = __ldg(fid + c0 + i);
+            st_fl[i] = __ldg(field + c0 + i);
+            st_x[i] = HAS_VAL ? __ldg(val + c0 + i) : 1.f;
         }
+        __syncthreads();
+        for (int i = 0; i < nst; i += FFM_GATHER_U) {
+            VT<VEC> v[FFM_GATHER_U];
+            float wv[FFM_GATHER_U];
 #pragma unroll
-        for (int u = 0; u < FFM_UNROLL; u++) {
-            if (i + u >= e0) break;
-            if (own) {
-                VT<VEC>& dst = S[fl[u] * A + t];
+            for (int u = 0; u < FFM_GATHER_U; u++) {
+                const bool ok = i + u < nst;
+                if (ok && own) v[u] = vload<VEC>(V + (size_t)st_f[i + u] * rowlen + (size_t)t * VEC);
+                else {
 #pragma unroll
-                for (int c = 0; c < VEC; c++) {
-                    const float tv = v[u].a[c] * x[u];
-                    dst.a[c] += tv;
-                    if (my_field == fl[u]) dsq += tv * tv;
+                    for (int c = 0; c < VEC; c++) v[u].a[c] = 0.f;
                 }
+                wv[u] = (ok && t == 0) ? __ldg(W + st_f[i + u]) : 0.f;
             }
-            if (t == 0) {
-                wsum += __ldg(W + f[u]) * x[u];  // fm_pred += W[fid] * X  (train_ffm_algo.cpp:60)
-                cnt[fl[u]] += 1;
+#pragma unroll
+            for (int u = 0; u < FFM_GATHER_U; u++) {
+                if (i + u >= nst) break;
+                const int flu = st_fl[i + u];
+                const float xu = st_x[i + u];
+                if (own) {
+                    VT<VEC>& dst = S[flu * A + t];
+#pragma unroll
+                    for (int c = 0; c < VEC; c++) {
+                        const float tv = v[u].a[c] * xu;
+                        dst.a[c] += tv;
+                        if (my_field == flu) dsq += tv * tv;
+                    }
+                }
+                if (t == 0) {
+                    wsum += wv[u] * xu;  // fm_pred += W[fid] * X  (train_ffm_algo.cpp:60)
+                    cnt[flu] += 1;
+                }
             }
         }
     }
@@ -165,6 +184,16 @@ __global__ void ffm_fused_kernel(const int64_t* __restrict__ row_ptr, const uint
         const float d = p - y;
         if (d != 0.f) {  // train_ffm_algo.cpp:81-83: rows with pred == label contribute nothing at all
             if (t == 0 && do_stats) loss_terms(p, y, loss, correct);
+            if (GROUPED) {
+                // ---- phase 3': T tile -> global, transposed through shared memory so that the stores are coalesced
+                const int FP = Fc * PPF;  // slots per [a] row
+                VT<VEC>* dst = reinterpret_cast<VT<VEC>*>(Tbuf) + (size_t)r * Fc * A;
+                for (int o = t; o < Fc * A; o += blockDim.x) {
+                    const int a = o / FP, rem = o - a * FP, b = rem / PPF, part = rem - b * PPF;
+                    dst[o] = S[b * A + a * PPF + part];  // T[a][b]
+                }
+                for (int b = t; b < Fc; b += blockDim.x) cntbuf[(size_t)r * Fc + b] = (uint16_t)min(cnt[b], 65535);
+            } else {
             // ---- phase 3: gradients ------------------------------------------------------------------
             const int my_cnt = own ? cnt[my_field] : 0;
             for (int64_t i = b0; i < e0; i += FFM_UNROLL) {
@@ -232,12 +261,13 @@ __global__ void ffm_fused_kernel(const int64_t* __restrict__ row_ptr, const uint
                 if (t == 0) bulk_wait_read_all();
                 __syncthreads();
             }
+            }  // !GROUPED
         }
     }
     if (TRAIN && do_stats) publish_stats(loss, correct, partial, done, out_slot, false);
 }
 
-static int ffm_launch(lctr_ctx* c, Slot& s, int64_t rb, int64_t re, bool train, bool stats) {
+static int ffm_launch(lctr_ctx* c, Slot& s, int64_t rb, int64_t re, bool train, bool stats, bool grouped = false) {
     const int k = (int)c->cfg.factor_cnt, Fc = (int)c->cfg.field_cnt;
     const int64_t rows = re - rb;
     if (rows <= 0) return 0;
@@ -250,18 +280,31 @@ static int ffm_launch(lctr_ctx* c, Slot& s, int64_t rb, int64_t re, bool train, 
     // REDs on C3 -- both hit the same L2 reduction rate (~0.75 TB/s of fp32 adds), see profiles/README.md
     static const bool use_bulk = getenv("LCTR_FFM_BULK") && atoi(getenv("LCTR_FFM_BULK")) == 1;
     const bool bulk = use_bulk && train && vec == 4 && (Fc * k * 4) % 16 == 0;
-    const size_t smem = ((size_t)Fc * A * vec * 4 + (size_t)Fc * 4 + 80 * 4 + 15) / 16 * 16 +
+    const size_t smem = ((size_t)Fc * A * vec * 4 + (size_t)Fc * 4 + 80 * 4 + (size_t)kFfmStage * 10 + 15) / 16 * 16 +
                         (bulk ? (size_t)FFM_UNROLL * A * vec * 4 : 0);
     LCTR_CHECK(smem <= 227 * 1024, "FFM field-pair tile needs %zu B shared memory (> 227 KB): Fc=%d k=%d", smem, Fc, k);
     double* out_slot = c->stats + 2 * (c->step % kStatRing);
     ProfScope prof(c, PROF_FFM_FUSED);
+    if (grouped) {
+        LCTR_CHECK(train && vec == 4 && c->ffm_T && c->ffm_cnt, "grouped FFM step needs k %% 4 == 0 and the tile buffer");
+        auto go = [&](auto kern) {
+            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            kern<<<(unsigned)rows, tpb, smem, c->stream>>>(s.row_ptr, s.fid, s.field, s.val, s.label, c->cW, c->cV, Fc, k, s.pred,
+                                                           c->cgW, c->cgV, nullptr, c->cfg.l2_reg, rb, c->stat_partial,
+                                                           c->stat_done, out_slot, stats ? 1 : 0, c->ffm_T, c->ffm_cnt);
+        };
+        if (s.has_val) go(ffm_fused_kernel<4, true, true, false, true>); else go(ffm_fused_kernel<4, false, true, false, true>);
+        c->launches++;
+        LCTR_CUDA(cudaGetLastError());
+        return 0;
+    }
 #define FFM_GO(VECN, HV, TR)                                                                                          \
     do {                                                                                                              \
         auto kern = bulk ? ffm_fused_kernel<VECN, HV, TR, (VECN == 4) && TR> : ffm_fused_kernel<VECN, HV, TR, false>; \
         LCTR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                \
         kern<<<(unsigned)rows, tpb, smem, c->stream>>>(s.row_ptr, s.fid, s.field, s.val, s.label, c->cW, c->cV, Fc, k, \
                                                        s.pred, c->cgW, c->cgV, c->cfg.world > 1 ? nullptr : c->touched, c->cfg.l2_reg, rb, \
-                                                       c->stat_partial, c->stat_done, out_slot, stats ? 1 : 0);      \
+                                                       c->stat_partial, c->stat_done, out_slot, stats ? 1 : 0, nullptr, nullptr); \
     } while (0)
 #define FFM_GO2(VECN)                                                                \
     do {                                                                             \
@@ -283,5 +326,9 @@ int launch_ffm_forward(lctr_ctx* c, Slot& s, int64_t rb, int64_t re, bool stats)
     return ffm_launch(c, s, rb, re, /*train=*/stats, stats);
 }
 int launch_ffm_backward(lctr_ctx*, Slot&, int64_t, int64_t) { return 0; }
+// forward half of the feature-grouped step: predictions, loss, and the T tiles for ffm_grouped.cu
+int launch_ffm_forward_tiles(lctr_ctx* c, Slot& s, int64_t rb, int64_t re) {
+    return ffm_launch(c, s, rb, re, true, true, true);
+}
 
 }  // namespace lctr

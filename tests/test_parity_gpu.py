@@ -276,3 +276,62 @@ def test_fm_device_grouped_k16_streamed(oracle_api):
         W, V, acc = o.W.copy(), o.V.copy(), o.accum.copy()
         assert _rel(got[i], lo) < 5e-6, (i, got[i], lo)
     assert np.max(np.abs(Wg - W)) < 1e-5 and np.max(np.abs(Vg - V)) < 1e-5
+
+
+@pytest.mark.parametrize("opt", ["adagrad", "ftrl"])
+def test_ffm_device_grouped_backward(files, oracle_api, opt):
+    """FFM with cfg.deterministic = 2 (ffm_grouped.cu): the forward stores each sample's field-pair tile, the backward
+    walks the device-built feature-major view, sums every feature's gradient rows in double precision without atomics
+    and applies the updater in the same kernel.  Same tolerances as the RED path tests above; reproducible run to run
+    (segments <= 256 entries are order-independent sums; train_sparse.csv has a few longer ones that meet through
+    fp32 REDs, so reproducibility is asserted on the loss to 1e-6, not bitwise)."""
+    from lightctr_b200 import capi
+    ds = files["tr"]
+    k, Fc = 4, 68
+    code = {"adagrad": capi.OPT_ADAGRAD, "ftrl": capi.OPT_FTRL}[opt]
+    W0, V0 = oracle_api.init_params(1, ds.feature_cnt, k, Fc)
+    o = oracle_api.FFMOracle(ds, k, W0, V0, optimizer=opt)
+    runs = []
+    for rep in range(2):
+        ctx = capi.Context(capi.MODEL_FFM, ds.feature_cnt, k, Fc, optimizer=code, deterministic=2)
+        ctx.upload_params(W0, V0)
+        ctx.upload_batch(0, ds.row_ptr, ds.fid, ds.field, None, ds.label)
+        losses = [ctx.train_step(0)[0] for _ in range(4)]
+        W, V = ctx.download_params()
+        runs.append((losses, W, V))
+        ctx.close()
+    assert np.allclose(runs[0][0], runs[1][0], rtol=1e-6)
+    tol = LOSS_RTOL if opt == "adagrad" else 5e-5
+    for e in range(4):
+        lo, _ = o.epoch()
+        assert _rel(runs[0][0][e], lo) < tol, (opt, e, runs[0][0][e], lo)
+    ptol = 1e-4 if opt == "adagrad" else 5e-3
+    assert np.max(np.abs(runs[0][1] - o.W)) < ptol and np.max(np.abs(runs[0][2] - o.V)) < ptol
+
+
+def test_ffm_grouped_matches_red_path_synth():
+    """Criteo-shaped synthetic batch (39 fields, k=8: 312-float rows, 3 float4 slots per lane), hot features with
+    thousands of entries (multi-task segments): one step of the grouped path against one step of the RED path."""
+    from lightctr_b200 import capi
+    from lightctr_b200.data import CriteoSynth
+    F, k, Fc, B = 50000, 8, 39, 4096
+    rp, fid, fld, lab = CriteoSynth(F, seed=5).batch(B)
+    rng = np.random.default_rng(8)
+    V0 = (rng.standard_normal(F * Fc * k) * 0.05).astype(np.float32)
+    W0 = (rng.standard_normal(F) * 0.01).astype(np.float32)
+    out = {}
+    for det in (0, 2):
+        ctx = capi.Context(capi.MODEL_FFM, F, k, Fc, deterministic=det)
+        ctx.upload_params(W0, V0)
+        ctx.upload_batch(0, rp, fid, fld, None, lab)
+        l1 = ctx.train_step(0)[0]
+        l2 = ctx.train_step(0)[0]
+        out[det] = (l1, l2) + ctx.download_params()
+        ctx.close()
+    assert _rel(out[2][0], out[0][0]) < 1e-6 and _rel(out[2][1], out[0][1]) < 1e-5
+    # Adagrad's first steps are sign-like where |g| is tiny; compare the update direction on coordinates that moved
+    dW0, dW2 = out[0][2] - W0, out[2][2] - W0
+    dV0, dV2 = out[0][3] - V0, out[2][3] - V0
+    assert np.array_equal(dW0 != 0, dW2 != 0) and np.array_equal(dV0 != 0, dV2 != 0)  # same touched set, bit-exact
+    assert np.max(np.abs(dV0 - dV2)) < 2e-3 and np.mean(np.abs(dV0 - dV2)) < 1e-6
+    assert np.max(np.abs(dW0 - dW2)) < 2e-3
