@@ -24,7 +24,7 @@ SYMBOLS = [
     "lctr_last_error", "lctr_abi_version", "lctr_create", "lctr_destroy", "lctr_sync", "lctr_upload_params",
     "lctr_download_params", "lctr_fill_params", "lctr_download_opt_state", "lctr_upload_opt_state", "lctr_upload_batch",
     "lctr_train_step", "lctr_train_batch", "lctr_train_batch_async", "lctr_wait", "lctr_predict", "lctr_download_sumvx", "lctr_download_pred",
-    "lctr_mlp_upload", "lctr_mlp_download", "lctr_mlp_set_mask", "lctr_mlp_download_grad", "lctr_ipc_export", "lctr_ipc_import",
+    "lctr_mlp_upload", "lctr_mlp_download", "lctr_mlp_set_mask", "lctr_mlp_download_grad", "lctr_set_dense_allreduce", "lctr_ipc_export", "lctr_ipc_import",
     "lctr_dense_grad_buffer", "lctr_load_libffm", "lctr_free_dataset", "lctr_launch_count", "lctr_stream", "lctr_profile", "lctr_profile_read",
 ]
 
@@ -81,6 +81,7 @@ def load_library():
     L.lctr_mlp_download.argtypes = [vp, C.c_int, f32p, f32p]
     L.lctr_mlp_set_mask.argtypes = [vp, C.c_int, f32p]
     L.lctr_mlp_download_grad.argtypes = [vp, C.c_int, f32p, f32p]
+    L.lctr_set_dense_allreduce.argtypes = [vp, ALLREDUCE_FN, vp]
     L.lctr_ipc_export.argtypes = [vp, vp, C.c_size_t, C.POINTER(C.c_size_t)]
     L.lctr_ipc_import.argtypes = [vp, vp, C.c_size_t]
     L.lctr_dense_grad_buffer.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_size_t)]
@@ -138,6 +139,9 @@ def load_libffm(path, field_cnt=0, feature_cnt=0):
                       np.ctypeslib.as_array(d.label, (max(lc, 1),))[:lc].copy(), d.feature_cnt, d.field_cnt)
     L.lctr_free_dataset(dp)
     return out
+
+
+ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p)
 
 
 class Context:
@@ -275,6 +279,19 @@ class Context:
         w, b = np.empty(n_in * n_out, np.float32), np.empty(n_out, np.float32)
         _chk(self.L.lctr_mlp_download(self.h, layer, w.ctypes.data, b.ctypes.data))
         return w, b
+
+    def set_dense_allreduce(self, fn):
+        """fn(dev_ptr:int, n_floats:int, cuda_stream:int) -> None: in-place SUM all-reduce enqueued on that stream."""
+        def tramp(user, buf, n, stream):
+            try:
+                fn(buf, n, stream or 0)
+                return 0
+            except Exception:  # exceptions must not cross the C boundary
+                import traceback
+                traceback.print_exc()
+                return 1
+        self._allreduce_cb = ALLREDUCE_FN(tramp)  # keep alive
+        _chk(self.L.lctr_set_dense_allreduce(self.h, self._allreduce_cb, None))
 
     def mlp_download_grad(self, layer, n_in, n_out):
         w, b = np.empty(n_in * n_out, np.float32), np.empty(n_out, np.float32)

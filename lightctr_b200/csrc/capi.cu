@@ -191,7 +191,6 @@ int lctr_create(const lctr_cfg* cfg, lctr_ctx** out) {
     c->Fl = (c->F + (size_t)c->cfg.world - 1) / (size_t)c->cfg.world;
     LCTR_CHECK(c->cfg.world == 1 || !cfg->deterministic, "lctr_create: deterministic modes are single-GPU only");
     LCTR_CHECK(cfg->deterministic >= 0 && cfg->deterministic <= 2, "lctr_create: deterministic must be 0, 1 or 2");
-    LCTR_CHECK(c->cfg.world == 1 || cfg->model != LCTR_MODEL_NFM, "lctr_create: multi-GPU NFM is not built");
     c->rowlen = cfg->model == LCTR_MODEL_FFM ? (size_t)cfg->field_cnt * cfg->factor_cnt : cfg->factor_cnt;
     cudaDeviceProp prop;
     LCTR_CUDA(cudaGetDeviceProperties(&prop, cfg->device));
@@ -469,6 +468,13 @@ int lctr_train_step(lctr_ctx* c, int slot, int64_t rb, int64_t re, float* loss_s
                 rc = launch_ffm_forward(c, s, rb, re, true) || launch_ffm_backward(c, s, rb, re) || launch_apply(c, re - rb);
             break;
         case LCTR_MODEL_NFM:
+            if (c->cfg.world > 1) {
+                // embeddings: owner-sharded pull / push like FM; dense layers: replicated, gradients all-reduced
+                rc = dist_pre_step(c, s, rb, re) || mlp_reserve(c, re - rb) || launch_fm_forward(c, s, rb, re, true, false) ||
+                     launch_nfm_mlp(c, s, rb, re, re - rb) || launch_fm_backward(c, s, rb, re, true) ||
+                     dist_post_step(c, re - rb);
+                break;
+            }
             rc = mlp_reserve(c, re - rb) || launch_fm_forward(c, s, rb, re, true, false) ||
                  launch_nfm_mlp(c, s, rb, re, re - rb);
             if (!rc) {

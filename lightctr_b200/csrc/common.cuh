@@ -135,6 +135,8 @@ struct lctr_ctx {
     float* ffm_T = nullptr;     // FFM grouped step: per-sample field-pair tiles [rows][Fc][Fc][k]
     uint16_t* ffm_cnt = nullptr; // [rows][Fc] features per field
     size_t ffm_T_rows = 0;
+    lctr_allreduce_fn dense_allreduce = nullptr;  // world > 1: sums dense_grad over the ranks on c->stream
+    void* dense_allreduce_user = nullptr;
     int mlp_tm = 0;             // bf16 mode: samples per CTA tile (128 or 64)
     size_t mlp_smem = 0;        // bf16 mode: dynamic shared memory per CTA
     int mlp_has_mask = 0;       // any dropout mask entry == 0
@@ -181,6 +183,19 @@ __device__ __forceinline__ void red_add_f32(float* addr, float v) {
     asm volatile("red.global.add.f32 [%0], %1;" ::"l"(addr), "f"(v) : "memory");
 }
 __device__ __forceinline__ float4 ldg_f4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+// Gather loads whose ISSUE ORDER matters: as volatile asm they stay where the source puts them (all gathers of a pass
+// back to back), where plain __ldg loads were sunk next to their uses -- one dependent round trip per row instead of
+// one per pass (seen in the SASS of the forward kernel, profiles/README.md).
+__device__ __forceinline__ float4 ldg_f4_pinned(const float* p) {
+    float4 v;
+    asm volatile("ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ float ldg_f32_pinned(const float* p) {
+    float v;
+    asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
+}
 
 // Sigmoid::forward, util/activations.h:65-72 (clamps at +-16; accurate expf, no fast-math)
 __device__ __forceinline__ float ref_sigmoid(float x) {
@@ -280,6 +295,7 @@ int ffm_grouped_reserve(lctr_ctx* c, int64_t rows);
 void ffm_grouped_free(lctr_ctx* c);
 int launch_ffm_forward_tiles(lctr_ctx* c, Slot& s, int64_t rb, int64_t re);
 int launch_ffm_backward_grouped(lctr_ctx* c, Slot& s, int64_t rb, int64_t re);
+int mlp_sync_dense_grad(lctr_ctx* c);
 int mlp_bf16_prepare(lctr_ctx* c);
 int mlp_bf16_refresh(lctr_ctx* c, int layer);
 int launch_nfm_mlp_bf16(lctr_ctx* c, Slot& s, int64_t rb, int64_t re, int64_t rows_divisor);

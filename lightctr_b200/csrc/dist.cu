@@ -142,7 +142,7 @@ pull_kernel(const uint32_t* __restrict__ uniq, const unsigned int* __restrict__ 
     }
 }
 
-// record layout (floats): [0] fid bits, [1] gW, [2 .. 2+rowlen) gV ; records are padded to a multiple of 4 floats.
+// record layout (floats): [0 .. rowlen) gV (16 B aligned), [rowlen] fid bits, [rowlen+1] gW ; padded to a multiple of 4.
 // Slots are reserved per CTA chunk of kPushChunk records: a shared histogram over the <= 8 destinations, ONE global
 // atomicAdd per destination per chunk (the per-record atomics of a naive version serialise on 8 counters), ranks by
 // a short scan over the chunk; then each warp copies its records with the row stores fully coalesced.
@@ -181,13 +181,32 @@ push_kernel(const uint32_t* __restrict__ uniq, const unsigned int* __restrict__ 
             float* rec = reinterpret_cast<float*>(P.mail[o] + (size_t)me * region_bytes + 64) + (size_t)slot * rec_floats;
             float* gsrc = cgV + (size_t)ff * rowlen;
             if (lane == 0) {
-                rec[0] = __uint_as_float(ff);
-                rec[1] = cgW[ff];
+                rec[rowlen] = __uint_as_float(ff);
+                rec[rowlen + 1] = cgW[ff];
                 cgW[ff] = 0.f;
             }
-            for (int i = lane; i < rowlen; i += 32) {
-                rec[2 + i] = gsrc[i];
-                gsrc[i] = 0.f;
+            if (rowlen % 4 == 0 && rowlen <= 128 * kMaxSl) {
+                // all 16 B loads of the row first, then the (posted) peer stores and the re-zeroing of update_g
+                const int slices = rowlen / 4;
+                float4 v[kMaxSl];
+#pragma unroll
+                for (int i = 0; i < kMaxSl; i++) {
+                    const int sl = lane + 32 * i;
+                    if (sl < slices) v[i] = *reinterpret_cast<const float4*>(gsrc + 4 * sl);
+                }
+#pragma unroll
+                for (int i = 0; i < kMaxSl; i++) {
+                    const int sl = lane + 32 * i;
+                    if (sl < slices) {
+                        *reinterpret_cast<float4*>(rec + 4 * sl) = v[i];
+                        *reinterpret_cast<float4*>(gsrc + 4 * sl) = make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                }
+            } else {
+                for (int i = lane; i < rowlen; i += 32) {
+                    rec[i] = gsrc[i];
+                    gsrc[i] = 0.f;
+                }
             }
         }
         __syncthreads();
@@ -211,6 +230,42 @@ push_red_kernel(const uint32_t* __restrict__ uniq, const unsigned int* __restric
     int lpr = 1;
     while (lpr < slices && lpr < 32) lpr <<= 1;
     const int G = 32 / lpr, q = lane % lpr, g = lane / lpr;
+    if (vec == 4 && slices <= lpr) {
+        // narrow rows (FM): one float4 per lane; kPullU row groups are loaded before the first RED leaves
+        for (unsigned b0 = warp * (G * kPullU); b0 < n; b0 += nwarps * (G * kPullU)) {
+            uint32_t f[kPullU];
+            float4 v[kPullU];
+            float w[kPullU];
+#pragma unroll
+            for (int u = 0; u < kPullU; u++) {
+                const unsigned idx = b0 + u * G + g;
+                f[u] = idx < n ? uniq[idx] : 0xffffffffu;
+                v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                w[u] = 0.f;
+                if (f[u] == 0xffffffffu) continue;
+                if (q < slices) v[u] = *reinterpret_cast<const float4*>(cgV + (size_t)f[u] * rowlen + 4 * q);
+                if (q == 0) w[u] = cgW[f[u]];
+            }
+#pragma unroll
+            for (int u = 0; u < kPullU; u++) {
+                if (f[u] == 0xffffffffu) continue;
+                const unsigned o = f[u] & mask;
+                const size_t l = f[u] >> shift;
+                if (q < slices) {
+                    *reinterpret_cast<float4*>(cgV + (size_t)f[u] * rowlen + 4 * q) = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (v[u].x != 0.f || v[u].y != 0.f || v[u].z != 0.f || v[u].w != 0.f)
+                        red_add_v4(pgV[o] + l * (size_t)rowlen + 4 * q, v[u]);
+                }
+                if (q == 0) {
+                    red_add_f32(pgW[o] + l, w[u]);
+                    cgW[f[u]] = 0.f;
+                    ptouched[o][l] = 1;
+                }
+            }
+        }
+        __threadfence_system();
+        return;
+    }
     for (unsigned b0 = warp * G; b0 < n; b0 += nwarps * G) {
         const unsigned idx = b0 + g;
         if (idx >= n) continue;
@@ -307,18 +362,27 @@ merge_kernel(const unsigned char* __restrict__ mailbox, int world, size_t region
         const float* recs = reinterpret_cast<const float*>(region + 64);
         for (unsigned idx = warp; idx < n; idx += nwarps) {
             const float* rec = recs + (size_t)idx * rec_floats;
-            const uint32_t f = __float_as_uint(rec[0]);
+            const uint32_t f = __float_as_uint(rec[rowlen]);
             const size_t l = f >> shift;
             float* gdst = gV + l * (size_t)rowlen;
-            if (rowlen % 4 == 0 && (rec_floats % 4) == 0) {
-                // gV row is 16 B aligned; the record payload starts at float 2 (8 B) -> scalar loads, vector REDs
-                for (int i = lane * 4; i < rowlen; i += 128)
-                    red_add_v4(gdst + i, make_float4(rec[2 + i], rec[3 + i], rec[4 + i], rec[5 + i]));
+            if (rowlen % 4 == 0 && (rec_floats % 4) == 0 && rowlen <= 128 * kMaxSl) {
+                const int slices = rowlen / 4;
+                float4 v[kMaxSl];
+#pragma unroll
+                for (int i = 0; i < kMaxSl; i++) {
+                    const int sl = lane + 32 * i;
+                    if (sl < slices) v[i] = *reinterpret_cast<const float4*>(rec + 4 * sl);
+                }
+#pragma unroll
+                for (int i = 0; i < kMaxSl; i++) {
+                    const int sl = lane + 32 * i;
+                    if (sl < slices) red_add_v4(gdst + 4 * sl, v[i]);
+                }
             } else {
-                for (int i = lane; i < rowlen; i += 32) red_add_f32(gdst + i, rec[2 + i]);
+                for (int i = lane; i < rowlen; i += 32) red_add_f32(gdst + i, rec[i]);
             }
             if (lane == 0) {
-                red_add_f32(gW + l, rec[1]);
+                red_add_f32(gW + l, rec[rowlen + 1]);
                 touched[l] = 1;
             }
         }

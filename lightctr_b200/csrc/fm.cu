@@ -300,7 +300,7 @@ static bool pick_shape(int k, Shape& sh) {
 // FACTOR-major -- T[c][j], rows K and K+1 hold dot and w*x -- so that the in-order scan of phase 2 reads four
 // features per LDS.128.  Same expression sequence as fm_forward_kernel; ~3x fewer LSU wavefronts per sample.
 template <int K, bool HAS_VAL, bool NFM>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(128, (K <= 16 ? 7 : 4))
 fm_forward_coalesced_kernel(const int64_t* __restrict__ row_ptr, const uint32_t* __restrict__ fid,
                             const float* __restrict__ val, const float* __restrict__ label, const float* __restrict__ W,
                             const float* __restrict__ V, float* __restrict__ pred, float* __restrict__ sumvx,
@@ -339,8 +339,8 @@ fm_forward_coalesced_kernel(const int64_t* __restrict__ row_ptr, const uint32_t*
                 const int j = it * G + g;  // feature index within the pass
                 const uint32_t f = __shfl_sync(kFull, j < 32 ? f0 : f1, j & 31);
                 xv[it] = HAS_VAL ? __shfl_sync(kFull, j < 32 ? x0 : x1, j & 31) : 1.f;
-                v[it] = qa ? ldg_f4(V + (size_t)f * K + 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);  // f = 0 beyond n: masked
-                wv[it] = q == 0 ? __ldg(W + f) : 0.f;
+                v[it] = qa ? ldg_f4_pinned(V + (size_t)f * K + 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);  // f = 0 beyond n: masked
+                wv[it] = q == 0 ? ldg_f32_pinned(W + f) : 0.f;
             }
 #pragma unroll
             for (int it = 0; it < NIT; it++) {
@@ -426,16 +426,19 @@ fm_forward_coalesced_kernel(const int64_t* __restrict__ row_ptr, const uint32_t*
 
 template <int K>
 static int fwd_go(lctr_ctx* c, Slot& s, bool nfm, int64_t rb, int64_t re, double* out_slot, int stats, const int64_t* hdr) {
-    const unsigned grid = (unsigned)((re - rb + 7) / 8);
     constexpr bool kCoalesced = (K % 8 == 0) && K <= 32;
     static const bool want_coalesced = !(getenv("LCTR_FWD_COALESCED") && atoi(getenv("LCTR_FWD_COALESCED")) == 0);
     const bool co = kCoalesced && want_coalesced;
-    const size_t smem = co ? (size_t)8 * (K + 2) * 68 * sizeof(float) : (size_t)8 * 64 * (K + 4) * sizeof(float);
+    // coalesced kernel: 4 warps per CTA (its 8 row gathers per pass are all in flight: ~70 registers per thread, and
+    // at batch 4096 / 148 SMs = 27.7 warps per SM every sample must be resident in ONE wave)
+    const int wpb = co ? 4 : 8;
+    const unsigned grid = (unsigned)((re - rb + wpb - 1) / wpb);
+    const size_t smem = co ? (size_t)wpb * (K + 2) * 68 * sizeof(float) : (size_t)wpb * 64 * (K + 4) * sizeof(float);
 #define FWD_GO(HV, NF)                                                                                         \
     do {                                                                                                       \
         auto kern = co ? fm_forward_coalesced_kernel<kCoalesced ? K : 8, HV, NF> : fm_forward_kernel<K, HV, NF>; \
         if (smem > 48 * 1024) LCTR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        kern<<<grid, 256, smem, c->stream>>>(s.row_ptr, s.fid, s.val, s.label, c->cW, c->cV, s.pred, s.sumvx, c->z, \
+        kern<<<grid, wpb * 32, smem, c->stream>>>(s.row_ptr, s.fid, s.val, s.label, c->cW, c->cV, s.pred, s.sumvx, c->z, \
                                              s.wide, rb, re, c->stat_partial, c->stat_done, out_slot, stats, hdr);  \
     } while (0)
     if (s.has_val) { if (nfm) FWD_GO(true, true); else FWD_GO(true, false); }

@@ -213,6 +213,16 @@ int mlp_reserve(lctr_ctx* c, int64_t rows) {
     return 0;
 }
 
+// world > 1: the dense gradients of the ranks are summed before the updater (data-parallel dense layers)
+int mlp_sync_dense_grad(lctr_ctx* c) {
+    if (c->cfg.world <= 1) return 0;
+    LCTR_CHECK(c->dense_allreduce, "NFM with world=%d needs lctr_set_dense_allreduce (dense gradients are all-reduced "
+               "between the MLP backward and its updater)", c->cfg.world);
+    LCTR_CHECK(c->dense_allreduce(c->dense_allreduce_user, c->dense_grad, c->dense_grad_n, (void*)c->stream) == 0,
+               "dense all-reduce callback failed");
+    return 0;
+}
+
 // forward MLP on c->z, loss, backward to c->dz, accumulate dW/db, Adagrad on the MLP (fp32, reference order).
 int launch_nfm_mlp(lctr_ctx* c, Slot& s, int64_t rb, int64_t re, int64_t rows_divisor) {
     const int B = (int)(re - rb);
@@ -250,6 +260,7 @@ int launch_nfm_mlp(lctr_ctx* c, Slot& s, int64_t rb, int64_t re, int64_t rows_di
                                                                                           L.in, L.out);
         c->launches += 3;
     }
+    if (mlp_sync_dense_grad(c)) return 1;
     // ---- Adagrad on bias then weights, per layer (fullyconnLayer.h:194-197)
     const uint64_t mb = c->cfg.minibatch_size ? c->cfg.minibatch_size : (uint64_t)rows_divisor;
     const float invB = (float)(1.0 / (double)mb);
@@ -276,6 +287,12 @@ int lctr_mlp_upload(lctr_ctx* c, int layer, const float* weight, const float* bi
     if (bias) LCTR_CUDA(cudaMemcpyAsync(L.b, bias, (size_t)L.out * sizeof(float), cudaMemcpyHostToDevice, c->stream));
     if (weight && mlp_bf16_refresh(c, layer)) return 1;
     LCTR_CUDA(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+int lctr_set_dense_allreduce(lctr_ctx* c, lctr_allreduce_fn fn, void* user) {
+    LCTR_CHECK(c, "null ctx");
+    c->dense_allreduce = fn;
+    c->dense_allreduce_user = user;
     return 0;
 }
 int lctr_mlp_download_grad(lctr_ctx* c, int layer, float* dweight, float* dbias) {

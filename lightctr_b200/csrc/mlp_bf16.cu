@@ -444,6 +444,8 @@ int launch_nfm_mlp_bf16(lctr_ctx* c, Slot& s, int64_t rb, int64_t re, int64_t ro
         nfm_mlp_fused_kernel<64><<<grid, 128, c->mlp_smem, c->stream>>>(P, c->z, c->dz, s.wide, s.label, s.pred, rb, B,
                                                                        c->stat_partial, c->stat_done, out_slot);
     c->launches++;
+    LCTR_CUDA(cudaGetLastError());
+    if (mlp_sync_dense_grad(c)) return 1;
     if (!c->mlp_skip_update) {
         DenseSegs S;
         S.n = 2 * nl;

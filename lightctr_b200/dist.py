@@ -32,6 +32,32 @@ def connect(ctx, group=None):
     dist.barrier(group)
 
 
+class _DevArray:
+    """Zero-copy view of a raw device pointer for torch.as_tensor (CUDA array interface v2)."""
+
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": "<f4", "data": (int(ptr), False), "version": 2}
+
+
+def attach_dense_allreduce(ctx, group=None):
+    """Install the dense-gradient all-reduce of the data-parallel NFM layers (lctr_set_dense_allreduce): NCCL on the
+    context's own stream (replaces Worker_RingReduce::syncGradient, distribut/ring_collect.h:48-72).  With a gloo group
+    (tests: several ranks sharing one GPU) the sum goes through the host."""
+    import torch
+    import torch.distributed as dist
+
+    def fn(ptr, n, stream):
+        t = torch.as_tensor(_DevArray(ptr, n), device="cuda")
+        with torch.cuda.stream(torch.cuda.ExternalStream(stream)):
+            if dist.get_backend(group) == "nccl":
+                dist.all_reduce(t, group=group)
+            else:
+                h = t.cpu()
+                dist.all_reduce(h, group=group)
+                t.copy_(h)
+    ctx.set_dense_allreduce(fn)
+
+
 def reduce_stats(loss, correct, group=None):
     """Sum of the per-rank (summed logloss, correct count): what a single process would print for the global batch."""
     import torch

@@ -28,16 +28,34 @@ def make_problem(args, rank):
     return batches, W0, V0
 
 
+NFM_HIDDEN = (32, 16)
+
+
+def make_mlp(args):
+    """Initial dense layers of the NFM runs (identical on every rank: the layers are replicated)."""
+    rng = np.random.default_rng(77)
+    dims = [args.k] + list(NFM_HIDDEN) + [1]
+    return [((rng.random((dims[i + 1], dims[i]), dtype=np.float32) - 0.5).astype(np.float32),
+             np.zeros(dims[i + 1], np.float32)) for i in range(len(dims) - 1)]
+
+
 def run_gpu(args, rank, world):
     import torch.distributed as dist
     from lightctr_b200 import capi, dist as ldist
     batches, W0, V0 = make_problem(args, rank)
-    model = capi.MODEL_FFM if args.model == "ffm" else capi.MODEL_FM
+    model = {"ffm": capi.MODEL_FFM, "fm": capi.MODEL_FM, "nfm": capi.MODEL_NFM}[args.model]
     dev = 0 if args.same_device else rank
+    import torch
+    torch.cuda.set_device(dev)
     ctx = capi.Context(model, args.F, args.k, 39 if args.model == "ffm" else 0, device=dev, rank=rank, world=world,
-                       minibatch_size=world * args.rows, max_nnz=args.rows * 200)
+                       minibatch_size=world * args.rows, max_nnz=args.rows * 200,
+                       hidden=NFM_HIDDEN if args.model == "nfm" else ())
     ctx.upload_params(W0, V0)
     ldist.connect(ctx)
+    if args.model == "nfm":
+        for l, (w, b) in enumerate(make_mlp(args)):
+            ctx.mlp_upload(l, w, b)
+        ldist.attach_dense_allreduce(ctx)
     stats = []
     for rp, fid, fld, lab in batches:
         ctx.upload_batch(0, rp, fid, fld if args.model == "ffm" else None, None, lab)
@@ -45,7 +63,13 @@ def run_gpu(args, rank, world):
         stats.append(ldist.reduce_stats(l, c))
     dist.barrier()
     W, V = ctx.download_params()
-    np.savez(os.path.join(args.out, "rank%d.npz" % rank), W=W, V=V, stats=np.array(stats))
+    extra = {}
+    if args.model == "nfm":
+        dims = [args.k] + list(NFM_HIDDEN) + [1]
+        for l in range(len(dims) - 1):
+            w, b = ctx.mlp_download(l, dims[l], dims[l + 1])
+            extra["mlp_w%d" % l], extra["mlp_b%d" % l] = w, b
+    np.savez(os.path.join(args.out, "rank%d.npz" % rank), W=W, V=V, stats=np.array(stats), **extra)
     dist.barrier()
     ctx.close()
 

@@ -80,6 +80,48 @@ def _oracle_global(oracle_api, world, F, k, rows, steps, model="fm"):
     return W, V, stats
 
 
+def _oracle_global_nfm(oracle_api, world, F, k, rows, steps):
+    """Single-process NFM oracle on the concatenated global batch: one minibatch of world*rows samples per step, masks
+    all ones, the same initial dense layers as tests/dist_worker.py."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import dist_worker
+
+    class A:
+        pass
+    a = A()
+    a.F, a.k, a.rows, a.steps, a.model = F, k, rows, steps, "nfm"
+    per_rank = [dist_worker.make_problem(a, r) for r in range(world)]
+    W, V = per_rank[0][1].copy(), per_rank[0][2].copy()
+    accum = np.zeros(F * (k + 1), np.float32)
+    mlp0 = dist_worker.make_mlp(a)
+    nl = len(mlp0)
+    state = {"weight": [w.reshape(-1).copy() for w, _ in mlp0], "bias": [b.copy() for _, b in mlp0], "accum": None}
+    stats = []
+    for s in range(steps):
+        rps, fids, flds, labs, off = [np.zeros(1, np.int64)], [], [], [], 0
+        for r in range(world):
+            rp, fid, fld, lab = per_rank[r][0][s]
+            rps.append(rp[1:] + off)
+            off += rp[-1]
+            fids.append(fid); flds.append(fld); labs.append(lab)
+        ds = oracle_api.Dataset(np.concatenate(rps), np.concatenate(fids), np.concatenate(flds).astype(np.uint32),
+                                np.ones(off, np.float32), np.concatenate(labs), F, 0)
+        B = world * rows
+        o = oracle_api.NFMOracle(ds, k, list(dist_worker.NFM_HIDDEN), W=W, V=V, batch_size=B, minibatch=B)
+        o.accum[:] = accum
+        for l in range(nl):
+            o.mlp.arrays("weight", l)[:] = state["weight"][l]
+            o.mlp.arrays("bias", l)[:] = state["bias"][l]
+            o.mlp.arrays("mask", l)[:] = 1.0
+            if state["accum"] is not None:
+                o.mlp.arrays("accum", l)[:] = state["accum"][l]
+        loss, acc = o.epoch()
+        W, V, accum = o.W.copy(), o.V.copy(), o.accum.copy()
+        state = {k2: [o.mlp.arrays(k2, l).copy() for l in range(nl)] for k2 in ("weight", "bias", "accum")}
+        stats.append((loss, acc * ds.rows))
+    return W, V, stats, state
+
+
 def _check(out, world, F, k, oracle, tol):
     from lightctr_b200 import dist as ldist
     parts = [np.load(os.path.join(out, "rank%d.npz" % r)) for r in range(world)]
@@ -128,3 +170,20 @@ def test_cuda_two_ranks_ffm(oracle_api, tmp_path):
     _launch(2, str(tmp_path), ["--mode", "gpu", "--same-device", "--model", "ffm", "--F", str(F), "--k", str(k),
                                "--rows", str(rows), "--steps", str(steps)], timeout=900)
     _check(str(tmp_path), 2, F, k, _oracle_global(oracle_api, 2, F, k, rows, steps, model="ffm"), 5e-5)
+
+
+@pytest.mark.gpu
+def test_cuda_two_ranks_nfm(oracle_api, tmp_path):
+    """NFM over 2 ranks: embeddings owner-sharded (pull / push), dense layers replicated with the per-rank dW / db summed
+    through lctr_set_dense_allreduce before the dense Adagrad (gloo through the host here: both ranks share cuda:0)."""
+    F, k, rows, steps = 8000, 16, 128, 3
+    _launch(2, str(tmp_path), ["--mode", "gpu", "--same-device", "--model", "nfm", "--F", str(F), "--k", str(k),
+                               "--rows", str(rows), "--steps", str(steps)], timeout=900)
+    Wo, Vo, so, mlp = _oracle_global_nfm(oracle_api, 2, F, k, rows, steps)
+    _check(str(tmp_path), 2, F, k, (Wo, Vo, so), 5e-5)
+    parts = [np.load(os.path.join(str(tmp_path), "rank%d.npz" % r)) for r in range(2)]
+    for l in range(len(mlp["weight"])):
+        for r in range(2):  # replicas stay identical and equal to the oracle's layers
+            assert np.max(np.abs(parts[r]["mlp_w%d" % l] - mlp["weight"][l])) < 5e-5
+            assert np.max(np.abs(parts[r]["mlp_b%d" % l] - mlp["bias"][l])) < 5e-5
+        assert np.array_equal(parts[0]["mlp_w%d" % l], parts[1]["mlp_w%d" % l])
