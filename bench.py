@@ -239,6 +239,8 @@ def main():
     if world > 1:
         from lightctr_b200 import dist as ldist
         ldist.connect(ctx)
+        if wl["model"] == "nfm":  # replicated dense layers: dW / db summed with NCCL on the context's stream every step
+            ldist.attach_dense_allreduce(ctx)
     NB = wl.get("nb", 8)
     batches = make_batches(wl, NB, seed_offset=rank)
     # pinned host copies (the end-to-end arm copies from these every step)
@@ -371,7 +373,8 @@ def main():
                                      "feature-grouped, atomic-free, fused updater (ffm_grouped.cu); grouping kernels inside the timed step")
                                     if det == 2 else "RED scatter + sparse apply"),
                        "parallelism": "1 GPU" if world == 1 else
-                       "dp%d rows + owner-sharded tables (fid mod %d), unique-id pull/push over NVLink peer memory" % (world, world)},
+                       ("dp%d rows + owner-sharded tables (fid mod %d), unique-id pull/push over NVLink peer memory" % (world, world))
+                       + ("; dense layers replicated, gradients NCCL all-reduced" if wl["model"] == "nfm" else "")},
             "clocks": clocks, "gpu_launches": int(launches), "kernels_ms": kernels,
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 16},
             "roofline": roof, "wall_s_timed_region": t_wall}

@@ -146,8 +146,6 @@ int lctr_mlp_download_grad(lctr_ctx* ctx, int layer, float* dweight, float* dbia
  * export this rank's table handles, gather them, import all peers'. */
 int lctr_ipc_export(lctr_ctx* ctx, void* handles_out, size_t cap, size_t* bytes);
 int lctr_ipc_import(lctr_ctx* ctx, const void* all_handles, size_t bytes_per_rank);
-/* device pointer + element count of the fused dense-gradient buffer (the BufferFusion of
- * fullyconnLayer.h:69-75) for an external ncclAllReduce; 0 elements when the model has no MLP */
 /* Data-parallel dense layers (world > 1, NFM): the per-rank weightDelta / biasDelta of the batch must be summed over
  * the ranks before the updater runs -- Worker_RingReduce::syncGradient (distribut/ring_collect.h:48-72) on the
  * BufferFusion of Fully_Conn_Layer::registerGradient (fullyconnLayer.h:69-75).  The library calls `fn` once per train
@@ -156,6 +154,8 @@ int lctr_ipc_import(lctr_ctx* ctx, const void* all_handles, size_t bytes_per_ran
  * comm, stream), or torch.distributed.all_reduce under that stream) and return 0.  Required when world > 1. */
 typedef int (*lctr_allreduce_fn)(void* user, float* dev_buf, size_t n_floats, void* cuda_stream);
 int lctr_set_dense_allreduce(lctr_ctx* ctx, lctr_allreduce_fn fn, void* user);
+/* device pointer + element count of the fused dense-gradient buffer (the BufferFusion of
+ * fullyconnLayer.h:69-75) for an external ncclAllReduce; 0 elements when the model has no MLP */
 int lctr_dense_grad_buffer(lctr_ctx* ctx, void** dev_ptr, size_t* n_floats);
 
 /* ---- host-side ingest (fm_algo_abst.h:70-107), bit-exact indexing ----------------------------- */
