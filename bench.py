@@ -343,6 +343,10 @@ def main():
         # grouped backward: one contiguous tile row per entry
         bytes_per_sample = {"ffm_fused": n * (Fc * k * 4 + 12) + (Fc * Fc * k * 4 if det == 2 else 0),
                             "fm_backward_csc": n * (Fc * k * 4 + 10)}
+    # DRAM traffic per launch (dram__bytes_read.sum + dram__bytes_write.sum) of ONE `ncu --set full` capture of the same
+    # workload, copied from profiles/ (the bench itself never runs under a profiler); None where no capture exists
+    NCU_TRAFFIC = {("fm_c2", "fm_backward_red"): (12_875_520, "profiles/ncu_r01_fm_c2_summary.txt"),
+                   ("fm_c2", "fm_forward"): (7_600_000, "profiles/ncu_r01_fm_c2_summary.txt")}
     roof = None
     if dom[0] is not None:
         ms, cnt = dom[1]
@@ -352,6 +356,9 @@ def main():
             roof = {"bound": "hbm", "kernel": dom[0], "achieved": achieved, "peak": peak, "unit": "GB/s",
                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": bps * B, "kernel_ms": ms / cnt}
+            tr = NCU_TRAFFIC.get((wname, dom[0])) if not args.batch and world == 1 else None
+            if tr:
+                roof["traffic"], roof["traffic_source"] = tr
     if dom[0] == "mlp" and cnt:  # dense layers: fwd + dX + dW = 6 flops per weight per sample
         dims = [k] + list(wl["hidden"]) + [1]
         flops = 6.0 * sum(dims[i] * dims[i + 1] for i in range(len(dims) - 1)) * B

@@ -29,7 +29,7 @@ typedef struct lctr_ctx lctr_ctx;
 enum { LCTR_MODEL_FM = 1, LCTR_MODEL_FFM = 2, LCTR_MODEL_NFM = 3 };
 /* updater = the reference's `_Num` family member (gradientUpdater.h:128-154 Adagrad,
  * :235-278 FTRL; momentumUpdater.h:172-215 Adam) */
-enum { LCTR_OPT_ADAGRAD = 0, LCTR_OPT_FTRL = 1, LCTR_OPT_ADAM = 2 };
+enum { LCTR_OPT_ADAGRAD = 0, LCTR_OPT_FTRL = 1, LCTR_OPT_ADAM = 2, LCTR_OPT_RMSPROP = 3 };
 enum { LCTR_ACT_SIGMOID = 0, LCTR_ACT_TANH = 1 };
 enum { LCTR_MLP_FP32 = 0, LCTR_MLP_BF16 = 1 };
 
@@ -60,18 +60,19 @@ typedef struct lctr_cfg {
     uint64_t max_rows, max_nnz;
     /* multi-GPU: this process' rank / world (1 process per GPU); tables are owner-sharded by fid % world */
     int32_t rank, world;
-    /* Backward scatter-add strategy (FM / NFM; FFM always uses REDs):
+    /* Backward scatter-add strategy (FFM: 0 and 2 only):
      *  0  vector REDs into update_g + sparse apply (sum order arbitrary, like the reference's Hogwild threads);
      *  1  feature-major (CSC) view of the slot built on the HOST at upload: every gradient is summed in ascending
      *     row order -- the order of the reference's canonical single-thread run -- no atomics, updater fused.
      *     csc_row_block = rows per train_step range (0 => whole slot; NFM: the minibatch size);
      *  2  the same view built on the DEVICE at upload (overlaps the previous step); entries of a feature arrive in
      *     arbitrary order and are accumulated in double precision, so the fp32 result is order-independent.
-     *     Whole-slot steps only, FM with k in {4, 8, 16, 32}.  Default for streamed batches. */
+     *     Whole-slot steps only; FM with k in {4, 8, 16, 32}, FFM with k % 4 == 0 and field_cnt * k <= 512. */
     int32_t deterministic;
     int32_t reserved0;
     uint64_t csc_row_block;
-    uint32_t reserved[4];
+    float ema_rate;           /* GradientUpdater::__global_ema_rate (RMSpropUpdater_Num, gradientUpdater.h:200-233); 0 => 0.99 (main.cpp:66) */
+    uint32_t reserved[3];
 } lctr_cfg;
 
 const char* lctr_last_error(void);
@@ -170,6 +171,25 @@ typedef struct lctr_dataset {
 } lctr_dataset;
 int lctr_load_libffm(const char* path, uint64_t field_cnt_in, uint64_t feature_cnt_in, lctr_dataset** out);
 int lctr_free_dataset(lctr_dataset* d);
+/* binary CSR cache of a parsed file: the sscanf-per-token parse is paid once */
+int lctr_save_dataset_bin(const lctr_dataset* d, const char* path);
+int lctr_load_dataset_bin(const char* path, lctr_dataset** out);
+
+/* ---- test-set metrics on the device ----------------------------------------- */
+/* Summed logloss and correct count of FM_Predict::Predict (predict/fm_predict.cpp:63-72) and AucEvaluator's AUC
+ * (util/evaluator.h:51-104, 2^24 - 1 buckets, fp32 trapezoid walk from the top bucket) over the pCTR / label arrays
+ * that lctr_predict left in `slot`.  The AUC is bit-identical to the reference's for the same pCTR values. */
+int lctr_eval(lctr_ctx* ctx, int slot, float* loss_sum, int64_t* correct, float* auc);
+/* test hook: overwrite the slot's pCTR array with host values */
+int lctr_upload_pred(lctr_ctx* ctx, int slot, const float* pctr);
+
+/* ---- checkpoint / resume ---------------------------------------------------- */
+/* FM_Algo_Abst::saveModel (fm_algo_abst.h:109-135) writes W and V as text (kept in the host shims); these dump and
+ * restore the complete trainer state in binary -- W, V, updater state (Adagrad accumulators | FTRL z, n | Adam m, v and
+ * its call counter), dense layers with their Adagrad state and dropout masks, step counter -- so that a restored
+ * trainer continues exactly where the saved one stopped.  The restoring ctx must have been created with the same cfg. */
+int lctr_save_checkpoint(lctr_ctx* ctx, const char* path);
+int lctr_load_checkpoint(lctr_ctx* ctx, const char* path);
 
 /* per-kernel device timing for bench.py's roofline: when enabled, every launch on the ctx stream is bracketed by
  * CUDA events; lctr_profile_read sums the elapsed ms and launch counts per kernel class

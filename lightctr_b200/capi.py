@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "lib", "liblightctr_b200.so")
 
 MODEL_FM, MODEL_FFM, MODEL_NFM = 1, 2, 3
-OPT_ADAGRAD, OPT_FTRL, OPT_ADAM = 0, 1, 2
+OPT_ADAGRAD, OPT_FTRL, OPT_ADAM, OPT_RMSPROP = 0, 1, 2, 3
 ACT_SIGMOID, ACT_TANH = 0, 1
 MLP_FP32, MLP_BF16 = 0, 1
 MAX_LAYERS = 8
@@ -24,7 +24,8 @@ SYMBOLS = [
     "lctr_last_error", "lctr_abi_version", "lctr_create", "lctr_destroy", "lctr_sync", "lctr_upload_params",
     "lctr_download_params", "lctr_fill_params", "lctr_download_opt_state", "lctr_upload_opt_state", "lctr_upload_batch",
     "lctr_train_step", "lctr_train_batch", "lctr_train_batch_async", "lctr_wait", "lctr_predict", "lctr_download_sumvx", "lctr_download_pred",
-    "lctr_mlp_upload", "lctr_mlp_download", "lctr_mlp_set_mask", "lctr_mlp_download_grad", "lctr_set_dense_allreduce", "lctr_ipc_export", "lctr_ipc_import",
+    "lctr_mlp_upload", "lctr_mlp_download", "lctr_mlp_set_mask", "lctr_mlp_download_grad", "lctr_set_dense_allreduce", "lctr_save_checkpoint", "lctr_load_checkpoint",
+    "lctr_save_dataset_bin", "lctr_load_dataset_bin", "lctr_eval", "lctr_upload_pred", "lctr_ipc_export", "lctr_ipc_import",
     "lctr_dense_grad_buffer", "lctr_load_libffm", "lctr_free_dataset", "lctr_launch_count", "lctr_stream", "lctr_profile", "lctr_profile_read",
 ]
 
@@ -38,7 +39,7 @@ class Cfg(C.Structure):
                 ("n_hidden", C.c_int32), ("hidden", C.c_uint32 * MAX_LAYERS), ("activation", C.c_int32),
                 ("mlp_precision", C.c_int32), ("max_rows", C.c_uint64), ("max_nnz", C.c_uint64), ("rank", C.c_int32),
                 ("world", C.c_int32), ("deterministic", C.c_int32), ("reserved0", C.c_int32),
-                ("csc_row_block", C.c_uint64), ("reserved", C.c_uint32 * 4)]
+                ("csc_row_block", C.c_uint64), ("ema_rate", C.c_float), ("reserved", C.c_uint32 * 3)]
 
 
 class DatasetC(C.Structure):
@@ -82,6 +83,12 @@ def load_library():
     L.lctr_mlp_set_mask.argtypes = [vp, C.c_int, f32p]
     L.lctr_mlp_download_grad.argtypes = [vp, C.c_int, f32p, f32p]
     L.lctr_set_dense_allreduce.argtypes = [vp, ALLREDUCE_FN, vp]
+    L.lctr_eval.argtypes = [vp, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_int64), C.POINTER(C.c_float)]
+    L.lctr_upload_pred.argtypes = [vp, C.c_int, f32p]
+    L.lctr_save_checkpoint.argtypes = [vp, C.c_char_p]
+    L.lctr_load_checkpoint.argtypes = [vp, C.c_char_p]
+    L.lctr_save_dataset_bin.argtypes = [C.POINTER(DatasetC), C.c_char_p]
+    L.lctr_load_dataset_bin.argtypes = [C.c_char_p, C.POINTER(C.POINTER(DatasetC))]
     L.lctr_ipc_export.argtypes = [vp, vp, C.c_size_t, C.POINTER(C.c_size_t)]
     L.lctr_ipc_import.argtypes = [vp, vp, C.c_size_t]
     L.lctr_dense_grad_buffer.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_size_t)]
@@ -141,6 +148,35 @@ def load_libffm(path, field_cnt=0, feature_cnt=0):
     return out
 
 
+def _dataset_from_c(d):
+    n, r, lc = d.nnz, d.rows, d.label_cnt
+    return HostDataset(np.ctypeslib.as_array(d.row_ptr, (r + 1,)).copy(),
+                       np.ctypeslib.as_array(d.fid, (max(n, 1),))[:n].copy(),
+                       np.ctypeslib.as_array(d.field, (max(n, 1),))[:n].copy(),
+                       np.ctypeslib.as_array(d.val, (max(n, 1),))[:n].copy(),
+                       np.ctypeslib.as_array(d.label, (max(lc, 1),))[:lc].copy(), d.feature_cnt, d.field_cnt)
+
+
+def libffm_to_bin(path, bin_path, field_cnt=0, feature_cnt=0):
+    """Parse a libffm text file once and write the binary CSR cache next to it."""
+    L = load_library()
+    dp = C.POINTER(DatasetC)()
+    _chk(L.lctr_load_libffm(path.encode(), field_cnt, feature_cnt, C.byref(dp)))
+    try:
+        _chk(L.lctr_save_dataset_bin(dp, bin_path.encode()))
+    finally:
+        L.lctr_free_dataset(dp)
+
+
+def load_dataset_bin(bin_path):
+    L = load_library()
+    dp = C.POINTER(DatasetC)()
+    _chk(L.lctr_load_dataset_bin(bin_path.encode(), C.byref(dp)))
+    out = _dataset_from_c(dp.contents)
+    L.lctr_free_dataset(dp)
+    return out
+
+
 ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p)
 
 
@@ -150,7 +186,7 @@ class Context:
     def __init__(self, model, feature_cnt, factor_cnt, field_cnt=0, optimizer=OPT_ADAGRAD, lr=0.05, l2=0.001,
                  minibatch_size=0, momentum=0.8, momentum_adam2=0.999, hidden=(), activation=ACT_SIGMOID,
                  mlp_precision=MLP_FP32, device=0, rank=0, world=1, deterministic=0, csc_row_block=0, max_rows=0,
-                 max_nnz=0):
+                 max_nnz=0, ema_rate=0.99):
         L = load_library()
         cfg = Cfg()
         cfg.abi_version = ABI_VERSION
@@ -158,6 +194,7 @@ class Context:
         cfg.feature_cnt, cfg.field_cnt, cfg.factor_cnt = feature_cnt, field_cnt, factor_cnt
         cfg.learning_rate, cfg.l2_reg, cfg.minibatch_size = lr, l2, minibatch_size
         cfg.momentum, cfg.momentum_adam2 = momentum, momentum_adam2
+        cfg.ema_rate = ema_rate
         cfg.n_hidden = len(hidden)
         for i, h in enumerate(hidden):
             cfg.hidden[i] = h
@@ -292,6 +329,22 @@ class Context:
                 return 1
         self._allreduce_cb = ALLREDUCE_FN(tramp)  # keep alive
         _chk(self.L.lctr_set_dense_allreduce(self.h, self._allreduce_cb, None))
+
+    def eval_metrics(self, slot):
+        """(summed logloss, correct count, AUC) of the slot's pCTR / labels, computed on the device."""
+        loss, correct, auc = C.c_float(), C.c_int64(), C.c_float()
+        _chk(self.L.lctr_eval(self.h, slot, C.byref(loss), C.byref(correct), C.byref(auc)))
+        return loss.value, correct.value, auc.value
+
+    def upload_pred(self, slot, pctr):
+        p = np.ascontiguousarray(pctr, np.float32)
+        _chk(self.L.lctr_upload_pred(self.h, slot, p.ctypes.data))
+
+    def save_checkpoint(self, path):
+        _chk(self.L.lctr_save_checkpoint(self.h, path.encode()))
+
+    def load_checkpoint(self, path):
+        _chk(self.L.lctr_load_checkpoint(self.h, path.encode()))
 
     def mlp_download_grad(self, layer, n_in, n_out):
         w, b = np.empty(n_in * n_out, np.float32), np.empty(n_out, np.float32)

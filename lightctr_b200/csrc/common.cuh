@@ -131,6 +131,7 @@ struct lctr_ctx {
     float *z = nullptr, *dz = nullptr;  // [B][k] NFM bi-interaction output and its gradient
     float* mlp_out = nullptr;           // [B]
     size_t mlp_cap_rows = 0;
+    void* auc_scratch = nullptr;  // metrics.cu: histograms + lists of lctr_eval
     int csc_in_step = 0;        // LCTR_CSC_IN_STEP=1: rebuild the feature-major view inside every train step (bench)
     float* ffm_T = nullptr;     // FFM grouped step: per-sample field-pair tiles [rows][Fc][Fc][k]
     uint16_t* ffm_cnt = nullptr; // [rows][Fc] features per field
@@ -295,6 +296,7 @@ int ffm_grouped_reserve(lctr_ctx* c, int64_t rows);
 void ffm_grouped_free(lctr_ctx* c);
 int launch_ffm_forward_tiles(lctr_ctx* c, Slot& s, int64_t rb, int64_t re);
 int launch_ffm_backward_grouped(lctr_ctx* c, Slot& s, int64_t rb, int64_t re);
+void metrics_free(lctr_ctx* c);
 int mlp_sync_dense_grad(lctr_ctx* c);
 int mlp_bf16_prepare(lctr_ctx* c);
 int mlp_bf16_refresh(lctr_ctx* c, int layer);

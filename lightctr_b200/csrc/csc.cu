@@ -225,7 +225,7 @@ __device__ __forceinline__ void accumulate(double (&u)[4], double& gws, const fl
 template <int K>
 __device__ __forceinline__ void apply_update(const ParamView& T, const OptParams& P, uint32_t f, int q, float w, float4 v,
                                              const double (&u)[4], double gws) {
-    const bool two = P.opt != LCTR_OPT_ADAGRAD;
+    const bool two = opt_two_states(P.opt);
     if (q == 0) {
         float ww = w, a = T.s1W[f], b2 = two ? T.s2W[f] : 0.f;
         update_one(P, P.corrW, ww, (float)gws, a, b2);

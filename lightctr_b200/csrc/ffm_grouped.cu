@@ -87,7 +87,7 @@ ffm_backward_grouped_kernel(FfmView C, FfmParams T, int Fc, int k, int NS, float
         const float w = T.W[f];
         const float4 v = own ? *reinterpret_cast<const float4*>(T.V + o) : make_float4(0.f, 0.f, 0.f, 0.f);
         // updater state of a single-task row is needed at the end: issue its loads now
-        const bool two = P.opt != LCTR_OPT_ADAGRAD;
+        const bool two = opt_two_states(P.opt);
         float4 a1 = make_float4(0.f, 0.f, 0.f, 0.f), b2 = a1;
         if (FUSE && single && own) {
             a1 = *reinterpret_cast<const float4*>(T.s1V + o);

@@ -553,7 +553,7 @@ fm_backward_csc_kernel(const int64_t* __restrict__ seg_ptr, const uint32_t* __re
         }
     }
     if (!sv) return;
-    const bool two = P.opt != LCTR_OPT_ADAGRAD;
+    const bool two = opt_two_states(P.opt);
     if (c == 0) {
         float ww = w, a = s1W[f], b2 = two ? s2W[f] : 0.f;
         update_one(P, P.corrW, ww, gwsum, a, b2);

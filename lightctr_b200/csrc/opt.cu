@@ -88,7 +88,7 @@ apply_kernel(const uint32_t* __restrict__ list, unsigned int* __restrict__ n_lis
     const int q = lane % LPR, g = lane / LPR;
     const unsigned warp = blockIdx.x * (blockDim.x >> 5) + wid;
     const unsigned nwarps = gridDim.x * (blockDim.x >> 5);
-    const bool two_state = P.opt != LCTR_OPT_ADAGRAD;
+    const bool two_state = opt_two_states(P.opt);
     const int slices = rowlen / VEC;
     const unsigned total = *reinterpret_cast<volatile unsigned int*>(n_list);
     {

@@ -15,7 +15,11 @@ struct OptParams {
     float beta1;
     float corrW, corrV;  // Adam bias corrections of the W call and the V call (iter++ per call)
     float alpha, beta, l1, l2;
+    float ema;        // RMSprop: GradientUpdater::__global_ema_rate
 };
+
+// updaters that carry a second state array (FTRL n, Adam v)
+__host__ __device__ __forceinline__ bool opt_two_states(int opt) { return opt == LCTR_OPT_FTRL || opt == LCTR_OPT_ADAM; }
 
 // one coordinate; arithmetic order as in the reference (compiled with -fmad=false)
 __device__ __forceinline__ void update_one(const OptParams& P, float corr, float& w, float g, float& s1, float& s2) {
@@ -38,6 +42,14 @@ __device__ __forceinline__ void update_one(const OptParams& P, float corr, float
                 if (t >= 0.f) t -= P.l1; else t += P.l1;
                 w = -t / ((P.beta + sqrtf(s2)) / P.alpha + P.l2);
             }
+        }
+    } else if (P.opt == LCTR_OPT_RMSPROP) {  // RMSpropUpdater_Num::update, gradientUpdater.h:216-229
+        float g1 = g / P.mb;
+        if (g1 != 0.f) {
+            s1 = (float)((double)(s1 * P.ema) + (1.0 - (double)P.ema) * (double)g1 * (double)g1);
+            const float tmp = (float)(1.0 / ((double)s1 + 1e-7));
+            g1 = g1 * sqrtf(tmp);
+            w = w - P.lr * g1;
         }
     } else {  // Adam (both moments decay with beta1 -- reference quirk, momentumUpdater.h:197-201)
         const float g1 = g / P.mb;
@@ -69,6 +81,7 @@ inline OptParams make_opt_params(lctr_ctx* c, int64_t rows_in_step) {
         it = ++c->adam_iter;
         P.corrV = (float)(sqrt(1 - pow((double)cf.momentum_adam2, (double)it)) / (1 - pow((double)cf.momentum, (double)it)));
     }
+    P.ema = cf.ema_rate != 0.f ? cf.ema_rate : 0.99f;
     P.alpha = cf.ftrl_alpha; P.beta = cf.ftrl_beta; P.l1 = cf.ftrl_lambda1; P.l2 = cf.ftrl_lambda2;
     return P;
 }

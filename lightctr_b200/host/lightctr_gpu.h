@@ -188,6 +188,7 @@ protected:
         cfg.minibatch_size = minibatch;
         cfg.momentum = MomentumUpdater::__global_momentum;
         cfg.momentum_adam2 = MomentumUpdater::__global_momentum_adam2;
+        cfg.ema_rate = GradientUpdater::__global_ema_rate;  // RMSpropUpdater_Num (updater = LCTR_OPT_RMSPROP)
         cfg.n_hidden = n_hidden;
         for (int i = 0; i < n_hidden; i++) cfg.hidden[i] = hidden[i];
         cfg.activation = LCTR_ACT_SIGMOID;

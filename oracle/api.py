@@ -69,6 +69,7 @@ def lib():
     L.orc_free_data.argtypes = [C.POINTER(_Data)]
     L.orc_adagrad.argtypes = [C.c_size_t, _f32p, _f32p, _f32p, C.c_size_t, C.c_float]
     L.orc_ftrl.argtypes = [C.c_size_t, _f32p, _f32p, _f32p, _f32p, C.c_int]
+    L.orc_rmsprop.argtypes = [C.c_size_t, _f32p, _f32p, _f32p, C.c_size_t, C.c_float, C.c_float]
     L.orc_adam.argtypes = [C.c_size_t, _f32p, _f32p, _f32p, _f32p, C.POINTER(C.c_size_t), C.c_size_t,
                            C.c_float, C.c_float, C.c_float]
     L.orc_fm_pass.argtypes = [C.c_int64, _i64p, _u32p, _f32p, _i32p, C.c_size_t, C.c_size_t, _f32p, _f32p,
@@ -186,6 +187,11 @@ class FMOracle:
         F, k = self.ds.feature_cnt, self.k
         L = lib()
         # ApplyGrad train_fm_algo.cpp:120-126 ; minibatch_size = dataRow_cnt (:38)
+        if getattr(self, "opt", "adagrad") == "rmsprop":  # `updater` member type switched to RMSpropUpdater_Num
+            ema = np.float32(getattr(self, "ema", 0.99))
+            L.orc_rmsprop(F, self.W, self.update_g[:F], self.accum[:F], self.ds.rows, self.lr, ema)
+            L.orc_rmsprop(F * k, self.V, self.update_g[F:], self.accum[F:], self.ds.rows, self.lr, ema)
+            return
         L.orc_adagrad(F, self.W, self.update_g[:F], self.accum[:F], self.ds.rows, self.lr)
         L.orc_adagrad(F * k, self.V, self.update_g[F:], self.accum[F:], self.ds.rows, self.lr)
 
@@ -196,9 +202,10 @@ class FMOracle:
 
 
 class FFMOracle:
-    """Train_FFM_Algo restated (train/train_ffm_algo.cpp).  optimizer in {adagrad, ftrl, adam}."""
+    """Train_FFM_Algo restated (train/train_ffm_algo.cpp).  optimizer in {adagrad, ftrl, adam, rmsprop}."""
 
-    def __init__(self, ds, k, W, V, lr=0.05, l2=0.001, optimizer="adagrad", beta1=0.8, beta2=0.999):
+    def __init__(self, ds, k, W, V, lr=0.05, l2=0.001, optimizer="adagrad", beta1=0.8, beta2=0.999, ema=0.99):
+        self.ema = np.float32(ema)
         self.ds, self.k, self.lr, self.l2 = ds, k, np.float32(lr), np.float32(l2)
         self.W, self.V = W.copy(), V.copy()
         self.opt = optimizer
@@ -227,6 +234,8 @@ class FFMOracle:
             g, a, b = self.update_g[lo:hi], self.s1[lo:hi], self.s2[lo:hi]
             if self.opt == "adagrad":
                 L.orc_adagrad(hi - lo, w, g, a, B, self.lr)
+            elif self.opt == "rmsprop":
+                L.orc_rmsprop(hi - lo, w, g, a, B, self.lr, self.ema)
             elif self.opt == "ftrl":
                 L.orc_ftrl(hi - lo, w, g, a, b, 1)
             elif self.opt == "adam":
@@ -333,6 +342,7 @@ def ref():
     R.ref_predict.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_int]
     R.ref_adagrad_update.argtypes = [C.c_size_t, C.c_size_t, C.c_float, _f32p, _f32p, _f32p]
     R.ref_ftrl_update.argtypes = [C.c_size_t, _f32p, _f32p, _f32p, _f32p]
+    R.ref_rmsprop_update.argtypes = [C.c_size_t, C.c_size_t, C.c_float, C.c_float, _f32p, _f32p, _f32p]
     R.ref_adam_update.argtypes = [C.c_size_t, C.c_size_t, C.c_float, C.c_float, C.c_float, C.c_size_t, _f32p, _f32p,
                                   _f32p, _f32p]
     R.ref_sigmoid.argtypes = [C.c_float]

@@ -238,6 +238,20 @@ void orc_adagrad(size_t len, float* w, float* g, float* accum, size_t minibatch,
     }
     memset(g, 0, len * sizeof(float)); /* :149 */
 }
+void orc_rmsprop(size_t len, float* w, float* g, float* accum, size_t minibatch, float lr, float ema) {
+    /* RMSpropUpdater_Num::update, gradientUpdater.h:216-229 */
+    for (size_t i = 0; i < len; i++) {
+        float gi = g[i] / (float)minibatch; /* :218 float / size_t -> float */
+        if (gi != 0) {
+            /* :221-223 float*float, then (1.0 - ema) * g * g in double, sum in double, stored to float */
+            accum[i] = (float)((double)(accum[i] * ema) + (1.0 - (double)ema) * (double)gi * (double)gi);
+            float tmp = (float)(1.0 / ((double)accum[i] + 1e-7)); /* :224 */
+            gi = gi * sqrtf(tmp);                                  /* :225 sqrt(float) -> std::sqrt(float) */
+            w[i] = w[i] - lr * gi;                                 /* :227 */
+        }
+        g[i] = 0.0f; /* :229 */
+    }
+}
 void orc_ftrl(size_t len, float* w, float* g, float* z, float* n, int zero_grad) {
     const float alpha = 0.15f, lambda1 = 1.0f, beta = 1.0f, lambda2 = 1.0f; /* gradientUpdater.h:275 */
     for (size_t i = 0; i < len; i++) { /* :254-272 */

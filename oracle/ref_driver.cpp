@@ -264,6 +264,17 @@ void ref_adagrad_update(size_t n, size_t minibatch, float lr, float* accum, floa
     u.update(0, n, w, g);
     memcpy(accum, u.__adagrad_accum.data(), sizeof(float) * n);
 }
+// RMSpropUpdater_Num::update (util/gradientUpdater.h:200-233).
+void ref_rmsprop_update(size_t n, size_t minibatch, float lr, float ema, float* accum, float* w, float* g) {
+    GradientUpdater::__global_minibatch_size = minibatch;
+    GradientUpdater::__global_learning_rate = lr;
+    GradientUpdater::__global_ema_rate = ema;
+    RMSpropUpdater_Num u;
+    u.learnable_params_cnt(n);
+    memcpy(u.__rms_accum.data(), accum, sizeof(float) * n);
+    u.update(0, n, w, g);
+    memcpy(accum, u.__rms_accum.data(), sizeof(float) * n);
+}
 // FTRLUpdater::update (util/gradientUpdater.h:252-273); state arrays z,n (sigma is scratch).
 void ref_ftrl_update(size_t n, float* z, float* nn, float* w, float* g) {
     FTRLUpdater u;

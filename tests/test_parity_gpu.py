@@ -103,16 +103,19 @@ def test_ffm_k4_parity(files, oracle_api):
     assert abs(pred.auc - oauc) < 2e-4
 
 
-@pytest.mark.parametrize("opt", ["ftrl", "adam"])
+@pytest.mark.parametrize("opt", ["ftrl", "adam", "rmsprop"])
 def test_ffm_other_updaters(files, oracle_api, opt):
     """C3-style: FFM with FTRLUpdater / AdamUpdater_Num as the `updater` member (SURVEY 8c last row)."""
     from lightctr_b200 import capi, trainers as T
     T.srand(1)
-    code = {"ftrl": capi.OPT_FTRL, "adam": capi.OPT_ADAM}[opt]
+    code = {"ftrl": capi.OPT_FTRL, "adam": capi.OPT_ADAM, "rmsprop": capi.OPT_RMSPROP}[opt]
+    # RMSprop's first step is lr / sqrt(1 - ema) = 10 lr per coordinate: run it with a learning rate a user would pick
+    lr = 0.002 if opt == "rmsprop" else 0.05
+    T.GradientUpdater.learning_rate = lr
     ffm = T.Train_FFM_Algo(files["train"], 1, 4, 68, optimizer=code)
     ds = files["tr"]
     W0, V0 = oracle_api.init_params(1, ds.feature_cnt, 4, 68)
-    o = oracle_api.FFMOracle(ds, 4, W0, V0, optimizer=opt)
+    o = oracle_api.FFMOracle(ds, 4, W0, V0, optimizer=opt, lr=lr)
     # FTRL has a hard threshold (|z| <= lambda1 -> w = 0, gradientUpdater.h:262-264) and Adam's first steps are
     # sign-like (m / sqrt(v)), so the fp32 re-association of the field-pair factorisation (ffm.cu) is amplified more
     # than under Adagrad: tolerance 5e-5 on the loss curve, 5e-4 abs on parameters (Adagrad above holds 1e-5 / 1e-4).
@@ -120,6 +123,7 @@ def test_ffm_other_updaters(files, oracle_api, opt):
         ffm.Train()
         lo, ao = o.epoch()
         assert _rel(ffm.loss_curve[-1], lo) < 5e-5, (opt, e, ffm.loss_curve[-1], lo)
+    T.GradientUpdater.learning_rate = 0.05
     assert np.max(np.abs(ffm.W - o.W)) < 5e-3
     assert np.max(np.abs(ffm.V - o.V)) < 5e-3  # FTRL: a coordinate crossing |z| = lambda1 jumps between 0 and ~1e-3
 
@@ -338,3 +342,140 @@ def test_ffm_grouped_matches_red_path_synth():
     assert np.array_equal(dW0 != 0, dW2 != 0) and np.array_equal(dV0 != 0, dV2 != 0)  # same touched set, bit-exact
     assert np.max(np.abs(dV0 - dV2)) < 2e-3 and np.mean(np.abs(dV0 - dV2)) < 1e-6
     assert np.max(np.abs(dW0 - dW2)) < 2e-3
+
+
+def test_device_metrics_auc_bit_exact(oracle_api):
+    """lctr_eval (csrc/metrics.cu): AucEvaluator's bucketed AUC on the device is bit-identical to the oracle's
+    restatement of util/evaluator.h:51-104 for the same pCTR array (integer histogram + the same fp32 trapezoid walk);
+    correct count equal; summed logloss within 1e-6 (device logf / log vs glibc)."""
+    from lightctr_b200 import capi
+    rng = np.random.default_rng(21)
+    n, F = 20000, 64
+    p = rng.random(n).astype(np.float32)
+    p[:500] = rng.choice(p[500:1000], 500)                    # ties: several rows per bucket
+    p[500:520] = np.float32(1e-7)                             # the sigmoid clamps (activations.h:65-72)
+    p[520:540] = np.float32(0.99999988)
+    p[540:560] = np.float32(0.5)
+    y = (rng.random(n) < 0.3).astype(np.int32)
+    ctx = capi.Context(capi.MODEL_FM, F, 8)
+    rp = np.arange(n + 1, dtype=np.int64)
+    ctx.upload_batch(0, rp, (np.arange(n) % F).astype(np.uint32), None, None, y)
+    ctx.upload_pred(0, p)
+    loss, correct, auc = ctx.eval_metrics(0)
+    lib = oracle_api.lib()
+    auc_o = lib.orc_auc(p, y, n)
+    assert np.float32(auc) == np.float32(auc_o), (auc, auc_o)
+    corr_o = int(np.sum((p > 0.5) & (y == 1)) + np.sum((p < 0.5) & (y == 0)))
+    assert correct == corr_o
+    loss_o = np.float32(0)
+    for pi, yi in zip(p, y):
+        t = float(-np.log(np.float32(pi))) if yi == 1 else -np.log(1.0 - float(pi))
+        loss_o = np.float32(float(loss_o) + t)
+    assert _rel(loss, float(loss_o)) < 1e-6
+    # second call on different data: the histograms were re-armed by the first
+    p2 = rng.random(n).astype(np.float32)
+    ctx.upload_pred(0, p2)
+    assert np.float32(ctx.eval_metrics(0)[2]) == np.float32(lib.orc_auc(p2, y, n))
+    # degenerate: one class only -> 0 (evaluator.h:90-93)
+    ctx.upload_batch(1, rp[:101], (np.arange(100) % F).astype(np.uint32), None, None, np.ones(100, np.int32))
+    ctx.upload_pred(1, p[:100])
+    assert ctx.eval_metrics(1)[2] == 0.0
+    ctx.close()
+
+
+def test_predict_then_device_metrics_match_host_path(files, oracle_api):
+    """FM_Predict on the test file: device metrics on the device-computed pCTR vs the oracle's predictor."""
+    from lightctr_b200 import capi, trainers as T
+    T.srand(1)
+    T.GradientUpdater.learning_rate = 0.05
+    fm = T.Train_FM_Algo(files["train"], 3, 8)
+    fm.Train()
+    pred = T.FM_Predict(fm, files["test"], True)
+    pred.Predict("")
+    loss, correct, auc = fm._ctx.eval_metrics(1)   # FM_Predict uploads the test rows into slot 1
+    assert _rel(loss, pred.loss) < 1e-5 and correct == pred.correct
+    assert abs(auc - pred.auc) < 1e-6              # same pCTR array, same walk
+
+
+@pytest.mark.parametrize("model,opt,det", [("fm", "adam", 1), ("fm", "adagrad", 2), ("nfm", "adagrad", 1), ("ffm", "ftrl", 2)])
+def test_checkpoint_resume_is_exact(files, model, opt, det, tmp_path):
+    """lctr_save_checkpoint / lctr_load_checkpoint: 3 steps + save + restore into a fresh ctx + 3 steps must equal 6
+    steps in one go, bit for bit, in the deterministic modes (updater state, Adam's call counter, dense layers and
+    their Adagrad state all travel)."""
+    from lightctr_b200 import capi
+    ds = files["tr"]
+    k, Fc = (4, 68) if model == "ffm" else (8, 0)
+    M = {"fm": capi.MODEL_FM, "ffm": capi.MODEL_FFM, "nfm": capi.MODEL_NFM}[model]
+    O = {"adagrad": capi.OPT_ADAGRAD, "ftrl": capi.OPT_FTRL, "adam": capi.OPT_ADAM}[opt]
+    rng = np.random.default_rng(2)
+    W0 = np.zeros(ds.feature_cnt, np.float32)
+    V0 = (rng.standard_normal(ds.feature_cnt * k * max(Fc, 1)) / 4).astype(np.float32)
+    hidden = (32,) if model == "nfm" else ()
+    mlp = [((rng.random((32, k), dtype=np.float32) - 0.5), np.zeros(32, np.float32)),
+           ((rng.random((1, 32), dtype=np.float32) - 0.5), np.zeros(1, np.float32))]
+    mask = (rng.random(32) < 0.8).astype(np.float32)
+
+    def make():
+        c = capi.Context(M, ds.feature_cnt, k, Fc, optimizer=O, deterministic=det, hidden=hidden,
+                         minibatch_size=ds.rows if model == "nfm" else 0, csc_row_block=ds.rows if model == "nfm" else 0)
+        c.upload_params(W0, V0)
+        if model == "nfm":
+            for l, (w, b) in enumerate(mlp):
+                c.mlp_upload(l, w, b)
+            c.mlp_set_mask(0, mask)
+        c.upload_batch(0, ds.row_ptr, ds.fid, ds.field if Fc else None, None, ds.label)
+        return c
+
+    a = make()
+    la = [a.train_step(0)[0] for _ in range(6)]
+    Wa, Va = a.download_params()
+    a.close()
+    b = make()
+    lb = [b.train_step(0)[0] for _ in range(3)]
+    path = str(tmp_path / "ckpt.bin")
+    b.save_checkpoint(path)
+    b.close()
+    c = make()
+    c.load_checkpoint(path)
+    lb += [c.train_step(0)[0] for _ in range(3)]
+    Wc, Vc = c.download_params()
+    if model == "nfm":
+        w0, _ = c.mlp_download(0, k, 32)
+        assert np.all(np.isfinite(w0))
+    c.close()
+    if model == "ffm":  # a few segments of train_sparse.csv exceed 256 entries and meet through fp32 REDs
+        assert np.allclose(la, lb, rtol=1e-6)
+        assert np.max(np.abs(Wa - Wc)) < 1e-5 and np.max(np.abs(Va - Vc)) < 1e-5
+    else:
+        assert la == lb
+        assert np.array_equal(Wa.view(np.uint32), Wc.view(np.uint32)) and np.array_equal(Va.view(np.uint32), Vc.view(np.uint32))
+    # a checkpoint of another trainer is refused
+    d = capi.Context(capi.MODEL_FM, ds.feature_cnt, k + 8 if model != "ffm" else 8)
+    with pytest.raises(capi.LctrError):
+        d.load_checkpoint(path)
+    d.close()
+
+
+def test_fm_rmsprop_updater(files, oracle_api):
+    """RMSpropUpdater_Num (util/gradientUpdater.h:200-233) as the trainer's `updater` member: FM k=8 in
+    the exact-order mode against the oracle (whose orc_rmsprop is pinned bit for bit to the compiled reference)."""
+    from lightctr_b200 import capi
+    ds = files["tr"]
+    k = 8
+    W0, V0 = oracle_api.init_params(1, ds.feature_cnt, k)
+    o = oracle_api.FMOracle(ds, k, W0, V0)
+    o.opt, o.ema = "rmsprop", 0.99
+    o.lr = np.float32(0.002)
+    ctx = capi.Context(capi.MODEL_FM, ds.feature_cnt, k, optimizer=capi.OPT_RMSPROP, deterministic=1, ema_rate=0.99,
+                       lr=0.002)
+    ctx.upload_params(W0, V0)
+    ctx.upload_batch(0, ds.row_ptr, ds.fid, None, None, ds.label)
+    for e in range(6):
+        lg = ctx.train_step(0)[0]
+        lo, _ = o.epoch()
+        assert _rel(lg, lo) < LOSS_RTOL, (e, lg, lo)
+    W, V = ctx.download_params()
+    assert np.max(np.abs(W - o.W)) < 1e-5 and np.max(np.abs(V - o.V)) < 1e-5
+    s1, _ = ctx.download_opt_state()
+    assert np.max(np.abs(s1 - o.accum)) < 1e-5 * max(1.0, float(np.max(np.abs(o.accum))))
+    ctx.close()
