@@ -167,7 +167,7 @@ int lctr_create(const lctr_cfg* cfg, lctr_ctx** out) {
     LCTR_CHECK(cfg->abi_version == LCTR_ABI_VERSION, "lctr_create: abi_version %u != %u", cfg->abi_version,
                LCTR_ABI_VERSION);
     LCTR_CHECK(cfg->model >= LCTR_MODEL_FM && cfg->model <= LCTR_MODEL_NFM, "lctr_create: bad model %d", cfg->model);
-    LCTR_CHECK(cfg->optimizer >= LCTR_OPT_ADAGRAD && cfg->optimizer <= LCTR_OPT_RMSPROP, "lctr_create: bad optimizer %d",
+    LCTR_CHECK(cfg->optimizer >= LCTR_OPT_ADAGRAD && cfg->optimizer <= LCTR_OPT_ADADELTA, "lctr_create: bad optimizer %d",
                cfg->optimizer);
     LCTR_CHECK(cfg->feature_cnt > 0 && cfg->feature_cnt < (1ull << 32), "lctr_create: feature_cnt out of range");
     LCTR_CHECK(cfg->factor_cnt > 0, "lctr_create: factor_cnt must be > 0");
@@ -198,7 +198,7 @@ int lctr_create(const lctr_cfg* cfg, lctr_ctx** out) {
     LCTR_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     const size_t FL = c->Fl;
     const size_t nv = FL * c->rowlen;
-    const bool two = cfg->optimizer == LCTR_OPT_FTRL || cfg->optimizer == LCTR_OPT_ADAM;
+    const bool two = cfg->optimizer == LCTR_OPT_FTRL || cfg->optimizer == LCTR_OPT_ADAM || cfg->optimizer == LCTR_OPT_ADADELTA;
     int rc = 0;
     rc |= dalloc(&c->W, FL); rc |= dalloc(&c->V, nv);
     rc |= dalloc(&c->gW, FL); rc |= dalloc(&c->gV, nv);

@@ -19,7 +19,7 @@ struct OptParams {
 };
 
 // updaters that carry a second state array (FTRL n, Adam v)
-__host__ __device__ __forceinline__ bool opt_two_states(int opt) { return opt == LCTR_OPT_FTRL || opt == LCTR_OPT_ADAM; }
+__host__ __device__ __forceinline__ bool opt_two_states(int opt) { return opt == LCTR_OPT_FTRL || opt == LCTR_OPT_ADAM || opt == LCTR_OPT_ADADELTA; }
 
 // one coordinate; arithmetic order as in the reference (compiled with -fmad=false)
 __device__ __forceinline__ void update_one(const OptParams& P, float corr, float& w, float g, float& s1, float& s2) {
@@ -50,6 +50,15 @@ __device__ __forceinline__ void update_one(const OptParams& P, float corr, float
             const float tmp = (float)(1.0 / ((double)s1 + 1e-7));
             g1 = g1 * sqrtf(tmp);
             w = w - P.lr * g1;
+        }
+    } else if (P.opt == LCTR_OPT_ADADELTA) {  // AdadeltaUpdater_Num::update, momentumUpdater.h:91-106 (s1 = E[g^2], s2 = E[d^2])
+        float g1 = g / P.mb;
+        if (g1 != 0.f) {
+            s1 = (float)((double)(s1 * P.beta1) + (1.0 - (double)P.beta1) * (double)g1 * (double)g1);
+            const float tmp = (float)(((double)s2 + 1e-7) / ((double)s1 + 1e-7));
+            g1 = g1 * sqrtf(tmp);
+            s2 = (float)((double)(s2 * P.beta1) + (1.0 - (double)P.beta1) * (double)g1 * (double)g1);
+            w = w - g1;
         }
     } else {  // Adam (both moments decay with beta1 -- reference quirk, momentumUpdater.h:197-201)
         const float g1 = g / P.mb;

@@ -69,6 +69,7 @@ def lib():
     L.orc_free_data.argtypes = [C.POINTER(_Data)]
     L.orc_adagrad.argtypes = [C.c_size_t, _f32p, _f32p, _f32p, C.c_size_t, C.c_float]
     L.orc_ftrl.argtypes = [C.c_size_t, _f32p, _f32p, _f32p, _f32p, C.c_int]
+    L.orc_adadelta.argtypes = [C.c_size_t, _f32p, _f32p, _f32p, _f32p, C.c_size_t, C.c_float]
     L.orc_rmsprop.argtypes = [C.c_size_t, _f32p, _f32p, _f32p, C.c_size_t, C.c_float, C.c_float]
     L.orc_adam.argtypes = [C.c_size_t, _f32p, _f32p, _f32p, _f32p, C.POINTER(C.c_size_t), C.c_size_t,
                            C.c_float, C.c_float, C.c_float]
@@ -202,7 +203,7 @@ class FMOracle:
 
 
 class FFMOracle:
-    """Train_FFM_Algo restated (train/train_ffm_algo.cpp).  optimizer in {adagrad, ftrl, adam, rmsprop}."""
+    """Train_FFM_Algo restated (train/train_ffm_algo.cpp).  optimizer in {adagrad, ftrl, adam, rmsprop, adadelta}."""
 
     def __init__(self, ds, k, W, V, lr=0.05, l2=0.001, optimizer="adagrad", beta1=0.8, beta2=0.999, ema=0.99):
         self.ema = np.float32(ema)
@@ -236,6 +237,8 @@ class FFMOracle:
                 L.orc_adagrad(hi - lo, w, g, a, B, self.lr)
             elif self.opt == "rmsprop":
                 L.orc_rmsprop(hi - lo, w, g, a, B, self.lr, self.ema)
+            elif self.opt == "adadelta":
+                L.orc_adadelta(hi - lo, w, g, a, b, B, self.beta1)
             elif self.opt == "ftrl":
                 L.orc_ftrl(hi - lo, w, g, a, b, 1)
             elif self.opt == "adam":
@@ -342,6 +345,7 @@ def ref():
     R.ref_predict.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_int]
     R.ref_adagrad_update.argtypes = [C.c_size_t, C.c_size_t, C.c_float, _f32p, _f32p, _f32p]
     R.ref_ftrl_update.argtypes = [C.c_size_t, _f32p, _f32p, _f32p, _f32p]
+    R.ref_adadelta_update.argtypes = [C.c_size_t, C.c_size_t, C.c_float, _f32p, _f32p, _f32p, _f32p]
     R.ref_rmsprop_update.argtypes = [C.c_size_t, C.c_size_t, C.c_float, C.c_float, _f32p, _f32p, _f32p]
     R.ref_adam_update.argtypes = [C.c_size_t, C.c_size_t, C.c_float, C.c_float, C.c_float, C.c_size_t, _f32p, _f32p,
                                   _f32p, _f32p]

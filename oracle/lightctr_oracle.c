@@ -252,6 +252,20 @@ void orc_rmsprop(size_t len, float* w, float* g, float* accum, size_t minibatch,
         g[i] = 0.0f; /* :229 */
     }
 }
+void orc_adadelta(size_t len, float* w, float* g, float* eg, float* ed, size_t minibatch, float momentum) {
+    /* AdadeltaUpdater_Num::update, momentumUpdater.h:91-106 */
+    for (size_t i = 0; i < len; i++) {
+        float gi = g[i] / (float)minibatch; /* :93 */
+        if (gi != 0) {
+            eg[i] = (float)((double)(eg[i] * momentum) + (1.0 - (double)momentum) * (double)gi * (double)gi); /* :95-96 */
+            float tmp = (float)(((double)ed[i] + 1e-7) / ((double)eg[i] + 1e-7));                              /* :97-98 */
+            gi = gi * sqrtf(tmp);                                                                               /* :99 */
+            ed[i] = (float)((double)(ed[i] * momentum) + (1.0 - (double)momentum) * (double)gi * (double)gi); /* :101-103 */
+            w[i] = w[i] - gi;                                                                                   /* :105 */
+        }
+        g[i] = 0.0f;
+    }
+}
 void orc_ftrl(size_t len, float* w, float* g, float* z, float* n, int zero_grad) {
     const float alpha = 0.15f, lambda1 = 1.0f, beta = 1.0f, lambda2 = 1.0f; /* gradientUpdater.h:275 */
     for (size_t i = 0; i < len; i++) { /* :254-272 */

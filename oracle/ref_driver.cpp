@@ -301,6 +301,18 @@ void ref_adam_update(size_t n, size_t minibatch, float lr, float beta1, float be
     memcpy(m, u.__adam_accum.data(), sizeof(float) * n);
     memcpy(v, u.__adam_accum.data() + n, sizeof(float) * n);
 }
+// AdadeltaUpdater_Num::update (util/momentumUpdater.h:74-111); eg = E[g^2], ed = E[delta^2].
+void ref_adadelta_update(size_t n, size_t minibatch, float momentum, float* eg, float* ed, float* w, float* g) {
+    GradientUpdater::__global_minibatch_size = minibatch;
+    MomentumUpdater::__global_momentum = momentum;
+    AdadeltaUpdater_Num u;
+    u.learnable_params_cnt(n);
+    memcpy(u.__adadelta_accum.data(), eg, sizeof(float) * n);
+    memcpy(u.__adadelta_accum.data() + n, ed, sizeof(float) * n);
+    u.update(0, n, w, g);
+    memcpy(eg, u.__adadelta_accum.data(), sizeof(float) * n);
+    memcpy(ed, u.__adadelta_accum.data() + n, sizeof(float) * n);
+}
 // Sigmoid::forward (util/activations.h:65-72) and avx_dotProduct (common/avx.h:109-127).
 float ref_sigmoid(float x) { Sigmoid s; return s.forward(x); }
 float ref_dot(const float* x, const float* y, size_t n) { return avx_dotProduct(x, y, n); }

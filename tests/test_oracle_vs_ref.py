@@ -167,6 +167,13 @@ def test_optimizer_units_bit_exact(oracle_api):
         L.orc_rmsprop(n, b[1], b[2], b[0], 1000, 0.05, 0.99)
         for x, y in zip(a, b):
             assert np.array_equal(_bits(x), _bits(y))
+        # adadelta
+        a = [x.copy() for x in (s1, s2, w, g)]
+        b = [x.copy() for x in (s1, s2, w, g)]
+        R.ref_adadelta_update(n, 1000, 0.8, a[0], a[1], a[2], a[3])
+        L.orc_adadelta(n, b[2], b[3], b[0], b[1], 1000, 0.8)
+        for x, y in zip(a, b):
+            assert np.array_equal(_bits(x), _bits(y))
         # ftrl
         a = [x.copy() for x in (s1, s2, w, g)]
         b = [x.copy() for x in (s1, s2, w, g)]

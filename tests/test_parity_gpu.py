@@ -103,12 +103,12 @@ def test_ffm_k4_parity(files, oracle_api):
     assert abs(pred.auc - oauc) < 2e-4
 
 
-@pytest.mark.parametrize("opt", ["ftrl", "adam", "rmsprop"])
+@pytest.mark.parametrize("opt", ["ftrl", "adam", "rmsprop", "adadelta"])
 def test_ffm_other_updaters(files, oracle_api, opt):
     """C3-style: FFM with FTRLUpdater / AdamUpdater_Num as the `updater` member (SURVEY 8c last row)."""
     from lightctr_b200 import capi, trainers as T
     T.srand(1)
-    code = {"ftrl": capi.OPT_FTRL, "adam": capi.OPT_ADAM, "rmsprop": capi.OPT_RMSPROP}[opt]
+    code = {"ftrl": capi.OPT_FTRL, "adam": capi.OPT_ADAM, "rmsprop": capi.OPT_RMSPROP, "adadelta": capi.OPT_ADADELTA}[opt]
     # RMSprop's first step is lr / sqrt(1 - ema) = 10 lr per coordinate: run it with a learning rate a user would pick
     lr = 0.002 if opt == "rmsprop" else 0.05
     T.GradientUpdater.learning_rate = lr
