@@ -77,12 +77,18 @@ compact_touched_kernel(uint8_t* __restrict__ touched, size_t F, uint32_t* __rest
 // slices spread over LPR lanes, SPL slices per lane (slice index = q + i*LPR).  ALL loads of a batch
 // (gradient, weight, state of U rows per lane group) are issued before the first update is computed, so one
 // HBM/L2 round trip covers 32/LPR*U rows.  The last block re-arms the list counter.
-template <int LPR, int VEC, int SPL, int U>
-__global__ void __launch_bounds__(256)
+// OPT: the updater as a compile-time constant (-1 = decide at run time).  With the five updaters' double-precision
+// divisions and square roots inlined U * (SPL * VEC + 1) times the run-time version is 8.7 K SASS instructions and 177
+// registers: ncu showed `stall no_instruction` (instruction-cache misses) as its top stall and one resident CTA per SM
+// (profiles/ncu_r01_fm_c2_v2_summary.txt).  The VEC = 4 instances are therefore specialised per updater.
+template <int LPR, int VEC, int SPL, int U, int OPT>
+__global__ void __launch_bounds__(256, (OPT >= 0 ? 2 : 1))
 apply_kernel(const uint32_t* __restrict__ list, unsigned int* __restrict__ n_list, unsigned int* __restrict__ done,
              int rowlen, float* __restrict__ W, float* __restrict__ V,
              float* __restrict__ gW, float* __restrict__ gV, float* __restrict__ s1W, float* __restrict__ s1V,
-             float* __restrict__ s2W, float* __restrict__ s2V, OptParams P) {
+             float* __restrict__ s2W, float* __restrict__ s2V, OptParams P_in) {
+    OptParams P = P_in;
+    if (OPT >= 0) P.opt = OPT;  // folds every `P.opt ==` test of update_one
     constexpr int G = 32 / LPR;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int q = lane % LPR, g = lane / LPR;
@@ -191,7 +197,18 @@ int launch_apply(lctr_ctx* c, int64_t rows_in_step) {
     compact_touched_kernel<<<grid_a, 256, 0, c->stream>>>(c->touched, c->Fl, c->touch_list, c->n_touch);
     c->launches++;
 #define APPLY_ARGS c->touch_list, c->n_touch, c->apply_done, rowlen, c->W, c->V, c->gW, c->gV, c->s1W, c->s1V, c->s2W, c->s2V, P
-#define APPLY_CASE(L, VV, S, UU) apply_kernel<L, VV, S, UU><<<grid, 256, 0, c->stream>>>(APPLY_ARGS)
+#define APPLY_GO(L, VV, S, UU, OO) apply_kernel<L, VV, S, UU, OO><<<grid, 256, 0, c->stream>>>(APPLY_ARGS)
+#define APPLY_CASE(L, VV, S, UU)                                             \
+    do {                                                                     \
+        if (VV != 4) { APPLY_GO(L, VV, S, UU, -1); break; }                  \
+        switch (P.opt) {                                                     \
+            case LCTR_OPT_ADAGRAD: APPLY_GO(L, VV, S, UU, LCTR_OPT_ADAGRAD); break;   \
+            case LCTR_OPT_FTRL: APPLY_GO(L, VV, S, UU, LCTR_OPT_FTRL); break;         \
+            case LCTR_OPT_ADAM: APPLY_GO(L, VV, S, UU, LCTR_OPT_ADAM); break;         \
+            case LCTR_OPT_RMSPROP: APPLY_GO(L, VV, S, UU, LCTR_OPT_RMSPROP); break;   \
+            default: APPLY_GO(L, VV, S, UU, LCTR_OPT_ADADELTA); break;                \
+        }                                                                    \
+    } while (0)
     if (vec == 4) {
         switch (lpr) {
             case 1: APPLY_CASE(1, 4, 1, 4); break;
@@ -222,6 +239,7 @@ int launch_apply(lctr_ctx* c, int64_t rows_in_step) {
         }
     }
 #undef APPLY_CASE
+#undef APPLY_GO
 #undef APPLY_ARGS
     c->launches++;
     LCTR_CUDA(cudaGetLastError());
