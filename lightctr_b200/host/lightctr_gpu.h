@@ -170,6 +170,7 @@ public:
     lctr_dataset* ds = nullptr;
     int updater = LCTR_OPT_ADAGRAD;  // the reference's `AdagradUpdater_Num updater;` member (fm_algo_abst.h:166)
     int deterministic = 1;           // ascending-row accumulation (== the reference's canonical proc_cnt=1 order)
+    int mlp_precision = LCTR_MLP_FP32;  // NFM dense layers: reference-order fp32 (parity) or LCTR_MLP_BF16 (tensor cores)
 
 protected:
     float __loss;
@@ -192,6 +193,7 @@ protected:
         cfg.n_hidden = n_hidden;
         for (int i = 0; i < n_hidden; i++) cfg.hidden[i] = hidden[i];
         cfg.activation = LCTR_ACT_SIGMOID;
+        cfg.mlp_precision = mlp_precision;
         cfg.deterministic = deterministic;
         cfg.csc_row_block = csc_block;
         LCTR_OK(lctr_create(&cfg, &ctx));
@@ -281,12 +283,26 @@ public:
         memset(sumVX, 0, sizeof(float) * dataRow_cnt * factor_cnt);
         layers.emplace_back(factor_cnt, hidden_layer_size);  // :21-27
         layers.emplace_back(hidden_layer_size, 1);
+        hidden_sizes.push_back((uint32_t)hidden_layer_size);
+    }
+    // config C4: the Fully_Conn_Layer chain factor_cnt -> hidden[0] -> ... -> 1 (Layer_Base's prevLayer / nextLayer
+    // chaining, layer_abst.h:27-40); RNG order = construction order, input to output, like the reference's ctor
+    Train_NFM_Algo(std::string _dataPath, size_t _epoch_cnt, size_t _factor_cnt, const std::vector<size_t>& _hidden)
+        : FM_Algo_Abst(_dataPath, _factor_cnt), epoch(_epoch_cnt), hidden_layer_size(_hidden.empty() ? 0 : _hidden[0]) {
+        if (_hidden.empty() || _hidden.size() > LCTR_MAX_LAYERS) { std::cout << "NFM needs 1.." << LCTR_MAX_LAYERS << " hidden layers" << std::endl; exit(1); }
+        L2Reg_ratio = 0.001f;
+        batch_size = GradientUpdater::__global_minibatch_size;
+        sumVX = new float[dataRow_cnt * factor_cnt];
+        memset(sumVX, 0, sizeof(float) * dataRow_cnt * factor_cnt);
+        size_t in = factor_cnt;
+        for (size_t h : _hidden) { layers.emplace_back(in, h); hidden_sizes.push_back((uint32_t)h); in = h; }
+        layers.emplace_back(in, 1);
     }
     void Train() {  // train_nfm_algo.cpp:30-54
         GradientUpdater::__global_bTraining = true;
         if (!ctx) {
-            uint32_t hidden[1] = {(uint32_t)hidden_layer_size};
-            make_ctx(LCTR_MODEL_NFM, GradientUpdater::__global_minibatch_size, batch_size, 1, hidden);
+            make_ctx(LCTR_MODEL_NFM, GradientUpdater::__global_minibatch_size, batch_size, (int)hidden_sizes.size(),
+                     hidden_sizes.data());
             for (size_t l = 0; l < layers.size(); l++) {
                 LCTR_OK(lctr_mlp_upload(ctx, (int)l, layers[l].weight.data(), layers[l].bias.data()));
                 LCTR_OK(lctr_mlp_set_mask(ctx, (int)l, layers[l].mask.data()));
@@ -317,6 +333,7 @@ public:
     }
     float last_loss() const { return loss; }
     std::vector<Fully_Conn_Layer_Host> layers;
+    std::vector<uint32_t> hidden_sizes;
 
 private:
     size_t epoch, batch_size, hidden_layer_size;

@@ -80,3 +80,28 @@ def test_cxx_nfm_driver(exe, files, oracle_api):
     want = [o.epoch()[0] for _ in range(2)]
     for g, w in zip(got, want):
         assert abs(g - w) <= 1e-5 * abs(w), (got, want)
+
+
+def test_cxx_nfm_layer_chain_fp32_and_bf16(exe, files):
+    """Config C4 through the C++ surface: Train_NFM_Algo(path, epoch, k, {64, 32}) (the Fully_Conn_Layer chain) in the
+    fp32 parity mode must print the same losses as the Python mirror of the same class (same rand() stream, same C ABI
+    calls), and the bf16 tensor-core mode must track it (dropout masks are identical in both modes)."""
+    from lightctr_b200 import trainers as T
+    a = subprocess.check_output([exe, "nfmc", files["train"], files["test"], "2", "16", "64,32", "1"], text=True)
+    b = subprocess.check_output([exe, "nfmc_bf16", files["train"], files["test"], "2", "16", "64,32", "1"], text=True)
+    la, lb = _losses(a, "loss"), _losses(b, "loss")
+    T.srand(1)
+    T.GradientUpdater.minibatch_size = 50
+    T.GradientUpdater.learning_rate = 0.05
+    nfm = T.Train_NFM_Algo(files["train"], 1, 16, [64, 32])
+    want = []
+    for _ in range(2):
+        nfm.Train()
+        want.append(nfm.loss_curve[-1])
+    assert len(la) == 2 and len(lb) == 2
+    for g, w in zip(la, want):
+        assert abs(g - w) <= 1e-5 * abs(w), (la, want)
+    for g, w in zip(lb, want):
+        # bf16 operands over 20 chaotic minibatch steps per epoch: a sanity band only -- the numerics of this mode are
+        # pinned in tests/test_mlp_bf16_gpu.py against a rounding-point-exact emulation
+        assert np.isfinite(g) and abs(g - w) <= 0.25 * abs(w), (lb, want)
