@@ -420,6 +420,20 @@ static int upload_batch_on(lctr_ctx* c, cudaStream_t st, int slot, int64_t rows,
 int lctr_upload_batch(lctr_ctx* c, int slot, int64_t rows, int64_t nnz, const int64_t* row_ptr, const uint32_t* fid,
                       const uint16_t* field, const float* val, const int32_t* label) {
     LCTR_CHECK(c, "null ctx");
+    // Resident datasets are validated once, on the host: an out-of-range id would otherwise surface as an illegal
+    // address inside a gather (the reference indexes W / V unchecked too, fm_algo_abst.h:146-151, but there feature_cnt
+    // is derived from the same file).  The streamed entry points (lctr_train_batch[_async]) trust their caller.
+    LCTR_CHECK(rows >= 0 && nnz >= 0 && row_ptr && (nnz == 0 || fid), "upload_batch: null input");
+    LCTR_CHECK(row_ptr[0] == 0 && row_ptr[rows] == nnz, "upload_batch: row_ptr must run from 0 to nnz (%lld .. %lld, nnz %lld)",
+               (long long)row_ptr[0], (long long)row_ptr[rows], (long long)nnz);
+    for (int64_t r = 0; r < rows; r++)
+        LCTR_CHECK(row_ptr[r] <= row_ptr[r + 1], "upload_batch: row_ptr decreases at row %lld", (long long)r);
+    for (int64_t i = 0; i < nnz; i++)
+        LCTR_CHECK(fid[i] < c->F, "upload_batch: fid %u at entry %lld >= feature_cnt %zu", fid[i], (long long)i, c->F);
+    if (c->cfg.model == LCTR_MODEL_FFM && field)
+        for (int64_t i = 0; i < nnz; i++)
+            LCTR_CHECK(field[i] < c->cfg.field_cnt, "upload_batch: field %u at entry %lld >= field_cnt %u", (unsigned)field[i],
+                       (long long)i, c->cfg.field_cnt);
     return upload_batch_on(c, c->stream, slot, rows, nnz, row_ptr, fid, field, val, label);
 }
 

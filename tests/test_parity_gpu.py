@@ -479,3 +479,23 @@ def test_fm_rmsprop_updater(files, oracle_api):
     s1, _ = ctx.download_opt_state()
     assert np.max(np.abs(s1 - o.accum)) < 1e-5 * max(1.0, float(np.max(np.abs(o.accum))))
     ctx.close()
+
+
+def test_upload_batch_rejects_malformed_input():
+    """Error convention of the boundary: int status + lctr_last_error, surfaced as LctrError."""
+    from lightctr_b200 import capi
+    ctx = capi.Context(capi.MODEL_FFM, 100, 4, 5)
+    rp = np.array([0, 2, 3], np.int64)
+    lab = np.array([1, 0], np.int32)
+    ok = dict(row_ptr=rp, fid=np.array([1, 2, 3], np.uint32), field=np.array([0, 1, 4], np.uint16))
+    ctx.upload_batch(0, ok["row_ptr"], ok["fid"], ok["field"], None, lab)
+    with pytest.raises(capi.LctrError, match="feature_cnt"):
+        ctx.upload_batch(0, rp, np.array([1, 2, 100], np.uint32), ok["field"], None, lab)
+    with pytest.raises(capi.LctrError, match="field_cnt"):
+        ctx.upload_batch(0, rp, ok["fid"], np.array([0, 1, 5], np.uint16), None, lab)
+    with pytest.raises(capi.LctrError, match="row_ptr"):
+        ctx.upload_batch(0, np.array([0, 3, 2], np.int64), ok["fid"], ok["field"], None, lab)
+    with pytest.raises(capi.LctrError, match="field array"):
+        ctx.upload_batch(0, rp, ok["fid"], None, None, lab)
+    assert ctx.train_step(0)[0] > 0  # the slot still holds the last good batch
+    ctx.close()
