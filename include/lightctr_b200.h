@@ -27,8 +27,8 @@ extern "C" {
 typedef struct lctr_ctx lctr_ctx;
 
 enum { LCTR_MODEL_FM = 1, LCTR_MODEL_FFM = 2, LCTR_MODEL_NFM = 3 };
-/* updater = the reference's `_Num` family member (gradientUpdater.h:128-154 Adagrad,
- * :235-278 FTRL; momentumUpdater.h:172-215 Adam) */
+/* updater = the reference's `_Num` family member (gradientUpdater.h:128-154 Adagrad, :200-233 RMSprop,
+ * :235-278 FTRL; momentumUpdater.h:74-111 Adadelta, :172-215 Adam) */
 enum { LCTR_OPT_ADAGRAD = 0, LCTR_OPT_FTRL = 1, LCTR_OPT_ADAM = 2, LCTR_OPT_RMSPROP = 3, LCTR_OPT_ADADELTA = 4 };
 enum { LCTR_ACT_SIGMOID = 0, LCTR_ACT_TANH = 1 };
 enum { LCTR_MLP_FP32 = 0, LCTR_MLP_BF16 = 1 };
