@@ -26,7 +26,10 @@ extern "C" {
 
 typedef struct lctr_ctx lctr_ctx;
 
-enum { LCTR_MODEL_FM = 1, LCTR_MODEL_FFM = 2, LCTR_MODEL_NFM = 3 };
+/* LCTR_MODEL_WND: Wide&Deep with the per-field concat input of Distributed_Algo_Abst (distributed_algo_abst.h:176-280):
+ * factor_cnt = the tensor width d (the reference's factor_dim 4), field_cnt > 0, hidden[] = the dense chain on the
+ * field_cnt * d input; single GPU, RED scatter. */
+enum { LCTR_MODEL_FM = 1, LCTR_MODEL_FFM = 2, LCTR_MODEL_NFM = 3, LCTR_MODEL_WND = 4 };
 /* updater = the reference's `_Num` family member (gradientUpdater.h:128-154 Adagrad, :200-233 RMSprop,
  * :235-278 FTRL; momentumUpdater.h:74-111 Adadelta, :172-215 Adam) */
 enum { LCTR_OPT_ADAGRAD = 0, LCTR_OPT_FTRL = 1, LCTR_OPT_ADAM = 2, LCTR_OPT_RMSPROP = 3, LCTR_OPT_ADADELTA = 4 };

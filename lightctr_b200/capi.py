@@ -12,7 +12,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "lib", "liblightctr_b200.so")
 
-MODEL_FM, MODEL_FFM, MODEL_NFM = 1, 2, 3
+MODEL_FM, MODEL_FFM, MODEL_NFM, MODEL_WND = 1, 2, 3, 4
 OPT_ADAGRAD, OPT_FTRL, OPT_ADAM, OPT_RMSPROP, OPT_ADADELTA = 0, 1, 2, 3, 4
 ACT_SIGMOID, ACT_TANH = 0, 1
 MLP_FP32, MLP_BF16 = 0, 1

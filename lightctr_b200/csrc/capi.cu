@@ -166,12 +166,16 @@ int lctr_create(const lctr_cfg* cfg, lctr_ctx** out) {
     LCTR_CHECK(cfg && out, "lctr_create: null argument");
     LCTR_CHECK(cfg->abi_version == LCTR_ABI_VERSION, "lctr_create: abi_version %u != %u", cfg->abi_version,
                LCTR_ABI_VERSION);
-    LCTR_CHECK(cfg->model >= LCTR_MODEL_FM && cfg->model <= LCTR_MODEL_NFM, "lctr_create: bad model %d", cfg->model);
+    LCTR_CHECK(cfg->model >= LCTR_MODEL_FM && cfg->model <= LCTR_MODEL_WND, "lctr_create: bad model %d", cfg->model);
     LCTR_CHECK(cfg->optimizer >= LCTR_OPT_ADAGRAD && cfg->optimizer <= LCTR_OPT_ADADELTA, "lctr_create: bad optimizer %d",
                cfg->optimizer);
     LCTR_CHECK(cfg->feature_cnt > 0 && cfg->feature_cnt < (1ull << 32), "lctr_create: feature_cnt out of range");
     LCTR_CHECK(cfg->factor_cnt > 0, "lctr_create: factor_cnt must be > 0");
     LCTR_CHECK(cfg->model != LCTR_MODEL_FFM || cfg->field_cnt > 0, "lctr_create: FFM needs field_cnt > 0");
+    if (cfg->model == LCTR_MODEL_WND) {
+        LCTR_CHECK(cfg->field_cnt > 0 && cfg->field_cnt <= 2048, "lctr_create: Wide&Deep needs 0 < field_cnt <= 2048");
+        LCTR_CHECK(cfg->world <= 1 && cfg->deterministic == 0, "lctr_create: Wide&Deep is single-GPU, RED scatter only");
+    }
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev == 0) {
@@ -234,7 +238,7 @@ int lctr_create(const lctr_cfg* cfg, lctr_ctx** out) {
     LCTR_CUDA(cudaMemsetAsync(c->stats, 0, sizeof(double) * 2 * kStatRing, c->stream));
     LCTR_CUDA(cudaMemsetAsync(c->stat_partial, 0, sizeof(double) * 2, c->stream));
     LCTR_CUDA(cudaMemsetAsync(c->stat_done, 0, sizeof(unsigned int), c->stream));
-    if (cfg->model == LCTR_MODEL_NFM) {
+    if (cfg->model == LCTR_MODEL_NFM || cfg->model == LCTR_MODEL_WND) {
         if (mlp_alloc(c)) { lctr_destroy(c); return 1; }
     }
     { const char* e = getenv("LCTR_CSC_IN_STEP"); c->csc_in_step = e && e[0] == '1'; }
@@ -259,6 +263,7 @@ int lctr_destroy(lctr_ctx* c) {
     mlp_free(c);
     ffm_grouped_free(c);
     metrics_free(c);
+    wnd_free(c);
     dist_free(c);
     csc_scratch_free(c);
     if (c->h_stats) cudaFreeHost(c->h_stats);
@@ -376,7 +381,8 @@ static int upload_batch_on(lctr_ctx* c, cudaStream_t st, int slot, int64_t rows,
     LCTR_CHECK(c, "null ctx");
     LCTR_CHECK(slot >= 0 && slot < kNumSlots, "slot %d out of range", slot);
     LCTR_CHECK(rows >= 0 && nnz >= 0 && row_ptr && (nnz == 0 || fid) && (rows == 0 || label), "upload_batch: null input");
-    LCTR_CHECK(c->cfg.model != LCTR_MODEL_FFM || field || nnz == 0, "upload_batch: FFM needs the field array");
+    LCTR_CHECK((c->cfg.model != LCTR_MODEL_FFM && c->cfg.model != LCTR_MODEL_WND) || field || nnz == 0,
+               "upload_batch: FFM / Wide&Deep need the field array");
     Slot& s = c->slots[slot];
     if (rows > s.cap_rows || nnz > s.cap_nnz) {
         LCTR_CUDA(cudaStreamSynchronize(c->stream));  // buffers about to be reallocated may still be in use
@@ -430,7 +436,7 @@ int lctr_upload_batch(lctr_ctx* c, int slot, int64_t rows, int64_t nnz, const in
         LCTR_CHECK(row_ptr[r] <= row_ptr[r + 1], "upload_batch: row_ptr decreases at row %lld", (long long)r);
     for (int64_t i = 0; i < nnz; i++)
         LCTR_CHECK(fid[i] < c->F, "upload_batch: fid %u at entry %lld >= feature_cnt %zu", fid[i], (long long)i, c->F);
-    if (c->cfg.model == LCTR_MODEL_FFM && field)
+    if ((c->cfg.model == LCTR_MODEL_FFM || c->cfg.model == LCTR_MODEL_WND) && field)
         for (int64_t i = 0; i < nnz; i++)
             LCTR_CHECK(field[i] < c->cfg.field_cnt, "upload_batch: field %u at entry %lld >= field_cnt %u", (unsigned)field[i],
                        (long long)i, c->cfg.field_cnt);
@@ -481,6 +487,10 @@ int lctr_train_step(lctr_ctx* c, int slot, int64_t rb, int64_t re, float* loss_s
                      launch_ffm_backward_grouped(c, s, rb, re);
             else
                 rc = launch_ffm_forward(c, s, rb, re, true) || launch_ffm_backward(c, s, rb, re) || launch_apply(c, re - rb);
+            break;
+        case LCTR_MODEL_WND:
+            rc = mlp_reserve(c, re - rb) || wnd_reserve(c, re - rb) || launch_wnd_forward(c, s, rb, re) ||
+                 launch_nfm_mlp(c, s, rb, re, re - rb) || launch_wnd_backward(c, s, rb, re) || launch_apply(c, re - rb);
             break;
         case LCTR_MODEL_NFM:
             if (c->cfg.world > 1) {

@@ -131,6 +131,8 @@ struct lctr_ctx {
     float *z = nullptr, *dz = nullptr;  // [B][k] NFM bi-interaction output and its gradient
     float* mlp_out = nullptr;           // [B]
     size_t mlp_cap_rows = 0;
+    uint32_t* wnd_src = nullptr;   // Wide&Deep: fid of the first entry of each field, [rows][Fc]
+    size_t wnd_cap_rows = 0;
     void* auc_scratch = nullptr;  // metrics.cu: histograms + lists of lctr_eval
     int csc_in_step = 0;        // LCTR_CSC_IN_STEP=1: rebuild the feature-major view inside every train step (bench)
     float* ffm_T = nullptr;     // FFM grouped step: per-sample field-pair tiles [rows][Fc][Fc][k]
@@ -297,6 +299,14 @@ void ffm_grouped_free(lctr_ctx* c);
 int launch_ffm_forward_tiles(lctr_ctx* c, Slot& s, int64_t rb, int64_t re);
 int launch_ffm_backward_grouped(lctr_ctx* c, Slot& s, int64_t rb, int64_t re);
 void metrics_free(lctr_ctx* c);
+int wnd_reserve(lctr_ctx* c, int64_t rows);
+void wnd_free(lctr_ctx* c);
+int launch_wnd_forward(lctr_ctx* c, Slot& s, int64_t rb, int64_t re);
+int launch_wnd_backward(lctr_ctx* c, Slot& s, int64_t rb, int64_t re);
+// width of the dense chain's input: k (NFM bi-interaction) or Fc * d (Wide&Deep concat)
+inline size_t mlp_in0(const lctr_cfg& cf) {
+    return cf.model == LCTR_MODEL_WND ? (size_t)cf.field_cnt * cf.factor_cnt : (size_t)cf.factor_cnt;
+}
 int mlp_sync_dense_grad(lctr_ctx* c);
 int mlp_bf16_prepare(lctr_ctx* c);
 int mlp_bf16_refresh(lctr_ctx* c, int layer);

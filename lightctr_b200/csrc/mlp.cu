@@ -142,7 +142,7 @@ int mlp_alloc(lctr_ctx* c) {
     LCTR_CHECK(cf.n_hidden >= 1 && cf.n_hidden <= LCTR_MAX_LAYERS, "NFM needs 1..%d hidden layers", LCTR_MAX_LAYERS);
     c->n_layers = cf.n_hidden + 1;
     size_t total = 0;
-    int in = (int)cf.factor_cnt;
+    int in = (int)mlp_in0(cf);
     for (int l = 0; l < c->n_layers; l++) {
         MlpLayer& L = c->layers[l];
         L.in = in;
@@ -198,7 +198,7 @@ int mlp_reserve(lctr_ctx* c, int64_t rows) {
     if ((size_t)rows <= c->mlp_cap_rows) return 0;
     LCTR_CUDA(cudaStreamSynchronize(c->stream));
     const size_t cap = (size_t)rows;
-    const size_t k = c->cfg.factor_cnt;
+    const size_t k = mlp_in0(c->cfg);
     if (c->z) cudaFree(c->z); if (c->dz) cudaFree(c->dz); if (c->mlp_out) cudaFree(c->mlp_out);
     LCTR_CUDA(cudaMalloc((void**)&c->z, cap * k * sizeof(float)));
     LCTR_CUDA(cudaMalloc((void**)&c->dz, cap * k * sizeof(float)));

@@ -88,6 +88,9 @@ def lib():
     L.orc_nfm_epoch.argtypes = [C.c_int64, _i64p, _u32p, _f32p, _i32p, C.c_size_t, C.c_size_t, _f32p, _f32p, _f32p,
                                 _f32p, _f32p, C.POINTER(_Mlp), C.c_size_t, C.c_size_t, C.c_float, C.c_float,
                                 C.c_float, C.POINTER(C.c_float), C.POINTER(C.c_size_t)]
+    L.orc_wnd_epoch.argtypes = [C.c_int64, _i64p, _u32p, _u32p, _f32p, _i32p, C.c_size_t, C.c_size_t, C.c_size_t, _f32p,
+                                _f32p, _f32p, _f32p, C.POINTER(_Mlp), C.c_size_t, C.c_size_t, C.c_float, C.c_float,
+                                C.c_float, C.POINTER(C.c_float), C.POINTER(C.c_size_t)]
     L.orc_predict.argtypes = [C.c_int64, _i64p, _u32p, _u32p, _f32p, _i32p, C.c_size_t, C.c_size_t, _f32p, _f32p,
                               C.c_void_p, C.c_int, _f32p, C.POINTER(C.c_float), C.POINTER(C.c_int),
                               C.POINTER(C.c_float)]
@@ -299,6 +302,29 @@ class NFMOracle:
         loss, acc = C.c_float(0), C.c_size_t(0)
         lib().orc_nfm_epoch(ds.rows, ds.row_ptr, ds.fid, ds.val, ds.label, ds.feature_cnt, self.k, self.W, self.V,
                             self.sumVX, self.update_g, self.accum, self.mlp.p, self.bs, self.mb, self.lr, self.l2,
+                            self.sr, C.byref(loss), C.byref(acc))
+        return loss.value, acc.value / ds.rows
+
+
+class WNDOracle:
+    """Wide&Deep with per-field concat input (Distributed_Algo_Abst::batchGradCompute restated as one synchronous
+    process; parity unpinned, see lightctr_oracle.c).  dims = [Fc*d, H.., 1]."""
+
+    def __init__(self, ds, d, hidden, W, E, lr=0.05, l2=0.001, batch_size=50, minibatch=50, sparse_rate=0.8, act=0):
+        self.ds, self.d = ds, d
+        F, Fc = ds.feature_cnt, ds.field_cnt
+        self.W, self.E = W.copy(), E.copy()
+        hidden = list(hidden) if isinstance(hidden, (list, tuple)) else [hidden]
+        self.mlp = Mlp([Fc * d] + hidden + [1], act, sparse_rate)
+        self.update_g = np.zeros(F * (d + 1), np.float32)
+        self.accum = np.zeros(F * (d + 1), np.float32)
+        self.lr, self.l2, self.bs, self.mb, self.sr = lr, l2, batch_size, minibatch, sparse_rate
+
+    def epoch(self):
+        ds = self.ds
+        loss, acc = C.c_float(0), C.c_size_t(0)
+        lib().orc_wnd_epoch(ds.rows, ds.row_ptr, ds.fid, ds.field, ds.val, ds.label, ds.feature_cnt, ds.field_cnt, self.d,
+                            self.W, self.E, self.update_g, self.accum, self.mlp.p, self.bs, self.mb, self.lr, self.l2,
                             self.sr, C.byref(loss), C.byref(acc))
         return loss.value, acc.value / ds.rows
 

@@ -568,6 +568,71 @@ void orc_nfm_epoch(int64_t rows, const int64_t* row_ptr, const uint32_t* fid, co
     *loss_out = loss; *acc_out = accuracy;
 }
 
+
+/* ============================ Wide&Deep with per-field concat input ============================ */
+/* Distributed_Algo_Abst::batchGradCompute (distributed_algo_abst.h:176-280) restated as ONE synchronous process:
+ * what a worker computes per row, with the pull = "read the current parameters" and the push = "add into update_g",
+ * applied once per minibatch by the trainer's updater (the reference applies pushes on asynchronous parameter
+ * servers with fp16 transport; SURVEY.md 8e lists those deltas).  PARITY UNPINNED: this class links ZeroMQ
+ * (third/zeromq, a Mach-O archive in the reference tree) and cannot be compiled here, so this restatement is checked
+ * against the source text only, not against reference outputs.
+ *   wide:  pred += w[fid] * X over the row's entries (:205-211)
+ *   deep:  input[field*d .. +d) = tensor of the FIRST entry of each field (:213-216, :224-229), 0 for absent fields
+ *   pCTR = sigmoid(pred + MLP(input)) (:236); loss / accuracy (:237-245, note >= 0.5)
+ *   gradW = loss * X + L2 * w (:256), pushed per entry; MLP backward from `loss` (:270-273); inputDelta is the
+ *   gradient of the first-entry tensors (:274-276); MLP applyBatchGradient after the batch (:283). */
+void orc_wnd_epoch(int64_t rows, const int64_t* row_ptr, const uint32_t* fid, const uint32_t* field,
+                   const float* val, const int* label, size_t F, size_t Fc, size_t d, float* W, float* E,
+                   float* update_g, float* accum, orc_mlp* mlp, size_t batch_size, size_t minibatch, float lr,
+                   float l2, float sparse_rate, float* loss_out, size_t* acc_out) {
+    float loss = 0; size_t accuracy = 0;
+    float* deep = (float*)malloc(sizeof(float) * Fc * d);
+    int64_t* first = (int64_t*)malloc(sizeof(int64_t) * Fc);
+    float* gE = update_g + F;
+    size_t n_batches = ((size_t)rows + batch_size - 1) / batch_size;
+    for (size_t p = 0; p < n_batches; p++) {
+        memset(update_g, 0, sizeof(float) * F * (d + 1));
+        int64_t rb = (int64_t)(p * batch_size), re = rb + (int64_t)batch_size;
+        if (re > rows) re = rows;
+        for (int64_t rid = rb; rid < re; rid++) {
+            float pred = 0.0f;
+            memset(deep, 0, sizeof(float) * Fc * d);
+            for (size_t a = 0; a < Fc; a++) first[a] = -1;
+            for (int64_t i = row_ptr[rid]; i < row_ptr[rid + 1]; i++) {
+                const size_t f = fid[i], a = field[i];
+                float wx = W[f] * val[i];
+                pred += wx;
+                if (first[a] < 0) { first[a] = (int64_t)f; memcpy(deep + a * d, E + f * d, sizeof(float) * d); }
+            }
+            const float fc = orc_mlp_forward(mlp, deep);
+            const float pCTR = orc_sigmoid(pred + fc);
+            {
+                double term = (label[rid] == 1) ? (double)(-logf(pCTR)) : -log(1.0 - (double)pCTR);
+                loss = (float)((double)loss + term);
+                if (pCTR >= 0.5 && label[rid] == 1) accuracy++;
+                else if (pCTR < 0.5 && label[rid] == 0) accuracy++;
+            }
+            const float lossv = pCTR - (float)label[rid];
+            for (int64_t i = row_ptr[rid]; i < row_ptr[rid + 1]; i++) {
+                const size_t f = fid[i];
+                float a = lossv * val[i], c = l2 * W[f];
+                update_g[f] = update_g[f] + (a + c);
+            }
+            orc_mlp_backward(mlp, lossv);
+            const float* delta = mlp->in_delta[0];
+            for (size_t a = 0; a < Fc; a++) {
+                if (first[a] < 0) continue;
+                for (size_t c = 0; c < d; c++) gE[(size_t)first[a] * d + c] = gE[(size_t)first[a] * d + c] + delta[a * d + c];
+            }
+        }
+        orc_adagrad(F, W, update_g, accum, minibatch, lr);
+        orc_adagrad(F * d, E, gE, accum + F, minibatch, lr);
+        orc_mlp_apply(mlp, minibatch, lr, sparse_rate);
+    }
+    free(deep); free(first);
+    *loss_out = loss; *acc_out = accuracy;
+}
+
 /* ============================ predict + AUC =================================================== */
 float orc_auc(const float* pctr, const int* label, size_t n) { /* evaluator.h:61-93 */
     const size_t kHashLen = (1u << 24) - 1;

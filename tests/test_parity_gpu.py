@@ -499,3 +499,49 @@ def test_upload_batch_rejects_malformed_input():
         ctx.upload_batch(0, rp, ok["fid"], None, None, lab)
     assert ctx.train_step(0)[0] > 0  # the slot still holds the last good batch
     ctx.close()
+
+
+@pytest.mark.parametrize("with_val", [False, True])
+def test_wide_and_deep_concat_variant(oracle_api, with_val):
+    """LCTR_MODEL_WND (csrc/wnd.cu): Distributed_Algo_Abst's per-field concat input against the
+    oracle's synchronous restatement orc_wnd_epoch (parity UNPINNED: that reference class cannot be compiled here).
+    Rows with repeated fields (only the first entry of a field feeds the deep part) and absent fields."""
+    from lightctr_b200 import capi
+    rng = np.random.default_rng(31)
+    rows, F, Fc, d, H = 300, 4000, 13, 4, 16
+    cnt = rng.integers(5, 30, rows)
+    rp = np.concatenate([[0], np.cumsum(cnt)]).astype(np.int64)
+    fid = np.concatenate([rng.choice(F, c, replace=False) for c in cnt]).astype(np.uint32)
+    fld = rng.integers(0, Fc, len(fid)).astype(np.uint32)          # unsorted fields, repeats within a row
+    val = (rng.random(len(fid)).astype(np.float32) + 0.5) if with_val else np.ones(len(fid), np.float32)
+    lab = (rng.random(rows) < 0.35).astype(np.int32)
+    W0 = (rng.standard_normal(F) * 0.01).astype(np.float32)
+    E0 = (rng.standard_normal(F * d) * 0.1).astype(np.float32)
+    ds = oracle_api.Dataset(rp, fid, fld, val, lab, F, Fc)
+    B = 100
+    o = oracle_api.WNDOracle(ds, d, [H], W0, E0, batch_size=B, minibatch=B)
+    dims = [Fc * d, H, 1]
+    layers = [(o.mlp.arrays("weight", l).copy(), o.mlp.arrays("bias", l).copy()) for l in range(2)]
+    ctx = capi.Context(capi.MODEL_WND, F, d, Fc, hidden=(H,), minibatch_size=B)
+    ctx.upload_params(W0, E0)
+    for l, (w, b) in enumerate(layers):
+        ctx.mlp_upload(l, w, b)
+    ctx.upload_batch(0, rp, fid, fld.astype(np.uint16), val if with_val else None, lab)
+    # the oracle re-draws its dropout masks after every minibatch: run it one minibatch at a time with masks = 1
+    for step in range(3):
+        rb, re = step * B, (step + 1) * B
+        sub = oracle_api.Dataset(rp[rb:re + 1] - rp[rb], fid[rp[rb]:rp[re]], fld[rp[rb]:rp[re]], val[rp[rb]:rp[re]],
+                                 lab[rb:re], F, Fc)
+        o.ds = sub
+        for l in range(2):
+            o.mlp.arrays("mask", l)[:] = 1.0
+        lo, ao = o.epoch()
+        lg, cg = ctx.train_step(0, rb, re)
+        assert _rel(lg, lo) < LOSS_RTOL, (step, lg, lo)
+        assert cg == round(ao * B)
+    W, E = ctx.download_params()
+    assert np.max(np.abs(W - o.W)) < 1e-5 and np.max(np.abs(E - o.E)) < 1e-5
+    for l in range(2):
+        w, b = ctx.mlp_download(l, dims[l], dims[l + 1])
+        assert np.max(np.abs(w - o.mlp.arrays("weight", l))) < 1e-5
+    ctx.close()
