@@ -48,6 +48,27 @@ class ClockSampler(threading.Thread):
         self.stop_flag = False
 
     def run(self):
+        # NVML (same counters as nvidia-smi, ~50 us per query) gives hundreds of samples inside a 20 ms timed region;
+        # the nvidia-smi loop of the recipe is the fallback (its process start alone outlasts a short region)
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.gpu)
+            mx = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            bits = {"hw_slowdown": pynvml.nvmlClocksThrottleReasonHwSlowdown,
+                    "hw_thermal_slowdown": pynvml.nvmlClocksThrottleReasonHwThermalSlowdown,
+                    "sw_thermal_slowdown": pynvml.nvmlClocksThrottleReasonSwThermalSlowdown,
+                    "sw_power_cap": pynvml.nvmlClocksThrottleReasonSwPowerCap}
+            while not self.stop_flag:
+                sm = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+                r = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                self.samples.append("%d,%d,%g,0,%s" % (self.gpu, sm, mx, ",".join(
+                    "Active" if r & bits[k] else "Not Active"
+                    for k in ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"))))
+                time.sleep(0.002)
+            return
+        except Exception:
+            pass
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.q,
                                           "--format=csv,noheader,nounits", "-lms", str(self.period)],
