@@ -180,6 +180,189 @@ def _run_reference(wl, steps, warmup, budget_s=20.0):
                        % (steps, rows, wl["F"], cores))
 
 
+def ncu_traffic(wname, kernel):
+    """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the CURRENT kernels, from the ncu
+    --set full capture summarised by scripts/ncu_summary.py --json into profiles/ncu_traffic.json (the bench itself
+    never runs under a profiler).  None where no capture exists."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if not os.path.exists(p):
+        return None, None
+    d = json.load(open(p)).get(wname, {})
+    for name, rec in d.get("kernels", {}).items():
+        if kernel in name:
+            return rec.get("dram_bytes"), "profiles/ncu_traffic.json <- %s" % d.get("source", "?")
+    return None, None
+
+
+def check_against_oracle(ctx, wl, batch, Fc):
+    """--check: step 0 of the benched batch against the CPU oracle from the same (downloaded) parameters."""
+    from oracle import api
+    rp, fid, fld, lab = batch
+    W0, V0 = ctx.download_params()
+    F, k = wl["F"], wl["k"]
+    ds = api.Dataset(rp, fid, fld.astype(np.uint32), np.ones(len(fid), np.float32), lab, F, Fc)
+    if wl["model"] == "fm":
+        o = api.FMOracle(ds, k, W0, V0)
+    elif wl["model"] == "ffm":
+        o = api.FFMOracle(ds, k, W0, V0, optimizer=wl["opt"])
+    else:
+        return {"supported": False, "why": "NFM chain check lives in tests/test_shapes_gpu.py"}
+    lg, _ = ctx.train_step(0)
+    lo, _ = o.epoch()
+    Wg, Vg = ctx.download_params()
+    rel = abs(lg - lo) / max(abs(lo), 1e-30)
+    out = {"supported": True, "loss_gpu": lg, "loss_oracle": lo, "loss_rel": rel, "max_dW": float(np.max(np.abs(Wg - o.W))),
+           "max_dV": float(np.max(np.abs(Vg - o.V))), "ok": bool(rel < 1e-5)}
+    ctx.upload_params(W0, V0)  # the timed run starts from the same parameters (updater state keeps one step: harmless)
+    return out
+
+
+def measure(wname, wl, args, rank, world, local_rank, dist, steps, warmup, do_e2e=True, split_global=0):
+    """One workload on this process group: K device-timed steps on resident batches (+ the end-to-end arm)."""
+    import torch
+    from lightctr_b200 import capi
+    model = {"fm": capi.MODEL_FM, "ffm": capi.MODEL_FFM, "nfm": capi.MODEL_NFM}[wl["model"]]
+    opt = {"adagrad": capi.OPT_ADAGRAD, "ftrl": capi.OPT_FTRL, "adam": capi.OPT_ADAM}[wl["opt"]]
+    F, k = wl["F"], wl["k"]
+    B = wl["batch"] if not split_global else split_global // world  # rows per GPU per step
+    Fc = N_FIELDS if wl["model"] == "ffm" else 0
+    # FM on one GPU: the order-free fused step (csrc/fm_fused.cu).  LCTR_BENCH_BACKWARD=grouped selects the
+    # feature-grouped modes of csc.cu / ffm_grouped.cu (their grouping kernels: at upload for FM, inside the step for FFM).
+    det = 2 if (world == 1 and wl["model"] in ("fm", "ffm") and os.environ.get("LCTR_BENCH_BACKWARD", "red") == "grouped") else 0
+    if det == 2 and wl["model"] == "ffm":
+        os.environ["LCTR_CSC_IN_STEP"] = "1"
+    mlp_bf16 = wl["model"] == "nfm" and os.environ.get("LCTR_BENCH_MLP", "bf16") == "bf16"
+    ctx = capi.Context(model, F, k, Fc, optimizer=opt, device=local_rank, deterministic=det, rank=rank, world=world,
+                       minibatch_size=(world * B if world > 1 else 0), max_nnz=B * 120, hidden=wl.get("hidden", ()),
+                       mlp_precision=capi.MLP_BF16 if mlp_bf16 else capi.MLP_FP32)
+    if wl["model"] == "nfm":  # FC chain initialised like fullyconnLayer.h:48-54 (U(-0.5,0.5), bias 0), masks all-ones
+        rng0 = np.random.default_rng(99)
+        dims = [k] + list(wl["hidden"]) + [1]
+        for li in range(len(dims) - 1):
+            ctx.mlp_upload(li, (rng0.random((dims[li + 1], dims[li]), dtype=np.float32) - 0.5), np.zeros(dims[li + 1], np.float32))
+    ctx.fill_params(1234, float(1.0 / np.sqrt(k)))  # random-init weights (W = 0, V ~ N(0,1)/sqrt(k)), on the device
+    if world > 1:
+        from lightctr_b200 import dist as ldist
+        ldist.connect(ctx)
+        if wl["model"] == "nfm":  # replicated dense layers: dW / db summed with NCCL on the context's stream every step
+            ldist.attach_dense_allreduce(ctx)
+    NB = wl.get("nb", 8)
+    wl_b = dict(wl, batch=B)
+    batches = make_batches(wl_b, NB, seed_offset=rank)
+    pinned = []
+    if do_e2e:  # pinned host copies (the end-to-end arm copies from these every step)
+        for (rp, fid, fld, lab) in batches:
+            pinned.append((torch.from_numpy(rp).pin_memory(), torch.from_numpy(fid.astype(np.int32)).pin_memory(),
+                           torch.from_numpy(fld.astype(np.int16)).pin_memory(), torch.from_numpy(lab).pin_memory()))
+    for i, (rp, fid, fld, lab) in enumerate(batches):
+        ctx.upload_batch(i, rp, fid, fld if Fc else None, None, lab)
+    nnz_mean = float(np.mean([len(b[1]) for b in batches]))
+    check = None
+    if args.check and world == 1:
+        check = check_against_oracle(ctx, wl_b, batches[0], Fc)
+    stream = torch.cuda.ExternalStream(ctx.stream())
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
+    do_flush = os.environ.get("LCTR_BENCH_NOFLUSH", "0") != "1"
+
+    def one_step(i, timed_events=None):
+        with torch.cuda.stream(stream):
+            if do_flush:
+                flush.zero_()
+            if timed_events is not None:
+                timed_events[0].record(stream)
+        ctx.train_step(i % NB, want_stats=False)
+        if timed_events is not None:
+            with torch.cuda.stream(stream):
+                timed_events[1].record(stream)
+
+    for i in range(max(warmup, 3)):
+        one_step(i)
+    ctx.sync()
+    ctx.profile(True)
+    ctx.profile_read(reset=True)
+    launches0 = ctx.launch_count()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t_wall0 = time.time()
+    for i in range(steps):
+        one_step(i, evs[i])
+    ctx.sync()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t_wall = time.time() - t_wall0
+    launches = ctx.launch_count() - launches0
+    prof = ctx.profile_read(reset=True)
+    step_ms = [a.elapsed_time(b) for a, b in evs]
+    ms_per_step = float(np.mean(step_ms))
+    if world > 1:  # device time, max over ranks
+        t = torch.tensor([ms_per_step], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_per_step = float(t[0])
+    value = world * B / (ms_per_step * 1e-3)
+
+    # ---- the embedding gather alone (BASELINE metric "embed-gather HBM GB/s vs peak"): the forward kernel of the model
+    # on the same resident batches, L2 flushed before every launch, timed with the per-kernel CUDA events -------------
+    gather = None
+    if wl["model"] == "fm" and world == 1:
+        for i in range(3 + min(steps, 50)):
+            with torch.cuda.stream(stream):
+                if do_flush:
+                    flush.zero_()
+            if i == 3:
+                ctx.sync()
+                ctx.profile_read(reset=True)
+            ctx.predict_resident(i % NB)
+        pg = ctx.profile_read(reset=True)
+        if "fm_forward" in pg:
+            gms, gcnt = pg["fm_forward"]
+            gather = {"ms": gms / gcnt, "launches": gcnt}
+    ctx.profile(False)
+
+    # ---- end-to-end arm: host buffers in, loss out, every step (C-ABI lctr_train_batch_async / lctr_wait) -------------
+    e2e = None
+    clocks = None
+    if do_e2e:
+        h2d = 8 * (B + 1) + 4 * nnz_mean + 4 * B + (2 * nnz_mean if Fc else 0)
+        host = [_host_arrays(p, Fc) for p in pinned]
+        for i in range(NB + 3):  # warm-up through the same pipelined entry points (allocates both pipeline slots)
+            ctx.wait(ctx.train_batch_async(*host[i % NB]))
+        ctx.sync()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.time()
+        prev = None
+        e2e_loss = 0.0
+        for i in range(steps):
+            t = ctx.train_batch_async(*host[i % NB])
+            if prev is not None:
+                e2e_loss += ctx.wait(prev)[0]
+            prev = t
+        e2e_loss += ctx.wait(prev)[0]
+        ctx.sync()
+        e2e_s = time.time() - t0
+        if world > 1:
+            t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e2e_s = float(t[0])
+        e2e = {"value": world * B * steps / e2e_s, "unit": "samples/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 16,
+               "l2": "not flushed: every step's batch arrives from pinned host memory, parameters stay L2-resident between "
+                     "steps as in a real training loop (the device-timed `value` flushes L2 before every step)"}
+    clocks = sampler.finish()
+    if world > 1:
+        dist.barrier()
+    ctx.close()
+    del flush
+    torch.cuda.empty_cache()
+    return dict(value=value, ms_per_step=ms_per_step, prof=prof, launches=launches, nnz_mean=nnz_mean, B=B, Fc=Fc, det=det,
+                mlp_bf16=mlp_bf16, e2e=e2e, clocks=clocks, t_wall=t_wall, gather=gather, check=check)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -188,6 +371,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-c5", action="store_true", help="skip the FFM C5 split-batch scaling measurement")
+    ap.add_argument("--check", action="store_true", help="compare step 0 of the benched batch with the CPU oracle")
     ap.add_argument("--batch", type=int, default=0, help="override the workload's rows per GPU per step (sweeps; "
                     "the headline configs are the defaults)")
     args = ap.parse_args()
@@ -221,7 +406,6 @@ def main():
 
     import torch
     from lightctr_b200 import build as lbuild
-    from lightctr_b200 import capi
     lbuild.build()
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (the product has no CPU path)")
@@ -230,145 +414,28 @@ def main():
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    model = {"fm": capi.MODEL_FM, "ffm": capi.MODEL_FFM, "nfm": capi.MODEL_NFM}[wl["model"]]
-    opt = {"adagrad": capi.OPT_ADAGRAD, "ftrl": capi.OPT_FTRL, "adam": capi.OPT_ADAM}[wl["opt"]]
-    F, k, B = wl["F"], wl["k"], wl["batch"]
-    Fc = N_FIELDS if wl["model"] == "ffm" else 0
-    # weak scaling: every rank trains its own batch of B rows per step (global batch world*B, the updater divides by
-    # it); W / V / updater state are owner-sharded over the ranks and exchanged per batch (csrc/dist.cu)
-    # backward strategy: RED scatter + sparse apply by default (every per-batch kernel is inside the timed region).
-    # LCTR_BENCH_BACKWARD=grouped selects the feature-grouped backward of csc.cu; its per-batch grouping kernels run
-    # at upload, i.e. OUTSIDE the device-timed `value` region but INSIDE the end-to-end region.
-    # For FFM, grouped selects the atomic-free step of ffm_grouped.cu; its grouping kernels are then rebuilt INSIDE every
-    # timed step (LCTR_CSC_IN_STEP=1), so `value` pays for them.  Measured r01: RED path 13.6M (C3) / 9.9M (C5)
-    # samples/s vs grouped 9.1M / 8.2M, so RED stays the default.
-    bw_default = "red"
-    det = 2 if (world == 1 and wl["model"] in ("fm", "ffm") and os.environ.get("LCTR_BENCH_BACKWARD", bw_default) == "grouped") else 0
-    if det == 2 and wl["model"] == "ffm":
-        os.environ["LCTR_CSC_IN_STEP"] = "1"
-    # NFM dense layers: bf16 tensor-core mode (config C4) unless LCTR_BENCH_MLP=fp32 asks for the reference-order fp32 MLP
-    mlp_bf16 = wl["model"] == "nfm" and os.environ.get("LCTR_BENCH_MLP", "bf16") == "bf16"
-    ctx = capi.Context(model, F, k, Fc, optimizer=opt, device=local_rank, deterministic=det, rank=rank, world=world,
-                       minibatch_size=(world * B if world > 1 else 0), max_nnz=B * 120, hidden=wl.get("hidden", ()),
-                       mlp_precision=capi.MLP_BF16 if mlp_bf16 else capi.MLP_FP32)
-    if wl["model"] == "nfm":  # FC chain initialised like fullyconnLayer.h:48-54 (U(-0.5,0.5), bias 0), masks all-ones
-        rng0 = np.random.default_rng(99)
-        dims = [k] + list(wl["hidden"]) + [1]
-        for li in range(len(dims) - 1):
-            ctx.mlp_upload(li, (rng0.random((dims[li + 1], dims[li]), dtype=np.float32) - 0.5), np.zeros(dims[li + 1], np.float32))
-    ctx.fill_params(1234, float(1.0 / np.sqrt(k)))  # random-init weights (W = 0, V ~ N(0,1)/sqrt(k)), on the device
-    if world > 1:
-        from lightctr_b200 import dist as ldist
-        ldist.connect(ctx)
-        if wl["model"] == "nfm":  # replicated dense layers: dW / db summed with NCCL on the context's stream every step
-            ldist.attach_dense_allreduce(ctx)
-    NB = wl.get("nb", 8)
-    batches = make_batches(wl, NB, seed_offset=rank)
-    # pinned host copies (the end-to-end arm copies from these every step)
-    pinned = []
-    for (rp, fid, fld, lab) in batches:
-        t_rp = torch.from_numpy(rp).pin_memory()
-        t_fid = torch.from_numpy(fid.astype(np.int32)).pin_memory()  # same bits as uint32
-        t_fld = torch.from_numpy(fld.astype(np.int16)).pin_memory()
-        t_lab = torch.from_numpy(lab).pin_memory()
-        pinned.append((t_rp, t_fid, t_fld, t_lab))
-    for i, (rp, fid, fld, lab) in enumerate(batches):
-        ctx.upload_batch(i, rp, fid, fld if Fc else None, None, lab)
-    nnz_mean = float(np.mean([len(b[1]) for b in batches]))
-    stream = torch.cuda.ExternalStream(ctx.stream())
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
-
-    do_flush = os.environ.get("LCTR_BENCH_NOFLUSH", "0") != "1"
-
-    def one_step(i, timed_events=None):
-        with torch.cuda.stream(stream):
-            if do_flush:
-                flush.zero_()
-            if timed_events is not None:
-                timed_events[0].record(stream)
-        ctx.train_step(i % NB, want_stats=False)
-        if timed_events is not None:
-            with torch.cuda.stream(stream):
-                timed_events[1].record(stream)
-
-    for i in range(max(args.warmup, 3)):
-        one_step(i)
-    ctx.sync()
-    ctx.profile(True)
-    ctx.profile_read(reset=True)
-    launches0 = ctx.launch_count()
-    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    t_wall0 = time.time()
-    for i in range(args.steps):
-        one_step(i, evs[i])
-    ctx.sync()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    t_wall = time.time() - t_wall0
-    launches = ctx.launch_count() - launches0
-    prof = ctx.profile_read(reset=True)
-    ctx.profile(False)
-    step_ms = [a.elapsed_time(b) for a, b in evs]
-    ms_per_step = float(np.mean(step_ms))
-    if world > 1:  # device time, max over ranks
-        t = torch.tensor([ms_per_step], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_per_step = float(t[0])
-    value = world * B / (ms_per_step * 1e-3)
-
-    # ---- end-to-end arm: host buffers in, loss out, every step (C-ABI lctr_train_batch) ------------------
-    h2d = 8 * (B + 1) + 4 * nnz_mean + 4 * B + (2 * nnz_mean if Fc else 0)
-    # every step: H2D of that step's CSR batch from pinned host memory, the train step, D2H of (loss, acc); the
-    # copy of batch i+1 overlaps the kernels of batch i (lctr_train_batch_async / lctr_wait, two batches in flight)
-    host = [_host_arrays(p, Fc) for p in pinned]
-    for i in range(NB + 3):  # warm-up through the same pipelined entry points (allocates both pipeline slots)
-        ctx.wait(ctx.train_batch_async(*host[i % NB]))
-    ctx.sync()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    t0 = time.time()
-    prev = None
-    e2e_loss = 0.0
-    for i in range(args.steps):
-        t = ctx.train_batch_async(*host[i % NB])
-        if prev is not None:
-            e2e_loss += ctx.wait(prev)[0]
-        prev = t
-    e2e_loss += ctx.wait(prev)[0]
-    ctx.sync()
-    e2e_s = time.time() - t0
-    if world > 1:
-        t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t[0])
-    clocks = sampler.finish()
-    e2e_value = world * B * args.steps / e2e_s
+    m = measure(wname, wl, args, rank, world, local_rank, dist, args.steps, args.warmup)
+    value, ms_per_step, prof, B, Fc, det, nnz_mean = m["value"], m["ms_per_step"], m["prof"], m["B"], m["Fc"], m["det"], m["nnz_mean"]
+    mlp_bf16 = m["mlp_bf16"]
+    k = wl["k"]
 
     # ---- roofline of the dominant kernel (algorithmic bytes per SURVEY.md 8d / DESIGN.md) -----------------
     peak, peak_src = measured_peaks()
     compute = {kk: vv for kk, vv in prof.items() if not kk.startswith("dist_")}
     dom = max(compute.items(), key=lambda kv: kv[1][0]) if compute else (None, (0.0, 0))
     n = nnz_mean / B
+    gather_bps = n * (4 * k + 12) + 8          # V row + W + fid + slot per entry, row_ptr per sample
+    scatter_bps = n * (4 * k + 4)              # one gradient row [gV | gW] per entry, RED into the compact buffer
     if wl["model"] in ("fm", "nfm"):
-        bytes_per_sample = {"fm_forward": n * (4 * k + 12) + 8, "fm_backward_red": n * (4 * k + 12) + 8,
-                            "fm_backward_csc": n * (4 * k + 12) + 8, "apply": None, "mlp": None}
+        bytes_per_sample = {"fm_forward": gather_bps, "fm_backward_red": gather_bps, "fm_fused": gather_bps + scatter_bps,
+                            "fm_backward_csc": gather_bps, "apply": None, "apply_compact": None, "mlp": None}
     else:
         # fused: one row gather per entry (+ the sample's Fc x Fc x k tile written once in grouped mode);
         # grouped backward: one contiguous tile row per entry
         bytes_per_sample = {"ffm_fused": n * (Fc * k * 4 + 12) + (Fc * Fc * k * 4 if det == 2 else 0),
                             "fm_backward_csc": n * (Fc * k * 4 + 10)}
-    # DRAM traffic per launch (dram__bytes_read.sum + dram__bytes_write.sum) of ONE `ncu --set full` capture of the same
-    # workload, copied from profiles/ (the bench itself never runs under a profiler); None where no capture exists
-    NCU_TRAFFIC = {("fm_c2", "fm_backward_red"): (12_875_520, "profiles/ncu_r01_fm_c2_summary.txt"),
-                   ("fm_c2", "fm_forward"): (7_600_000, "profiles/ncu_r01_fm_c2_summary.txt")}
     roof = None
+    cnt = 0
     if dom[0] is not None:
         ms, cnt = dom[1]
         bps = bytes_per_sample.get(dom[0])
@@ -376,10 +443,12 @@ def main():
             achieved = bps * B / (ms / cnt * 1e-3) / 1e9
             roof = {"bound": "hbm", "kernel": dom[0], "achieved": achieved, "peak": peak, "unit": "GB/s",
                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                    "algorithmic_bytes_per_launch": bps * B, "kernel_ms": ms / cnt}
-            tr = NCU_TRAFFIC.get((wname, dom[0])) if not args.batch and world == 1 else None
-            if tr:
-                roof["traffic"], roof["traffic_source"] = tr
+                    "algorithmic_bytes_per_launch": bps * B, "kernel_ms": ms / cnt,
+                    "bytes": ("gather n(4k+12)+8 + scatter n(4k+4) per sample" if dom[0] == "fm_fused" else "gather bytes per sample (SURVEY 8d)")}
+            if not args.batch and world == 1:
+                roof["traffic"], src = ncu_traffic(wname, dom[0])
+                if src:
+                    roof["traffic_source"] = src
     if dom[0] == "mlp" and cnt:  # dense layers: fwd + dX + dW = 6 flops per weight per sample
         dims = [k] + list(wl["hidden"]) + [1]
         flops = 6.0 * sum(dims[i] * dims[i + 1] for i in range(len(dims) - 1)) * B
@@ -388,7 +457,21 @@ def main():
         roof = {"bound": "tensor", "kernel": "mlp (nfm_mlp_fused_kernel + dense Adagrad)", "achieved": achieved, "peak": tpeak,
                 "unit": "TFLOP/s", "frac": achieved / tpeak, "traffic": None, "peak_source": tsrc,
                 "algorithmic_flops_per_launch": flops, "kernel_ms": ms / cnt}
+    roof_gather = None
+    if m["gather"]:
+        gms = m["gather"]["ms"]
+        ach = gather_bps * B / (gms * 1e-3) / 1e9
+        roof_gather = {"bound": "hbm", "kernel": "fm_fused_kernel<MODE 0> (forward gather alone, lctr_predict)", "achieved": ach,
+                       "peak": peak, "unit": "GB/s", "frac": ach / peak, "kernel_ms": gms, "launches": m["gather"]["launches"],
+                       "algorithmic_bytes_per_launch": gather_bps * B, "peak_source": peak_src}
+        tr, src = ncu_traffic(wname, "fm_forward") if not args.batch else (None, None)
+        roof_gather["traffic"] = tr
     kernels = {name: {"ms": v[0] / max(v[1], 1), "launches": v[1]} for name, v in prof.items()}
+    bw_desc = ("RED scatter + sparse apply" if not (wl["model"] == "fm" and world == 1) else
+               "order-free fused step: one gather, RED scatter into the batch-compact buffer (hot-slot replicas), compact updater")
+    if det == 2:
+        bw_desc = ("feature-grouped on device + fused updater (csc.cu)" if wl["model"] == "fm" else
+                   "feature-grouped, atomic-free, fused updater (ffm_grouped.cu); grouping kernels inside the timed step")
     line = {"metric": metric, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16 dense layers (fp32 accumulate, fp32 masters) + f32 embeddings" if mlp_bf16 else "f32",
@@ -397,15 +480,24 @@ def main():
                        "global_batch": world * B, "nnz_per_row": n,
                        **({"mlp": "bf16 mma, fused fwd+bwd per 128-sample tile" if mlp_bf16 else "fp32 reference-order"}
                           if wl["model"] == "nfm" else {}),
-                       "backward": (("feature-grouped on device + fused updater (csc.cu)" if wl["model"] == "fm" else
-                                     "feature-grouped, atomic-free, fused updater (ffm_grouped.cu); grouping kernels inside the timed step")
-                                    if det == 2 else "RED scatter + sparse apply"),
+                       "backward": bw_desc,
                        "parallelism": "1 GPU" if world == 1 else
                        ("dp%d rows + owner-sharded tables (fid mod %d), unique-id pull/push over NVLink peer memory" % (world, world))
                        + ("; dense layers replicated, gradients NCCL all-reduced" if wl["model"] == "nfm" else "")},
-            "clocks": clocks, "gpu_launches": int(launches), "kernels_ms": kernels,
-            "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 16},
-            "roofline": roof, "wall_s_timed_region": t_wall}
+            "clocks": m["clocks"], "gpu_launches": int(m["launches"]), "kernels_ms": kernels,
+            "e2e": m["e2e"], "roofline": roof, "roofline_gather": roof_gather, "wall_s_timed_region": m["t_wall"]}
+    if m["check"] is not None:
+        line["check"] = m["check"]
+    # ---- north-star scaling config: FFM C5 (k=8, 10 M features) with the GLOBAL batch 65 536 split across the ranks
+    # (strong scaling), measured by every default run so that the driver's N = 1, 2, 4, 8 records carry it ----
+    if not args.no_c5 and not args.workload and not args.batch:
+        wl5 = dict(WORKLOADS["ffm_c5"])
+        c5 = measure("ffm_c5", wl5, args, rank, world, local_rank, dist, steps=max(5, min(args.steps, 10)), warmup=3, do_e2e=False,
+                     split_global=wl5["batch"])
+        line["c5"] = {"workload": "FFM k=8, 39 fields, 10M features, GLOBAL batch 65536 split across %d GPU(s), Adagrad" % world,
+                      "n": world, "split": "strong (global batch fixed at 65536)", "rows_per_gpu": c5["B"], "value": c5["value"],
+                      "unit": "samples/s", "ms_per_step": c5["ms_per_step"],
+                      "kernels_ms": {nm: {"ms": v[0] / max(v[1], 1), "launches": v[1]} for nm, v in c5["prof"].items()}}
     if not args.no_cpu_baseline and rank == 0 and world == 1:
         r = run_reference(wl, 50, 1, budget_s=15.0)
         if r is not None:
@@ -415,8 +507,6 @@ def main():
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
-    ctx.close()
-    if world > 1:
         dist.destroy_process_group()
     return 0
 

@@ -297,6 +297,10 @@ class Context:
         _chk(self.L.lctr_predict(self.h, slot, quirk_sumvx_slot, out.ctypes.data))
         return out
 
+    def predict_resident(self, slot, quirk_sumvx_slot=-1):
+        """forward only, predictions stay on the device (no host copy, no synchronisation)"""
+        _chk(self.L.lctr_predict(self.h, slot, quirk_sumvx_slot, None))
+
     def download_sumvx(self, slot):
         out = np.empty(self.slot_rows[slot] * self.k, np.float32)
         _chk(self.L.lctr_download_sumvx(self.h, slot, out.ctypes.data))
@@ -356,7 +360,7 @@ class Context:
         _chk(self.L.lctr_mlp_set_mask(self.h, layer, m.ctypes.data))
 
     PROF_NAMES = ["fm_forward", "fm_backward_red", "apply", "ffm_fused", "fm_backward_csc", "mlp", "dist_mark", "dist_compact",
-                  "dist_pull", "dist_push", "dist_barrier0", "dist_merge", "dist_barrier1", "csc_build", "", ""]
+                  "dist_pull", "dist_push", "dist_barrier0", "dist_merge", "dist_barrier1", "csc_build", "fm_fused", "apply_compact"]
 
     def profile(self, enable=True):
         _chk(self.L.lctr_profile(self.h, 1 if enable else 0))

@@ -257,6 +257,7 @@ int lctr_destroy(lctr_ctx* c) {
         dfree(s.row_ptr); dfree(s.fid); dfree(s.field); dfree(s.val); dfree(s.label); dfree(s.pred); dfree(s.sumvx);
         dfree(s.wide);
         dfree(s.blk_seg_ptr); dfree(s.seg_ptr); dfree(s.seg_fid); dfree(s.ent_row); dfree(s.ent_x); dfree(s.ent_field);
+        dfree(s.ent_slot); dfree(s.hot_of); dfree(s.hot_slot); dfree(s.n_hot);
         dfree(s.uniq); dfree(s.n_uniq); dfree(s.short_list); dfree(s.long_list); dfree(s.csc_totals); dfree(s.csc_acc); dfree(s.csc_arrived);
         delete s.h_blk_seg_ptr; s.h_blk_seg_ptr = nullptr;
     }
@@ -265,6 +266,7 @@ int lctr_destroy(lctr_ctx* c) {
     metrics_free(c);
     wnd_free(c);
     dist_free(c);
+    fused_free(c);
     csc_scratch_free(c);
     if (c->h_stats) cudaFreeHost(c->h_stats);
     if (c->h_stat_ring) cudaFreeHost(c->h_stat_ring);
@@ -410,6 +412,10 @@ static int upload_batch_on(lctr_ctx* c, cudaStream_t st, int slot, int64_t rows,
         }
     }
     if (c->cfg.world > 1 && dist_build_uniq(c, s, st)) return 1;
+    s.fused_valid = false;
+    if (fused_supported(c) && rows > 0 && nnz > 0) {  // slot map of the batch for the order-free fused step
+        if (fused_reserve(c, s, nnz) || fused_build_slot(c, s, st, nullptr, rows, nnz)) return 1;
+    }
     s.csc_block = 0;
     s.dev_csc = false;
     if (grouped) {
@@ -475,6 +481,8 @@ int lctr_train_step(lctr_ctx* c, int slot, int64_t rb, int64_t re, float* loss_s
                 rc = launch_fm_forward(c, s, rb, re, false, true) || launch_fm_backward_devcsc(c, s, rb, re);
             else if (c->cfg.deterministic)
                 rc = launch_fm_forward(c, s, rb, re, false, true) || launch_fm_backward_csc(c, s, rb, re, false);
+            else if (s.fused_valid)  // order-free: one gather, RED scatter into the batch-compact buffer, compact updater
+                rc = launch_fm_fused(c, s, rb, re, true, nullptr, nullptr) || launch_apply_compact(c, s, re - rb, nullptr, nullptr);
             else
                 rc = launch_fm_forward(c, s, rb, re, false, true) || launch_fm_backward(c, s, rb, re, false) ||
                      launch_apply(c, re - rb);
@@ -665,13 +673,15 @@ int lctr_predict(lctr_ctx* c, int slot, int quirk_sumvx_slot, float* pctr) {
     Slot& s = c->slots[slot];
     int rc = 0;
     if (c->cfg.model == LCTR_MODEL_FFM) {
-        rc = launch_ffm_forward(c, s, 0, s.rows, false);
+        // parity mode: the reference's own pair loop order; otherwise the field-pair factorised forward
+        rc = c->cfg.deterministic == 1 ? launch_ffm_predict_inorder(c, s) : launch_ffm_forward(c, s, 0, s.rows, false);
     } else if (c->cfg.model == LCTR_MODEL_FM) {
         if (quirk_sumvx_slot >= 0) {
             LCTR_CHECK(quirk_sumvx_slot < kNumSlots, "quirk slot out of range");
             rc = launch_predict_quirk(c, s, c->slots[quirk_sumvx_slot]);
         } else {
-            rc = launch_fm_forward(c, s, 0, s.rows, false, false);
+            // order-free contexts predict with the shuffle-tree forward; parity contexts with the in-order one
+            rc = fused_supported(c) ? launch_fm_forward_tree(c, s, 0, s.rows, false) : launch_fm_forward(c, s, 0, s.rows, false, false);
         }
     } else {
         set_error("lctr_predict: the reference ships no NFM predictor (main.cpp:230-233)");

@@ -32,7 +32,7 @@ void set_error(const char* fmt, ...);
 
 constexpr int kNumSlots = 8;
 constexpr int kNumProf = 16;  // per-kernel timing buckets
-enum { PROF_FM_FWD = 0, PROF_FM_BWD_RED = 1, PROF_APPLY = 2, PROF_FFM_FUSED = 3, PROF_FM_BWD_CSC = 4, PROF_MLP = 5, PROF_DIST_MARK = 6, PROF_DIST_COMPACT = 7, PROF_DIST_PULL = 8, PROF_DIST_PUSH = 9, PROF_DIST_BAR0 = 10, PROF_DIST_MERGE = 11, PROF_DIST_BAR1 = 12, PROF_CSC_BUILD = 13 };
+enum { PROF_FM_FWD = 0, PROF_FM_BWD_RED = 1, PROF_APPLY = 2, PROF_FFM_FUSED = 3, PROF_FM_BWD_CSC = 4, PROF_MLP = 5, PROF_DIST_MARK = 6, PROF_DIST_COMPACT = 7, PROF_DIST_PULL = 8, PROF_DIST_PUSH = 9, PROF_DIST_BAR0 = 10, PROF_DIST_MERGE = 11, PROF_DIST_BAR1 = 12, PROF_CSC_BUILD = 13, PROF_FM_FUSED = 14, PROF_APPLY_COMPACT = 15 };
 constexpr int kStatRing = 64;
 constexpr unsigned kFull = 0xffffffffu;
 
@@ -73,6 +73,13 @@ struct Slot {
     unsigned int* n_uniq = nullptr;
     int64_t cap_uniq = 0;
     bool uniq_valid = false;
+    // order-free fused FM step (fm_fused.cu): per-entry slot of the gradient row (or kHotBit | replica block), the hot
+    // slots' replica-block index per slot and their list; `uniq` / `n_uniq` above hold the key set
+    uint32_t* ent_slot = nullptr;
+    int64_t cap_ent_slot = 0;
+    uint32_t *hot_of = nullptr, *hot_slot = nullptr;
+    unsigned int* n_hot = nullptr;
+    bool fused_valid = false;
 };
 
 // captured graphs of one slot of the streamed pipeline (capi.cu)
@@ -98,7 +105,7 @@ struct MlpLayer {
 
 }  // namespace lctr
 
-namespace lctr { struct DistState; }
+namespace lctr { struct DistState; struct FusedState; }
 struct lctr_ctx {
     lctr_cfg cfg;
     cudaStream_t stream = nullptr;
@@ -112,6 +119,7 @@ struct lctr_ctx {
     // world == 1; in multi-GPU mode a full-size local cache of the rows pulled this step + local gradient buffers
     float *cW = nullptr, *cV = nullptr, *cgW = nullptr, *cgV = nullptr;
     lctr::DistState* dist = nullptr;
+    lctr::FusedState* fused = nullptr;  // order-free fused FM step (fm_fused.cu)
     uint32_t* touch_list = nullptr;      // compacted fids of the step (stage A of the sparse apply)
     unsigned int* n_touch = nullptr;     // list length (device)
     unsigned int* apply_done = nullptr;  // block-completion counter of stage B
@@ -146,6 +154,8 @@ struct lctr_ctx {
     int mlp_skip_update = 0;    // LCTR_MLP_SKIP_UPDATE=1: leave the dense gradients in place (tests read them)
     int sm_count = 148;
     int64_t launches = 0;
+    const float* fwd_quirk_sumvx = nullptr;  // FM_Predict quirk: training sumVX rows used by the next forward launch
+    int64_t fwd_quirk_rows = 0;
     void* csc_scratch = nullptr;  // csc.cu: dense count / offset arrays of the device-side grouping
     // optional per-kernel timing (lctr_profile): events bracket every launch on the ctx stream
     int profiling = 0;
@@ -198,6 +208,26 @@ __device__ __forceinline__ float ldg_f32_pinned(const float* p) {
     float v;
     asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(v) : "l"(p));
     return v;
+}
+
+// avx_dotProduct(x, y, n) (common/avx.h:102-127) with strided operands, evaluated by ONE thread in the
+// reference's order: 8 lane accumulators over the full 8-chunks, the hsum tree, then the scalar tail.
+template <typename FX, typename FY>
+__device__ __forceinline__ float avx_dot_seq(FX x, FY y, int n) {
+    float result = 0.f;
+    int i = 0;
+    if (n > 7) {
+        float d[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        for (; i + 8 <= n; i += 8) {
+#pragma unroll
+            for (int l = 0; l < 8; l++) d[l] = d[l] + x(i + l) * y(i + l);
+        }
+        const float a0 = d[4] + d[0], a1 = d[5] + d[1], a2 = d[6] + d[2], a3 = d[7] + d[3];
+        const float b0 = a0 + a2, b1 = a1 + a3;
+        result = result + (b0 + b1);
+    }
+    for (; i < n; i++) result = result + x(i) * y(i);
+    return result;
 }
 
 // Sigmoid::forward, util/activations.h:65-72 (clamps at +-16; accurate expf, no fast-math)
@@ -283,6 +313,17 @@ int launch_fm_forward_ex(lctr_ctx* c, Slot& s, int64_t rb, int64_t re, bool nfm,
 bool csc_device_supported(const lctr_ctx* c);
 void csc_scratch_free(lctr_ctx* c);
 int launch_predict_quirk(lctr_ctx* c, Slot& s, Slot& train);
+// fm_fused.cu: order-free FM step over a batch-compact gradient buffer (cfg.deterministic == 0, one GPU)
+bool fused_supported(const lctr_ctx* c);
+void fused_free(lctr_ctx* c);
+int fused_reserve(lctr_ctx* c, Slot& s, int64_t nnz);
+int fused_build_slot(lctr_ctx* c, Slot& s, cudaStream_t st, const int64_t* hdr, int64_t rows_cap, int64_t nnz_cap);
+int launch_fm_fused(lctr_ctx* c, Slot& s, int64_t rb, int64_t re, bool stats, const int64_t* hdr, double* out_slot_override);
+int launch_fm_forward_tree(lctr_ctx* c, Slot& s, int64_t rb, int64_t re, bool stats);
+int launch_apply_compact(lctr_ctx* c, Slot& s, int64_t rows_in_step, const OptParams* P_host, const OptParams* dP);
+void fused_opt_params(lctr_ctx* c, int64_t rows, void* out);
+void* fused_dev_opt(lctr_ctx* c);
+int launch_ffm_predict_inorder(lctr_ctx* c, Slot& s);
 // multi-GPU (dist.cu)
 int dist_alloc(lctr_ctx* c);
 int dist_free(lctr_ctx* c);

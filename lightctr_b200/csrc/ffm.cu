@@ -267,6 +267,61 @@ __global__ void ffm_fused_kernel(const int64_t* __restrict__ row_ptr, const uint
     if (TRAIN && do_stats) publish_stats(loss, correct, partial, done, out_slot, false);
 }
 
+// FM_Predict, field-aware branch (predict/fm_predict.cpp:34-53) in the reference's OWN order -- no field-pair factorisation:
+// warp = sample; for entry i the lanes form the pair terms field_w * X * X2 of 32 partners j at a time (each dot product in
+// the avx lane order of common/avx.h:102-127), and the scalar chain fm_pred += ... is replayed in j order through shuffles,
+// so the float sequence is exactly the reference's double loop.  O(n^2 k) per sample: the parity predictor
+// (cfg.deterministic == 1); the factorised forward above is the throughput predictor.
+template <bool HAS_VAL>
+__global__ void __launch_bounds__(256)
+ffm_predict_inorder_kernel(const int64_t* __restrict__ row_ptr, const uint32_t* __restrict__ fid,
+                           const uint16_t* __restrict__ field, const float* __restrict__ val, const float* __restrict__ W,
+                           const float* __restrict__ V, int Fc, int k, float* __restrict__ pred, int64_t rows) {
+    const int lane = threadIdx.x & 31;
+    const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (r >= rows) return;
+    const int64_t b = row_ptr[r], e = row_ptr[r + 1];
+    const size_t rs = (size_t)Fc * k;
+    float fm = 0.f;
+    for (int64_t i = b; i < e; i++) {
+        const size_t f1 = fid[i];
+        const int fl1 = field[i];
+        const float X = HAS_VAL ? val[i] : 1.f;
+        fm = fm + W[f1] * X;                                                   // fm_predict.cpp:40
+        for (int64_t j0 = i + 1; j0 < e; j0 += 32) {
+            const int64_t j = j0 + lane;
+            float t = 0.f;
+            if (j < e) {
+                const size_t f2 = fid[j];
+                const int fl2 = field[j];
+                const float* a = V + f1 * rs + (size_t)fl2 * k;                // getV_field(fid, field2, 0)   :47
+                const float* c = V + f2 * rs + (size_t)fl1 * k;                // getV_field(fid2, field, 0)   :48
+                const float fw = avx_dot_seq([&](int q) { return a[q]; }, [&](int q) { return c[q]; }, k);
+                t = fw * X;
+                t = t * (HAS_VAL ? val[j] : 1.f);                              // field_w * X * X2             :49
+            }
+            const int cnt = (int)min((int64_t)32, e - j0);
+            for (int l = 0; l < cnt; l++) fm = fm + __shfl_sync(kFull, t, l);  // fm_pred += ... in j order
+        }
+    }
+    if (lane == 0) pred[r] = ref_sigmoid(fm);                                  // :56
+}
+
+int launch_ffm_predict_inorder(lctr_ctx* c, Slot& s) {
+    if (s.rows <= 0) return 0;
+    LCTR_CHECK(s.has_field, "FFM batch uploaded without the field array");
+    const unsigned grid = (unsigned)((s.rows + 7) / 8);
+    if (s.has_val)
+        ffm_predict_inorder_kernel<true><<<grid, 256, 0, c->stream>>>(s.row_ptr, s.fid, s.field, s.val, c->cW, c->cV,
+                                                                      (int)c->cfg.field_cnt, (int)c->cfg.factor_cnt, s.pred, s.rows);
+    else
+        ffm_predict_inorder_kernel<false><<<grid, 256, 0, c->stream>>>(s.row_ptr, s.fid, s.field, s.val, c->cW, c->cV,
+                                                                       (int)c->cfg.field_cnt, (int)c->cfg.factor_cnt, s.pred, s.rows);
+    c->launches++;
+    LCTR_CUDA(cudaGetLastError());
+    return 0;
+}
+
 static int ffm_launch(lctr_ctx* c, Slot& s, int64_t rb, int64_t re, bool train, bool stats, bool grouped = false) {
     const int k = (int)c->cfg.factor_cnt, Fc = (int)c->cfg.field_cnt;
     const int64_t rows = re - rb;

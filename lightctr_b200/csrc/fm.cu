@@ -74,7 +74,8 @@ fm_forward_kernel(const int64_t* __restrict__ row_ptr, const uint32_t* __restric
                   const float* __restrict__ val, const float* __restrict__ label, const float* __restrict__ W,
                   const float* __restrict__ V, float* __restrict__ pred, float* __restrict__ sumvx,
                   float* __restrict__ z_out, float* __restrict__ wide_out, int64_t rb, int64_t re_arg, double* partial,
-                  unsigned int* done, double* out_slot, int do_stats, const int64_t* __restrict__ hdr) {
+                  unsigned int* done, double* out_slot, int do_stats, const int64_t* __restrict__ hdr,
+                  const float* __restrict__ quirk_sumvx, int64_t quirk_rows) {
     const int64_t re = hdr ? hdr[0] : re_arg;  // graph launches read the batch size from the slot header
     constexpr int STR = K + 4;     // tile row: t[0..K), dot, w*x, pad (16 B aligned, conflict-free strides)
     constexpr int NB = 64;         // features per pass (two 32-lane gathers in flight)
@@ -155,8 +156,9 @@ fm_forward_kernel(const int64_t* __restrict__ row_ptr, const uint32_t* __restric
             if (lane < K) z_out[(size_t)(r - rb) * K + lane] = z + s * (s * 0.5f);
             if (lane == 0) wide_out[r] = fm;
         } else {
-            // avx_dotProduct(sumVX, sumVX, K) across lanes 0..K-1 in the reference's order, via the tile
-            if (lane < K) tile[lane] = s;
+            // avx_dotProduct(sumVX, sumVX, K) across lanes 0..K-1 in the reference's order, via the tile.
+            // FM_Predict quirk (predict/fm_predict.cpp:31): the TRAINING sumVX row of the same index instead
+            if (lane < K) tile[lane] = quirk_sumvx ? (r < quirk_rows ? quirk_sumvx[(size_t)r * K + lane] : 0.f) : s;
             __syncwarp();
             if (lane == 0) {
                 float sv[K];
@@ -239,32 +241,6 @@ fm_backward_kernel(const int64_t* __restrict__ row_ptr, const uint32_t* __restri
 }
 
 // ------------------------------------------------------------------------------------------------
-// FM_Predict quirk mode (predict/fm_predict.cpp:20-33): pred = sum w x - 0.5 sum|vx|^2 + 0.5|sumVX_train[rid]|^2
-// ------------------------------------------------------------------------------------------------
-__global__ void fm_predict_quirk_kernel(const int64_t* __restrict__ row_ptr, const uint32_t* __restrict__ fid,
-                                        const float* __restrict__ val, const float* __restrict__ W,
-                                        const float* __restrict__ V, int k, const float* __restrict__ train_sumvx,
-                                        int64_t train_rows, float* __restrict__ pred, int64_t rows) {
-    const int lane = threadIdx.x & 31;
-    const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (r >= rows) return;
-    float wsum = 0.f, sq = 0.f;
-    for (int64_t i = row_ptr[r] + lane; i < row_ptr[r + 1]; i += 32) {
-        const uint32_t f = fid[i];
-        const float x = val ? val[i] : 1.f;
-        wsum += W[f] * x;
-        for (int c = 0; c < k; c++) { const float t = V[(size_t)f * k + c] * x; sq += t * t; }
-    }
-    wsum = warp_sum(wsum);
-    sq = warp_sum(sq);
-    float ss = 0.f;
-    if (r < train_rows)
-        for (int c = lane; c < k; c += 32) { const float t = train_sumvx[(size_t)r * k + c]; ss += t * t; }
-    ss = warp_sum(ss);
-    if (lane == 0) pred[r] = ref_sigmoid((float)((double)wsum + 0.5 * ((double)ss - (double)sq)));
-}
-
-// ------------------------------------------------------------------------------------------------
 // launchers
 // ------------------------------------------------------------------------------------------------
 struct Shape { int lpr, vec; };
@@ -306,7 +282,7 @@ fm_forward_coalesced_kernel(const int64_t* __restrict__ row_ptr, const uint32_t*
                             const float* __restrict__ V, float* __restrict__ pred, float* __restrict__ sumvx,
                             float* __restrict__ z_out, float* __restrict__ wide_out, int64_t rb, int64_t re_arg,
                             double* partial, unsigned int* done, double* out_slot, int do_stats,
-                            const int64_t* __restrict__ hdr) {
+                            const int64_t* __restrict__ hdr, const float* __restrict__ quirk_sumvx, int64_t quirk_rows) {
     static_assert(K % 8 == 0 && K <= 32, "coalesced forward: K in {8, 16, 24, 32}");
     const int64_t re = hdr ? hdr[0] : re_arg;
     constexpr int LPR = K / 4 >= 8 ? 8 : (K / 4 >= 4 ? 4 : 2);  // lanes per row (power of two >= K/4 for K=24 -> 8)
@@ -407,7 +383,7 @@ fm_forward_coalesced_kernel(const int64_t* __restrict__ row_ptr, const uint32_t*
             if (lane < K) z_out[(size_t)(r - rb) * K + lane] = z + s * (s * 0.5f);
             if (lane == 0) wide_out[r] = fm;
         } else {
-            if (lane < K) tile[lane] = s;
+            if (lane < K) tile[lane] = quirk_sumvx ? (r < quirk_rows ? quirk_sumvx[(size_t)r * K + lane] : 0.f) : s;  // fm_predict.cpp:31
             __syncwarp();
             if (lane == 0) {
                 float sv[K];
@@ -439,7 +415,8 @@ static int fwd_go(lctr_ctx* c, Slot& s, bool nfm, int64_t rb, int64_t re, double
         auto kern = co ? fm_forward_coalesced_kernel<kCoalesced ? K : 8, HV, NF> : fm_forward_kernel<K, HV, NF>; \
         if (smem > 48 * 1024) LCTR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
         kern<<<grid, wpb * 32, smem, c->stream>>>(s.row_ptr, s.fid, s.val, s.label, c->cW, c->cV, s.pred, s.sumvx, c->z, \
-                                             s.wide, rb, re, c->stat_partial, c->stat_done, out_slot, stats, hdr);  \
+                                             s.wide, rb, re, c->stat_partial, c->stat_done, out_slot, stats, hdr,   \
+                                             c->fwd_quirk_sumvx, c->fwd_quirk_rows);                               \
     } while (0)
     if (s.has_val) { if (nfm) FWD_GO(true, true); else FWD_GO(true, false); }
     else { if (nfm) FWD_GO(false, true); else FWD_GO(false, false); }
@@ -611,15 +588,17 @@ int launch_fm_backward_csc(lctr_ctx* c, Slot& s, int64_t rb, int64_t re, bool nf
     return 0;
 }
 
+// FM_Predict quirk mode (predict/fm_predict.cpp:20-33): pred = sum w x - 0.5 sum|vx|^2 + 0.5|sumVX_train[rid]|^2, evaluated
+// by the in-order forward kernel (same arithmetic sequence as the reference's loop) with the training rows' sumVX
+// substituted in the last term.
 int launch_predict_quirk(lctr_ctx* c, Slot& s, Slot& train) {
     if (s.rows <= 0) return 0;
-    const unsigned grid = (unsigned)((s.rows + 7) / 8);
-    fm_predict_quirk_kernel<<<grid, 256, 0, c->stream>>>(s.row_ptr, s.fid, s.has_val ? s.val : nullptr, c->cW, c->cV,
-                                                         (int)c->cfg.factor_cnt, train.sumvx, train.rows, s.pred,
-                                                         s.rows);
-    c->launches++;
-    LCTR_CUDA(cudaGetLastError());
-    return 0;
+    c->fwd_quirk_sumvx = train.sumvx;
+    c->fwd_quirk_rows = train.rows;
+    const int rc = launch_fm_forward(c, s, 0, s.rows, false, false);
+    c->fwd_quirk_sumvx = nullptr;
+    c->fwd_quirk_rows = 0;
+    return rc;
 }
 
 }  // namespace lctr

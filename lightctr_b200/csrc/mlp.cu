@@ -16,26 +16,6 @@
 
 namespace lctr {
 
-// avx_dotProduct(x, y, n) (common/avx.h:102-127) with strided operands, evaluated by ONE thread in the
-// reference's order: 8 lane accumulators over the full 8-chunks, the hsum tree, then the scalar tail.
-template <typename FX, typename FY>
-__device__ __forceinline__ float avx_dot_seq(FX x, FY y, int n) {
-    float result = 0.f;
-    int i = 0;
-    if (n > 7) {
-        float d[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        for (; i + 8 <= n; i += 8) {
-#pragma unroll
-            for (int l = 0; l < 8; l++) d[l] = d[l] + x(i + l) * y(i + l);
-        }
-        const float a0 = d[4] + d[0], a1 = d[5] + d[1], a2 = d[6] + d[2], a3 = d[7] + d[3];
-        const float b0 = a0 + a2, b1 = a1 + a3;
-        result = result + (b0 + b1);
-    }
-    for (; i < n; i++) result = result + x(i) * y(i);
-    return result;
-}
-
 // Fully_Conn_Layer::forward (fullyconnLayer.h:80-118), one thread per (sample, output neuron).
 __global__ void fc_forward_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
                                   const float* __restrict__ mask, float* __restrict__ y, int B, int in, int out,

@@ -190,14 +190,28 @@ class FMOracle:
     def apply(self):
         F, k = self.ds.feature_cnt, self.k
         L = lib()
-        # ApplyGrad train_fm_algo.cpp:120-126 ; minibatch_size = dataRow_cnt (:38)
-        if getattr(self, "opt", "adagrad") == "rmsprop":  # `updater` member type switched to RMSpropUpdater_Num
-            ema = np.float32(getattr(self, "ema", 0.99))
-            L.orc_rmsprop(F, self.W, self.update_g[:F], self.accum[:F], self.ds.rows, self.lr, ema)
-            L.orc_rmsprop(F * k, self.V, self.update_g[F:], self.accum[F:], self.ds.rows, self.lr, ema)
-            return
-        L.orc_adagrad(F, self.W, self.update_g[:F], self.accum[:F], self.ds.rows, self.lr)
-        L.orc_adagrad(F * k, self.V, self.update_g[F:], self.accum[F:], self.ds.rows, self.lr)
+        # ApplyGrad train_fm_algo.cpp:120-126 ; minibatch_size = dataRow_cnt (:38).  `opt` switches the type of the
+        # trainer's `updater` member (adagrad is the shipped one); W call first, then V call, as in the reference
+        opt = getattr(self, "opt", "adagrad")
+        B = self.ds.rows
+        if opt in ("ftrl", "adam", "adadelta") and not hasattr(self, "s2"):
+            self.s2 = np.zeros(F * (k + 1), np.float32)
+            self.iter = C.c_size_t(0)
+        for (w, lo, hi) in ((self.W, 0, F), (self.V, F, F * (k + 1))):
+            g, a = self.update_g[lo:hi], self.accum[lo:hi]
+            if opt == "adagrad":
+                L.orc_adagrad(hi - lo, w, g, a, B, self.lr)
+            elif opt == "rmsprop":
+                L.orc_rmsprop(hi - lo, w, g, a, B, self.lr, np.float32(getattr(self, "ema", 0.99)))
+            elif opt == "adadelta":
+                L.orc_adadelta(hi - lo, w, g, a, self.s2[lo:hi], B, np.float32(getattr(self, "beta1", 0.8)))
+            elif opt == "ftrl":
+                L.orc_ftrl(hi - lo, w, g, a, self.s2[lo:hi], 1)
+            elif opt == "adam":
+                L.orc_adam(hi - lo, w, g, a, self.s2[lo:hi], C.byref(self.iter), B, self.lr,
+                           np.float32(getattr(self, "beta1", 0.8)), np.float32(getattr(self, "beta2", 0.999)))
+            else:
+                raise ValueError(opt)
 
     def epoch(self):
         r = self.forward_backward()

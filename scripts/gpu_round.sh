@@ -1,0 +1,43 @@
+#!/bin/bash
+# One GPU-box session of the round: tests, bench lines, ncu evidence.  Everything lands under gpurun_out/.
+#   TAG=r02a STEPS="tests bench sweep ncu" bash scripts/gpu_round.sh
+TAG=${TAG:-r02}
+STEPS=${STEPS:-"tests bench sweep ncu"}
+O=gpurun_out
+mkdir -p $O
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active --format=csv > $O/smi_$TAG.txt 2>&1
+for s in $STEPS; do
+case $s in
+tests)
+  timeout 1500 python -m pytest tests -m gpu -x -q ${PYTEST_ARGS:-} > $O/pytest_$TAG.log 2>&1; echo "pytest rc=$?" >> $O/pytest_$TAG.log
+  tail -n 15 $O/pytest_$TAG.log ;;
+newtests)
+  timeout 900 python -m pytest tests/test_fm_fused_gpu.py -m gpu -x -q > $O/pytest_new_$TAG.log 2>&1; echo "pytest rc=$?" >> $O/pytest_new_$TAG.log
+  tail -n 15 $O/pytest_new_$TAG.log ;;
+bench)
+  timeout 900 python bench.py --check > $O/bench_${TAG}_fm_c2.json 2> $O/bench_${TAG}_fm_c2.err; echo "bench rc=$?"
+  tail -c 600 $O/bench_${TAG}_fm_c2.err ;;
+benchquick)
+  timeout 600 python bench.py --no-c5 --no-cpu-baseline --steps 100 > $O/bench_${TAG}_fm_c2_quick.json 2> $O/bench_${TAG}_fm_c2_quick.err; echo "bench rc=$?"
+  tail -c 600 $O/bench_${TAG}_fm_c2_quick.err ;;
+ref)
+  timeout 600 python bench.py --impl reference --steps 20 --warmup 3 > $O/bench_${TAG}_reference.json 2> $O/bench_${TAG}_reference.err ;;
+sweep)
+  for b in 65536 262144; do
+    timeout 600 python bench.py --batch $b --steps 20 --warmup 3 --no-cpu-baseline --no-c5 > $O/bench_${TAG}_fm_c2_b$b.json 2> $O/bench_${TAG}_fm_c2_b$b.err
+  done ;;
+others)
+  for w in ffm_c3 nfm_c4 ffm_c5; do
+    timeout 900 python bench.py --workload $w --steps 20 --warmup 3 --no-cpu-baseline > $O/bench_${TAG}_$w.json 2> $O/bench_${TAG}_$w.err
+  done ;;
+ncu)
+  timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 120 -c 200 --csv --log-file $O/launches_${TAG}_fm_c2.csv \
+      python bench.py --steps 30 --warmup 5 --no-cpu-baseline --no-c5 > $O/ncu_launch_$TAG.log 2>&1
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:"fm_fused_kernel|apply_compact" -s 30 -c 6 \
+      -o $O/prof_${TAG}_fm_c2 -f python bench.py --steps 6 --warmup 3 --no-cpu-baseline --no-c5 > $O/ncu_full_$TAG.log 2>&1
+  echo "ncu rc=$?" ;;
+lab)
+  bash scripts/lab/run_lab.sh > /dev/null 2>&1; cp $O/lab_b4096.txt $O/lab_${TAG}_b4096.txt; cp $O/lab_b65536.txt $O/lab_${TAG}_b65536.txt ;;
+esac
+done
+ls -la $O | tail -n 30

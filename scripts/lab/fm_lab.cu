@@ -217,16 +217,17 @@ int main(int argc, char** argv) {
     float* s1V = dmalloc<float>(F * K);
     fill_v_kernel<<<SM * 8, 256, 0, st>>>(V, F * K, 0.25f);
     fill_v_kernel<<<SM * 8, 256, 0, st>>>(W, F, 0.01f);
-    uint8_t* mark = dmalloc<uint8_t>(F + 512);
+    const size_t MT = mark_rows(F);
+    uint8_t* mark = dmalloc<uint8_t>(128 * MT + 512);
     uint32_t* slot_of = dmalloc<uint32_t>(F);
     uint32_t* uniq = dmalloc<uint32_t>(nnz + 64);
     unsigned* n_uniq = dmalloc<unsigned>(1);
     uint32_t* ent_slot = dmalloc<uint32_t>(nnz + 64);
     unsigned* cnt = dmalloc<unsigned>(nnz + 64);
-    unsigned* seg_ptr = dmalloc<unsigned>(nnz + 64);
-    uint32_t* srt_row = dmalloc<uint32_t>(nnz + 64);
-    uint32_t* srt_slot = dmalloc<uint32_t>(nnz + 64);
-    uint32_t* srt_fid = dmalloc<uint32_t>(nnz + 64);
+    uint32_t* hot_of = dmalloc<uint32_t>(nnz + 64);
+    unsigned* n_hot = dmalloc<unsigned>(1);
+    uint32_t* hot_slot = dmalloc<uint32_t>(kHotMax);
+    uint32_t* ent_slot_nohot = dmalloc<uint32_t>(nnz + 64);
     float* pred = dmalloc<float>(B);
     float* pred_ref = dmalloc<float>(B);
     float* sumvx = dmalloc<float>(B * K);
@@ -240,87 +241,92 @@ int main(int argc, char** argv) {
 
     // ------------------------------------------------------------------ prep: slot map
     const unsigned mg = (unsigned)std::min<int64_t>((nnz + 255) / 256, (int64_t)SM * 8);
-    const size_t ntiles = (F + 511) / 512;
+    const unsigned mkg = (unsigned)std::min<int64_t>((nnz + 2047) / 2048, (int64_t)SM * 4);
+    const size_t ntiles = (128 * mark_rows(F) + 511) / 512;
     const unsigned cg = (unsigned)std::min<size_t>((ntiles + 7) / 8, (size_t)SM * 8);
+    const unsigned sg = (unsigned)std::min<int64_t>(((int64_t)kHotSampleRows * 128 + 255) / 256, (int64_t)SM * 8);
     auto prep_slotmap = [&]() {
         CK(cudaMemsetAsync(n_uniq, 0, 4, st));
-        slotmap_mark_kernel<<<mg, 256, 0, st>>>(d_fid, nullptr, nnz, mark);
-        slotmap_compact_kernel<<<cg, 256, 0, st>>>(mark, F, uniq, n_uniq, slot_of);
-        slotmap_assign_kernel<<<mg, 256, 0, st>>>(d_fid, nullptr, nnz, slot_of, ent_slot);
+        CK(cudaMemsetAsync(n_hot, 0, 4, st));
+        slotmap_mark_kernel<<<mkg, 256, 0, st>>>(d_fid, nullptr, nnz, mark, MT);
+        slotmap_compact_kernel<<<cg, 256, 0, st>>>(mark, MT, uniq, n_uniq, slot_of);
+        slotmap_sample_kernel<<<sg, 256, 0, st>>>(d_rp, d_fid, nullptr, B, slot_of, cnt);
+        slotmap_hot_kernel<<<SM * 2, 256, 0, st>>>(cnt, n_uniq, nullptr, B, hot_of, hot_slot, n_hot);
+        slotmap_assign_kernel<<<mg, 256, 0, st>>>(d_fid, nullptr, nnz, slot_of, hot_of, ent_slot);
     };
     prep_slotmap();
     CK(cudaStreamSynchronize(st));
     unsigned U = 0;
     CK(cudaMemcpy(&U, n_uniq, 4, cudaMemcpyDeviceToHost));
-    printf("# unique features U=%u (%.2f entries per unique)\n", U, (double)nnz / U);
-    printf("prep_slotmap(mark+compact+assign)_us,%.2f\n", time_us(prep_slotmap));
-    printf("prep_mark_us,%.2f\n", time_us([&]() { slotmap_mark_kernel<<<mg, 256, 0, st>>>(d_fid, nullptr, nnz, mark); }));
-    printf("prep_compact(empty map)_us,%.2f\n", time_us([&]() { CK(cudaMemsetAsync(n_uniq, 0, 4, st)); slotmap_compact_kernel<<<cg, 256, 0, st>>>(mark, F, uniq, n_uniq, slot_of); }));
-    prep_slotmap();  // restore a consistent map (the timing above compacted an empty mark map)
+    unsigned NH = 0;
+    CK(cudaMemcpy(&NH, n_hot, 4, cudaMemcpyDeviceToHost));
+    printf("# unique features U=%u (%.2f entries per unique), hot slots %u (cap %d)\n", U, (double)nnz / U, NH, kHotMax);
+    printf("prep_slotmap(mark+compact+sample+hot+assign)_us,%.2f\n", time_us(prep_slotmap));
+    printf("prep_sample_us,%.2f\n", time_us([&]() { slotmap_sample_kernel<<<sg, 256, 0, st>>>(d_rp, d_fid, nullptr, B, slot_of, cnt); }));
+    CK(cudaMemsetAsync(cnt, 0, (size_t)(nnz + 64) * 4, st));
+    printf("prep_assign_us,%.2f\n", time_us([&]() { slotmap_assign_kernel<<<mg, 256, 0, st>>>(d_fid, nullptr, nnz, slot_of, hot_of, ent_slot); }));
+    printf("prep_mark_us,%.2f\n", time_us([&]() { slotmap_mark_kernel<<<mkg, 256, 0, st>>>(d_fid, nullptr, nnz, mark, MT); }));
+    printf("prep_compact(empty map)_us,%.2f\n", time_us([&]() { CK(cudaMemsetAsync(n_uniq, 0, 4, st)); slotmap_compact_kernel<<<cg, 256, 0, st>>>(mark, MT, uniq, n_uniq, slot_of); }));
+    {   // the five kernels of the build, timed one by one inside the sequence (L2 flushed first)
+        cudaEvent_t ev[8];
+        for (auto& e : ev) CK(cudaEventCreate(&e));
+        CK(cudaMemsetAsync(g_flush, 1, kFlushBytes, st));
+        CK(cudaMemsetAsync(n_uniq, 0, 4, st));
+        CK(cudaMemsetAsync(n_hot, 0, 4, st));
+        CK(cudaEventRecord(ev[0], st));
+        slotmap_mark_kernel<<<mkg, 256, 0, st>>>(d_fid, nullptr, nnz, mark, MT);
+        CK(cudaEventRecord(ev[1], st));
+        slotmap_compact_kernel<<<cg, 256, 0, st>>>(mark, MT, uniq, n_uniq, slot_of);
+        CK(cudaEventRecord(ev[2], st));
+        slotmap_sample_kernel<<<sg, 256, 0, st>>>(d_rp, d_fid, nullptr, B, slot_of, cnt);
+        CK(cudaEventRecord(ev[3], st));
+        slotmap_hot_kernel<<<SM * 2, 256, 0, st>>>(cnt, n_uniq, nullptr, B, hot_of, hot_slot, n_hot);
+        CK(cudaEventRecord(ev[4], st));
+        slotmap_assign_kernel<<<mg, 256, 0, st>>>(d_fid, nullptr, nnz, slot_of, hot_of, ent_slot);
+        CK(cudaEventRecord(ev[5], st));
+        CK(cudaStreamSynchronize(st));
+        const char* nm[5] = {"mark", "compact", "sample", "hot", "assign"};
+        for (int i = 0; i < 5; i++) { float ms; CK(cudaEventElapsedTime(&ms, ev[i], ev[i + 1])); printf("prep_seq_%s_us,%.2f\n", nm[i], ms * 1e3f); }
+    }
+    slotmap_assign_kernel<<<mg, 256, 0, st>>>(d_fid, nullptr, nnz, slot_of, nullptr, ent_slot_nohot);
     CK(cudaStreamSynchronize(st));
     G = dmalloc<float>((size_t)(U + 64) * GSmax);
     float* Gref = dmalloc<float>((size_t)(U + 64) * GSmax);
     float* G2 = dmalloc<float>((size_t)(U + 64) * GSmax);
-
-    // ------------------------------------------------------------------ prep: slot-sorted entry list
-    const unsigned rg = (unsigned)((B + 255) / 256);
-    auto prep_sorted = [&]() {
-        sorted_count_kernel<<<rg, 256, 0, st>>>(d_rp, ent_slot, B, nullptr, cnt);
-        sorted_scan_kernel<<<1, 1024, 0, st>>>(cnt, n_uniq, seg_ptr);
-        sorted_fill_kernel<<<rg, 256, 0, st>>>(d_rp, d_fid, ent_slot, nullptr, B, nullptr, seg_ptr, cnt, srt_row, srt_slot, srt_fid, nullptr);
-        CK(cudaMemsetAsync(cnt, 0, (size_t)U * 4, st));  // cursor back to zero for the next build
-    };
-    prep_sorted();
-    CK(cudaStreamSynchronize(st));
-    {   // check: sorted by slot, every entry present once
-        std::vector<uint32_t> ss(nnz), sr(nnz), sf(nnz), es(nnz);
-        CK(cudaMemcpy(ss.data(), srt_slot, nnz * 4, cudaMemcpyDeviceToHost));
-        CK(cudaMemcpy(sr.data(), srt_row, nnz * 4, cudaMemcpyDeviceToHost));
-        CK(cudaMemcpy(sf.data(), srt_fid, nnz * 4, cudaMemcpyDeviceToHost));
-        std::vector<uint32_t> hu(U);
-        CK(cudaMemcpy(hu.data(), uniq, (size_t)U * 4, cudaMemcpyDeviceToHost));
-        long bad = 0;
-        for (int64_t i = 1; i < nnz; i++) if (ss[i] < ss[i - 1]) bad++;
-        for (int64_t i = 0; i < nnz; i++) if (ss[i] >= U || hu[ss[i]] != sf[i]) bad++;
-        std::vector<int> per_row(B, 0);
-        for (int64_t i = 0; i < nnz; i++) per_row[sr[i]]++;
-        for (int64_t r = 0; r < B; r++) if (per_row[r] != hb.row_ptr[r + 1] - hb.row_ptr[r]) bad++;
-        printf("# sorted-list check: %ld violations\n", bad);
-    }
-    printf("prep_sorted(count+scan+fill)_us,%.2f\n", time_us(prep_sorted));
-    printf("prep_sorted_count_us,%.2f\n", time_us([&]() { sorted_count_kernel<<<rg, 256, 0, st>>>(d_rp, ent_slot, B, nullptr, cnt); }));
-    CK(cudaMemsetAsync(cnt, 0, (size_t)(nnz + 64) * 4, st));
-    prep_sorted();
-    CK(cudaStreamSynchronize(st));
+    float* Ghot = dmalloc<float>((size_t)kHotMax * kHotRep * GSmax);
 
     // ------------------------------------------------------------------ step kernels
     const float l2 = 0.001f;
-    const unsigned fgrid = (unsigned)((B + 3) / 4);
+    const unsigned fgrid = (unsigned)std::min<int64_t>((B + 3) / 4, (int64_t)SM * 4);
     OptParams P;
     memset(&P, 0, sizeof(P));
     P.opt = LCTR_OPT_ADAGRAD; P.invB = (float)(1.0 / (double)B); P.mb = (float)B; P.lr = 0.1f; P.corrW = P.corrV = 1.f;
-    for (int GS : {20, 32}) {
+    for (int GS : {32}) {
         auto fused = [&]() {
-            fm_fused_kernel<K, false, 1, false><<<fgrid, 128, 0, st>>>(d_rp, d_fid, ent_slot, nullptr, d_label, W, V, pred, sumvx, dvec, G, GS, l2,
+            fm_fused_kernel<K, false, 1, false><<<fgrid, 128, 0, st>>>(d_rp, d_fid, ent_slot, nullptr, d_label, W, V, pred, sumvx, dvec, G, Ghot, GS, l2,
+                                                                         0, B, nullptr, partial, done, out_slot, 1);
+        };
+        auto fused3 = [&]() {
+            fm_fused_kernel<K, false, 1, false, 3><<<std::min<unsigned>(fgrid, SM * 3), 128, 0, st>>>(d_rp, d_fid, ent_slot, nullptr, d_label, W, V, pred, sumvx, dvec, G, Ghot, GS, l2,
+                                                                         0, B, nullptr, partial, done, out_slot, 1);
+        };
+        auto fused_nohot = [&]() {
+            fm_fused_kernel<K, false, 1, false><<<fgrid, 128, 0, st>>>(d_rp, d_fid, ent_slot_nohot, nullptr, d_label, W, V, pred, sumvx, dvec, G, Ghot, GS, l2,
                                                                          0, B, nullptr, partial, done, out_slot, 1);
         };
         auto fwd = [&]() {
-            fm_fused_kernel<K, false, 0, true><<<fgrid, 128, 0, st>>>(d_rp, d_fid, d_fid, nullptr, d_label, W, V, pred, sumvx, dvec, nullptr, GS, l2,
+            fm_fused_kernel<K, false, 0, true><<<fgrid, 128, 0, st>>>(d_rp, d_fid, d_fid, nullptr, d_label, W, V, pred, sumvx, dvec, nullptr, nullptr, GS, l2,
                                                                         0, B, nullptr, partial, done, out_slot, 1);
         };
-        auto bwd_sorted = [&]() {
-            const int chunk = (32 / (K / 4)) * 8;
-            const unsigned g2 = (unsigned)((nnz + chunk * 4 - 1) / (chunk * 4));
-            fm_bwd_sorted_kernel<K, false><<<g2, 128, 0, st>>>(srt_row, srt_slot, srt_fid, nullptr, nnz, nullptr, sumvx, dvec, W, V, G, GS, l2);
-        };
         auto apply = [&]() {
-            apply_compact_kernel<K, LCTR_OPT_ADAGRAD><<<SM * 2, 256, 0, st>>>(uniq, n_uniq, G, GS, W, V, s1W, s1V, nullptr, nullptr, P, nullptr);
+            apply_compact_kernel<K, LCTR_OPT_ADAGRAD><<<SM * 2, 256, 0, st>>>(uniq, n_uniq, G, hot_of, hot_slot, n_hot, Ghot, GS, W, V, s1W, s1V, nullptr, nullptr, P, nullptr);
         };
         // validation against the naive kernel (gradients only; apply is skipped so that parameters stay put)
         CK(cudaMemsetAsync(G, 0, (size_t)(U + 64) * GSmax * 4, st));
         CK(cudaMemsetAsync(Gref, 0, (size_t)(U + 64) * GSmax * 4, st));
         CK(cudaMemsetAsync(G2, 0, (size_t)(U + 64) * GSmax * 4, st));
-        ref_step_kernel<<<(unsigned)((B + 127) / 128), 128, 0, st>>>(d_rp, d_fid, ent_slot, d_label, W, V, K, pred_ref, Gref, GS, l2, B);
+        CK(cudaMemsetAsync(Ghot, 0, (size_t)kHotMax * kHotRep * GSmax * 4, st));
+        ref_step_kernel<<<(unsigned)((B + 127) / 128), 128, 0, st>>>(d_rp, d_fid, ent_slot_nohot, d_label, W, V, K, pred_ref, Gref, GS, l2, B);
         fused();
         CK(cudaStreamSynchronize(st));
         CK(cudaGetLastError());
@@ -330,38 +336,52 @@ int main(int argc, char** argv) {
             CK(cudaMemcpy(b.data(), Gref, b.size() * 4, cudaMemcpyDeviceToHost));
             CK(cudaMemcpy(pa.data(), pred, B * 4, cudaMemcpyDeviceToHost));
             CK(cudaMemcpy(pb.data(), pred_ref, B * 4, cudaMemcpyDeviceToHost));
+            {   // fold the hot replicas into their slots
+                std::vector<float> hh((size_t)kHotMax * kHotRep * GS);
+                std::vector<uint32_t> ho(U);
+                CK(cudaMemcpy(hh.data(), Ghot, hh.size() * 4, cudaMemcpyDeviceToHost));
+                CK(cudaMemcpy(ho.data(), hot_of, (size_t)U * 4, cudaMemcpyDeviceToHost));
+                for (unsigned sl = 0; sl < U; sl++)
+                    if (ho[sl] != 0xffffffffu)
+                        for (int rp = 0; rp < kHotRep; rp++)
+                            for (int c = 0; c < GS; c++) a[(size_t)sl * GS + c] += hh[((size_t)ho[sl] * kHotRep + rp) * GS + c];
+            }
             double mg_ = 0, mp = 0, mx = 0;
             for (size_t i = 0; i < a.size(); i++) { mg_ = std::max(mg_, (double)fabsf(a[i] - b[i])); mx = std::max(mx, (double)fabsf(b[i])); }
             for (int64_t i = 0; i < B; i++) mp = std::max(mp, (double)fabsf(pa[i] - pb[i]));
             printf("# GS=%d fused vs naive: max|dG|=%.3g (max|G|=%.3g) max|dpred|=%.3g\n", GS, mg_, mx, mp);
-            // sorted backward into G2 (uses sumvx/dvec of the fused run)
-            float* Gsave = G;
-            G = G2;
-            bwd_sorted();
-            CK(cudaStreamSynchronize(st));
-            CK(cudaGetLastError());
-            G = Gsave;
-            CK(cudaMemcpy(a.data(), G2, a.size() * 4, cudaMemcpyDeviceToHost));
-            mg_ = 0;
-            for (size_t i = 0; i < a.size(); i++) mg_ = std::max(mg_, (double)fabsf(a[i] - b[i]));
-            printf("# GS=%d sorted-bwd vs naive: max|dG|=%.3g\n", GS, mg_);
         }
         CK(cudaMemsetAsync(G, 0, (size_t)(U + 64) * GSmax * 4, st));
+        CK(cudaMemsetAsync(Ghot, 0, (size_t)kHotMax * kHotRep * GSmax * 4, st));
         const double gather_bytes = ((double)nnz / B * (4 * K + 12) + 8) * B;
         float t;
         t = time_us(fwd);
         printf("GS=%d,fwd_only_us,%.2f,gather_GBps,%.1f\n", GS, t, gather_bytes / t * 1e-3);
         t = time_us(fused);
         printf("GS=%d,fused_fwd_bwd_red_us,%.2f,gather_GBps,%.1f\n", GS, t, gather_bytes / t * 1e-3);
+        t = time_us(fused3);
+        printf("GS=%d,fused_minb3_us,%.2f,gather_GBps,%.1f\n", GS, t, gather_bytes / t * 1e-3);
+        t = time_us(fused_nohot);
+        printf("GS=%d,fused_nohot_us,%.2f,gather_GBps,%.1f\n", GS, t, gather_bytes / t * 1e-3);
         t = time_us([&]() { fused(); apply(); });
         printf("GS=%d,step_red(fused+apply)_us,%.2f\n", GS, t);
-        CK(cudaMemsetAsync(G, 0, (size_t)(U + 64) * GSmax * 4, st));
-        t = time_us(bwd_sorted);
-        printf("GS=%d,bwd_sorted_us,%.2f\n", GS, t);
-        t = time_us([&]() { fwd(); bwd_sorted(); apply(); });
-        printf("GS=%d,step_sorted(fwd+bwd_sorted+apply)_us,%.2f\n", GS, t);
-        t = time_us([&]() { fwd(); bwd_sorted(); apply(); }, 9, false);
-        printf("GS=%d,step_sorted_noflush_us,%.2f\n", GS, t);
+        {   // apply alone, right after a fused launch (G hot in L2 as in the real step)
+            std::vector<float> ts;
+            cudaEvent_t ea, eb;
+            cudaEventCreate(&ea); cudaEventCreate(&eb);
+            for (int i = 0; i < 7; i++) {
+                CK(cudaMemsetAsync(g_flush, i, kFlushBytes, st));
+                fused();
+                CK(cudaEventRecord(ea, st));
+                apply();
+                CK(cudaEventRecord(eb, st));
+                CK(cudaStreamSynchronize(st));
+                float ms; CK(cudaEventElapsedTime(&ms, ea, eb));
+                ts.push_back(ms * 1e3f);
+            }
+            std::sort(ts.begin(), ts.end());
+            printf("GS=%d,apply_after_fused_us,%.2f\n", GS, ts[ts.size() / 2]);
+        }
         t = time_us([&]() { fused(); apply(); }, 9, false);
         printf("GS=%d,step_red_noflush_us,%.2f\n", GS, t);
         // re-zero state touched by apply so both layouts start alike
@@ -394,24 +414,24 @@ int main(int argc, char** argv) {
     auto report = [&](const char* name, float us, double adds_per_entry, double lines_per_entry) {
         printf("red,%s,us,%.2f,Gadds_s,%.1f,Glines_s,%.2f\n", name, us, nnz * adds_per_entry / us * 1e-3, nnz * lines_per_entry / us * 1e-3);
     };
-    report("compact_zipf_v64B+w_merged_stride20", time_us([&]() { red_bench_kernel<4, true, true><<<rgrid, 256, 0, st>>>(ent_slot, nnz, G, 20, G, 20, 16); }), 17, 1);
-    report("compact_zipf_v64B+w_merged_stride32", time_us([&]() { red_bench_kernel<4, true, true><<<rgrid, 256, 0, st>>>(ent_slot, nnz, G, 32, G, 32, 16); }), 17, 1);
-    report("compact_zipf_v64B_only_stride16", time_us([&]() { red_bench_kernel<4, true, false><<<rgrid, 256, 0, st>>>(ent_slot, nnz, G, 16, nullptr, 0, 0); }), 16, 1);
-    report("compact_zipf_v64B+w_separate", time_us([&]() { red_bench_kernel<4, true, true><<<rgrid, 256, 0, st>>>(ent_slot, nnz, G, 16, Gref, 1, 0); }), 17, 2);
-    report("compact_zipf_w_only", time_us([&]() { red_bench_kernel<4, true, true><<<rgrid, 256, 0, st>>>(ent_slot, nnz, nullptr, 16, Gref, 1, 0); }), 1, 1);
+    report("compact_zipf_v64B+w_merged_stride20", time_us([&]() { red_bench_kernel<4, true, true><<<rgrid, 256, 0, st>>>(ent_slot_nohot, nnz, G, 20, G, 20, 16); }), 17, 1);
+    report("compact_zipf_v64B+w_merged_stride32", time_us([&]() { red_bench_kernel<4, true, true><<<rgrid, 256, 0, st>>>(ent_slot_nohot, nnz, G, 32, G, 32, 16); }), 17, 1);
+    report("compact_zipf_v64B_only_stride16", time_us([&]() { red_bench_kernel<4, true, false><<<rgrid, 256, 0, st>>>(ent_slot_nohot, nnz, G, 16, nullptr, 0, 0); }), 16, 1);
+    report("compact_zipf_v64B+w_separate", time_us([&]() { red_bench_kernel<4, true, true><<<rgrid, 256, 0, st>>>(ent_slot_nohot, nnz, G, 16, Gref, 1, 0); }), 17, 2);
+    report("compact_zipf_w_only", time_us([&]() { red_bench_kernel<4, true, true><<<rgrid, 256, 0, st>>>(ent_slot_nohot, nnz, nullptr, 16, Gref, 1, 0); }), 1, 1);
     report("sparse_fid_zipf_v64B+w_separate(r01 layout)", time_us([&]() { red_bench_kernel<4, true, true><<<rgrid, 256, 0, st>>>(d_fid, nnz, gVs, 16, gWs, 1, 0); }), 17, 2);
     report("sparse_fid_zipf_v64B_only", time_us([&]() { red_bench_kernel<4, true, false><<<rgrid, 256, 0, st>>>(d_fid, nnz, gVs, 16, nullptr, 0, 0); }), 16, 1);
     report("compact_uniform_v64B+w_merged_stride20", time_us([&]() { red_bench_kernel<4, true, true><<<rgrid, 256, 0, st>>>(rand_u, nnz, G, 20, G, 20, 16); }), 17, 1);
     report("sparse_uniform_v64B+w_separate", time_us([&]() { red_bench_kernel<4, true, true><<<rgrid, 256, 0, st>>>(rand_f, nnz, gVs, 16, gWs, 1, 0); }), 17, 2);
-    report("compact_zipf_scalar16x4B_stride20", time_us([&]() { red_bench_kernel<16, false, false><<<rgrid, 256, 0, st>>>(ent_slot, nnz, G, 20, nullptr, 0, 0); }), 16, 1);
-    report("compact_zipf_v128B_stride32", time_us([&]() { red_bench_kernel<8, true, false><<<rgrid, 256, 0, st>>>(ent_slot, nnz, G, 32, nullptr, 0, 0); }), 32, 1);
-    report("compact_zipf_v64B+w_merged_stride20_noflush", time_us([&]() { red_bench_kernel<4, true, true><<<rgrid, 256, 0, st>>>(ent_slot, nnz, G, 20, G, 20, 16); }, 9, false), 17, 1);
+    report("compact_zipf_scalar16x4B_stride20", time_us([&]() { red_bench_kernel<16, false, false><<<rgrid, 256, 0, st>>>(ent_slot_nohot, nnz, G, 20, nullptr, 0, 0); }), 16, 1);
+    report("compact_zipf_v128B_stride32", time_us([&]() { red_bench_kernel<8, true, false><<<rgrid, 256, 0, st>>>(ent_slot_nohot, nnz, G, 32, nullptr, 0, 0); }), 32, 1);
+    report("compact_zipf_v64B+w_merged_stride20_noflush", time_us([&]() { red_bench_kernel<4, true, true><<<rgrid, 256, 0, st>>>(ent_slot_nohot, nnz, G, 20, G, 20, 16); }, 9, false), 17, 1);
     // gathers with the same mapping
     {
         float t = time_us([&]() { gather_bench_kernel<4><<<rgrid, 256, 0, st>>>(d_fid, nnz, V, 16, dvec); });
         printf("gather,table_V_fid_zipf_64B,us,%.2f,GBps,%.1f\n", t, nnz * 64.0 / t * 1e-3);
-        t = time_us([&]() { gather_bench_kernel<4><<<rgrid, 256, 0, st>>>(srt_row, nnz, sumvx, 16, dvec); });
-        printf("gather,sumvx_rows_64B,us,%.2f,GBps,%.1f\n", t, nnz * 64.0 / t * 1e-3);
+        t = time_us([&]() { gather_bench_kernel<4><<<rgrid, 256, 0, st>>>(ent_slot_nohot, nnz, G, 32, dvec); });
+        printf("gather,compact_rows_64B,us,%.2f,GBps,%.1f\n", t, nnz * 64.0 / t * 1e-3);
         t = time_us([&]() { gather_bench_kernel<4><<<rgrid, 256, 0, st>>>(rand_f, nnz, V, 16, dvec); });
         printf("gather,table_V_uniform_64B,us,%.2f,GBps,%.1f\n", t, nnz * 64.0 / t * 1e-3);
     }

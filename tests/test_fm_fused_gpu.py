@@ -1,0 +1,177 @@
+"""GPU parity tests of the order-free fused FM step (csrc/fm_fused.cu: slot map at upload, gather + RED scatter into the
+batch-compact buffer with hot-slot replicas, compact updater) against the CPU oracle, through the C ABI.
+
+The path sums gradients with REDs in arbitrary order (like the reference's own multi-threaded Hogwild mode),
+so it is held to PER-STEP parity from identical state: summed logloss 1e-6 .. 2e-6 relative (tolerance stated at each
+assert; north-star bar 1e-5), parameters to fp32 re-association noise."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _rel(a, b):
+    return abs(a - b) / max(abs(b), 1e-30)
+
+
+def _synth(F, B, seed, with_val=False):
+    from lightctr_b200.data import CriteoSynth
+    rp, fid, fld, lab = CriteoSynth(F, seed=seed).batch(B)
+    val = None
+    if with_val:
+        val = (0.5 + np.random.default_rng(seed).random(len(fid))).astype(np.float32)
+    return rp, fid, fld, lab, val
+
+
+OPTS = {"adagrad": 0, "ftrl": 1, "adam": 2, "rmsprop": 3, "adadelta": 4}
+
+
+@pytest.mark.parametrize("opt", ["adagrad", "ftrl", "adam", "rmsprop", "adadelta"])
+@pytest.mark.parametrize("k,with_val", [(16, False), (8, True), (4, False), (32, True)])
+def test_fused_step_vs_oracle(oracle_api, opt, k, with_val):
+    """Three consecutive steps on one synthetic Criteo-shaped batch (hot ids of the small-vocabulary fields -> replica
+    rows are exercised; k = 4, 8, 16, 32 = every lane layout of the kernel; with and without feature values)."""
+    from lightctr_b200 import capi
+    F, B = 20000, 700
+    rp, fid, fld, lab, val = _synth(F, B, 5 + k, with_val)
+    rng = np.random.default_rng(k)
+    W0 = (rng.standard_normal(F) * 0.01).astype(np.float32)
+    V0 = (rng.standard_normal(F * k) / np.sqrt(k)).astype(np.float32) * np.float32(0.5)
+    lr = 0.002 if opt == "rmsprop" else 0.05
+    ds = oracle_api.Dataset(rp, fid, fld.astype(np.uint32), val if with_val else np.ones(len(fid), np.float32), lab, F, 0)
+    o = oracle_api.FMOracle(ds, k, W0, V0, lr=lr)
+    o.opt = opt
+    ctx = capi.Context(capi.MODEL_FM, F, k, optimizer=OPTS[opt], deterministic=0, lr=lr)
+    ctx.upload_params(W0, V0)
+    ctx.upload_batch(0, rp, fid, None, val, lab)
+    for step in range(3):
+        lg, cg = ctx.train_step(0)
+        lo, ao = o.epoch()
+        # step 0 starts from identical state: only the summation order differs (observed <= 3e-7); later steps carry the
+        # re-association noise of the previous updates through sign-like first updater steps
+        assert _rel(lg, lo) < (1e-6 if step == 0 else 1e-5), (opt, k, step, lg, lo)
+        assert abs(cg - round(ao * B)) <= 1
+        if step == 0:
+            Wg, Vg = ctx.download_params()
+            # FTRL has a hard threshold (|z| <= lambda1 -> w = 0): a coordinate within rounding of it may flip
+            tol = 5e-3 if opt == "ftrl" else 2e-5
+            assert np.max(np.abs(Wg - o.W)) < tol and np.max(np.abs(Vg - o.V)) < tol, (opt, k)
+    assert ctx.launch_count() > 0
+    ctx.close()
+
+
+def test_fused_long_rows_and_window_overflow(oracle_api):
+    """Rows longer than the kernel's register window (k = 16: 128 entries; k = 8: 256) take the re-gather loop."""
+    from lightctr_b200 import capi
+    rng = np.random.default_rng(2)
+    F, rows = 5000, 64
+    for k in (16, 8):
+        nn = rng.integers(1, 400, rows)
+        nn[0], nn[1], nn[2] = 129, 128, 1
+        rp = np.concatenate([[0], np.cumsum(nn)]).astype(np.int64)
+        fid = np.concatenate([rng.choice(F, n, replace=False) for n in nn]).astype(np.uint32)
+        lab = (rng.random(rows) < 0.3).astype(np.int32)
+        val = (0.5 + rng.random(len(fid))).astype(np.float32)
+        W0 = (rng.standard_normal(F) * 0.01).astype(np.float32)
+        V0 = (rng.standard_normal(F * k) * 0.05).astype(np.float32)
+        ds = oracle_api.Dataset(rp, fid, np.zeros(len(fid), np.uint32), val, lab, F, 0)
+        o = oracle_api.FMOracle(ds, k, W0, V0)
+        ctx = capi.Context(capi.MODEL_FM, F, k, deterministic=0)
+        ctx.upload_params(W0, V0)
+        ctx.upload_batch(0, rp, fid, None, val, lab)
+        lg, _ = ctx.train_step(0)
+        lo, _ = o.epoch()
+        assert _rel(lg, lo) < 1e-6, (k, lg, lo)
+        Wg, Vg = ctx.download_params()
+        assert np.max(np.abs(Wg - o.W)) < 2e-5 and np.max(np.abs(Vg - o.V)) < 2e-5
+        assert np.max(np.abs(ctx.download_sumvx(0) - o.sumVX)) < 1e-4
+        ctx.close()
+
+
+def test_fused_every_row_shares_one_id(oracle_api):
+    """One id present in ALL rows (multiplicity = batch size): the hot-replica path must fold exactly."""
+    from lightctr_b200 import capi
+    rng = np.random.default_rng(9)
+    F, rows, k = 3000, 2048, 16
+    per = 6
+    fid = np.empty((rows, per), np.uint32)
+    fid[:, 0] = 7
+    fid[:, 1] = 11 + (np.arange(rows) % 3)
+    for r in range(rows):
+        fid[r, 2:] = rng.choice(np.arange(100, F), per - 2, replace=False)
+    rp = (np.arange(rows + 1) * per).astype(np.int64)
+    fid = fid.ravel()
+    lab = (rng.random(rows) < 0.4).astype(np.int32)
+    W0 = (rng.standard_normal(F) * 0.01).astype(np.float32)
+    V0 = (rng.standard_normal(F * k) * 0.1).astype(np.float32)
+    ds = oracle_api.Dataset(rp, fid, np.zeros(len(fid), np.uint32), np.ones(len(fid), np.float32), lab, F, 0)
+    o = oracle_api.FMOracle(ds, k, W0, V0)
+    ctx = capi.Context(capi.MODEL_FM, F, k, deterministic=0)
+    ctx.upload_params(W0, V0)
+    ctx.upload_batch(0, rp, fid, None, None, lab)
+    for step in range(2):
+        lg, _ = ctx.train_step(0)
+        lo, _ = o.epoch()
+        assert _rel(lg, lo) < 2e-6, (step, lg, lo)
+    Wg, Vg = ctx.download_params()
+    # id 7 sums 2048 terms in a different order than the CPU's row order: 1e-4 absolute on a coordinate of magnitude ~0.1
+    assert np.max(np.abs(Wg - o.W)) < 1e-4 and np.max(np.abs(Vg - o.V)) < 1e-4
+    ctx.close()
+
+
+def test_fused_c2_shape_one_step(oracle_api):
+    """BASELINE configs[1] at its exact shape -- FM k=16, 1 M features, 39 fields, batch 4096, Adagrad -- one step of the
+    benched kernels against the oracle on the SAME batch bench.py times (same generator and seed)."""
+    from lightctr_b200 import capi
+    from lightctr_b200.data import BASE_SEED, CriteoSynth
+    F, k, B = 1_000_000, 16, 4096
+    rp, fid, fld, lab = CriteoSynth(F, seed=BASE_SEED).batch(B)
+    rng = np.random.default_rng(1)
+    W0 = (rng.standard_normal(F) * 0.01).astype(np.float32)
+    V0 = (rng.standard_normal(F * k) / 4).astype(np.float32)
+    ds = oracle_api.Dataset(rp, fid, fld.astype(np.uint32), np.ones(len(fid), np.float32), lab, F, 0)
+    o = oracle_api.FMOracle(ds, k, W0, V0)
+    ctx = capi.Context(capi.MODEL_FM, F, k, deterministic=0)
+    ctx.upload_params(W0, V0)
+    ctx.upload_batch(0, rp, fid, None, None, lab)
+    lg, cg = ctx.train_step(0)
+    lo, ao = o.epoch()
+    assert _rel(lg, lo) < 1e-6, (lg, lo)
+    assert abs(cg - round(ao * B)) <= 1
+    Wg, Vg = ctx.download_params()
+    assert np.max(np.abs(Wg - o.W)) < 2e-5 and np.max(np.abs(Vg - o.V)) < 2e-5
+    s1, _ = ctx.download_opt_state()
+    assert np.allclose(s1, o.accum, rtol=1e-4, atol=1e-9)
+    # second step from the updated state (hot replicas and the compact buffer must have been re-zeroed exactly)
+    lg2, _ = ctx.train_step(0)
+    lo2, _ = o.epoch()
+    assert _rel(lg2, lo2) < 1e-5, (lg2, lo2)
+    ctx.close()
+
+
+def test_fused_sub_ranges_of_a_resident_slot(oracle_api):
+    """lctr_train_step on row sub-ranges of a resident slot (the slot map covers the whole slot; a step touches a subset
+    of its key set): two half steps == the oracle run on the two halves as separate datasets."""
+    from lightctr_b200 import capi
+    F, B, k = 8000, 600, 16
+    rp, fid, fld, lab, _ = _synth(F, B, 31)
+    rng = np.random.default_rng(6)
+    W0 = np.zeros(F, np.float32)
+    V0 = (rng.standard_normal(F * k) / 4).astype(np.float32)
+    ctx = capi.Context(capi.MODEL_FM, F, k, deterministic=0)
+    ctx.upload_params(W0, V0)
+    ctx.upload_batch(0, rp, fid, None, None, lab)
+    W, V, acc = W0.copy(), V0.copy(), np.zeros(F * (k + 1), np.float32)
+    for (rb, re) in ((0, 250), (250, 600)):
+        lg, _ = ctx.train_step(0, rb, re)
+        sub_rp = (rp[rb:re + 1] - rp[rb]).astype(np.int64)
+        sl = slice(rp[rb], rp[re])
+        ds = oracle_api.Dataset(sub_rp, fid[sl], fld[sl].astype(np.uint32), np.ones(rp[re] - rp[rb], np.float32), lab[rb:re], F, 0)
+        o = oracle_api.FMOracle(ds, k, W, V)
+        o.accum[:] = acc
+        lo, _ = o.epoch()
+        W, V, acc = o.W.copy(), o.V.copy(), o.accum.copy()
+        assert _rel(lg, lo) < 2e-6, (rb, lg, lo)
+    Wg, Vg = ctx.download_params()
+    assert np.max(np.abs(Wg - W)) < 2e-5 and np.max(np.abs(Vg - V)) < 2e-5
+    ctx.close()
