@@ -365,6 +365,7 @@ int lctr_download_opt_state(lctr_ctx* c, float* s1, float* s2) {
 }
 int lctr_upload_opt_state(lctr_ctx* c, const float* s1, const float* s2) {
     LCTR_CHECK(c, "null ctx");
+    LCTR_CHECK(c->cfg.world == 1, "optimizer-state transfer is single-GPU only (the state arrays are sharded by owner)");
     const size_t nv = c->F * c->rowlen;
     if (s1) {
         LCTR_CUDA(cudaMemcpyAsync(c->s1W, s1, c->F * sizeof(float), cudaMemcpyHostToDevice, c->stream));
@@ -465,6 +466,8 @@ int lctr_train_step(lctr_ctx* c, int slot, int64_t rb, int64_t re, float* loss_s
     Slot& s = c->slots[slot];
     LCTR_CHECK(rb >= 0 && re <= s.rows && rb <= re, "train_step: rows [%lld,%lld) outside slot (%lld rows)",
                (long long)rb, (long long)re, (long long)s.rows);
+    LCTR_CHECK(c->cfg.world == 1 || c->cfg.minibatch_size > 0,
+               "train_step: multi-GPU contexts need cfg.minibatch_size = the GLOBAL batch (the updater's divisor)");
     const uint64_t step = c->step;
     int rc = 0;
     if (c->csc_in_step && c->cfg.deterministic == 2 && c->cfg.world == 1 && rb == 0 && re == s.rows && s.nnz > 0) {
@@ -670,6 +673,9 @@ int lctr_wait(lctr_ctx* c, uint64_t ticket, float* loss_sum, float* acc_cnt) {
 int lctr_predict(lctr_ctx* c, int slot, int quirk_sumvx_slot, float* pctr) {
     LCTR_CHECK(c, "null ctx");
     LCTR_CHECK(slot >= 0 && slot < kNumSlots, "slot %d out of range", slot);
+    // world > 1: the compute view only holds the rows pulled by the last train step, at their pre-update values
+    LCTR_CHECK(c->cfg.world == 1, "lctr_predict: multi-GPU contexts keep sharded tables; download the parameters "
+                                  "(lctr_download_params) into a single-GPU context to predict");
     Slot& s = c->slots[slot];
     int rc = 0;
     if (c->cfg.model == LCTR_MODEL_FFM) {

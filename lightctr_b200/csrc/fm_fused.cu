@@ -179,8 +179,9 @@ int launch_fm_forward_tree(lctr_ctx* c, Slot& s, int64_t rb, int64_t re, bool st
 template <int K>
 static void apply_go(lctr_ctx* c, Slot& s, const OptParams& P, const OptParams* P_dev) {
     FusedState* f = c->fused;
-    const unsigned grid = (unsigned)c->sm_count * 2;
-#define AC_ARGS s.uniq, s.n_uniq, f->G, s.hot_of, s.hot_slot, s.n_hot, f->Ghot, f->GS, c->W, c->V, c->s1W, c->s1V, c->s2W, c->s2V, P, P_dev
+    const int main_blocks = c->sm_count * 3;
+    const unsigned grid = (unsigned)(main_blocks + kHotMax / 8);  // + one warp per possible hot slot
+#define AC_ARGS s.uniq, s.n_uniq, f->G, s.hot_of, s.hot_slot, s.n_hot, f->Ghot, f->GS, main_blocks, c->W, c->V, c->s1W, c->s1V, c->s2W, c->s2V, P, P_dev
     switch (P.opt) {
         case LCTR_OPT_ADAGRAD: apply_compact_kernel<K, LCTR_OPT_ADAGRAD><<<grid, 256, 0, c->stream>>>(AC_ARGS); break;
         case LCTR_OPT_FTRL: apply_compact_kernel<K, LCTR_OPT_FTRL><<<grid, 256, 0, c->stream>>>(AC_ARGS); break;

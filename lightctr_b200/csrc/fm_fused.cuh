@@ -419,24 +419,26 @@ fm_fused_kernel(const int64_t* __restrict__ row_ptr, const uint32_t* __restrict_
 // feature uniq[i]; LPR lanes per row, GR rows per warp step, U steps in flight.  Zeroes G on the way (the memset of
 // gradientUpdater.h:149).
 template <int K, int OPT>
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(256, 3)
 apply_compact_kernel(const uint32_t* __restrict__ uniq, const unsigned int* __restrict__ n_uniq, float* __restrict__ G,
                      const uint32_t* __restrict__ hot_of, const uint32_t* __restrict__ hot_slot,
-                     const unsigned int* __restrict__ n_hot, float* __restrict__ Ghot, int GS, float* __restrict__ W,
-                     float* __restrict__ V, float* __restrict__ s1W, float* __restrict__ s1V, float* __restrict__ s2W,
-                     float* __restrict__ s2V, OptParams P_in, const OptParams* __restrict__ P_dev) {
+                     const unsigned int* __restrict__ n_hot, float* __restrict__ Ghot, int GS, int main_blocks,
+                     float* __restrict__ W, float* __restrict__ V, float* __restrict__ s1W, float* __restrict__ s1V,
+                     float* __restrict__ s2W, float* __restrict__ s2V, OptParams P_in, const OptParams* __restrict__ P_dev) {
     constexpr int LPR = K / 4, GR = 32 / LPR, U = 2;
     OptParams P = P_dev ? *P_dev : P_in;
     P.opt = OPT;
     constexpr bool two = OPT == LCTR_OPT_FTRL || OPT == LCTR_OPT_ADAM || OPT == LCTR_OPT_ADADELTA;
     const int lane = threadIdx.x & 31;
-    const unsigned warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const unsigned nwarps = gridDim.x * (blockDim.x >> 5);
-    // ---- hot slots: one warp each.  The kHotRep replica rows form a [kHotRep][GS] tile: lane = column, so every load is
-    // one fully coalesced row; column c < K is gV[c], column K is gW.  The warp folds, updates and re-zeroes.
-    if (hot_of) {
+    // ---- hot slots: the blocks BEYOND main_blocks, one warp per hot slot (the two kinds of work have equally long
+    // dependent-load chains, so they run side by side instead of one after the other).  The kHotRep replica rows form a
+    // [kHotRep][GS] tile: lane = column, so every load is one fully coalesced row and all rows are requested at once;
+    // column c < K is gV[c], column K is gW.  The warp folds, updates and re-zeroes.
+    if ((int)blockIdx.x >= main_blocks) {
+        const unsigned hwarp = (blockIdx.x - main_blocks) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+        const unsigned nhw = (gridDim.x - main_blocks) * (blockDim.x >> 5);
         const unsigned nh = min(*n_hot, (unsigned)kHotMax);
-        for (unsigned h = warp; h < nh; h += nwarps) {
+        for (unsigned h = hwarp; h < nh; h += nhw) {
             const uint32_t slot = __ldg(hot_slot + h);
             const uint32_t f = __ldg(uniq + slot);
             float* tile = Ghot + (size_t)h * kHotRep * GS;
@@ -445,36 +447,36 @@ apply_compact_kernel(const uint32_t* __restrict__ uniq, const unsigned int* __re
                 const int ncol = GS < 32 ? GS : 32;             // columns covered per pass
                 const int col = c0 + lane % ncol;
                 const int grp = lane / ncol, ngrp = 32 / ncol;  // GS < 32: several replica rows per load
-                float sum = 0.f;
-                for (int r0 = grp; r0 < kHotRep; r0 += 8 * ngrp) {
-                    float t[8];
+                float t[kHotRep];
 #pragma unroll
-                    for (int i = 0; i < 8; i++) t[i] = r0 + i * ngrp < kHotRep ? __ldcg(tile + (size_t)(r0 + i * ngrp) * GS + col) : 0.f;
-#pragma unroll
-                    for (int i = 0; i < 8; i++) {
-                        sum += t[i];
-                        if (r0 + i * ngrp < kHotRep) tile[(size_t)(r0 + i * ngrp) * GS + col] = 0.f;
-                    }
+                for (int i = 0; i < kHotRep; i++)
+                    t[i] = (i < kHotRep / ngrp) ? __ldcg(tile + (size_t)(grp + i * ngrp) * GS + col) : 0.f;
+                float wv = 0.f, av = 0.f, bv = 0.f;
+                const bool mine = grp == 0 && col <= K;
+                const size_t o = col < K ? (size_t)f * K + col : (size_t)f;
+                if (mine) {
+                    wv = col < K ? V[o] : W[o];
+                    av = col < K ? s1V[o] : s1W[o];
+                    if (two) bv = col < K ? s2V[o] : s2W[o];
                 }
-                for (int o = ncol; o < 32; o <<= 1) sum += __shfl_xor_sync(kFull, sum, o);
-                if (grp == 0 && col <= K) {
-                    // (every entry of a hot slot carries kHotBit, so its ordinary row G[slot] stays zero)
-                    if (col < K) {
-                        const size_t o = (size_t)f * K + col;
-                        float w = V[o], a = s1V[o], b2 = two ? s2V[o] : 0.f;
-                        update_one(P, P.corrV, w, sum, a, b2);
-                        V[o] = w; s1V[o] = a;
-                        if (two) s2V[o] = b2;
-                    } else {
-                        float w = W[f], a = s1W[f], b2 = two ? s2W[f] : 0.f;
-                        update_one(P, P.corrW, w, sum, a, b2);
-                        W[f] = w; s1W[f] = a;
-                        if (two) s2W[f] = b2;
-                    }
+                float sum = 0.f;
+#pragma unroll
+                for (int i = 0; i < kHotRep; i++) {
+                    sum += t[i];
+                    if (i < kHotRep / ngrp) tile[(size_t)(grp + i * ngrp) * GS + col] = 0.f;
+                }
+                for (int o2 = ncol; o2 < 32; o2 <<= 1) sum += __shfl_xor_sync(kFull, sum, o2);
+                if (mine) {  // (every entry of a hot slot carries kHotBit, so its ordinary row G[slot] stays zero)
+                    update_one(P, col < K ? P.corrV : P.corrW, wv, sum, av, bv);
+                    if (col < K) { V[o] = wv; s1V[o] = av; if (two) s2V[o] = bv; }
+                    else { W[o] = wv; s1W[o] = av; if (two) s2W[o] = bv; }
                 }
             }
         }
+        return;
     }
+    const unsigned warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const unsigned nwarps = (unsigned)main_blocks * (blockDim.x >> 5);
     // ---- ordinary slots
     const int q = lane % LPR, g = lane / LPR;
     const unsigned total = *n_uniq;

@@ -319,7 +319,7 @@ int main(int argc, char** argv) {
                                                                         0, B, nullptr, partial, done, out_slot, 1);
         };
         auto apply = [&]() {
-            apply_compact_kernel<K, LCTR_OPT_ADAGRAD><<<SM * 2, 256, 0, st>>>(uniq, n_uniq, G, hot_of, hot_slot, n_hot, Ghot, GS, W, V, s1W, s1V, nullptr, nullptr, P, nullptr);
+            apply_compact_kernel<K, LCTR_OPT_ADAGRAD><<<SM * 3 + kHotMax / 8, 256, 0, st>>>(uniq, n_uniq, G, hot_of, hot_slot, n_hot, Ghot, GS, SM * 3, W, V, s1W, s1V, nullptr, nullptr, P, nullptr);
         };
         // validation against the naive kernel (gradients only; apply is skipped so that parameters stay put)
         CK(cudaMemsetAsync(G, 0, (size_t)(U + 64) * GSmax * 4, st));

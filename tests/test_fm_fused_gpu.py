@@ -44,18 +44,22 @@ def test_fused_step_vs_oracle(oracle_api, opt, k, with_val):
     ctx = capi.Context(capi.MODEL_FM, F, k, optimizer=OPTS[opt], deterministic=0, lr=lr)
     ctx.upload_params(W0, V0)
     ctx.upload_batch(0, rp, fid, None, val, lab)
+    F1 = F * (k + 1)
     for step in range(3):
+        # every step starts from the ORACLE's exact state (parameters + updater state), so only the summation order of
+        # this one step differs: observed <= 3e-7 on the loss.  (Left to itself the path drifts like the reference's own
+        # Hogwild mode: the sign-like first updater steps amplify fp32 re-association noise to ~1e-5 within 3 steps.)
+        if step > 0:
+            ctx.upload_params(o.W, o.V)
+            ctx.upload_opt_state(o.accum, getattr(o, "s2", np.zeros(F1, np.float32)))
         lg, cg = ctx.train_step(0)
         lo, ao = o.epoch()
-        # step 0 starts from identical state: only the summation order differs (observed <= 3e-7); later steps carry the
-        # re-association noise of the previous updates through sign-like first updater steps
-        assert _rel(lg, lo) < (1e-6 if step == 0 else 1e-5), (opt, k, step, lg, lo)
+        assert _rel(lg, lo) < 1e-6, (opt, k, step, lg, lo)
         assert abs(cg - round(ao * B)) <= 1
-        if step == 0:
-            Wg, Vg = ctx.download_params()
-            # FTRL has a hard threshold (|z| <= lambda1 -> w = 0): a coordinate within rounding of it may flip
-            tol = 5e-3 if opt == "ftrl" else 2e-5
-            assert np.max(np.abs(Wg - o.W)) < tol and np.max(np.abs(Vg - o.V)) < tol, (opt, k)
+        Wg, Vg = ctx.download_params()
+        # FTRL has a hard threshold (|z| <= lambda1 -> w = 0): a coordinate within rounding of it may flip
+        tol = 5e-3 if opt == "ftrl" else 2e-5
+        assert np.max(np.abs(Wg - o.W)) < tol and np.max(np.abs(Vg - o.V)) < tol, (opt, k, step)
     assert ctx.launch_count() > 0
     ctx.close()
 
