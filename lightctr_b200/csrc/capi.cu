@@ -6,7 +6,7 @@
 #include <algorithm>
 #include <vector>
 
-#include "common.cuh"
+#include "opt.cuh"
 
 namespace lctr {
 static thread_local std::string g_err;
@@ -58,7 +58,8 @@ static int slot_reserve(lctr_ctx* c, Slot& s, int64_t rows, int64_t nnz) {
     return 0;
 }
 
-__global__ void label_to_float_kernel(const int32_t* in, float* out, int64_t n) {
+__global__ void label_to_float_kernel(const int32_t* in, float* out, int64_t n_arg, const int64_t* hdr) {
+    const int64_t n = hdr ? hdr[0] : n_arg;
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = (float)in[i];
 }
@@ -407,7 +408,7 @@ static int upload_batch_on(lctr_ctx* c, cudaStream_t st, int slot, int64_t rows,
         // labels travel as int32 and are widened on device (the reference compares a `float target`)
         LCTR_CUDA(cudaMemcpyAsync(tmp, label, (size_t)rows * sizeof(int32_t), cudaMemcpyHostToDevice, st));
         if (!grouped) {
-            label_to_float_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>(tmp, s.label, rows);
+            label_to_float_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>(tmp, s.label, rows, nullptr);
             c->launches++;
             LCTR_CUDA(cudaGetLastError());
         }
@@ -562,23 +563,45 @@ static int pipe_graph_capture(lctr_ctx* c, int p, bool has_val) {
         LCTR_CUDA(cudaMallocHost((void**)&g.h_stat, 2 * sizeof(double)));
     }
     s.has_val = has_val;
+    {   // the launchers pick their updater instance from the host copy at capture time: give it the context's updater
+        OptParams* hp = reinterpret_cast<OptParams*>(g.h_opt);
+        memset(hp, 0, csc_opt_params_size());
+        hp->opt = c->cfg.optimizer;
+    }
     cudaGraph_t graph;
+    const bool fused = fused_supported(c);
     // ---- build graph (copy stream)
     LCTR_CUDA(cudaStreamBeginCapture(c->copy_stream, cudaStreamCaptureModeThreadLocal));
-    LCTR_CUDA(cudaMemcpyAsync(g.d_hdr, g.h_hdr, 2 * sizeof(int64_t), cudaMemcpyHostToDevice, c->copy_stream));
-    int rc = csc_build_device(c, s, c->copy_stream, reinterpret_cast<int32_t*>(s.pred), g.d_hdr, s.cap_rows, s.cap_nnz);
-    LCTR_CUDA(cudaStreamEndCapture(c->copy_stream, &graph));
-    if (rc) return 1;
+    int rc = cudaMemcpyAsync(g.d_hdr, g.h_hdr, 2 * sizeof(int64_t), cudaMemcpyHostToDevice, c->copy_stream) != cudaSuccess;
+    if (!rc) {
+        if (fused) {  // labels widened, then the slot map of the batch (fm_fused.cu)
+            label_to_float_kernel<<<(unsigned)((s.cap_rows + 255) / 256), 256, 0, c->copy_stream>>>(
+                reinterpret_cast<int32_t*>(s.pred), s.label, s.cap_rows, g.d_hdr);
+            c->launches++;
+            rc = fused_build_slot(c, s, c->copy_stream, g.d_hdr, s.cap_rows, s.cap_nnz);
+        } else {
+            rc = csc_build_device(c, s, c->copy_stream, reinterpret_cast<int32_t*>(s.pred), g.d_hdr, s.cap_rows, s.cap_nnz);
+        }
+    }
+    cudaError_t ce = cudaStreamEndCapture(c->copy_stream, &graph);  // always closes the capture, also on error paths
+    if (rc || ce != cudaSuccess) { set_error("streamed pipeline: capture of the build graph failed (%s)", cudaGetErrorString(ce)); return 1; }
     LCTR_CUDA(cudaGraphInstantiate(&g.build, graph, 0));
     cudaGraphDestroy(graph);
     // ---- step graph (compute stream)
     LCTR_CUDA(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
-    LCTR_CUDA(cudaMemcpyAsync(g.d_opt, g.h_opt, csc_opt_params_size(), cudaMemcpyHostToDevice, c->stream));
-    rc = launch_fm_forward_ex(c, s, 0, s.cap_rows, false, true, g.d_hdr, g.d_stat) ||
-         launch_fm_backward_devcsc_ex(c, s, 0, s.cap_rows, reinterpret_cast<const OptParams*>(g.h_opt), g.d_opt);
-    LCTR_CUDA(cudaMemcpyAsync(g.h_stat, g.d_stat, 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-    LCTR_CUDA(cudaStreamEndCapture(c->stream, &graph));
-    if (rc) return 1;
+    rc = cudaMemcpyAsync(g.d_opt, g.h_opt, csc_opt_params_size(), cudaMemcpyHostToDevice, c->stream) != cudaSuccess;
+    if (!rc) {
+        if (fused)
+            rc = launch_fm_fused(c, s, 0, s.cap_rows, true, g.d_hdr, g.d_stat) ||
+                 launch_apply_compact(c, s, s.cap_rows, reinterpret_cast<const OptParams*>(g.h_opt),
+                                      reinterpret_cast<const OptParams*>(g.d_opt));
+        else
+            rc = launch_fm_forward_ex(c, s, 0, s.cap_rows, false, true, g.d_hdr, g.d_stat) ||
+                 launch_fm_backward_devcsc_ex(c, s, 0, s.cap_rows, reinterpret_cast<const OptParams*>(g.h_opt), g.d_opt);
+    }
+    if (!rc) rc = cudaMemcpyAsync(g.h_stat, g.d_stat, 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream) != cudaSuccess;
+    ce = cudaStreamEndCapture(c->stream, &graph);
+    if (rc || ce != cudaSuccess) { set_error("streamed pipeline: capture of the step graph failed (%s)", cudaGetErrorString(ce)); return 1; }
     LCTR_CUDA(cudaGraphInstantiate(&g.step, graph, 0));
     cudaGraphDestroy(graph);
     g.cap_rows = s.cap_rows; g.cap_nnz = s.cap_nnz; g.has_val = has_val;
@@ -597,7 +620,7 @@ static int train_batch_async_graph(lctr_ctx* c, int64_t rows, int64_t nnz, const
         LCTR_CUDA(cudaStreamSynchronize(c->copy_stream));
         if (rows > s.cap_rows || nnz > s.cap_nnz)  // head-room so that slightly larger batches do not re-capture
             if (slot_reserve(c, s, std::max(rows, s.cap_rows) + rows / 8 + 64, std::max(nnz, s.cap_nnz) + nnz / 8 + 1024)) return 1;
-        if (csc_reserve(c, s, s.cap_nnz)) return 1;
+        if (fused_supported(c) ? fused_reserve(c, s, s.cap_nnz) : csc_reserve(c, s, s.cap_nnz)) return 1;
         LCTR_CUDA(cudaStreamSynchronize(c->stream));
         if (pipe_graph_capture(c, p, val != nullptr)) return 1;
     }
@@ -611,11 +634,13 @@ static int train_batch_async_graph(lctr_ctx* c, int64_t rows, int64_t nnz, const
     LCTR_CUDA(cudaGraphLaunch(g.build, c->copy_stream));
     LCTR_CUDA(cudaEventRecord(c->ev_copied[p], c->copy_stream));
     LCTR_CUDA(cudaStreamWaitEvent(c->stream, c->ev_copied[p], 0));
-    csc_opt_params(c, rows, g.h_opt);
+    const bool fused = fused_supported(c);
+    if (fused) fused_opt_params(c, rows, g.h_opt); else csc_opt_params(c, rows, g.h_opt);
     LCTR_CUDA(cudaGraphLaunch(g.step, c->stream));
     LCTR_CUDA(cudaEventRecord(c->ev_computed[p], c->stream));
-    s.dev_csc = true;
-    c->launches += 8;  // kernels inside the two graphs
+    s.dev_csc = !fused;
+    s.fused_valid = fused;
+    c->launches += 8;  // kernels inside the two graphs (6 + 2 on the fused path, 5 + 3 on the grouped one)
     g.ticket = c->step;
     *ticket = c->step++;
     c->pipe_issued++;
@@ -628,7 +653,8 @@ int lctr_train_batch_async(lctr_ctx* c, int64_t rows, int64_t nnz, const int64_t
     LCTR_CHECK(c->cfg.deterministic != 1, "streamed batches need cfg.deterministic 0 (RED scatter) or 2 (device grouping)");
     if (pipe_init(c)) return 1;
     LCTR_CHECK(c->pipe_issued - c->pipe_waited < 2, "more than 2 streamed batches outstanding: call lctr_wait first");
-    if (c->cfg.deterministic == 2 && c->cfg.world == 1 && c->cfg.model == LCTR_MODEL_FM && !c->profiling && rows > 0 && nnz > 0)
+    if ((c->cfg.deterministic == 2 || fused_supported(c)) && c->cfg.world == 1 && c->cfg.model == LCTR_MODEL_FM && !c->profiling &&
+        rows > 0 && nnz > 0)
         return train_batch_async_graph(c, rows, nnz, row_ptr, fid, val, label, ticket);
     const int p = (int)(c->pipe_issued & 1);
     const int slot = kNumSlots - 2 + p;

@@ -26,6 +26,16 @@ def _synth(F, B, seed, with_val=False):
 OPTS = {"adagrad": 0, "ftrl": 1, "adam": 2, "rmsprop": 3, "adadelta": 4}
 
 
+def _params_close(got, want, tol, threshold_updater):
+    """max |got - want| < tol; for updaters with a discontinuity (FTRL: |z| <= lambda1 -> w = 0; Adam: the first steps
+    are m / sqrt(v) = +-sqrt(1 - beta), i.e. the SIGN of a gradient sum that may be within rounding of 0) a few
+    coordinates may land on the other side of it: at most 1e-5 of them, each by at most one such jump (1e-2)."""
+    d = np.abs(got - want)
+    if not threshold_updater:
+        return float(d.max()) < tol
+    return float(np.mean(d > tol)) <= 1e-5 and float(d.max()) < 1e-2
+
+
 @pytest.mark.parametrize("opt", ["adagrad", "ftrl", "adam", "rmsprop", "adadelta"])
 @pytest.mark.parametrize("k,with_val", [(16, False), (8, True), (4, False), (32, True)])
 def test_fused_step_vs_oracle(oracle_api, opt, k, with_val):
@@ -57,9 +67,8 @@ def test_fused_step_vs_oracle(oracle_api, opt, k, with_val):
         assert _rel(lg, lo) < 1e-6, (opt, k, step, lg, lo)
         assert abs(cg - round(ao * B)) <= 1
         Wg, Vg = ctx.download_params()
-        # FTRL has a hard threshold (|z| <= lambda1 -> w = 0): a coordinate within rounding of it may flip
-        tol = 5e-3 if opt == "ftrl" else 2e-5
-        assert np.max(np.abs(Wg - o.W)) < tol and np.max(np.abs(Vg - o.V)) < tol, (opt, k, step)
+        thr = opt in ("ftrl", "adam")
+        assert _params_close(Wg, o.W, 2e-5, thr) and _params_close(Vg, o.V, 2e-5, thr), (opt, k, step)
     assert ctx.launch_count() > 0
     ctx.close()
 
