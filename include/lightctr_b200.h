@@ -150,6 +150,9 @@ int lctr_mlp_download_grad(lctr_ctx* ctx, int layer, float* dweight, float* dbia
  * export this rank's table handles, gather them, import all peers'. */
 int lctr_ipc_export(lctr_ctx* ctx, void* handles_out, size_t cap, size_t* bytes);
 int lctr_ipc_import(lctr_ctx* ctx, const void* all_handles, size_t bytes_per_rank);
+/* device memory of the context in bytes: table shard + updater state, and (world > 1) the exchange arena, caches and
+ * inboxes -- owner-sharding keeps the second number O(keys of a batch), not O(feature_cnt) */
+int lctr_device_bytes(lctr_ctx* ctx, uint64_t* shard_bytes, uint64_t* exchange_bytes);
 /* Data-parallel dense layers (world > 1, NFM): the per-rank weightDelta / biasDelta of the batch must be summed over
  * the ranks before the updater runs -- Worker_RingReduce::syncGradient (distribut/ring_collect.h:48-72) on the
  * BufferFusion of Fully_Conn_Layer::registerGradient (fullyconnLayer.h:69-75).  The library calls `fn` once per train

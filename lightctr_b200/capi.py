@@ -26,7 +26,7 @@ SYMBOLS = [
     "lctr_train_step", "lctr_train_batch", "lctr_train_batch_async", "lctr_wait", "lctr_predict", "lctr_download_sumvx", "lctr_download_pred",
     "lctr_mlp_upload", "lctr_mlp_download", "lctr_mlp_set_mask", "lctr_mlp_download_grad", "lctr_set_dense_allreduce", "lctr_save_checkpoint", "lctr_load_checkpoint",
     "lctr_save_dataset_bin", "lctr_load_dataset_bin", "lctr_eval", "lctr_upload_pred", "lctr_ipc_export", "lctr_ipc_import",
-    "lctr_dense_grad_buffer", "lctr_load_libffm", "lctr_free_dataset", "lctr_launch_count", "lctr_stream", "lctr_profile", "lctr_profile_read",
+    "lctr_dense_grad_buffer", "lctr_device_bytes", "lctr_load_libffm", "lctr_free_dataset", "lctr_launch_count", "lctr_stream", "lctr_profile", "lctr_profile_read",
 ]
 
 
@@ -381,6 +381,11 @@ class Context:
     def ipc_import(self, all_blobs, bytes_per_rank):
         buf = C.create_string_buffer(all_blobs, len(all_blobs))
         _chk(self.L.lctr_ipc_import(self.h, buf, bytes_per_rank))
+
+    def device_bytes(self):
+        a, b = C.c_uint64(), C.c_uint64()
+        _chk(self.L.lctr_device_bytes(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
 
     def launch_count(self):
         return self.L.lctr_launch_count(self.h)

@@ -258,7 +258,7 @@ int lctr_destroy(lctr_ctx* c) {
         dfree(s.row_ptr); dfree(s.fid); dfree(s.field); dfree(s.val); dfree(s.label); dfree(s.pred); dfree(s.sumvx);
         dfree(s.wide);
         dfree(s.blk_seg_ptr); dfree(s.seg_ptr); dfree(s.seg_fid); dfree(s.ent_row); dfree(s.ent_x); dfree(s.ent_field);
-        dfree(s.ent_slot); dfree(s.hot_of); dfree(s.hot_slot); dfree(s.n_hot);
+        dfree(s.ent_slot); dfree(s.ent_pslot); dfree(s.hot_of); dfree(s.hot_slot); dfree(s.n_hot);
         dfree(s.uniq); dfree(s.n_uniq); dfree(s.short_list); dfree(s.long_list); dfree(s.csc_totals); dfree(s.csc_acc); dfree(s.csc_arrived);
         delete s.h_blk_seg_ptr; s.h_blk_seg_ptr = nullptr;
     }
@@ -413,10 +413,12 @@ static int upload_batch_on(lctr_ctx* c, cudaStream_t st, int slot, int64_t rows,
             LCTR_CUDA(cudaGetLastError());
         }
     }
-    if (c->cfg.world > 1 && dist_build_uniq(c, s, st)) return 1;
     s.fused_valid = false;
-    if (fused_supported(c) && rows > 0 && nnz > 0) {  // slot map of the batch for the order-free fused step
+    if ((fused_supported(c) || c->cfg.world > 1) && rows > 0 && nnz > 0) {
+        // slot map of the batch: the gradient rows of the order-free fused step; on several GPUs also the key set of the
+        // pull / push exchange, whose per-owner lists go out right away (posted stores, overlapping the previous step)
         if (fused_reserve(c, s, nnz) || fused_build_slot(c, s, st, nullptr, rows, nnz)) return 1;
+        if (c->cfg.world > 1 && dist_send_keys(c, s, slot, st)) return 1;
     }
     s.csc_block = 0;
     s.dev_csc = false;
@@ -453,6 +455,7 @@ int lctr_upload_batch(lctr_ctx* c, int slot, int64_t rows, int64_t nnz, const in
 
 static int read_stats(lctr_ctx* c, uint64_t step, float* loss_sum, float* acc_cnt) {
     if (!loss_sum && !acc_cnt) return 0;
+    if (c->cfg.world > 1 && dist_check_overflow(c)) return 1;
     LCTR_CUDA(cudaMemcpyAsync(c->h_stats, c->stats + 2 * (step % kStatRing), 2 * sizeof(double), cudaMemcpyDeviceToHost,
                               c->stream));
     LCTR_CUDA(cudaStreamSynchronize(c->stream));
@@ -478,9 +481,12 @@ int lctr_train_step(lctr_ctx* c, int slot, int64_t rb, int64_t re, float* loss_s
     }
     switch (c->cfg.model) {
         case LCTR_MODEL_FM:
-            if (c->cfg.world > 1)
-                rc = dist_pre_step(c, s, rb, re) || launch_fm_forward(c, s, rb, re, false, true) ||
-                     launch_fm_backward(c, s, rb, re, false) || dist_post_step(c, re - rb);
+            if (c->cfg.world > 1 && fused_kernels_ok(c))
+                rc = dist_pre_step(c, s, slot, true) || launch_fm_fused(c, s, rb, re, true, nullptr, nullptr) ||
+                     dist_post_step(c, s, slot, re - rb);
+            else if (c->cfg.world > 1)
+                rc = dist_pre_step(c, s, slot, false) || launch_fm_forward(c, s, rb, re, false, true) ||
+                     launch_fm_backward(c, s, rb, re, false) || dist_post_step(c, s, slot, re - rb);
             else if (c->cfg.deterministic == 2)
                 rc = launch_fm_forward(c, s, rb, re, false, true) || launch_fm_backward_devcsc(c, s, rb, re);
             else if (c->cfg.deterministic)
@@ -493,7 +499,7 @@ int lctr_train_step(lctr_ctx* c, int slot, int64_t rb, int64_t re, float* loss_s
             break;
         case LCTR_MODEL_FFM:
             if (c->cfg.world > 1)
-                rc = dist_pre_step(c, s, rb, re) || launch_ffm_forward(c, s, rb, re, true) || dist_post_step(c, re - rb);
+                rc = dist_pre_step(c, s, slot, false) || launch_ffm_forward(c, s, rb, re, true) || dist_post_step(c, s, slot, re - rb);
             else if (c->cfg.deterministic == 2)
                 rc = ffm_grouped_reserve(c, s.rows) || launch_ffm_forward_tiles(c, s, rb, re) ||
                      launch_ffm_backward_grouped(c, s, rb, re);
@@ -507,9 +513,9 @@ int lctr_train_step(lctr_ctx* c, int slot, int64_t rb, int64_t re, float* loss_s
         case LCTR_MODEL_NFM:
             if (c->cfg.world > 1) {
                 // embeddings: owner-sharded pull / push like FM; dense layers: replicated, gradients all-reduced
-                rc = dist_pre_step(c, s, rb, re) || mlp_reserve(c, re - rb) || launch_fm_forward(c, s, rb, re, true, false) ||
+                rc = dist_pre_step(c, s, slot, false) || mlp_reserve(c, re - rb) || launch_fm_forward(c, s, rb, re, true, false) ||
                      launch_nfm_mlp(c, s, rb, re, re - rb) || launch_fm_backward(c, s, rb, re, true) ||
-                     dist_post_step(c, re - rb);
+                     dist_post_step(c, s, slot, re - rb);
                 break;
             }
             rc = mlp_reserve(c, re - rb) || launch_fm_forward(c, s, rb, re, true, false) ||

@@ -34,6 +34,8 @@ constexpr int kNumSlots = 8;
 constexpr int kNumProf = 16;  // per-kernel timing buckets
 enum { PROF_FM_FWD = 0, PROF_FM_BWD_RED = 1, PROF_APPLY = 2, PROF_FFM_FUSED = 3, PROF_FM_BWD_CSC = 4, PROF_MLP = 5, PROF_DIST_MARK = 6, PROF_DIST_COMPACT = 7, PROF_DIST_PULL = 8, PROF_DIST_PUSH = 9, PROF_DIST_BAR0 = 10, PROF_DIST_MERGE = 11, PROF_DIST_BAR1 = 12, PROF_CSC_BUILD = 13, PROF_FM_FUSED = 14, PROF_APPLY_COMPACT = 15 };
 constexpr int kStatRing = 64;
+constexpr int kHotRep = 32;      // fm_fused: replica rows per hot slot of the batch-compact gradient buffer
+constexpr int kHotMax = 2048;    // hot slots per batch (ids beyond the cap stay ordinary slots)
 constexpr unsigned kFull = 0xffffffffu;
 
 // One resident CSR batch / dataset (FM_Algo_Abst::dataSet + label, fm_algo_abst.h:156,170).
@@ -76,6 +78,7 @@ struct Slot {
     // order-free fused FM step (fm_fused.cu): per-entry slot of the gradient row (or kHotBit | replica block), the hot
     // slots' replica-block index per slot and their list; `uniq` / `n_uniq` above hold the key set
     uint32_t* ent_slot = nullptr;
+    uint32_t* ent_pslot = nullptr;  // multi-GPU: plain slot per entry = row of the batch-compact parameter cache
     int64_t cap_ent_slot = 0;
     uint32_t *hot_of = nullptr, *hot_slot = nullptr;
     unsigned int* n_hot = nullptr;
@@ -105,7 +108,24 @@ struct MlpLayer {
 
 }  // namespace lctr
 
-namespace lctr { struct DistState; struct FusedState; }
+namespace lctr {
+struct DistState;
+struct OptParams;
+// slot map scratch + batch-compact gradient buffers of the order-free fused FM step (fm_fused.cu); the slot map part is
+// also what the multi-GPU exchange is keyed by (dist.cu)
+struct FusedState {
+    uint8_t* mark = nullptr;      // 128 * T permuted byte marks
+    size_t T = 0;
+    uint32_t* slot_of = nullptr;  // F: fid -> slot of the batch being built
+    unsigned int* cnt = nullptr;  // sampled multiplicities (zero between builds)
+    size_t cnt_cap = 0;
+    float* G = nullptr;           // [G_rows][GS] compact gradient rows (zero between steps)
+    size_t G_rows = 0;
+    float* Ghot = nullptr;        // [kHotMax][kHotRep][GS] replica rows of the hot slots (zero between steps)
+    OptParams* d_opt = nullptr;   // updater parameters in device memory (graph launches)
+    int GS = 0;                   // 0: slot map only (models without the fused kernels)
+};
+}  // namespace lctr
 struct lctr_ctx {
     lctr_cfg cfg;
     cudaStream_t stream = nullptr;
@@ -154,6 +174,9 @@ struct lctr_ctx {
     int mlp_skip_update = 0;    // LCTR_MLP_SKIP_UPDATE=1: leave the dense gradients in place (tests read them)
     int sm_count = 148;
     int64_t launches = 0;
+    const unsigned long long* apply_wait_flags = nullptr;  // multi-GPU owner: flags the sparse apply polls before it starts
+    int apply_wait_n = 0;
+    unsigned long long apply_wait_epoch = 0;
     const float* fwd_quirk_sumvx = nullptr;  // FM_Predict quirk: training sumVX rows used by the next forward launch
     int64_t fwd_quirk_rows = 0;
     void* csc_scratch = nullptr;  // csc.cu: dense count / offset arrays of the device-side grouping
@@ -315,9 +338,11 @@ void csc_scratch_free(lctr_ctx* c);
 int launch_predict_quirk(lctr_ctx* c, Slot& s, Slot& train);
 // fm_fused.cu: order-free FM step over a batch-compact gradient buffer (cfg.deterministic == 0, one GPU)
 bool fused_supported(const lctr_ctx* c);
+bool fused_kernels_ok(const lctr_ctx* c);
 void fused_free(lctr_ctx* c);
 int fused_reserve(lctr_ctx* c, Slot& s, int64_t nnz);
 int fused_build_slot(lctr_ctx* c, Slot& s, cudaStream_t st, const int64_t* hdr, int64_t rows_cap, int64_t nnz_cap);
+void dist_wait_info(lctr_ctx* c, const unsigned long long** flags, int* n, unsigned long long* epoch);
 int launch_fm_fused(lctr_ctx* c, Slot& s, int64_t rb, int64_t re, bool stats, const int64_t* hdr, double* out_slot_override);
 int launch_fm_forward_tree(lctr_ctx* c, Slot& s, int64_t rb, int64_t re, bool stats);
 int launch_apply_compact(lctr_ctx* c, Slot& s, int64_t rows_in_step, const OptParams* P_host, const OptParams* dP);
@@ -327,10 +352,13 @@ int launch_ffm_predict_inorder(lctr_ctx* c, Slot& s);
 // multi-GPU (dist.cu)
 int dist_alloc(lctr_ctx* c);
 int dist_free(lctr_ctx* c);
-int dist_build_uniq(lctr_ctx* c, Slot& s, cudaStream_t st);        // per-slot key set, at upload
-int dist_pre_step(lctr_ctx* c, Slot& s, int64_t rb, int64_t re);   // unique ids of the batch + pull their rows
-int dist_post_step(lctr_ctx* c, int64_t rows_divisor);             // push gradients, owner-side merge + update
-__global__ void compact_touched_kernel(uint8_t* touched, size_t F, uint32_t* list, unsigned int* n_list);
+int dist_send_keys(lctr_ctx* c, Slot& s, int slot, cudaStream_t st);               // at upload: key lists -> the owners' inboxes
+int dist_pre_step(lctr_ctx* c, Slot& s, int slot, bool in_kernel_wait);           // owner-driven pull of the step's rows
+int dist_post_step(lctr_ctx* c, Slot& s, int slot, int64_t rows_divisor);         // push gradients, owner-side merge + update
+int dist_check_overflow(lctr_ctx* c);
+size_t dist_bytes(const lctr_ctx* c);
+__global__ void compact_touched_kernel(uint8_t* touched, size_t F, uint32_t* list, unsigned int* n_list,
+                                       const unsigned long long* wait_flags, int n_wait, unsigned long long wait_epoch);
 int mlp_alloc(lctr_ctx* c);
 int mlp_free(lctr_ctx* c);
 int mlp_reserve(lctr_ctx* c, int64_t rows);

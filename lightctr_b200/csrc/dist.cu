@@ -7,20 +7,26 @@
 // fp16 on the wire, no |g| thresholding of pushes, owner = fid mod R instead of the murmur DHT ring.
 //
 // Tables are owner-sharded: row f lives on rank f % R at shard-local index f / R.  Every rank maps every peer's
-// W/V shard, mailbox and barrier words through CUDA IPC.  One training step on rank r:
-//   1 mark      byte-mark the fids of MY batch in a local map              (mark_kernel)
-//   2 compact   -> list of my unique fids (the "pull_map" keys)            (compact_touched_kernel)
-//   3 pull      copy each unique row W[f], V[f,:] from its owner's shard (peer loads, one read per unique id per
-//               rank) into my full-size local cache                        (pull_kernel)
-//   4 fwd/bwd   the single-GPU kernels on the cache + local update_g        (fm.cu / ffm.cu, unchanged)
-//   5 push      one record {fid, gW, gV[rowlen]} per unique id into the OWNER's mailbox[src = r] with plain peer
-//               stores; zero my local update_g row                         (push_kernel, push_counts_kernel)
-//   6 barrier   all pushes landed                                          (rank_barrier_kernel: release/acquire
-//                                                                           flags in peer memory, no host round trip)
-//   7 merge     owner adds the R mailboxes into its shard's update_g with local REDs and marks touched
-//   8 apply     the single-GPU sparse updater on the shard               (opt.cu, unchanged)
-//   9 barrier   updated rows visible before anybody's next pull
-// NVLink carries each unique row once per rank and direction (vs. once per occurrence for naive peer gathers).
+// W / V / update_g shards, touched map and ONE arena (flags, key inboxes, parameter cache, gradient inboxes) through
+// CUDA IPC.  Per-rank memory is the shard plus O(keys of a batch): the compute kernels work on a BATCH-COMPACT cache
+// (row = slot of the batch's key set, fm_fused.cu's slot map) instead of full-size copies of the tables.
+//
+//   upload (depends only on the batch; on the upload stream, overlaps the previous step)
+//     slot map of my batch (mark / compact / assign) and, per owner o, the list {shard-local row, my slot} of the keys
+//     o owns, written straight into o's key inbox with posted stores + a generation flag        (send_keys_kernel)
+//   step
+//     1 serve   OWNER-driven pull: I read the key lists my peers posted and WRITE the rows they asked for into their
+//               caches (posted peer stores instead of read round trips), then raise "rows delivered" on each peer
+//                                                                                                (serve_pull_kernel)
+//     2 compute the single-GPU kernels on the cache; the first one waits (in-kernel) for every owner's flag
+//     3 push    FM (64 B rows): the slot's gradient row (hot replicas folded) is added into the owner's update_g with
+//               peer vector REDs; FFM (1.2 KB rows): plain posted stores into the owner's gradient inbox at the
+//               position of the key in the list it received -- no slot reservation; then "pushes landed" flags
+//                                                                              (push_fused_kernel / push_rows_kernel)
+//     4 owner   wide rows: inbox rows are added into update_g (local REDs)                        (merge_kernel)
+//               sparse updater on the shard; its first kernel waits for every requester's flag   (opt.cu)
+// Launches per step: 5 (FM) / 6 (FFM); the barriers of the r01 protocol are flags written at the tail of one kernel and
+// polled at the head of the next -- no barrier launches, no host involvement.
 #include <stdlib.h>
 #include <string.h>
 
@@ -32,196 +38,146 @@
 namespace lctr {
 
 constexpr int kMaxWorld = 8;
+constexpr int kHotRepD = kHotRep, kHotMaxD = kHotMax;
+constexpr int kNumHandles = 6;  // W, V, gW, gV, touched, arena
 
-struct PeerPtrs {
-    float* W[kMaxWorld];
-    float* V[kMaxWorld];
-    unsigned char* mail[kMaxWorld];
-    unsigned long long* bar[kMaxWorld];
+struct Peer {
+    float *W, *V, *gW, *gV;
+    uint8_t* touched;
+    unsigned char* arena;
 };
-struct PeerPtrs2 {  // second set (update_g shards + touched maps), kept in device memory
-    float* gW[kMaxWorld];
-    float* gV[kMaxWorld];
-    uint8_t* touched[kMaxWorld];
-    unsigned long long* bar[kMaxWorld];
+struct PeerTable { Peer p[kMaxWorld]; };
+
+// byte offsets inside the arena (identical on every rank)
+struct ArenaLayout {
+    size_t flags;        // u64 [3 + kNumSlots][kMaxWorld]: row 0 rows delivered, 1 pushes landed, 3 + s keys of slot s
+    size_t key_inbox;    // [kNumSlots][2][world] regions (2: parity of the slot's upload generation -- a list may still be read
+                         // by a slower owner's merge when its sender already uploads the slot's next batch):
+                         // 64 B header {u32 count} + cap_pair x uint2 {row, requester slot}
+    size_t key_region;   // bytes per region
+    size_t cacheW;       // cap_keys floats
+    size_t cacheV;       // cap_keys x rowlen floats
+    size_t grad_inbox;   // [world] regions of cap_pair x recw floats (wide rows only)
+    size_t grad_region;  // bytes per region
+    size_t total;
 };
+enum { FLAG_PULLED = 0, FLAG_PUSHED = 1, FLAG_KEYS = 3 };
 
 struct DistState {
     int rank = 0, world = 1, shift = 0;
-    uint8_t* mark = nullptr;        // F bytes (global fid), per-step fallback on the compute stream
-    uint8_t* mark_up = nullptr;     // F bytes, used by uploads (their own stream)
-    uint32_t* uniq = nullptr;       // unique fids of my batch
-    unsigned int* n_uniq = nullptr;
-    unsigned int* push_cnt = nullptr;  // [world] records written per destination this step
-    unsigned int* scratch_done = nullptr;
-    // exported buffers (owned by this rank)
-    unsigned char* mailbox = nullptr;  // world regions: [src][header 64 B | cap records]
-    unsigned long long* bar = nullptr; // [2][world] epoch words written by peers
-    size_t rec_floats = 0, rec_cap = 0, region_bytes = 0;
-    PeerPtrs peers;                 // device pointers valid in THIS process
-    PeerPtrs2 peers2;
-    PeerPtrs2* d_peers2 = nullptr;  // device copy
-    void* opened[kMaxWorld][7] = {{nullptr}};
+    unsigned char* arena = nullptr;
+    ArenaLayout A;
+    PeerTable peers;
+    size_t cap_keys = 0, cap_pair = 0;
+    int recw = 0;                     // floats per gradient-inbox record: rowlen + 4 ([gV | gW | pad])
+    bool mailbox = false;             // wide rows: stores into the owner's inbox + owner-side merge
+    unsigned int* send_cnt = nullptr; // [kMaxWorld] records appended per owner by the running send_keys
+    uint32_t* opos = nullptr;         // [kNumSlots][cap_keys]: position of my slot's key in its owner's list
+    unsigned int* done_ctr = nullptr; // [4] last-block counters
+    int* overflow = nullptr;          // device flag: a key list outgrew cap_pair
+    float *cgV = nullptr, *cgW = nullptr;  // [cap_keys][rowlen], [cap_keys]: compact gradient rows of the non-fused kernels
+    void* opened[kMaxWorld][kNumHandles] = {{nullptr}};
     bool imported = false;
-    bool use_mailbox = false;       // LCTR_DIST_PUSH=mailbox selects the record/merge variant
-    bool bar1_pending = false;      // barrier 1 has been signalled but not yet waited for
-    const uint32_t* cur_uniq = nullptr;       // key set of the step in flight (slot-owned or the per-step list)
-    unsigned int* cur_n = nullptr;
-    bool cur_dynamic = false;
     unsigned long long epoch = 0;
+    unsigned long long gen[kNumSlots] = {0};
+    size_t bytes = 0;                 // device memory this module allocated
 };
 
+__device__ __forceinline__ unsigned long long* flag_ptr(unsigned char* arena, const ArenaLayout& A, int row, int col) {
+    return reinterpret_cast<unsigned long long*>(arena + A.flags) + (size_t)row * kMaxWorld + col;
+}
+__device__ __forceinline__ void wait_flags(unsigned char* my_arena, const ArenaLayout& A, int row, int world,
+                                           unsigned long long value) {
+    if ((int)threadIdx.x < world) {
+        const volatile unsigned long long* f = flag_ptr(my_arena, A, row, threadIdx.x);
+        while (*f < value) __nanosleep(40);
+    }
+    __syncthreads();
+    __threadfence_system();
+}
+// every block: fence its stores, count in; the last block raises flag[row][me] = value on every peer
+__device__ __forceinline__ void raise_flags_last_block(const PeerTable& P, const ArenaLayout& A, int row, int me, int world,
+                                                       unsigned long long value, unsigned int* ctr) {
+    __threadfence_system();
+    __syncthreads();
+    __shared__ bool last;
+    if (threadIdx.x == 0) last = atomicAdd(ctr, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (last) {
+        __threadfence_system();
+        if ((int)threadIdx.x < world) {
+            volatile unsigned long long* f = flag_ptr(P.p[threadIdx.x].arena, A, row, me);
+            *f = value;
+        }
+        if (threadIdx.x == 0) *ctr = 0;
+        __threadfence_system();
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void mark_kernel(const uint32_t* __restrict__ fid, int64_t b, int64_t e, uint8_t* __restrict__ mark) {
-    for (int64_t i = b + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < e; i += (int64_t)gridDim.x * blockDim.x)
-        mark[fid[i]] = 1;
-}
-
-// each unique row is read ONCE from its owner (peer or local shard) into the local cache.  LPR lanes cover a row with
-// 16 B loads (slices q, q+LPR, ...: up to kMaxSl per lane), G = 32/LPR rows per warp step, and kPullU steps are kept in
-// flight before the first store so that one NVLink round trip covers G*kPullU rows.
-constexpr int kMaxSl = 4;
-constexpr int kPullU = 4;
+// upload: per owner, the list of {shard-local row, my slot} -> the owner's key inbox
+// ---------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-pull_kernel(const uint32_t* __restrict__ uniq, const unsigned int* __restrict__ n_uniq, PeerPtrs P, int shift,
-            unsigned mask, int rowlen, float* __restrict__ cW, float* __restrict__ cV) {
+send_keys_kernel(const uint32_t* __restrict__ uniq, const unsigned int* __restrict__ n_uniq, PeerTable P, ArenaLayout A,
+                 int me, int world, int slot, int shift, unsigned cap_pair, unsigned int* __restrict__ send_cnt,
+                 uint32_t* __restrict__ opos, int* __restrict__ overflow) {
+    __shared__ unsigned s_cnt[kMaxWorld], s_base[kMaxWorld];
     const unsigned n = *n_uniq;
-    const int lane = threadIdx.x & 31;
-    const unsigned warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const unsigned nwarps = gridDim.x * (blockDim.x >> 5);
-    const int vec = (rowlen % 4 == 0) ? 4 : 1;
-    const int slices = rowlen / vec;
-    int lpr = 1;
-    while (lpr < slices && lpr < 32) lpr <<= 1;
-    const int G = 32 / lpr, q = lane % lpr, g = lane / lpr;
-    if (vec == 4 && slices <= lpr * kMaxSl) {
-        for (unsigned b0 = warp * (G * kPullU); b0 < n; b0 += nwarps * (G * kPullU)) {
-            uint32_t f[kPullU];
-            float4 v[kPullU][kMaxSl];
-            float w[kPullU];
-#pragma unroll
-            for (int u = 0; u < kPullU; u++) {
-                const unsigned idx = b0 + u * G + g;
-                f[u] = idx < n ? uniq[idx] : 0xffffffffu;
-                if (f[u] == 0xffffffffu) continue;
-                const unsigned o = f[u] & mask;
-                const size_t l = f[u] >> shift;
-                const float* src = P.V[o] + l * (size_t)rowlen;
-#pragma unroll
-                for (int i = 0; i < kMaxSl; i++) {
-                    const int sl = q + i * lpr;
-                    if (sl < slices) v[u][i] = *reinterpret_cast<const float4*>(src + 4 * sl);
-                }
-                if (q == 0) w[u] = P.W[o][l];
-            }
-#pragma unroll
-            for (int u = 0; u < kPullU; u++) {
-                if (f[u] == 0xffffffffu) continue;
-                float* dst = cV + (size_t)f[u] * rowlen;
-#pragma unroll
-                for (int i = 0; i < kMaxSl; i++) {
-                    const int sl = q + i * lpr;
-                    if (sl < slices) *reinterpret_cast<float4*>(dst + 4 * sl) = v[u][i];
-                }
-                if (q == 0) cW[f[u]] = w[u];
-            }
-        }
-        return;
-    }
-    for (unsigned b0 = warp * G; b0 < n; b0 += nwarps * G) {  // generic fallback (odd row lengths)
-        const unsigned idx = b0 + g;
-        if (idx >= n) continue;
-        const uint32_t f = uniq[idx];
-        const unsigned o = f & mask;
-        const size_t l = f >> shift;
-        const float* src = P.V[o] + l * (size_t)rowlen;
-        float* dst = cV + (size_t)f * rowlen;
-        for (int sl = q * vec; sl < rowlen; sl += lpr * vec)
-            for (int c = 0; c < vec; c++) dst[sl + c] = src[sl + c];
-        if (q == 0) cW[f] = P.W[o][l];
-    }
-}
-
-// record layout (floats): [0 .. rowlen) gV (16 B aligned), [rowlen] fid bits, [rowlen+1] gW ; padded to a multiple of 4.
-// Slots are reserved per CTA chunk of kPushChunk records: a shared histogram over the <= 8 destinations, ONE global
-// atomicAdd per destination per chunk (the per-record atomics of a naive version serialise on 8 counters), ranks by
-// a short scan over the chunk; then each warp copies its records with the row stores fully coalesced.
-constexpr int kPushChunk = 64;
-__global__ void __launch_bounds__(256)
-push_kernel(const uint32_t* __restrict__ uniq, const unsigned int* __restrict__ n_uniq, PeerPtrs P, int me, int shift,
-            unsigned mask, int rowlen, int rec_floats, size_t region_bytes, unsigned rec_cap,
-            float* __restrict__ cgW, float* __restrict__ cgV, unsigned int* __restrict__ push_cnt) {
-    __shared__ uint32_t s_f[kPushChunk];
-    __shared__ unsigned s_slot[kPushChunk];
-    __shared__ unsigned s_hist[kMaxWorld], s_base[kMaxWorld];
-    const unsigned n = *n_uniq;
-    const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
-    for (unsigned c0 = blockIdx.x * kPushChunk; c0 < n; c0 += gridDim.x * kPushChunk) {
-        if (t < kMaxWorld) s_hist[t] = 0;
+    const unsigned mask = (unsigned)world - 1;
+    for (unsigned c0 = blockIdx.x * blockDim.x; c0 < n; c0 += gridDim.x * blockDim.x) {
+        if (threadIdx.x < kMaxWorld) s_cnt[threadIdx.x] = 0;
         __syncthreads();
-        uint32_t f = 0xffffffffu;
-        if (t < kPushChunk && c0 + t < n) { f = uniq[c0 + t]; atomicAdd(&s_hist[f & mask], 1u); }
-        if (t < kPushChunk) s_f[t] = f;
-        __syncthreads();
-        if (t < kMaxWorld && s_hist[t]) s_base[t] = atomicAdd(&push_cnt[t], s_hist[t]);
-        __syncthreads();
-        if (t < kPushChunk && f != 0xffffffffu) {
-            const unsigned o = f & mask;
-            unsigned rank = 0;
-            for (int j = 0; j < t; j++) rank += (s_f[j] != 0xffffffffu && (s_f[j] & mask) == o) ? 1u : 0u;
-            s_slot[t] = s_base[o] + rank;
+        const unsigned i = c0 + threadIdx.x;
+        uint32_t f = 0;
+        unsigned o = 0, rk = 0;
+        if (i < n) {
+            f = uniq[i];
+            o = f & mask;
+            rk = atomicAdd(&s_cnt[o], 1u);
         }
         __syncthreads();
-        for (int rI = wid; rI < kPushChunk; rI += (int)(blockDim.x >> 5)) {
-            const uint32_t ff = s_f[rI];
-            if (ff == 0xffffffffu) continue;
-            const unsigned slot = s_slot[rI];
-            if (slot >= rec_cap) continue;
-            const unsigned o = ff & mask;
-            float* rec = reinterpret_cast<float*>(P.mail[o] + (size_t)me * region_bytes + 64) + (size_t)slot * rec_floats;
-            float* gsrc = cgV + (size_t)ff * rowlen;
-            if (lane == 0) {
-                rec[rowlen] = __uint_as_float(ff);
-                rec[rowlen + 1] = cgW[ff];
-                cgW[ff] = 0.f;
-            }
-            if (rowlen % 4 == 0 && rowlen <= 128 * kMaxSl) {
-                // all 16 B loads of the row first, then the (posted) peer stores and the re-zeroing of update_g
-                const int slices = rowlen / 4;
-                float4 v[kMaxSl];
-#pragma unroll
-                for (int i = 0; i < kMaxSl; i++) {
-                    const int sl = lane + 32 * i;
-                    if (sl < slices) v[i] = *reinterpret_cast<const float4*>(gsrc + 4 * sl);
-                }
-#pragma unroll
-                for (int i = 0; i < kMaxSl; i++) {
-                    const int sl = lane + 32 * i;
-                    if (sl < slices) {
-                        *reinterpret_cast<float4*>(rec + 4 * sl) = v[i];
-                        *reinterpret_cast<float4*>(gsrc + 4 * sl) = make_float4(0.f, 0.f, 0.f, 0.f);
-                    }
-                }
+        if (threadIdx.x < world && s_cnt[threadIdx.x]) s_base[threadIdx.x] = atomicAdd(&send_cnt[threadIdx.x], s_cnt[threadIdx.x]);
+        __syncthreads();
+        if (i < n) {
+            const unsigned j = s_base[o] + rk;
+            if (j < cap_pair) {
+                uint2* pairs = reinterpret_cast<uint2*>(P.p[o].arena + A.key_inbox + ((size_t)slot * world + me) * A.key_region + 64);
+                pairs[j] = make_uint2(f >> shift, i);
+                opos[i] = j;
             } else {
-                for (int i = lane; i < rowlen; i += 32) {
-                    rec[i] = gsrc[i];
-                    gsrc[i] = 0.f;
-                }
+                *overflow = 1;
+                opos[i] = 0xffffffffu;
             }
         }
         __syncthreads();
     }
     __threadfence_system();
 }
+// counts into the owners' headers, counters re-armed, then the generation flag of (slot, me) on every owner
+__global__ void send_keys_finish_kernel(PeerTable P, ArenaLayout A, int me, int world, int slot, int flag_slot, unsigned cap_pair,
+                                        unsigned int* send_cnt, unsigned long long gen) {
+    const int o = threadIdx.x;
+    __threadfence_system();
+    if (o < world) {
+        unsigned int* hdr = reinterpret_cast<unsigned int*>(P.p[o].arena + A.key_inbox + ((size_t)slot * world + me) * A.key_region);
+        hdr[0] = min(send_cnt[o], cap_pair);
+        send_cnt[o] = 0;
+        __threadfence_system();
+        volatile unsigned long long* f = flag_ptr(P.p[o].arena, A, FLAG_KEYS + flag_slot, me);
+        *f = gen;
+    }
+    __threadfence_system();
+}
 
-// push variant without mailboxes: each unique row's gradient is added straight into the OWNER's update_g with vector
-// REDs through the peer mapping (NVLink forwards the atomics) and the owner's touched byte is set with a peer store.
-// G rows per warp step; the local update_g row is zeroed on the way.  One RED row per unique id per rank.
+// ---------------------------------------------------------------------------------------------------------------
+// step 1: owner-driven pull
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kMaxSl = 4;
 __global__ void __launch_bounds__(256)
-push_red_kernel(const uint32_t* __restrict__ uniq, const unsigned int* __restrict__ n_uniq, float* const* __restrict__ pgW,
-                float* const* __restrict__ pgV, uint8_t* const* __restrict__ ptouched, int shift, unsigned mask, int rowlen,
-                float* __restrict__ cgW, float* __restrict__ cgV) {
-    const unsigned n = *n_uniq;
+serve_pull_kernel(PeerTable P, ArenaLayout A, int me, int world, int slot, int flag_slot, unsigned long long gen,
+                  unsigned long long epoch, int rowlen, const float* __restrict__ W, const float* __restrict__ V,
+                  unsigned int* done_ctr) {
+    wait_flags(P.p[me].arena, A, FLAG_KEYS + flag_slot, world, gen);  // every requester's key list of this upload has landed
     const int lane = threadIdx.x & 31;
     const unsigned warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const unsigned nwarps = gridDim.x * (blockDim.x >> 5);
@@ -230,159 +186,252 @@ push_red_kernel(const uint32_t* __restrict__ uniq, const unsigned int* __restric
     int lpr = 1;
     while (lpr < slices && lpr < 32) lpr <<= 1;
     const int G = 32 / lpr, q = lane % lpr, g = lane / lpr;
-    if (vec == 4 && slices <= lpr) {
-        // narrow rows (FM): one float4 per lane; kPullU row groups are loaded before the first RED leaves
-        for (unsigned b0 = warp * (G * kPullU); b0 < n; b0 += nwarps * (G * kPullU)) {
-            uint32_t f[kPullU];
-            float4 v[kPullU];
-            float w[kPullU];
+    for (int r = 0; r < world; r++) {
+        const unsigned char* region = P.p[me].arena + A.key_inbox + ((size_t)slot * world + r) * A.key_region;
+        const unsigned n = *reinterpret_cast<const volatile unsigned int*>(region);
+        const uint2* pairs = reinterpret_cast<const uint2*>(region + 64);
+        float* cW = reinterpret_cast<float*>(P.p[r].arena + A.cacheW);
+        float* cV = reinterpret_cast<float*>(P.p[r].arena + A.cacheV);
+        if (vec == 4 && slices <= lpr * kMaxSl) {
+            constexpr int U = 4;  // row groups in flight before the first (posted) store leaves
+            for (unsigned b0 = warp * (G * U); b0 < n; b0 += nwarps * (G * U)) {
+                uint2 pr[U];
+                float4 v[U][kMaxSl];
+                float w[U];
 #pragma unroll
-            for (int u = 0; u < kPullU; u++) {
-                const unsigned idx = b0 + u * G + g;
-                f[u] = idx < n ? uniq[idx] : 0xffffffffu;
-                v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-                w[u] = 0.f;
-                if (f[u] == 0xffffffffu) continue;
-                if (q < slices) v[u] = *reinterpret_cast<const float4*>(cgV + (size_t)f[u] * rowlen + 4 * q);
-                if (q == 0) w[u] = cgW[f[u]];
-            }
+                for (int u = 0; u < U; u++) {
+                    const unsigned j = b0 + u * G + g;
+                    pr[u] = j < n ? pairs[j] : make_uint2(0xffffffffu, 0);
+                    if (pr[u].x == 0xffffffffu) continue;
+                    const float* src = V + (size_t)pr[u].x * rowlen;
 #pragma unroll
-            for (int u = 0; u < kPullU; u++) {
-                if (f[u] == 0xffffffffu) continue;
-                const unsigned o = f[u] & mask;
-                const size_t l = f[u] >> shift;
-                if (q < slices) {
-                    *reinterpret_cast<float4*>(cgV + (size_t)f[u] * rowlen + 4 * q) = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (v[u].x != 0.f || v[u].y != 0.f || v[u].z != 0.f || v[u].w != 0.f)
-                        red_add_v4(pgV[o] + l * (size_t)rowlen + 4 * q, v[u]);
+                    for (int i = 0; i < kMaxSl; i++) {
+                        const int sl = q + i * lpr;
+                        if (sl < slices) v[u][i] = *reinterpret_cast<const float4*>(src + 4 * sl);
+                    }
+                    if (q == 0) w[u] = W[pr[u].x];
                 }
-                if (q == 0) {
-                    red_add_f32(pgW[o] + l, w[u]);
-                    cgW[f[u]] = 0.f;
-                    ptouched[o][l] = 1;
+#pragma unroll
+                for (int u = 0; u < U; u++) {
+                    if (pr[u].x == 0xffffffffu) continue;
+                    float* dst = cV + (size_t)pr[u].y * rowlen;
+#pragma unroll
+                    for (int i = 0; i < kMaxSl; i++) {
+                        const int sl = q + i * lpr;
+                        if (sl < slices) *reinterpret_cast<float4*>(dst + 4 * sl) = v[u][i];
+                    }
+                    if (q == 0) cW[pr[u].y] = w[u];
                 }
-            }
-        }
-        __threadfence_system();
-        return;
-    }
-    for (unsigned b0 = warp * G; b0 < n; b0 += nwarps * G) {
-        const unsigned idx = b0 + g;
-        if (idx >= n) continue;
-        const uint32_t f = uniq[idx];
-        const unsigned o = f & mask;
-        const size_t l = f >> shift;
-        float* src = cgV + (size_t)f * rowlen;
-        float* dst = pgV[o] + l * (size_t)rowlen;
-        if (vec == 4) {
-            for (int sl = q; sl < slices; sl += lpr) {
-                const float4 v = *reinterpret_cast<const float4*>(src + 4 * sl);
-                *reinterpret_cast<float4*>(src + 4 * sl) = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (v.x != 0.f || v.y != 0.f || v.z != 0.f || v.w != 0.f) red_add_v4(dst + 4 * sl, v);
             }
         } else {
-            for (int sl = q; sl < slices; sl += lpr) {
-                const float v = src[sl];
-                src[sl] = 0.f;
-                if (v != 0.f) red_add_f32(dst + sl, v);
+            for (unsigned j = warp * G + g; j < n; j += nwarps * G) {  // generic fallback (odd row lengths)
+                const uint2 pr = pairs[j];
+                const float* src = V + (size_t)pr.x * rowlen;
+                float* dst = cV + (size_t)pr.y * rowlen;
+                for (int sl = q * vec; sl < rowlen; sl += lpr * vec)
+                    for (int c = 0; c < vec; c++) dst[sl + c] = src[sl + c];
+                if (q == 0) cW[pr.y] = W[pr.x];
             }
         }
-        if (q == 0) {
-            red_add_f32(pgW[o] + l, cgW[f]);
-            cgW[f] = 0.f;
-            ptouched[o][l] = 1;
+    }
+    raise_flags_last_block(P, A, FLAG_PULLED, me, world, epoch, done_ctr);
+}
+
+// stand-alone wait for compute kernels without an in-kernel wait (FFM / NFM / non-fused FM)
+__global__ void wait_flags_kernel(PeerTable P, ArenaLayout A, int me, int row, int world, unsigned long long value) {
+    wait_flags(P.p[me].arena, A, row, world, value);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// step 3: push
+// ---------------------------------------------------------------------------------------------------------------
+// FM fused path: row i of G (stride GS, [gV (K) | gW]) + the replica rows of hot slots -> the owner's update_g (peer REDs).
+// Blocks < main_blocks walk the ordinary slots, LPR lanes per row; the others fold one hot slot per warp (lane = column).
+template <int K>
+__global__ void __launch_bounds__(256)
+push_fused_kernel(const uint32_t* __restrict__ uniq, const unsigned int* __restrict__ n_uniq, float* __restrict__ G,
+                  const uint32_t* __restrict__ hot_of, const uint32_t* __restrict__ hot_slot,
+                  const unsigned int* __restrict__ n_hot, float* __restrict__ Ghot, int GS, int main_blocks, PeerTable P,
+                  ArenaLayout A, int me, int world, int shift, unsigned long long epoch, unsigned int* done_ctr) {
+    constexpr int LPR = K / 4, GR = 32 / LPR, U = 4;
+    const unsigned mask = (unsigned)world - 1;
+    const int lane = threadIdx.x & 31;
+    if ((int)blockIdx.x >= main_blocks) {
+        const unsigned hwarp = (blockIdx.x - main_blocks) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+        const unsigned nhw = (gridDim.x - main_blocks) * (blockDim.x >> 5);
+        const unsigned nh = min(*n_hot, (unsigned)kHotMaxD);
+        for (unsigned h = hwarp; h < nh; h += nhw) {
+            const uint32_t f = __ldg(uniq + __ldg(hot_slot + h));
+            const unsigned o = f & mask;
+            const size_t l = f >> shift;
+            float* tile = Ghot + (size_t)h * kHotRepD * GS;
+            for (int c0 = 0; c0 < K + 1; c0 += 32) {
+                const int ncol = GS < 32 ? GS : 32;
+                const int col = c0 + lane % ncol;
+                const int grp = lane / ncol, ngrp = 32 / ncol;
+                float sum = 0.f;
+#pragma unroll 8
+                for (int i = 0; i < kHotRepD; i++) {
+                    if (i < kHotRepD / ngrp) {
+                        float* p = tile + (size_t)(grp + i * ngrp) * GS + col;
+                        sum += __ldcg(p);
+                        *p = 0.f;
+                    }
+                }
+                for (int o2 = ncol; o2 < 32; o2 <<= 1) sum += __shfl_xor_sync(kFull, sum, o2);
+                if (grp == 0 && col <= K && sum != 0.f) {
+                    red_add_f32(col < K ? P.p[o].gV + l * K + col : P.p[o].gW + l, sum);
+                    P.p[o].touched[l] = 1;  // (idempotent byte store; every lane that sent something marks the row)
+                }
+            }
+        }
+    } else {
+        const int q = lane % LPR, g = lane / LPR;
+        const unsigned warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+        const unsigned nwarps = (unsigned)main_blocks * (blockDim.x >> 5);
+        const unsigned total = *n_uniq;
+        for (unsigned b0 = warp * (GR * U); b0 < total; b0 += nwarps * (GR * U)) {
+            uint32_t f[U];
+            float4 v[U];
+            float w[U];
+            bool ok[U];
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                const unsigned idx = b0 + u * GR + g;
+                ok[u] = idx < total && __ldg(hot_of + idx) == 0xffffffffu;
+                f[u] = ok[u] ? __ldg(uniq + idx) : 0u;
+                v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                w[u] = 0.f;
+                if (ok[u]) {
+                    v[u] = *reinterpret_cast<const float4*>(G + (size_t)idx * GS + 4 * q);
+                    if (q == 0) w[u] = G[(size_t)idx * GS + K];
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                if (!ok[u]) continue;
+                const unsigned idx = b0 + u * GR + g;
+                const unsigned o = f[u] & mask;
+                const size_t l = f[u] >> shift;
+                if (v[u].x != 0.f || v[u].y != 0.f || v[u].z != 0.f || v[u].w != 0.f) {
+                    red_add_v4(P.p[o].gV + l * K + 4 * q, v[u]);
+                    *reinterpret_cast<float4*>(G + (size_t)idx * GS + 4 * q) = make_float4(0.f, 0.f, 0.f, 0.f);
+                    P.p[o].touched[l] = 1;  // (idempotent byte store; every lane that sent something marks the row)
+                }
+                if (q == 0 && w[u] != 0.f) {
+                    red_add_f32(P.p[o].gW + l, w[u]);
+                    G[(size_t)idx * GS + K] = 0.f;
+                    P.p[o].touched[l] = 1;
+                }
+            }
         }
     }
-    __threadfence_system();
+    raise_flags_last_block(P, A, FLAG_PUSHED, me, world, epoch, done_ctr);
 }
 
-__global__ void reset_counter_kernel(unsigned int* n) { *n = 0; }
-
-// barrier split in two so that rank-local work can sit between signalling and waiting
-__global__ void rank_arrive_kernel(unsigned long long* const* __restrict__ pbar, int me, int world, int which,
-                                   unsigned long long epoch) {
-    const int d = threadIdx.x;
-    __threadfence_system();
-    if (d < world) {
-        volatile unsigned long long* theirs = pbar[d] + (size_t)which * kMaxWorld + me;
-        *theirs = epoch;
-    }
-    __threadfence_system();
-}
-__global__ void rank_wait_kernel(unsigned long long* const* __restrict__ pbar, int me, int world, int which,
-                                 unsigned long long epoch) {
-    const int d = threadIdx.x;
-    if (d < world) {
-        volatile unsigned long long* mine = pbar[me] + (size_t)which * kMaxWorld + d;
-        while (*mine < epoch) { __nanosleep(32); }
-    }
-    __syncthreads();
-    __threadfence_system();
-}
-
-// publish my record counts into every owner's mailbox header and re-arm the local counters / unique list
-__global__ void push_counts_kernel(PeerPtrs P, int me, int world, size_t region_bytes, unsigned rec_cap,
-                                   unsigned int* push_cnt, unsigned int* n_uniq) {
-    const int d = threadIdx.x;
-    if (d < world) {
-        unsigned int* hdr = reinterpret_cast<unsigned int*>(P.mail[d] + (size_t)me * region_bytes);
-        hdr[0] = min(push_cnt[d], rec_cap);
-        push_cnt[d] = 0;
-    }
-    if (d == 0) *n_uniq = 0;
-    __threadfence_system();
-}
-
-// all-ranks barrier through peer memory: write my epoch into slot [me] of every rank's word array, then wait until
-// every slot of MY array has reached the epoch.  One tiny kernel per rank; no host involvement.
-__global__ void rank_barrier_kernel(PeerPtrs P, int me, int world, int which, unsigned long long epoch) {
-    const int d = threadIdx.x;
-    __threadfence_system();
-    if (d < world) {
-        volatile unsigned long long* theirs = P.bar[d] + (size_t)which * kMaxWorld + me;
-        *theirs = epoch;
-        __threadfence_system();
-        volatile unsigned long long* mine = P.bar[me] + (size_t)which * kMaxWorld + d;
-        while (*mine < epoch) { __nanosleep(64); }
-    }
-    __syncthreads();
-    __threadfence_system();
-}
-
-// owner side: fold the R mailboxes into the shard's update_g (local REDs) and mark the shard-local rows
+// generic path (FFM / NFM / non-fused FM): compact rows cgV[slot][rowlen], cgW[slot].  MAILBOX: posted stores into the
+// owner's gradient inbox at the position of the key in the list the owner received (opos); otherwise peer REDs into the
+// owner's update_g.  One warp per row, 16 B slices, all loads of a row before its stores; the local rows are re-zeroed.
+template <bool MAILBOX>
 __global__ void __launch_bounds__(256)
-merge_kernel(const unsigned char* __restrict__ mailbox, int world, size_t region_bytes, int rec_floats, int rowlen,
-             int shift, float* __restrict__ gW, float* __restrict__ gV, uint8_t* __restrict__ touched) {
+push_rows_kernel(const uint32_t* __restrict__ uniq, const unsigned int* __restrict__ n_uniq, const uint32_t* __restrict__ opos,
+                 float* __restrict__ cgW, float* __restrict__ cgV, int rowlen, int recw, PeerTable P, ArenaLayout A, int me,
+                 int world, int shift, unsigned long long epoch, unsigned int* done_ctr) {
+    const unsigned n = *n_uniq;
+    const unsigned mask = (unsigned)world - 1;
     const int lane = threadIdx.x & 31;
     const unsigned warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const unsigned nwarps = gridDim.x * (blockDim.x >> 5);
+    const bool vec4 = rowlen % 4 == 0 && rowlen <= 128 * kMaxSl;
+    const int slices = rowlen / 4;
+    for (unsigned i = warp; i < n; i += nwarps) {
+        const uint32_t f = uniq[i];
+        const unsigned o = f & mask;
+        const size_t l = f >> shift;
+        float* gsrc = cgV + (size_t)i * rowlen;
+        const float gw = cgW[i];
+        float* dstrow;
+        if (MAILBOX) {
+            const uint32_t j = opos[i];
+            if (j == 0xffffffffu) continue;  // list overflow: reported through the overflow flag at upload
+            dstrow = reinterpret_cast<float*>(P.p[o].arena + A.grad_inbox + (size_t)me * A.grad_region) + (size_t)j * recw;
+        } else {
+            dstrow = P.p[o].gV + l * rowlen;
+        }
+        if (vec4) {
+            float4 v[kMaxSl];
+#pragma unroll
+            for (int s = 0; s < kMaxSl; s++) {
+                const int sl = lane + 32 * s;
+                if (sl < slices) v[s] = *reinterpret_cast<const float4*>(gsrc + 4 * sl);
+            }
+#pragma unroll
+            for (int s = 0; s < kMaxSl; s++) {
+                const int sl = lane + 32 * s;
+                if (sl < slices) {
+                    if (MAILBOX) *reinterpret_cast<float4*>(dstrow + 4 * sl) = v[s];
+                    else if (v[s].x != 0.f || v[s].y != 0.f || v[s].z != 0.f || v[s].w != 0.f) red_add_v4(dstrow + 4 * sl, v[s]);
+                    *reinterpret_cast<float4*>(gsrc + 4 * sl) = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            }
+        } else {
+            for (int c = lane; c < rowlen; c += 32) {
+                const float v = gsrc[c];
+                if (MAILBOX) dstrow[c] = v;
+                else if (v != 0.f) red_add_f32(dstrow + c, v);
+                gsrc[c] = 0.f;
+            }
+        }
+        if (lane == 0) {
+            if (MAILBOX) dstrow[rowlen] = gw;
+            else {
+                red_add_f32(P.p[o].gW + l, gw);
+                P.p[o].touched[l] = 1;
+            }
+            cgW[i] = 0.f;
+        }
+    }
+    raise_flags_last_block(P, A, FLAG_PUSHED, me, world, epoch, done_ctr);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// step 4 (wide rows): owner folds the R gradient inboxes into its shard's update_g (local REDs) and marks the rows
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+merge_kernel(PeerTable P, ArenaLayout A, int me, int world, int slot, unsigned long long epoch, int rowlen, int recw,
+             float* __restrict__ gW, float* __restrict__ gV, uint8_t* __restrict__ touched) {
+    wait_flags(P.p[me].arena, A, FLAG_PUSHED, world, epoch);  // every requester's records have landed
+    const int lane = threadIdx.x & 31;
+    const unsigned warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const unsigned nwarps = gridDim.x * (blockDim.x >> 5);
+    const bool vec4 = rowlen % 4 == 0 && recw % 4 == 0 && rowlen <= 128 * kMaxSl;
+    const int slices = rowlen / 4;
     for (int src = 0; src < world; src++) {
-        const unsigned char* region = mailbox + (size_t)src * region_bytes;
+        const unsigned char* region = P.p[me].arena + A.key_inbox + ((size_t)slot * world + src) * A.key_region;
         const unsigned n = *reinterpret_cast<const volatile unsigned int*>(region);
-        const float* recs = reinterpret_cast<const float*>(region + 64);
-        for (unsigned idx = warp; idx < n; idx += nwarps) {
-            const float* rec = recs + (size_t)idx * rec_floats;
-            const uint32_t f = __float_as_uint(rec[rowlen]);
-            const size_t l = f >> shift;
+        const uint2* pairs = reinterpret_cast<const uint2*>(region + 64);
+        const float* recs = reinterpret_cast<const float*>(P.p[me].arena + A.grad_inbox + (size_t)src * A.grad_region);
+        for (unsigned j = warp; j < n; j += nwarps) {
+            const float* rec = recs + (size_t)j * recw;
+            const size_t l = pairs[j].x;
             float* gdst = gV + l * (size_t)rowlen;
-            if (rowlen % 4 == 0 && (rec_floats % 4) == 0 && rowlen <= 128 * kMaxSl) {
-                const int slices = rowlen / 4;
+            if (vec4) {
                 float4 v[kMaxSl];
 #pragma unroll
-                for (int i = 0; i < kMaxSl; i++) {
-                    const int sl = lane + 32 * i;
-                    if (sl < slices) v[i] = *reinterpret_cast<const float4*>(rec + 4 * sl);
+                for (int s = 0; s < kMaxSl; s++) {
+                    const int sl = lane + 32 * s;
+                    if (sl < slices) v[s] = __ldcg(reinterpret_cast<const float4*>(rec + 4 * sl));
                 }
 #pragma unroll
-                for (int i = 0; i < kMaxSl; i++) {
-                    const int sl = lane + 32 * i;
-                    if (sl < slices) red_add_v4(gdst + 4 * sl, v[i]);
+                for (int s = 0; s < kMaxSl; s++) {
+                    const int sl = lane + 32 * s;
+                    if (sl < slices && (v[s].x != 0.f || v[s].y != 0.f || v[s].z != 0.f || v[s].w != 0.f)) red_add_v4(gdst + 4 * sl, v[s]);
                 }
             } else {
-                for (int i = lane; i < rowlen; i += 32) red_add_f32(gdst + i, rec[i]);
+                for (int c = lane; c < rowlen; c += 32) red_add_f32(gdst + c, __ldcg(rec + c));
             }
             if (lane == 0) {
-                red_add_f32(gW + l, rec[rowlen + 1]);
+                red_add_f32(gW + l, __ldcg(rec + rowlen));
                 touched[l] = 1;
             }
         }
@@ -390,6 +439,8 @@ merge_kernel(const unsigned char* __restrict__ mailbox, int world, size_t region
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
 int dist_alloc(lctr_ctx* c) {
     const int R = c->cfg.world;
     LCTR_CHECK(R <= kMaxWorld && (R & (R - 1)) == 0, "world=%d: need a power of two <= %d", R, kMaxWorld);
@@ -397,46 +448,49 @@ int dist_alloc(lctr_ctx* c) {
     c->dist = d;
     d->rank = c->cfg.rank; d->world = R;
     while ((1 << d->shift) < R) d->shift++;
-    const size_t nv = c->F * c->rowlen;
-    LCTR_CUDA(cudaMalloc((void**)&c->cW, c->F * sizeof(float)));
-    LCTR_CUDA(cudaMalloc((void**)&c->cV, nv * sizeof(float)));
-    LCTR_CUDA(cudaMalloc((void**)&c->cgW, c->F * sizeof(float)));
-    LCTR_CUDA(cudaMalloc((void**)&c->cgV, nv * sizeof(float)));
-    LCTR_CUDA(cudaMemsetAsync(c->cW, 0, c->F * sizeof(float), c->stream));
-    LCTR_CUDA(cudaMemsetAsync(c->cV, 0, nv * sizeof(float), c->stream));
-    LCTR_CUDA(cudaMemsetAsync(c->cgW, 0, c->F * sizeof(float), c->stream));
-    LCTR_CUDA(cudaMemsetAsync(c->cgV, 0, nv * sizeof(float), c->stream));
-    LCTR_CUDA(cudaMalloc((void**)&d->mark, c->F + 512));
-    LCTR_CUDA(cudaMemsetAsync(d->mark, 0, c->F + 512, c->stream));
-    LCTR_CUDA(cudaMalloc((void**)&d->mark_up, c->F + 512));
-    LCTR_CUDA(cudaMemsetAsync(d->mark_up, 0, c->F + 512, c->stream));
-    const size_t cap = c->cfg.max_nnz ? std::min<size_t>(c->cfg.max_nnz, c->F) : c->F;
-    LCTR_CUDA(cudaMalloc((void**)&d->uniq, (c->F + 32) * sizeof(uint32_t)));
-    LCTR_CUDA(cudaMalloc((void**)&d->n_uniq, sizeof(unsigned int)));
-    LCTR_CUDA(cudaMalloc((void**)&d->push_cnt, kMaxWorld * sizeof(unsigned int)));
-    LCTR_CUDA(cudaMalloc((void**)&d->scratch_done, sizeof(unsigned int)));
-    LCTR_CUDA(cudaMemsetAsync(d->n_uniq, 0, sizeof(unsigned int), c->stream));
-    LCTR_CUDA(cudaMemsetAsync(d->push_cnt, 0, kMaxWorld * sizeof(unsigned int), c->stream));
-    LCTR_CUDA(cudaMemsetAsync(d->scratch_done, 0, sizeof(unsigned int), c->stream));
-    // push variant: narrow rows (FM) go straight into the owner's update_g with peer REDs; wide rows (FFM) are cheaper
-    // as plain peer stores into a mailbox + owner-side merge (measured on C5: 12.8 vs 14.2 ms per step)
+    // keys of one batch: at most its entry count (cfg.max_nnz), at most the id space
+    d->cap_keys = c->cfg.max_nnz ? std::min<size_t>(c->cfg.max_nnz, c->F) : c->F;
+    // keys one requester sends one owner: U / R on average (owner = fid mod R); twice that plus slack, at most the shard
+    d->cap_pair = std::min<size_t>(c->Fl, 2 * d->cap_keys / R + 4096);
+    d->recw = (int)((c->rowlen + 4 + 3) / 4 * 4);
     const char* pm0 = getenv("LCTR_DIST_PUSH");
-    d->use_mailbox = pm0 ? strcmp(pm0, "mailbox") == 0 : c->rowlen >= 64;
-    d->rec_floats = ((2 + c->rowlen) + 3) / 4 * 4;
-    // records one source may send to one owner per step: at most the owner's shard size (distinct fids)
-    d->rec_cap = d->use_mailbox ? std::min<size_t>(cap, c->Fl) : 0;
-    d->region_bytes = (64 + d->rec_cap * d->rec_floats * sizeof(float) + 255) / 256 * 256;
-    LCTR_CUDA(cudaMalloc((void**)&d->mailbox, d->region_bytes * R));
-    LCTR_CUDA(cudaMemsetAsync(d->mailbox, 0, d->region_bytes * R, c->stream));
-    LCTR_CUDA(cudaMalloc((void**)&d->bar, 2 * kMaxWorld * sizeof(unsigned long long)));
-    LCTR_CUDA(cudaMemsetAsync(d->bar, 0, 2 * kMaxWorld * sizeof(unsigned long long), c->stream));
+    d->mailbox = pm0 ? strcmp(pm0, "mailbox") == 0 : c->rowlen >= 64;
+    ArenaLayout& A = d->A;
+    size_t off = 0;
+    A.flags = off; off = align_up(off + (size_t)(3 + kNumSlots) * kMaxWorld * sizeof(unsigned long long), 256);
+    A.key_region = align_up(64 + d->cap_pair * sizeof(uint2), 256);
+    A.key_inbox = off; off += A.key_region * kNumSlots * 2 * R;
+    A.cacheW = off; off = align_up(off + d->cap_keys * sizeof(float), 256);
+    A.cacheV = off; off = align_up(off + d->cap_keys * c->rowlen * sizeof(float), 256);
+    A.grad_region = d->mailbox ? align_up(d->cap_pair * (size_t)d->recw * sizeof(float), 256) : 0;
+    A.grad_inbox = off; off += A.grad_region * R;
+    A.total = off;
+    LCTR_CUDA(cudaMalloc((void**)&d->arena, A.total));
+    LCTR_CUDA(cudaMemsetAsync(d->arena, 0, A.total, c->stream));
+    d->bytes += A.total;
+    LCTR_CUDA(cudaMalloc((void**)&d->send_cnt, kMaxWorld * sizeof(unsigned int)));
+    LCTR_CUDA(cudaMemsetAsync(d->send_cnt, 0, kMaxWorld * sizeof(unsigned int), c->stream));
+    LCTR_CUDA(cudaMalloc((void**)&d->opos, (size_t)kNumSlots * d->cap_keys * sizeof(uint32_t)));
+    d->bytes += (size_t)kNumSlots * d->cap_keys * sizeof(uint32_t);
+    LCTR_CUDA(cudaMalloc((void**)&d->done_ctr, 4 * sizeof(unsigned int)));
+    LCTR_CUDA(cudaMemsetAsync(d->done_ctr, 0, 4 * sizeof(unsigned int), c->stream));
+    LCTR_CUDA(cudaMalloc((void**)&d->overflow, sizeof(int)));
+    LCTR_CUDA(cudaMemsetAsync(d->overflow, 0, sizeof(int), c->stream));
+    if (!fused_kernels_ok(c)) {  // the fused FM kernels keep their gradients in fm_fused.cu's G / Ghot
+        LCTR_CUDA(cudaMalloc((void**)&d->cgW, d->cap_keys * sizeof(float)));
+        LCTR_CUDA(cudaMalloc((void**)&d->cgV, d->cap_keys * c->rowlen * sizeof(float)));
+        LCTR_CUDA(cudaMemsetAsync(d->cgW, 0, d->cap_keys * sizeof(float), c->stream));
+        LCTR_CUDA(cudaMemsetAsync(d->cgV, 0, d->cap_keys * c->rowlen * sizeof(float), c->stream));
+        d->bytes += d->cap_keys * (c->rowlen + 1) * sizeof(float);
+    }
+    // compute view: the batch-compact cache and gradient rows (indexed by slot)
+    c->cW = reinterpret_cast<float*>(d->arena + A.cacheW);
+    c->cV = reinterpret_cast<float*>(d->arena + A.cacheV);
+    c->cgW = d->cgW;
+    c->cgV = d->cgV;
     memset(&d->peers, 0, sizeof(d->peers));
-    d->peers.W[d->rank] = c->W; d->peers.V[d->rank] = c->V;
-    d->peers.mail[d->rank] = d->mailbox; d->peers.bar[d->rank] = d->bar;
-    memset(&d->peers2, 0, sizeof(d->peers2));
-    d->peers2.gW[d->rank] = c->gW; d->peers2.gV[d->rank] = c->gV; d->peers2.touched[d->rank] = c->touched;
-    d->peers2.bar[d->rank] = d->bar;
-    LCTR_CUDA(cudaMalloc((void**)&d->d_peers2, sizeof(PeerPtrs2)));
+    Peer& me = d->peers.p[d->rank];
+    me.W = c->W; me.V = c->V; me.gW = c->gW; me.gV = c->gV; me.touched = c->touched; me.arena = d->arena;
     return 0;
 }
 
@@ -444,128 +498,119 @@ int dist_free(lctr_ctx* c) {
     DistState* d = c->dist;
     if (!d) return 0;
     for (int r = 0; r < d->world; r++)
-        for (int j = 0; j < 7; j++)
+        for (int j = 0; j < kNumHandles; j++)
             if (d->opened[r][j]) cudaIpcCloseMemHandle(d->opened[r][j]);
-    if (d->d_peers2) cudaFree(d->d_peers2);
-    if (c->cW) cudaFree(c->cW); if (c->cV) cudaFree(c->cV); if (c->cgW) cudaFree(c->cgW); if (c->cgV) cudaFree(c->cgV);
+    cudaFree(d->arena); cudaFree(d->send_cnt); cudaFree(d->opos); cudaFree(d->done_ctr); cudaFree(d->overflow);
+    if (d->cgW) cudaFree(d->cgW);
+    if (d->cgV) cudaFree(d->cgV);
     c->cW = c->cV = c->cgW = c->cgV = nullptr;
-    cudaFree(d->mark); cudaFree(d->mark_up); cudaFree(d->uniq); cudaFree(d->n_uniq); cudaFree(d->push_cnt); cudaFree(d->scratch_done);
-    cudaFree(d->mailbox); cudaFree(d->bar);
     delete d;
     c->dist = nullptr;
     return 0;
 }
 
-static int barrier(lctr_ctx* c, int which) {
+size_t dist_bytes(const lctr_ctx* c) { return c->dist ? c->dist->bytes : 0; }
+
+void dist_wait_info(lctr_ctx* c, const unsigned long long** flags, int* n, unsigned long long* epoch) {
     DistState* d = c->dist;
-    rank_barrier_kernel<<<1, 32, 0, c->stream>>>(d->peers, d->rank, d->world, which, d->epoch);
-    c->launches++;
-    LCTR_CUDA(cudaGetLastError());
-    return 0;
+    *flags = reinterpret_cast<const unsigned long long*>(d->arena + d->A.flags) + (size_t)FLAG_PULLED * kMaxWorld;
+    *n = d->world;
+    *epoch = d->epoch;
 }
 
-// key set of a whole slot (its unique fids), computed once per upload on the upload stream: mark + compact depend
-// only on the batch, not on the parameters, so for streamed batches they overlap the previous step's kernels
-int dist_build_uniq(lctr_ctx* c, Slot& s, cudaStream_t st) {
+// key lists of the slot's batch -> the owners' inboxes (after the slot map of fm_fused.cu has been built on `st`)
+int dist_send_keys(lctr_ctx* c, Slot& s, int slot, cudaStream_t st) {
     DistState* d = c->dist;
-    s.uniq_valid = false;
-    if (!d || s.nnz == 0) return 0;
-    const int64_t need = std::min<int64_t>(s.nnz, (int64_t)c->F);
-    if (need > s.cap_uniq) {
-        LCTR_CUDA(cudaStreamSynchronize(c->stream));
-        if (s.uniq) cudaFree(s.uniq);
-        if (!s.n_uniq) LCTR_CUDA(cudaMalloc((void**)&s.n_uniq, sizeof(unsigned int)));
-        const int64_t cap = std::max<int64_t>(need, s.cap_uniq + s.cap_uniq / 2);
-        LCTR_CUDA(cudaMalloc((void**)&s.uniq, (size_t)(cap + 32) * sizeof(uint32_t)));
-        s.cap_uniq = cap;
-    }
-    // a private mark map per upload stream would be needed if two uploads ran concurrently; uploads are serialised
-    // on their stream, and the per-step fallback below uses the same map only on the compute stream when no slot
-    // list exists, so one map suffices
-    LCTR_CUDA(cudaMemsetAsync(s.n_uniq, 0, sizeof(unsigned int), st));
-    const unsigned mg = (unsigned)std::min<int64_t>((s.nnz + 255) / 256, (int64_t)c->sm_count * 8);
-    mark_kernel<<<std::max(mg, 1u), 256, 0, st>>>(s.fid, 0, s.nnz, d->mark_up);
-    const size_t ntiles = (c->F + 511) / 512;
-    const unsigned cg = (unsigned)std::min<size_t>((ntiles + 7) / 8, (size_t)c->sm_count * 8);
-    compact_touched_kernel<<<std::max(cg, 1u), 256, 0, st>>>(d->mark_up, c->F, s.uniq, s.n_uniq);
+    LCTR_CHECK(d->imported, "multi-GPU upload before lctr_ipc_import");
+    LCTR_CHECK((size_t)std::min<int64_t>(s.nnz, (int64_t)c->F) <= d->cap_keys,
+               "batch of %lld entries exceeds the key capacity %zu of the multi-GPU context (cfg.max_nnz)", (long long)s.nnz, d->cap_keys);
+    d->gen[slot]++;
+    const int slot2 = slot * 2 + (int)(d->gen[slot] & 1);
+    const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>((std::min<int64_t>(s.nnz, (int64_t)c->F) + 255) / 256, (int64_t)c->sm_count * 4));
+    send_keys_kernel<<<grid, 256, 0, st>>>(s.uniq, s.n_uniq, d->peers, d->A, d->rank, d->world, slot2, d->shift, (unsigned)d->cap_pair,
+                                           d->send_cnt, d->opos + (size_t)slot * d->cap_keys, d->overflow);
+    send_keys_finish_kernel<<<1, 32, 0, st>>>(d->peers, d->A, d->rank, d->world, slot2, slot, (unsigned)d->cap_pair, d->send_cnt, d->gen[slot]);
     c->launches += 2;
     LCTR_CUDA(cudaGetLastError());
-    s.uniq_valid = true;
     return 0;
 }
 
-int dist_pre_step(lctr_ctx* c, Slot& s, int64_t rb, int64_t re) {
+// host-visible check (called where the host synchronises anyway): a key list that outgrew its inbox region is an error,
+// never a silent drop
+int dist_check_overflow(lctr_ctx* c) {
+    DistState* d = c->dist;
+    int h = 0;
+    LCTR_CUDA(cudaMemcpyAsync(&h, d->overflow, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    LCTR_CUDA(cudaStreamSynchronize(c->stream));
+    LCTR_CHECK(h == 0, "multi-GPU: a per-owner key list outgrew its inbox (%zu records); raise cfg.max_nnz", d->cap_pair);
+    return 0;
+}
+
+int dist_pre_step(lctr_ctx* c, Slot& s, int slot, bool in_kernel_wait) {
     DistState* d = c->dist;
     LCTR_CHECK(d->imported, "multi-GPU step before lctr_ipc_import");
-    if (re - rb <= 0) return 0;
-    const unsigned mask = (unsigned)d->world - 1;
-    if (s.uniq_valid && rb == 0 && re == s.rows) {
-        d->cur_uniq = s.uniq; d->cur_n = s.n_uniq; d->cur_dynamic = false;
-    } else {
-        // a sub-range of the slot: build the key set of just these rows on the compute stream
-        int64_t rp[2];
-        LCTR_CUDA(cudaMemcpyAsync(&rp[0], s.row_ptr + rb, sizeof(int64_t), cudaMemcpyDeviceToHost, c->stream));
-        LCTR_CUDA(cudaMemcpyAsync(&rp[1], s.row_ptr + re, sizeof(int64_t), cudaMemcpyDeviceToHost, c->stream));
-        LCTR_CUDA(cudaStreamSynchronize(c->stream));
-        const unsigned mg = (unsigned)std::min<int64_t>((rp[1] - rp[0] + 255) / 256, (int64_t)c->sm_count * 8);
-        { ProfScope prof(c, PROF_DIST_MARK);
-        mark_kernel<<<std::max(mg, 1u), 256, 0, c->stream>>>(s.fid, rp[0], rp[1], d->mark); }
-        const size_t ntiles = (c->F + 511) / 512;
-        const unsigned cg = (unsigned)std::min<size_t>((ntiles + 7) / 8, (size_t)c->sm_count * 8);
-        { ProfScope prof(c, PROF_DIST_COMPACT);
-        compact_touched_kernel<<<std::max(cg, 1u), 256, 0, c->stream>>>(d->mark, c->F, d->uniq, d->n_uniq); }
-        c->launches += 2;
-        d->cur_uniq = d->uniq; d->cur_n = d->n_uniq; d->cur_dynamic = true;
-    }
-    if (d->bar1_pending) {  // every owner's update of the previous step must be visible before the pull
-        ProfScope prof(c, PROF_DIST_BAR1);
-        rank_wait_kernel<<<1, 32, 0, c->stream>>>(d->d_peers2->bar, d->rank, d->world, 1, d->epoch);
-        c->launches++;
-        d->bar1_pending = false;
-    }
+    LCTR_CHECK(s.fused_valid, "multi-GPU step on a slot without its key set");
+    d->epoch++;
     { ProfScope prof(c, PROF_DIST_PULL);
-    pull_kernel<<<c->sm_count * 4, 256, 0, c->stream>>>(d->cur_uniq, d->cur_n, d->peers, d->shift, mask, (int)c->rowlen,
-                                                        c->cW, c->cV); }
+    serve_pull_kernel<<<c->sm_count * 4, 256, 0, c->stream>>>(d->peers, d->A, d->rank, d->world, slot * 2 + (int)(d->gen[slot] & 1), slot,
+                                                             d->gen[slot], d->epoch, (int)c->rowlen, c->W, c->V, d->done_ctr + 0); }
     c->launches++;
+    if (!in_kernel_wait) {
+        ProfScope prof(c, PROF_DIST_BAR1);
+        wait_flags_kernel<<<1, 32, 0, c->stream>>>(d->peers, d->A, d->rank, FLAG_PULLED, d->world, d->epoch);
+        c->launches++;
+    }
     LCTR_CUDA(cudaGetLastError());
     return 0;
 }
 
-int dist_post_step(lctr_ctx* c, int64_t rows_divisor) {
+template <int K>
+static void push_fused_go(lctr_ctx* c, Slot& s) {
     DistState* d = c->dist;
-    const unsigned mask = (unsigned)d->world - 1;
-    d->epoch++;
-    if (d->use_mailbox) {
-        { ProfScope prof(c, PROF_DIST_PUSH);
-        push_kernel<<<c->sm_count * 4, 256, 0, c->stream>>>(d->cur_uniq, d->cur_n, d->peers, d->rank, d->shift, mask,
-                                                            (int)c->rowlen, (int)d->rec_floats, d->region_bytes,
-                                                            (unsigned)d->rec_cap, c->cgW, c->cgV, d->push_cnt);
-        push_counts_kernel<<<1, 32, 0, c->stream>>>(d->peers, d->rank, d->world, d->region_bytes, (unsigned)d->rec_cap,
-                                                    d->push_cnt, d->cur_dynamic ? d->cur_n : d->scratch_done); }
-        c->launches += 2;
-        { ProfScope prof(c, PROF_DIST_BAR0);
-        if (barrier(c, 0)) return 1; }
-        { ProfScope prof(c, PROF_DIST_MERGE);
-        merge_kernel<<<c->sm_count * 4, 256, 0, c->stream>>>(d->mailbox, d->world, d->region_bytes, (int)d->rec_floats,
-                                                             (int)c->rowlen, d->shift, c->gW, c->gV, c->touched); }
+    FusedState* f = c->fused;
+    const int main_blocks = c->sm_count * 2;
+    push_fused_kernel<K><<<main_blocks + kHotMaxD / 8, 256, 0, c->stream>>>(s.uniq, s.n_uniq, f->G, s.hot_of, s.hot_slot, s.n_hot, f->Ghot,
+                                                                          f->GS, main_blocks, d->peers, d->A, d->rank, d->world,
+                                                                          d->shift, d->epoch, d->done_ctr + 1);
+}
+
+int dist_post_step(lctr_ctx* c, Slot& s, int slot, int64_t rows_divisor) {
+    DistState* d = c->dist;
+    if (fused_kernels_ok(c)) {
+        ProfScope prof(c, PROF_DIST_PUSH);
+        switch ((int)c->cfg.factor_cnt) {
+            case 4: push_fused_go<4>(c, s); break;
+            case 8: push_fused_go<8>(c, s); break;
+            case 16: push_fused_go<16>(c, s); break;
+            default: push_fused_go<32>(c, s); break;
+        }
         c->launches++;
     } else {
         { ProfScope prof(c, PROF_DIST_PUSH);
-        push_red_kernel<<<c->sm_count * 4, 256, 0, c->stream>>>(d->cur_uniq, d->cur_n, d->d_peers2->gW, d->d_peers2->gV,
-                                                                d->d_peers2->touched, d->shift, mask, (int)c->rowlen,
-                                                                c->cgW, c->cgV);
-        if (d->cur_dynamic) { reset_counter_kernel<<<1, 1, 0, c->stream>>>(d->cur_n); c->launches++; } }
+        const uint32_t* opos = d->opos + (size_t)slot * d->cap_keys;
+        if (d->mailbox)
+            push_rows_kernel<true><<<c->sm_count * 4, 256, 0, c->stream>>>(s.uniq, s.n_uniq, opos, d->cgW, d->cgV, (int)c->rowlen, d->recw,
+                                                                           d->peers, d->A, d->rank, d->world, d->shift, d->epoch, d->done_ctr + 1);
+        else
+            push_rows_kernel<false><<<c->sm_count * 4, 256, 0, c->stream>>>(s.uniq, s.n_uniq, opos, d->cgW, d->cgV, (int)c->rowlen, d->recw,
+                                                                            d->peers, d->A, d->rank, d->world, d->shift, d->epoch, d->done_ctr + 1); }
         c->launches++;
-        { ProfScope prof(c, PROF_DIST_BAR0);
-        if (barrier(c, 0)) return 1; }
+        if (d->mailbox) {
+            ProfScope prof(c, PROF_DIST_MERGE);
+            merge_kernel<<<c->sm_count * 4, 256, 0, c->stream>>>(d->peers, d->A, d->rank, d->world, slot * 2 + (int)(d->gen[slot] & 1), d->epoch, (int)c->rowlen, d->recw,
+                                                                 c->gW, c->gV, c->touched);
+            c->launches++;
+        }
     }
-    if (launch_apply(c, rows_divisor)) return 1;
-    // barrier 1 is split: signal now, wait at the start of the next step after its rank-local mark + compact
-    rank_arrive_kernel<<<1, 32, 0, c->stream>>>(d->d_peers2->bar, d->rank, d->world, 1, d->epoch);
-    c->launches++;
-    d->bar1_pending = true;
     LCTR_CUDA(cudaGetLastError());
-    return 0;
+    // owner: sparse updater on the shard; its first kernel waits for "pushes landed" unless the merge already did
+    const unsigned long long* pushed = reinterpret_cast<const unsigned long long*>(d->arena + d->A.flags) + (size_t)FLAG_PUSHED * kMaxWorld;
+    c->apply_wait_flags = (fused_kernels_ok(c) || !d->mailbox) ? pushed : nullptr;
+    c->apply_wait_n = d->world;
+    c->apply_wait_epoch = d->epoch;
+    const int rc = launch_apply(c, rows_divisor);
+    c->apply_wait_flags = nullptr;
+    return rc;
 }
 
 }  // namespace lctr
@@ -574,11 +619,11 @@ using namespace lctr;
 
 extern "C" {
 
-// handles exported per rank, in this order: W, V shards, mailbox, barrier words, update_g W, V shards, touched map
+// handles exported per rank, in this order: W, V shards, update_g W, V shards, touched map, arena
 int lctr_ipc_export(lctr_ctx* c, void* handles_out, size_t cap, size_t* bytes) {
     LCTR_CHECK(c && bytes, "null argument");
     LCTR_CHECK(c->dist, "lctr_ipc_export: ctx was created with world == 1");
-    const size_t need = 7 * sizeof(cudaIpcMemHandle_t);
+    const size_t need = kNumHandles * sizeof(cudaIpcMemHandle_t);
     *bytes = need;
     if (!handles_out) return 0;
     LCTR_CHECK(cap >= need, "lctr_ipc_export: need %zu bytes", need);
@@ -586,39 +631,45 @@ int lctr_ipc_export(lctr_ctx* c, void* handles_out, size_t cap, size_t* bytes) {
     LCTR_CUDA(cudaStreamSynchronize(c->stream));
     LCTR_CUDA(cudaIpcGetMemHandle(&h[0], c->W));
     LCTR_CUDA(cudaIpcGetMemHandle(&h[1], c->V));
-    LCTR_CUDA(cudaIpcGetMemHandle(&h[2], c->dist->mailbox));
-    LCTR_CUDA(cudaIpcGetMemHandle(&h[3], c->dist->bar));
-    LCTR_CUDA(cudaIpcGetMemHandle(&h[4], c->gW));
-    LCTR_CUDA(cudaIpcGetMemHandle(&h[5], c->gV));
-    LCTR_CUDA(cudaIpcGetMemHandle(&h[6], c->touched));
+    LCTR_CUDA(cudaIpcGetMemHandle(&h[2], c->gW));
+    LCTR_CUDA(cudaIpcGetMemHandle(&h[3], c->gV));
+    LCTR_CUDA(cudaIpcGetMemHandle(&h[4], c->touched));
+    LCTR_CUDA(cudaIpcGetMemHandle(&h[5], c->dist->arena));
     return 0;
 }
 
 int lctr_ipc_import(lctr_ctx* c, const void* all_handles, size_t bytes_per_rank) {
     LCTR_CHECK(c && all_handles, "null argument");
     LCTR_CHECK(c->dist, "lctr_ipc_import: ctx was created with world == 1");
-    LCTR_CHECK(bytes_per_rank == 7 * sizeof(cudaIpcMemHandle_t), "lctr_ipc_import: bytes_per_rank %zu", bytes_per_rank);
+    LCTR_CHECK(bytes_per_rank == kNumHandles * sizeof(cudaIpcMemHandle_t), "lctr_ipc_import: bytes_per_rank %zu", bytes_per_rank);
     DistState* d = c->dist;
     const unsigned char* base = reinterpret_cast<const unsigned char*>(all_handles);
     for (int r = 0; r < d->world; r++) {
         if (r == d->rank) continue;
         const cudaIpcMemHandle_t* h = reinterpret_cast<const cudaIpcMemHandle_t*>(base + (size_t)r * bytes_per_rank);
-        for (int j = 0; j < 7; j++) {
+        for (int j = 0; j < kNumHandles; j++) {
             cudaIpcMemHandle_t hh;
             memcpy(&hh, &h[j], sizeof(hh));
             LCTR_CUDA(cudaIpcOpenMemHandle(&d->opened[r][j], hh, cudaIpcMemLazyEnablePeerAccess));
         }
-        d->peers.W[r] = (float*)d->opened[r][0];
-        d->peers.V[r] = (float*)d->opened[r][1];
-        d->peers.mail[r] = (unsigned char*)d->opened[r][2];
-        d->peers.bar[r] = (unsigned long long*)d->opened[r][3];
-        d->peers2.gW[r] = (float*)d->opened[r][4];
-        d->peers2.gV[r] = (float*)d->opened[r][5];
-        d->peers2.touched[r] = (uint8_t*)d->opened[r][6];
-        d->peers2.bar[r] = d->peers.bar[r];
+        Peer& p = d->peers.p[r];
+        p.W = (float*)d->opened[r][0];
+        p.V = (float*)d->opened[r][1];
+        p.gW = (float*)d->opened[r][2];
+        p.gV = (float*)d->opened[r][3];
+        p.touched = (uint8_t*)d->opened[r][4];
+        p.arena = (unsigned char*)d->opened[r][5];
     }
-    LCTR_CUDA(cudaMemcpy(d->d_peers2, &d->peers2, sizeof(PeerPtrs2), cudaMemcpyHostToDevice));
     d->imported = true;
+    return 0;
+}
+
+/* device memory of this context in bytes: table shard + updater state + multi-GPU arena / caches */
+int lctr_device_bytes(lctr_ctx* c, uint64_t* shard_bytes, uint64_t* exchange_bytes) {
+    LCTR_CHECK(c, "null ctx");
+    const bool two = c->s2W != nullptr;
+    if (shard_bytes) *shard_bytes = (uint64_t)(c->Fl * (c->rowlen + 1) * sizeof(float) * (two ? 4 : 3) + c->Fl);
+    if (exchange_bytes) *exchange_bytes = (uint64_t)dist_bytes(c);
     return 0;
 }
 

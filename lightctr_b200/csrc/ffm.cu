@@ -357,7 +357,7 @@ static int ffm_launch(lctr_ctx* c, Slot& s, int64_t rb, int64_t re, bool train, 
     do {                                                                                                              \
         auto kern = bulk ? ffm_fused_kernel<VECN, HV, TR, (VECN == 4) && TR> : ffm_fused_kernel<VECN, HV, TR, false>; \
         LCTR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                \
-        kern<<<(unsigned)rows, tpb, smem, c->stream>>>(s.row_ptr, s.fid, s.field, s.val, s.label, c->cW, c->cV, Fc, k, \
+        kern<<<(unsigned)rows, tpb, smem, c->stream>>>(s.row_ptr, c->cfg.world > 1 ? s.ent_pslot : s.fid, s.field, s.val, s.label, c->cW, c->cV, Fc, k, \
                                                        s.pred, c->cgW, c->cgV, c->cfg.world > 1 ? nullptr : c->touched, c->cfg.l2_reg, rb, \
                                                        c->stat_partial, c->stat_done, out_slot, stats ? 1 : 0, nullptr, nullptr); \
     } while (0)

@@ -414,7 +414,7 @@ static int fwd_go(lctr_ctx* c, Slot& s, bool nfm, int64_t rb, int64_t re, double
     do {                                                                                                       \
         auto kern = co ? fm_forward_coalesced_kernel<kCoalesced ? K : 8, HV, NF> : fm_forward_kernel<K, HV, NF>; \
         if (smem > 48 * 1024) LCTR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        kern<<<grid, wpb * 32, smem, c->stream>>>(s.row_ptr, s.fid, s.val, s.label, c->cW, c->cV, s.pred, s.sumvx, c->z, \
+        kern<<<grid, wpb * 32, smem, c->stream>>>(s.row_ptr, c->cfg.world > 1 ? s.ent_pslot : s.fid, s.val, s.label, c->cW, c->cV, s.pred, s.sumvx, c->z, \
                                              s.wide, rb, re, c->stat_partial, c->stat_done, out_slot, stats, hdr,   \
                                              c->fwd_quirk_sumvx, c->fwd_quirk_rows);                               \
     } while (0)
@@ -463,7 +463,7 @@ int launch_fm_backward(lctr_ctx* c, Slot& s, int64_t rb, int64_t re, bool nfm) {
     if (rows <= 0) return 0;
     const unsigned grid = (unsigned)((rows + 7) / 8);
     ProfScope prof(c, PROF_FM_BWD_RED);
-    FM_DISPATCH(fm_backward_kernel, s.row_ptr, s.fid, s.val, s.label, c->cW, c->cV, k, s.pred, s.sumvx, c->dz, c->cgW,
+    FM_DISPATCH(fm_backward_kernel, s.row_ptr, c->cfg.world > 1 ? s.ent_pslot : s.fid, s.val, s.label, c->cW, c->cV, k, s.pred, s.sumvx, c->dz, c->cgW,
                 c->cgV, c->cfg.world > 1 ? nullptr : c->touched, c->cfg.l2_reg, rb, re);
     c->launches++;
     LCTR_CUDA(cudaGetLastError());

@@ -10,24 +10,13 @@
 
 namespace lctr {
 
-struct FusedState {
-    uint8_t* mark = nullptr;      // 128 * T permuted byte marks
-    size_t T = 0;
-    uint32_t* slot_of = nullptr;  // F: fid -> slot of the batch being built
-    unsigned int* cnt = nullptr;  // sampled multiplicities (zero between builds)
-    size_t cnt_cap = 0;
-    float* G = nullptr;           // [G_rows][GS] compact gradient rows (zero between steps)
-    size_t G_rows = 0;
-    float* Ghot = nullptr;        // [kHotMax][kHotRep][GS] replica rows of the hot slots (zero between steps)
-    OptParams* d_opt = nullptr;   // updater parameters in device memory (graph launches)
-    int GS = 0;
-};
-
-bool fused_supported(const lctr_ctx* c) {
+// the fused kernels exist for FM with K in {4, 8, 16, 32}, order-free mode; on one GPU they read the tables directly,
+// on several (dist.cu) the batch-compact cache of the pulled rows
+bool fused_kernels_ok(const lctr_ctx* c) {
     const int k = (int)c->cfg.factor_cnt;
-    return c->cfg.model == LCTR_MODEL_FM && c->cfg.world == 1 && c->cfg.deterministic == 0 &&
-           (k == 4 || k == 8 || k == 16 || k == 32);
+    return c->cfg.model == LCTR_MODEL_FM && c->cfg.deterministic == 0 && (k == 4 || k == 8 || k == 16 || k == 32);
 }
+bool fused_supported(const lctr_ctx* c) { return c->cfg.world == 1 && fused_kernels_ok(c); }
 
 void fused_free(lctr_ctx* c) {
     FusedState* f = c->fused;
@@ -42,12 +31,14 @@ static int fused_init(lctr_ctx* c) {
     FusedState* f = new FusedState();
     c->fused = f;
     f->T = mark_rows(c->F);
-    f->GS = grad_stride((int)c->cfg.factor_cnt);
+    f->GS = fused_kernels_ok(c) ? grad_stride((int)c->cfg.factor_cnt) : 0;  // other models: slot map only
     LCTR_CUDA(cudaMalloc((void**)&f->mark, 128 * f->T + 512));
     LCTR_CUDA(cudaMemsetAsync(f->mark, 0, 128 * f->T + 512, c->stream));
     LCTR_CUDA(cudaMalloc((void**)&f->slot_of, c->F * sizeof(uint32_t)));
-    LCTR_CUDA(cudaMalloc((void**)&f->Ghot, (size_t)kHotMax * kHotRep * f->GS * sizeof(float)));
-    LCTR_CUDA(cudaMemsetAsync(f->Ghot, 0, (size_t)kHotMax * kHotRep * f->GS * sizeof(float), c->stream));
+    if (f->GS) {
+        LCTR_CUDA(cudaMalloc((void**)&f->Ghot, (size_t)kHotMax * kHotRep * f->GS * sizeof(float)));
+        LCTR_CUDA(cudaMemsetAsync(f->Ghot, 0, (size_t)kHotMax * kHotRep * f->GS * sizeof(float), c->stream));
+    }
     LCTR_CUDA(cudaMalloc((void**)&f->d_opt, sizeof(OptParams)));
     LCTR_CUDA(cudaStreamSynchronize(c->stream));
     return 0;
@@ -61,8 +52,11 @@ int fused_reserve(lctr_ctx* c, Slot& s, int64_t nnz) {
     if (nnz > s.cap_ent_slot) {
         LCTR_CUDA(cudaStreamSynchronize(c->stream));
         if (s.ent_slot) cudaFree(s.ent_slot);
+        if (s.ent_pslot) cudaFree(s.ent_pslot);
+        s.ent_pslot = nullptr;
         const int64_t cap = std::max<int64_t>(nnz, s.cap_ent_slot + s.cap_ent_slot / 2);
         LCTR_CUDA(cudaMalloc((void**)&s.ent_slot, (size_t)(cap + 64) * sizeof(uint32_t)));
+        if (c->cfg.world > 1) LCTR_CUDA(cudaMalloc((void**)&s.ent_pslot, (size_t)(cap + 64) * sizeof(uint32_t)));
         s.cap_ent_slot = cap;
     }
     if (need_u > s.cap_uniq || !s.hot_of) {
@@ -85,7 +79,7 @@ int fused_reserve(lctr_ctx* c, Slot& s, int64_t nnz) {
         LCTR_CUDA(cudaMemset(f->cnt, 0, (size_t)(s.cap_uniq + 64) * sizeof(unsigned int)));
         f->cnt_cap = (size_t)s.cap_uniq;
     }
-    if ((size_t)s.cap_uniq > f->G_rows) {
+    if (f->GS && (size_t)s.cap_uniq > f->G_rows) {
         LCTR_CUDA(cudaStreamSynchronize(c->stream));
         if (f->G) cudaFree(f->G);
         LCTR_CUDA(cudaMalloc((void**)&f->G, (size_t)(s.cap_uniq + 64) * f->GS * sizeof(float)));
@@ -109,12 +103,17 @@ int fused_build_slot(lctr_ctx* c, Slot& s, cudaStream_t st, const int64_t* hdr, 
     const size_t ntiles = (128 * f->T + 511) / 512;
     const unsigned cg = (unsigned)std::max<size_t>(1, std::min<size_t>((ntiles + 7) / 8, (size_t)SM * 8));
     slotmap_compact_kernel<<<cg, 256, 0, st>>>(f->mark, f->T, s.uniq, s.n_uniq, f->slot_of);
-    const unsigned sg = (unsigned)std::min<int64_t>(((int64_t)kHotSampleRows * 128 + 255) / 256, (int64_t)SM * 8);
-    slotmap_sample_kernel<<<sg, 256, 0, st>>>(s.row_ptr, s.fid, hdr, rows_cap, f->slot_of, f->cnt);
-    slotmap_hot_kernel<<<SM * 2, 256, 0, st>>>(f->cnt, s.n_uniq, hdr, rows_cap, s.hot_of, s.hot_slot, s.n_hot);
+    const bool hot = f->GS != 0;  // replica rows only exist for the fused FM kernels
+    if (hot) {
+        const unsigned sg = (unsigned)std::min<int64_t>(((int64_t)kHotSampleRows * 128 + 255) / 256, (int64_t)SM * 8);
+        slotmap_sample_kernel<<<sg, 256, 0, st>>>(s.row_ptr, s.fid, hdr, rows_cap, f->slot_of, f->cnt);
+        slotmap_hot_kernel<<<SM * 2, 256, 0, st>>>(f->cnt, s.n_uniq, hdr, rows_cap, s.hot_of, s.hot_slot, s.n_hot);
+        c->launches += 2;
+    }
     const unsigned ag = (unsigned)std::max<int64_t>(1, std::min<int64_t>((nnz_cap + 255) / 256, (int64_t)SM * 8));
-    slotmap_assign_kernel<<<ag, 256, 0, st>>>(s.fid, hdr, nnz_cap, f->slot_of, s.hot_of, s.ent_slot);
-    c->launches += 5;
+    slotmap_assign_kernel<<<ag, 256, 0, st>>>(s.fid, hdr, nnz_cap, f->slot_of, hot ? s.hot_of : nullptr, s.ent_slot,
+                                              c->cfg.world > 1 ? s.ent_pslot : nullptr);
+    c->launches += 3;
     LCTR_CUDA(cudaGetLastError());
     s.fused_valid = true;
     return 0;
@@ -124,8 +123,15 @@ template <int K>
 static void fused_go(lctr_ctx* c, Slot& s, int64_t rb, int64_t re, int stats, double* out_slot, const int64_t* hdr) {
     FusedState* f = c->fused;
     const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>((re - rb + 3) / 4, (int64_t)c->sm_count * 4));
-#define FUSED_ARGS s.row_ptr, s.fid, s.ent_slot, s.val, s.label, c->W, c->V, s.pred, s.sumvx, nullptr, f->G, f->Ghot, f->GS, \
-                   c->cfg.l2_reg, rb, re, hdr, c->stat_partial, c->stat_done, out_slot, stats
+    // one GPU: parameters straight from the tables (index = fid); several: from the batch-compact cache the owners filled
+    // (index = plain slot), after the owners' "rows delivered" flags of this step (dist.cu)
+    const bool multi = c->cfg.world > 1;
+    const unsigned long long* wf = nullptr;
+    int nw = 0;
+    unsigned long long ep = 0;
+    if (multi) dist_wait_info(c, &wf, &nw, &ep);
+#define FUSED_ARGS s.row_ptr, multi ? s.ent_pslot : s.fid, s.ent_slot, s.val, s.label, c->cW, c->cV, s.pred, s.sumvx, nullptr, f->G, \
+                   f->Ghot, f->GS, c->cfg.l2_reg, rb, re, hdr, c->stat_partial, c->stat_done, out_slot, stats, wf, nw, ep
     if (s.has_val) fm_fused_kernel<K, true, 1, false><<<grid, 128, 0, c->stream>>>(FUSED_ARGS);
     else fm_fused_kernel<K, false, 1, false><<<grid, 128, 0, c->stream>>>(FUSED_ARGS);
 #undef FUSED_ARGS

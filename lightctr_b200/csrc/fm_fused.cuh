@@ -28,8 +28,6 @@
 
 namespace lctr {
 
-constexpr int kHotRep = 32;      // replica rows per hot slot
-constexpr int kHotMax = 2048;    // hot slots per batch (ids beyond the cap stay ordinary slots)
 constexpr int kHotSampleRows = 512;
 constexpr uint32_t kHotBit = 0x80000000u;
 // stride (floats) of a compact gradient row [gV (k) | gW | pad]: power of two >= k + 1 (rows never straddle a 128 B line)
@@ -178,15 +176,17 @@ slotmap_hot_kernel(unsigned int* __restrict__ cnt, const unsigned int* __restric
 }
 
 // ent_slot[i]: the slot of entry i, or kHotBit | replica-block index when the slot is hot
+// ent_pslot (optional): always the plain slot -- the row of the entry's parameters in a batch-compact cache (multi-GPU)
 __global__ void __launch_bounds__(256)
 slotmap_assign_kernel(const uint32_t* __restrict__ fid, const int64_t* __restrict__ hdr, int64_t nnz_arg,
                       const uint32_t* __restrict__ slot_of, const uint32_t* __restrict__ hot_of,
-                      uint32_t* __restrict__ ent_slot) {
+                      uint32_t* __restrict__ ent_slot, uint32_t* __restrict__ ent_pslot) {
     const int64_t nnz = hdr ? hdr[1] : nnz_arg;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nnz; i += (int64_t)gridDim.x * blockDim.x) {
         const uint32_t sl = slot_of[fid[i]];
         const uint32_t h = hot_of ? hot_of[sl] : 0xffffffffu;
-        ent_slot[i] = h != 0xffffffffu ? (kHotBit | h) : sl;
+        if (ent_slot) ent_slot[i] = h != 0xffffffffu ? (kHotBit | h) : sl;
+        if (ent_pslot) ent_pslot[i] = sl;
     }
 }
 
@@ -207,8 +207,17 @@ fm_fused_kernel(const int64_t* __restrict__ row_ptr, const uint32_t* __restrict_
                 const float* __restrict__ val, const float* __restrict__ label, const float* __restrict__ W,
                 const float* __restrict__ V, float* __restrict__ pred, float* __restrict__ sumvx, float* __restrict__ dvec,
                 float* __restrict__ G, float* __restrict__ Ghot, int GS, float l2, int64_t rb, int64_t re_arg,
-                const int64_t* __restrict__ hdr, double* partial, unsigned int* done, double* out_slot, int do_stats) {
+                const int64_t* __restrict__ hdr, double* partial, unsigned int* done, double* out_slot, int do_stats,
+                const unsigned long long* wait_flags = nullptr, int n_wait = 0, unsigned long long wait_epoch = 0) {
     static_assert(K % 4 == 0 && K <= 32 && (K / 4 & (K / 4 - 1)) == 0, "fused FM step: K in {4, 8, 16, 32}");
+    if (wait_flags) {  // multi-GPU: the owners' rows of this step must have landed in the cache (dist.cu)
+        if (threadIdx.x < n_wait) {
+            const volatile unsigned long long* f = wait_flags + threadIdx.x;
+            while (*f < wait_epoch) __nanosleep(40);
+        }
+        __syncthreads();
+        __threadfence_system();
+    }
     constexpr int LPR = K / 4;                           // lanes per V row (one float4 each)
     constexpr int GR = 32 / LPR;                         // rows per gather instruction
     constexpr int NPASS = K <= 8 ? 8 : (K == 16 ? 4 : 2);  // 32-entry passes whose rows stay in registers

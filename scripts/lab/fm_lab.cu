@@ -252,7 +252,7 @@ int main(int argc, char** argv) {
         slotmap_compact_kernel<<<cg, 256, 0, st>>>(mark, MT, uniq, n_uniq, slot_of);
         slotmap_sample_kernel<<<sg, 256, 0, st>>>(d_rp, d_fid, nullptr, B, slot_of, cnt);
         slotmap_hot_kernel<<<SM * 2, 256, 0, st>>>(cnt, n_uniq, nullptr, B, hot_of, hot_slot, n_hot);
-        slotmap_assign_kernel<<<mg, 256, 0, st>>>(d_fid, nullptr, nnz, slot_of, hot_of, ent_slot);
+        slotmap_assign_kernel<<<mg, 256, 0, st>>>(d_fid, nullptr, nnz, slot_of, hot_of, ent_slot, nullptr);
     };
     prep_slotmap();
     CK(cudaStreamSynchronize(st));
@@ -264,7 +264,7 @@ int main(int argc, char** argv) {
     printf("prep_slotmap(mark+compact+sample+hot+assign)_us,%.2f\n", time_us(prep_slotmap));
     printf("prep_sample_us,%.2f\n", time_us([&]() { slotmap_sample_kernel<<<sg, 256, 0, st>>>(d_rp, d_fid, nullptr, B, slot_of, cnt); }));
     CK(cudaMemsetAsync(cnt, 0, (size_t)(nnz + 64) * 4, st));
-    printf("prep_assign_us,%.2f\n", time_us([&]() { slotmap_assign_kernel<<<mg, 256, 0, st>>>(d_fid, nullptr, nnz, slot_of, hot_of, ent_slot); }));
+    printf("prep_assign_us,%.2f\n", time_us([&]() { slotmap_assign_kernel<<<mg, 256, 0, st>>>(d_fid, nullptr, nnz, slot_of, hot_of, ent_slot, nullptr); }));
     printf("prep_mark_us,%.2f\n", time_us([&]() { slotmap_mark_kernel<<<mkg, 256, 0, st>>>(d_fid, nullptr, nnz, mark, MT); }));
     printf("prep_compact(empty map)_us,%.2f\n", time_us([&]() { CK(cudaMemsetAsync(n_uniq, 0, 4, st)); slotmap_compact_kernel<<<cg, 256, 0, st>>>(mark, MT, uniq, n_uniq, slot_of); }));
     {   // the five kernels of the build, timed one by one inside the sequence (L2 flushed first)
@@ -282,13 +282,13 @@ int main(int argc, char** argv) {
         CK(cudaEventRecord(ev[3], st));
         slotmap_hot_kernel<<<SM * 2, 256, 0, st>>>(cnt, n_uniq, nullptr, B, hot_of, hot_slot, n_hot);
         CK(cudaEventRecord(ev[4], st));
-        slotmap_assign_kernel<<<mg, 256, 0, st>>>(d_fid, nullptr, nnz, slot_of, hot_of, ent_slot);
+        slotmap_assign_kernel<<<mg, 256, 0, st>>>(d_fid, nullptr, nnz, slot_of, hot_of, ent_slot, nullptr);
         CK(cudaEventRecord(ev[5], st));
         CK(cudaStreamSynchronize(st));
         const char* nm[5] = {"mark", "compact", "sample", "hot", "assign"};
         for (int i = 0; i < 5; i++) { float ms; CK(cudaEventElapsedTime(&ms, ev[i], ev[i + 1])); printf("prep_seq_%s_us,%.2f\n", nm[i], ms * 1e3f); }
     }
-    slotmap_assign_kernel<<<mg, 256, 0, st>>>(d_fid, nullptr, nnz, slot_of, nullptr, ent_slot_nohot);
+    slotmap_assign_kernel<<<mg, 256, 0, st>>>(d_fid, nullptr, nnz, slot_of, nullptr, ent_slot_nohot, nullptr);
     CK(cudaStreamSynchronize(st));
     G = dmalloc<float>((size_t)(U + 64) * GSmax);
     float* Gref = dmalloc<float>((size_t)(U + 64) * GSmax);

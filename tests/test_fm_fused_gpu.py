@@ -155,10 +155,13 @@ def test_fused_c2_shape_one_step(oracle_api):
     assert np.max(np.abs(Wg - o.W)) < 2e-5 and np.max(np.abs(Vg - o.V)) < 2e-5
     s1, _ = ctx.download_opt_state()
     assert np.allclose(s1, o.accum, rtol=1e-4, atol=1e-9)
-    # second step from the updated state (hot replicas and the compact buffer must have been re-zeroed exactly)
+    # second step, again from the oracle's exact state (hot replicas and the compact buffer must have been re-zeroed
+    # exactly by the first one; left to itself the path drifts by ~2e-5 here, like the reference's Hogwild mode)
+    ctx.upload_params(o.W, o.V)
+    ctx.upload_opt_state(o.accum)
     lg2, _ = ctx.train_step(0)
     lo2, _ = o.epoch()
-    assert _rel(lg2, lo2) < 1e-5, (lg2, lo2)
+    assert _rel(lg2, lo2) < 1e-6, (lg2, lo2)
     ctx.close()
 
 
