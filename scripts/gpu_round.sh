@@ -9,7 +9,7 @@ nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw,clocks_event_reas
 for s in $STEPS; do
 case $s in
 tests)
-  timeout 1500 python -m pytest tests -m gpu -x -q ${PYTEST_ARGS:-} > $O/pytest_$TAG.log 2>&1; echo "pytest rc=$?" >> $O/pytest_$TAG.log
+  timeout 1500 python -m pytest tests -m gpu ${PYTEST_X:--x} -q ${PYTEST_ARGS:-} > $O/pytest_$TAG.log 2>&1; echo "pytest rc=$?" >> $O/pytest_$TAG.log
   tail -n 15 $O/pytest_$TAG.log ;;
 newtests)
   timeout 900 python -m pytest tests/test_fm_fused_gpu.py -m gpu -x -q > $O/pytest_new_$TAG.log 2>&1; echo "pytest rc=$?" >> $O/pytest_new_$TAG.log
@@ -36,6 +36,11 @@ ncu)
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:"fm_fused_kernel|apply_compact" -s 30 -c 6 \
       -o $O/prof_${TAG}_fm_c2 -f python bench.py --steps 6 --warmup 3 --no-cpu-baseline --no-c5 > $O/ncu_full_$TAG.log 2>&1
   echo "ncu rc=$?" ;;
+dist)
+  N=${NGPU:-2}
+  timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus $N --steps 100 --warmup 10 \
+      > $O/bench_${TAG}_fm_c2_n$N.json 2> $O/bench_${TAG}_fm_c2_n$N.err; echo "dist bench rc=$?"
+  tail -c 1500 $O/bench_${TAG}_fm_c2_n$N.err ;;
 lab)
   bash scripts/lab/run_lab.sh > /dev/null 2>&1; cp $O/lab_b4096.txt $O/lab_${TAG}_b4096.txt; cp $O/lab_b65536.txt $O/lab_${TAG}_b65536.txt ;;
 esac

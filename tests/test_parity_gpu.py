@@ -169,9 +169,10 @@ def test_fm_red_path_per_step_parity(files, oracle_api):
             ctx.upload_opt_state(o.accum)
             lg, cg = ctx.train_step(0)
             lo, ao = o.epoch()
-            assert _rel(lg, lo) < 1e-6, (e, lg, lo)
+            # order-free forward (shuffle-tree sums over ~282 entries per row) + RED-order scatter: observed <= 2.1e-6
+            assert _rel(lg, lo) < 5e-6, (e, lg, lo)
             Wg, Vg = ctx.download_params()
-            # RED order reassociation only: observed <= 2e-6 abs
+            # re-association only: observed <= 2e-6 abs
             assert np.max(np.abs(Wg - o.W)) < 2e-5 and np.max(np.abs(Vg - o.V)) < 2e-5, e
             s1, _ = ctx.download_opt_state()
             assert np.allclose(s1, o.accum, rtol=1e-4, atol=1e-9)
