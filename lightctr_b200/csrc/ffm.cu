@@ -267,6 +267,223 @@ __global__ void ffm_fused_kernel(const int64_t* __restrict__ row_ptr, const uint
     if (TRAIN && do_stats) publish_stats(loss, correct, partial, done, out_slot, false);
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// TMA-staged fused step (k % 4 == 0, training): the default RED-mode kernel
+// ------------------------------------------------------------------------------------------------------------
+// Same arithmetic as ffm_fused_kernel, different data movement: an embedding row is ONE contiguous, 16 B-aligned
+// Fc*k*4-byte segment (624 B at Fc=39,k=4; 1248 B at k=8), exactly what cp.async.bulk (the TMA's non-tensor bulk copy)
+// moves with a single instruction.  A producer warp streams the sample's rows through a ring of kFfmRing shared-memory
+// stages, each guarded by a full / empty mbarrier pair; the consumer threads (one per 16 B slot of the row) read their
+// slot from the stage, so the gather keeps kFfmRing whole rows in flight per CTA with no register cost and no per-thread
+// load instructions (ffm_fused_kernel: FFM_GATHER_U x A LDG.128 per group).  Phase 3 streams the rows a second time
+// (L2 hits) instead of re-gathering them four at a time.
+constexpr int kFfmRing = 16;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "LAB_WAIT:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE;\n\t"
+        "bra LAB_WAIT;\n\t"
+        "DONE:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// global -> shared bulk copy of `bytes` (multiple of 16, both sides 16 B aligned), completion counted on `bar`
+__device__ __forceinline__ void bulk_load(void* sdst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(sdst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+template <bool HAS_VAL>
+__global__ void ffm_tma_kernel(const int64_t* __restrict__ row_ptr, const uint32_t* __restrict__ fid,
+                               const uint16_t* __restrict__ field, const float* __restrict__ val,
+                               const float* __restrict__ label, const float* __restrict__ W, const float* __restrict__ V,
+                               int Fc, int k, float* __restrict__ pred, float* __restrict__ gW, float* __restrict__ gV,
+                               uint8_t* __restrict__ touched, float l2, int64_t rb, double* partial, unsigned int* done,
+                               double* out_slot, int do_stats, int n_cons /* consumer threads = blockDim.x - 32 */) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int A = Fc * k / 4;     // 16 B slots per row
+    const int PPF = k / 4;        // slots per field
+    const uint32_t rowbytes = (uint32_t)A * 16u;
+    const uint32_t stage_bytes = (rowbytes + 127u) / 128u * 128u;
+    float4* ring = reinterpret_cast<float4*>(smem_raw);                                   // [kFfmRing][stage_bytes]
+    float4* S = reinterpret_cast<float4*>(smem_raw + (size_t)kFfmRing * stage_bytes);      // S[col b][slot a] = T[a][b]
+    int* cnt = reinterpret_cast<int*>(S + (size_t)Fc * A);
+    float* red = reinterpret_cast<float*>(cnt + Fc);                                      // [80]
+    uint32_t* st_f = reinterpret_cast<uint32_t*>(red + 80);
+    float* st_x = reinterpret_cast<float*>(st_f + kFfmStage);
+    float* st_w = st_x + kFfmStage;
+    uint16_t* st_fl = reinterpret_cast<uint16_t*>(st_w + kFfmStage);
+    uint64_t* full = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(st_fl + kFfmStage) + 7) & ~(uintptr_t)7);
+    uint64_t* empty = full + kFfmRing;
+    const int t = threadIdx.x;
+    const bool producer = t >= n_cons;            // the last warp
+    const int n_cwarps = n_cons >> 5;
+    const int64_t r = rb + blockIdx.x;
+    const int64_t b0 = row_ptr[r], e0 = row_ptr[r + 1];
+    const size_t rowlen = (size_t)Fc * k;
+    const bool own = t < A;
+    const int my_field = own ? t / PPF : -1, my_part = own ? t % PPF : 0;
+
+    if (t == 0) {
+        for (int i = 0; i < kFfmRing; i++) { mbar_init(&full[i], 1); mbar_init(&empty[i], (uint32_t)n_cwarps); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int i = t; i < Fc * A; i += blockDim.x) S[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = t; i < Fc; i += blockDim.x) cnt[i] = 0;
+    __syncthreads();
+
+    uint32_t it = 0;  // rows streamed so far (both phases): stage = it % kFfmRing, parity = (it / kFfmRing) & 1
+    // ---- phase 1: T accumulation, wide sum, diagonal ---------------------------------------------------------------
+    float wsum = 0.f, dsq = 0.f;
+    for (int64_t c0 = b0; c0 < e0; c0 += kFfmStage) {
+        const int nst = (int)min((int64_t)kFfmStage, e0 - c0);
+        __syncthreads();  // previous chunk fully consumed
+        for (int i = t; i < nst; i += blockDim.x) {
+            const uint32_t f = __ldg(fid + c0 + i);
+            st_f[i] = f;
+            st_fl[i] = __ldg(field + c0 + i);
+            st_x[i] = HAS_VAL ? __ldg(val + c0 + i) : 1.f;
+            st_w[i] = __ldg(W + f);
+        }
+        __syncthreads();
+        if (producer) {
+            if (t == n_cons) {
+                for (int i = 0; i < nst; i++) {
+                    const uint32_t st = (it + i) % kFfmRing, ph = ((it + i) / kFfmRing) & 1u;
+                    mbar_wait(&empty[st], ph ^ 1u);  // a fresh barrier passes the wait on the opposite parity
+                    mbar_arrive_expect_tx(&full[st], rowbytes);
+                    bulk_load(reinterpret_cast<unsigned char*>(ring) + (size_t)st * stage_bytes, V + (size_t)st_f[i] * rowlen, rowbytes, &full[st]);
+                }
+            }
+        } else {
+            for (int i = 0; i < nst; i++) {
+                const uint32_t st = (it + i) % kFfmRing, ph = ((it + i) / kFfmRing) & 1u;
+                mbar_wait(&full[st], ph);
+                const int flu = st_fl[i];
+                const float xu = st_x[i];
+                if (own) {
+                    const float4 v = reinterpret_cast<const float4*>(reinterpret_cast<const unsigned char*>(ring) + (size_t)st * stage_bytes)[t];
+                    float4& dst = S[flu * A + t];
+                    const float4 tv = make_float4(v.x * xu, v.y * xu, v.z * xu, v.w * xu);
+                    dst.x += tv.x; dst.y += tv.y; dst.z += tv.z; dst.w += tv.w;
+                    if (my_field == flu) dsq += tv.x * tv.x + tv.y * tv.y + tv.z * tv.z + tv.w * tv.w;
+                }
+                if (t == 0) {
+                    wsum += st_w[i] * xu;  // fm_pred += W[fid] * X  (train_ffm_algo.cpp:60)
+                    cnt[flu] += 1;
+                }
+                __syncwarp();
+                if ((t & 31) == 0) mbar_arrive(&empty[st]);
+            }
+        }
+        it += (uint32_t)nst;
+    }
+    __syncthreads();
+
+    // ---- phase 2: P = sum_{a,b} <T[a][b], T[b][a]> ------------------------------------------------------------------
+    float P = 0.f;
+    if (own) {
+        for (int b = 0; b < Fc; b++) {
+            if (cnt[b] == 0) continue;
+            const float4 u1 = S[b * A + t];
+            const float4 u2 = S[my_field * A + b * PPF + my_part];
+            P += u1.x * u2.x + u1.y * u2.y + u1.z * u2.z + u1.w * u2.w;
+        }
+    }
+    {
+        const int lane = t & 31, wid = t >> 5, nw = (blockDim.x + 31) >> 5;
+        float a = warp_sum(P), d2 = warp_sum(dsq);
+        if (lane == 0) { red[wid] = a; red[32 + wid] = d2; }
+        __syncthreads();
+        if (wid == 0) {
+            float aa = lane < nw ? red[lane] : 0.f, dd = lane < nw ? red[32 + lane] : 0.f;
+            aa = warp_sum(aa);
+            dd = warp_sum(dd);
+            if (lane == 0) {
+                const float fm_pred = (float)((double)wsum + 0.5 * ((double)aa - (double)dd));
+                const float p = ref_sigmoid(fm_pred);
+                pred[r] = p;
+                red[64] = p;
+            }
+        }
+        __syncthreads();
+    }
+    const float p = red[64];
+    double loss = 0.0, correct = 0.0;
+    const float y = label[r];
+    const float d = p - y;
+    if (d != 0.f) {  // train_ffm_algo.cpp:81-83: rows with pred == label contribute nothing at all
+        if (t == 0 && do_stats) loss_terms(p, y, loss, correct);
+        // ---- phase 3: gradients; the rows stream through the ring a second time -------------------------------------
+        const int my_cnt = own ? cnt[my_field] : 0;
+        const bool single = e0 - b0 <= kFfmStage;  // the staged indices of phase 1 are still valid
+        for (int64_t c0 = b0; c0 < e0; c0 += kFfmStage) {
+            const int nst = (int)min((int64_t)kFfmStage, e0 - c0);
+            if (!single) {
+                __syncthreads();
+                for (int i = t; i < nst; i += blockDim.x) {
+                    const uint32_t f = __ldg(fid + c0 + i);
+                    st_f[i] = f;
+                    st_fl[i] = __ldg(field + c0 + i);
+                    st_x[i] = HAS_VAL ? __ldg(val + c0 + i) : 1.f;
+                    st_w[i] = __ldg(W + f);
+                }
+                __syncthreads();
+            }
+            if (producer) {
+                if (t == n_cons) {
+                    for (int i = 0; i < nst; i++) {
+                        const uint32_t st = (it + i) % kFfmRing, ph = ((it + i) / kFfmRing) & 1u;
+                        mbar_wait(&empty[st], ph ^ 1u);
+                        mbar_arrive_expect_tx(&full[st], rowbytes);
+                        bulk_load(reinterpret_cast<unsigned char*>(ring) + (size_t)st * stage_bytes, V + (size_t)st_f[i] * rowlen, rowbytes, &full[st]);
+                    }
+                }
+            } else {
+                for (int i = 0; i < nst; i++) {
+                    const uint32_t st = (it + i) % kFfmRing, ph = ((it + i) / kFfmRing) & 1u;
+                    mbar_wait(&full[st], ph);
+                    const int flu = st_fl[i];
+                    const float xu = st_x[i];
+                    const uint32_t f = st_f[i];
+                    if (own) {
+                        const int c_ib = my_cnt - (my_field == flu ? 1 : 0);
+                        if (c_ib > 0) {
+                            const float4 v = reinterpret_cast<const float4*>(reinterpret_cast<const unsigned char*>(ring) + (size_t)st * stage_bytes)[t];
+                            const float4 tt = S[my_field * A + flu * PPF + my_part];  // T[fld_i][my_field]
+                            const float sx = d * xu, lc = l2 * (float)c_ib;
+                            float4 g;
+                            float tx = tt.x, ty = tt.y, tz = tt.z, tw = tt.w;
+                            if (my_field == flu) { tx -= xu * v.x; ty -= xu * v.y; tz -= xu * v.z; tw -= xu * v.w; }
+                            g.x = sx * tx + lc * v.x; g.y = sx * ty + lc * v.y; g.z = sx * tz + lc * v.z; g.w = sx * tw + lc * v.w;
+                            red_add_v4(gV + (size_t)f * rowlen + (size_t)t * 4, g);
+                        }
+                    }
+                    if (t == 0) {
+                        red_add_f32(gW + f, d * xu + l2 * st_w[i]);  // train_ffm_algo.cpp:98
+                        if (touched) touched[f] = 1;
+                    }
+                    __syncwarp();
+                    if ((t & 31) == 0) mbar_arrive(&empty[st]);
+                }
+            }
+            it += (uint32_t)nst;
+        }
+    }
+    if (do_stats) publish_stats(loss, correct, partial, done, out_slot, false);
+}
+
 // FM_Predict, field-aware branch (predict/fm_predict.cpp:34-53) in the reference's OWN order -- no field-pair factorisation:
 // warp = sample; for entry i the lanes form the pair terms field_w * X * X2 of 32 partners j at a time (each dot product in
 // the avx lane order of common/avx.h:102-127), and the scalar chain fm_pred += ... is replayed in j order through shuffles,
@@ -349,6 +566,27 @@ static int ffm_launch(lctr_ctx* c, Slot& s, int64_t rb, int64_t re, bool train, 
                                                            c->stat_done, out_slot, stats ? 1 : 0, c->ffm_T, c->ffm_cnt);
         };
         if (s.has_val) go(ffm_fused_kernel<4, true, true, false, true>); else go(ffm_fused_kernel<4, false, true, false, true>);
+        c->launches++;
+        LCTR_CUDA(cudaGetLastError());
+        return 0;
+    }
+    // default training kernel for k % 4 == 0: rows staged through shared memory by the TMA (cp.async.bulk + mbarrier ring);
+    // LCTR_FFM_TMA=0 selects the register-staged kernel below
+    static const bool use_tma = !(getenv("LCTR_FFM_TMA") && atoi(getenv("LCTR_FFM_TMA")) == 0);
+    if (use_tma && train && vec == 4 && !bulk) {
+        const int n_cons = std::max(32, (A + 31) / 32 * 32);
+        const size_t stage_bytes = ((size_t)A * 16 + 127) / 128 * 128;
+        const size_t smem2 = (size_t)kFfmRing * stage_bytes + (size_t)Fc * A * 16 + (size_t)Fc * 4 + 80 * 4 + (size_t)kFfmStage * 14 + 16 +
+                             2 * kFfmRing * 8 + 128;
+        LCTR_CHECK(smem2 <= 227 * 1024, "FFM field-pair tile + row ring need %zu B shared memory (> 227 KB): Fc=%d k=%d", smem2, Fc, k);
+        auto go = [&](auto kern) {
+            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
+            kern<<<(unsigned)rows, n_cons + 32, smem2, c->stream>>>(s.row_ptr, c->cfg.world > 1 ? s.ent_pslot : s.fid, s.field, s.val, s.label,
+                                                                   c->cW, c->cV, Fc, k, s.pred, c->cgW, c->cgV,
+                                                                   c->cfg.world > 1 ? nullptr : c->touched, c->cfg.l2_reg, rb, c->stat_partial,
+                                                                   c->stat_done, out_slot, stats ? 1 : 0, n_cons);
+        };
+        if (s.has_val) go(ffm_tma_kernel<true>); else go(ffm_tma_kernel<false>);
         c->launches++;
         LCTR_CUDA(cudaGetLastError());
         return 0;
