@@ -272,19 +272,15 @@ __global__ void ffm_fused_kernel(const int64_t* __restrict__ row_ptr, const uint
 // ------------------------------------------------------------------------------------------------------------
 // Same arithmetic as ffm_fused_kernel, different data movement: an embedding row is ONE contiguous, 16 B-aligned
 // Fc*k*4-byte segment (624 B at Fc=39,k=4; 1248 B at k=8), exactly what cp.async.bulk (the TMA's non-tensor bulk copy)
-// moves with a single instruction.  A producer warp streams the sample's rows through a ring of kFfmRing shared-memory
-// stages, each guarded by a full / empty mbarrier pair; the consumer threads (one per 16 B slot of the row) read their
-// slot from the stage, so the gather keeps kFfmRing whole rows in flight per CTA with no register cost and no per-thread
-// load instructions (ffm_fused_kernel: FFM_GATHER_U x A LDG.128 per group).  Phase 3 streams the rows a second time
-// (L2 hits) instead of re-gathering them four at a time.
-constexpr int kFfmRing = 16;
-
+// moves with a single instruction.  The rows of a chunk of up to CR entries of the sample (the whole sample, typically)
+// are requested at once -- one bulk copy per row, all completing on ONE mbarrier armed with the chunk's byte count -- so
+// CR whole rows are in flight per CTA at no register cost and without per-thread load instructions, and the gradient
+// phase reads the rows from shared memory again instead of gathering them a second time.
+// (A first version streamed single rows through a 16-stage full/empty ring fed by a producer warp: the two mbarrier
+// hand-shakes per row cost more than the 16 B of work a consumer thread has per row; 510 vs 425 us on C3.)
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
@@ -310,25 +306,22 @@ __global__ void ffm_tma_kernel(const int64_t* __restrict__ row_ptr, const uint32
                                const float* __restrict__ label, const float* __restrict__ W, const float* __restrict__ V,
                                int Fc, int k, float* __restrict__ pred, float* __restrict__ gW, float* __restrict__ gV,
                                uint8_t* __restrict__ touched, float l2, int64_t rb, double* partial, unsigned int* done,
-                               double* out_slot, int do_stats, int n_cons /* consumer threads = blockDim.x - 32 */) {
+                               double* out_slot, int do_stats, int CR /* rows per chunk */) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int A = Fc * k / 4;     // 16 B slots per row
     const int PPF = k / 4;        // slots per field
     const uint32_t rowbytes = (uint32_t)A * 16u;
     const uint32_t stage_bytes = (rowbytes + 127u) / 128u * 128u;
-    float4* ring = reinterpret_cast<float4*>(smem_raw);                                   // [kFfmRing][stage_bytes]
-    float4* S = reinterpret_cast<float4*>(smem_raw + (size_t)kFfmRing * stage_bytes);      // S[col b][slot a] = T[a][b]
+    unsigned char* rows = smem_raw;                                                         // [CR][stage_bytes]
+    float4* S = reinterpret_cast<float4*>(smem_raw + (size_t)CR * stage_bytes);             // S[col b][slot a] = T[a][b]
     int* cnt = reinterpret_cast<int*>(S + (size_t)Fc * A);
-    float* red = reinterpret_cast<float*>(cnt + Fc);                                      // [80]
+    float* red = reinterpret_cast<float*>(cnt + Fc);                                        // [80]
     uint32_t* st_f = reinterpret_cast<uint32_t*>(red + 80);
-    float* st_x = reinterpret_cast<float*>(st_f + kFfmStage);
-    float* st_w = st_x + kFfmStage;
-    uint16_t* st_fl = reinterpret_cast<uint16_t*>(st_w + kFfmStage);
-    uint64_t* full = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(st_fl + kFfmStage) + 7) & ~(uintptr_t)7);
-    uint64_t* empty = full + kFfmRing;
+    float* st_x = reinterpret_cast<float*>(st_f + CR);
+    float* st_w = st_x + CR;
+    uint16_t* st_fl = reinterpret_cast<uint16_t*>(st_w + CR);
+    uint64_t* bar = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(st_fl + CR) + 7) & ~(uintptr_t)7);
     const int t = threadIdx.x;
-    const bool producer = t >= n_cons;            // the last warp
-    const int n_cwarps = n_cons >> 5;
     const int64_t r = rb + blockIdx.x;
     const int64_t b0 = row_ptr[r], e0 = row_ptr[r + 1];
     const size_t rowlen = (size_t)Fc * k;
@@ -336,19 +329,16 @@ __global__ void ffm_tma_kernel(const int64_t* __restrict__ row_ptr, const uint32
     const int my_field = own ? t / PPF : -1, my_part = own ? t % PPF : 0;
 
     if (t == 0) {
-        for (int i = 0; i < kFfmRing; i++) { mbar_init(&full[i], 1); mbar_init(&empty[i], (uint32_t)n_cwarps); }
+        mbar_init(bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     for (int i = t; i < Fc * A; i += blockDim.x) S[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int i = t; i < Fc; i += blockDim.x) cnt[i] = 0;
-    __syncthreads();
 
-    uint32_t it = 0;  // rows streamed so far (both phases): stage = it % kFfmRing, parity = (it / kFfmRing) & 1
-    // ---- phase 1: T accumulation, wide sum, diagonal ---------------------------------------------------------------
-    float wsum = 0.f, dsq = 0.f;
-    for (int64_t c0 = b0; c0 < e0; c0 += kFfmStage) {
-        const int nst = (int)min((int64_t)kFfmStage, e0 - c0);
-        __syncthreads();  // previous chunk fully consumed
+    uint32_t uses = 0;  // completed phases of `bar`: its parity
+    // stage the indices of entries [c0, c0 + nst), then request their rows (one bulk copy each) and wait for all of them
+    auto load_chunk = [&](int64_t c0, int nst) {
+        __syncthreads();  // the previous chunk's rows and indices are no longer read; barrier init / S zeroing done
         for (int i = t; i < nst; i += blockDim.x) {
             const uint32_t f = __ldg(fid + c0 + i);
             st_f[i] = f;
@@ -357,37 +347,35 @@ __global__ void ffm_tma_kernel(const int64_t* __restrict__ row_ptr, const uint32
             st_w[i] = __ldg(W + f);
         }
         __syncthreads();
-        if (producer) {
-            if (t == n_cons) {
-                for (int i = 0; i < nst; i++) {
-                    const uint32_t st = (it + i) % kFfmRing, ph = ((it + i) / kFfmRing) & 1u;
-                    mbar_wait(&empty[st], ph ^ 1u);  // a fresh barrier passes the wait on the opposite parity
-                    mbar_arrive_expect_tx(&full[st], rowbytes);
-                    bulk_load(reinterpret_cast<unsigned char*>(ring) + (size_t)st * stage_bytes, V + (size_t)st_f[i] * rowlen, rowbytes, &full[st]);
-                }
-            }
-        } else {
+        if (t == 0) mbar_arrive_expect_tx(bar, (uint32_t)nst * rowbytes);
+        for (int i = t; i < nst; i += blockDim.x)
+            bulk_load(rows + (size_t)i * stage_bytes, V + (size_t)st_f[i] * rowlen, rowbytes, bar);
+        mbar_wait(bar, uses & 1u);
+        uses++;
+    };
+
+    // ---- phase 1: T accumulation, wide sum, diagonal ---------------------------------------------------------------
+    float wsum = 0.f, dsq = 0.f;
+    for (int64_t c0 = b0; c0 < e0; c0 += CR) {
+        const int nst = (int)min((int64_t)CR, e0 - c0);
+        load_chunk(c0, nst);
+        if (own) {
             for (int i = 0; i < nst; i++) {
-                const uint32_t st = (it + i) % kFfmRing, ph = ((it + i) / kFfmRing) & 1u;
-                mbar_wait(&full[st], ph);
                 const int flu = st_fl[i];
                 const float xu = st_x[i];
-                if (own) {
-                    const float4 v = reinterpret_cast<const float4*>(reinterpret_cast<const unsigned char*>(ring) + (size_t)st * stage_bytes)[t];
-                    float4& dst = S[flu * A + t];
-                    const float4 tv = make_float4(v.x * xu, v.y * xu, v.z * xu, v.w * xu);
-                    dst.x += tv.x; dst.y += tv.y; dst.z += tv.z; dst.w += tv.w;
-                    if (my_field == flu) dsq += tv.x * tv.x + tv.y * tv.y + tv.z * tv.z + tv.w * tv.w;
-                }
-                if (t == 0) {
-                    wsum += st_w[i] * xu;  // fm_pred += W[fid] * X  (train_ffm_algo.cpp:60)
-                    cnt[flu] += 1;
-                }
-                __syncwarp();
-                if ((t & 31) == 0) mbar_arrive(&empty[st]);
+                const float4 v = reinterpret_cast<const float4*>(rows + (size_t)i * stage_bytes)[t];
+                float4& dst = S[flu * A + t];
+                const float4 tv = make_float4(v.x * xu, v.y * xu, v.z * xu, v.w * xu);
+                dst.x += tv.x; dst.y += tv.y; dst.z += tv.z; dst.w += tv.w;
+                if (my_field == flu) dsq += tv.x * tv.x + tv.y * tv.y + tv.z * tv.z + tv.w * tv.w;
             }
         }
-        it += (uint32_t)nst;
+        if (t == 0) {
+            for (int i = 0; i < nst; i++) {
+                wsum += st_w[i] * st_x[i];  // fm_pred += W[fid] * X  (train_ffm_algo.cpp:60)
+                cnt[st_fl[i]] += 1;
+            }
+        }
     }
     __syncthreads();
 
@@ -425,60 +413,36 @@ __global__ void ffm_tma_kernel(const int64_t* __restrict__ row_ptr, const uint32
     const float d = p - y;
     if (d != 0.f) {  // train_ffm_algo.cpp:81-83: rows with pred == label contribute nothing at all
         if (t == 0 && do_stats) loss_terms(p, y, loss, correct);
-        // ---- phase 3: gradients; the rows stream through the ring a second time -------------------------------------
+        // ---- phase 3: gradients, from the rows still in shared memory (one chunk) or streamed a second time -----------
         const int my_cnt = own ? cnt[my_field] : 0;
-        const bool single = e0 - b0 <= kFfmStage;  // the staged indices of phase 1 are still valid
-        for (int64_t c0 = b0; c0 < e0; c0 += kFfmStage) {
-            const int nst = (int)min((int64_t)kFfmStage, e0 - c0);
-            if (!single) {
-                __syncthreads();
-                for (int i = t; i < nst; i += blockDim.x) {
-                    const uint32_t f = __ldg(fid + c0 + i);
-                    st_f[i] = f;
-                    st_fl[i] = __ldg(field + c0 + i);
-                    st_x[i] = HAS_VAL ? __ldg(val + c0 + i) : 1.f;
-                    st_w[i] = __ldg(W + f);
-                }
-                __syncthreads();
-            }
-            if (producer) {
-                if (t == n_cons) {
-                    for (int i = 0; i < nst; i++) {
-                        const uint32_t st = (it + i) % kFfmRing, ph = ((it + i) / kFfmRing) & 1u;
-                        mbar_wait(&empty[st], ph ^ 1u);
-                        mbar_arrive_expect_tx(&full[st], rowbytes);
-                        bulk_load(reinterpret_cast<unsigned char*>(ring) + (size_t)st * stage_bytes, V + (size_t)st_f[i] * rowlen, rowbytes, &full[st]);
-                    }
-                }
-            } else {
+        const bool resident = e0 - b0 <= CR;
+        for (int64_t c0 = b0; c0 < e0; c0 += CR) {
+            const int nst = (int)min((int64_t)CR, e0 - c0);
+            if (!resident) load_chunk(c0, nst);
+            if (own) {
                 for (int i = 0; i < nst; i++) {
-                    const uint32_t st = (it + i) % kFfmRing, ph = ((it + i) / kFfmRing) & 1u;
-                    mbar_wait(&full[st], ph);
                     const int flu = st_fl[i];
+                    const int c_ib = my_cnt - (my_field == flu ? 1 : 0);
+                    if (c_ib <= 0) continue;
                     const float xu = st_x[i];
-                    const uint32_t f = st_f[i];
-                    if (own) {
-                        const int c_ib = my_cnt - (my_field == flu ? 1 : 0);
-                        if (c_ib > 0) {
-                            const float4 v = reinterpret_cast<const float4*>(reinterpret_cast<const unsigned char*>(ring) + (size_t)st * stage_bytes)[t];
-                            const float4 tt = S[my_field * A + flu * PPF + my_part];  // T[fld_i][my_field]
-                            const float sx = d * xu, lc = l2 * (float)c_ib;
-                            float4 g;
-                            float tx = tt.x, ty = tt.y, tz = tt.z, tw = tt.w;
-                            if (my_field == flu) { tx -= xu * v.x; ty -= xu * v.y; tz -= xu * v.z; tw -= xu * v.w; }
-                            g.x = sx * tx + lc * v.x; g.y = sx * ty + lc * v.y; g.z = sx * tz + lc * v.z; g.w = sx * tw + lc * v.w;
-                            red_add_v4(gV + (size_t)f * rowlen + (size_t)t * 4, g);
-                        }
-                    }
-                    if (t == 0) {
-                        red_add_f32(gW + f, d * xu + l2 * st_w[i]);  // train_ffm_algo.cpp:98
-                        if (touched) touched[f] = 1;
-                    }
-                    __syncwarp();
-                    if ((t & 31) == 0) mbar_arrive(&empty[st]);
+                    const float4 v = reinterpret_cast<const float4*>(rows + (size_t)i * stage_bytes)[t];
+                    const float4 tt = S[my_field * A + flu * PPF + my_part];  // T[fld_i][my_field]
+                    const float sx = d * xu, lc = l2 * (float)c_ib;
+                    float tx = tt.x, ty = tt.y, tz = tt.z, tw = tt.w;
+                    if (my_field == flu) { tx -= xu * v.x; ty -= xu * v.y; tz -= xu * v.z; tw -= xu * v.w; }
+                    const float4 g = make_float4(sx * tx + lc * v.x, sx * ty + lc * v.y, sx * tz + lc * v.z, sx * tw + lc * v.w);
+                    red_add_v4(gV + (size_t)st_f[i] * rowlen + (size_t)t * 4, g);
                 }
             }
-            it += (uint32_t)nst;
+            // wide gradients by the threads past the row slots (or thread 0 when there are none)
+            const int w0 = A < (int)blockDim.x ? A : 0, wn = A < (int)blockDim.x ? (int)blockDim.x - A : 1;
+            if (t >= w0 && t < w0 + wn) {
+                for (int i = t - w0; i < nst; i += wn) {
+                    const uint32_t f = st_f[i];
+                    red_add_f32(gW + f, d * st_x[i] + l2 * st_w[i]);  // train_ffm_algo.cpp:98
+                    if (touched) touched[f] = 1;
+                }
+            }
         }
     }
     if (do_stats) publish_stats(loss, correct, partial, done, out_slot, false);
@@ -574,17 +538,24 @@ static int ffm_launch(lctr_ctx* c, Slot& s, int64_t rb, int64_t re, bool train, 
     // LCTR_FFM_TMA=0 selects the register-staged kernel below
     static const bool use_tma = !(getenv("LCTR_FFM_TMA") && atoi(getenv("LCTR_FFM_TMA")) == 0);
     if (use_tma && train && vec == 4 && !bulk) {
-        const int n_cons = std::max(32, (A + 31) / 32 * 32);
+        // rows per chunk: as many as leave 3 (narrow rows) or 2 CTAs per SM, at least 40, at most 96
         const size_t stage_bytes = ((size_t)A * 16 + 127) / 128 * 128;
-        const size_t smem2 = (size_t)kFfmRing * stage_bytes + (size_t)Fc * A * 16 + (size_t)Fc * 4 + 80 * 4 + (size_t)kFfmStage * 14 + 16 +
-                             2 * kFfmRing * 8 + 128;
-        LCTR_CHECK(smem2 <= 227 * 1024, "FFM field-pair tile + row ring need %zu B shared memory (> 227 KB): Fc=%d k=%d", smem2, Fc, k);
+        const size_t fixed = (size_t)Fc * A * 16 + (size_t)Fc * 4 + 80 * 4 + 64 + 1024;
+        int CR = 0;
+        for (int ncta = 3; ncta >= 1 && CR < 40; ncta--) {
+            const size_t budget = (size_t)227 * 1024 / ncta;
+            CR = budget > fixed ? (int)((budget - fixed) / (stage_bytes + 14)) : 0;
+        }
+        CR = std::min(CR, 96);
+        LCTR_CHECK(CR >= 8, "FFM field-pair tile + row buffer do not fit 227 KB shared memory: Fc=%d k=%d", Fc, k);
+        const size_t smem2 = (size_t)CR * (stage_bytes + 14) + fixed;
+        const int tpb2 = std::max(64, (A + 31) / 32 * 32);
         auto go = [&](auto kern) {
             cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
-            kern<<<(unsigned)rows, n_cons + 32, smem2, c->stream>>>(s.row_ptr, c->cfg.world > 1 ? s.ent_pslot : s.fid, s.field, s.val, s.label,
-                                                                   c->cW, c->cV, Fc, k, s.pred, c->cgW, c->cgV,
-                                                                   c->cfg.world > 1 ? nullptr : c->touched, c->cfg.l2_reg, rb, c->stat_partial,
-                                                                   c->stat_done, out_slot, stats ? 1 : 0, n_cons);
+            kern<<<(unsigned)rows, tpb2, smem2, c->stream>>>(s.row_ptr, c->cfg.world > 1 ? s.ent_pslot : s.fid, s.field, s.val, s.label,
+                                                            c->cW, c->cV, Fc, k, s.pred, c->cgW, c->cgV,
+                                                            c->cfg.world > 1 ? nullptr : c->touched, c->cfg.l2_reg, rb, c->stat_partial,
+                                                            c->stat_done, out_slot, stats ? 1 : 0, CR);
         };
         if (s.has_val) go(ffm_tma_kernel<true>); else go(ffm_tma_kernel<false>);
         c->launches++;
