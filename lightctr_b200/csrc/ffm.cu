@@ -534,9 +534,12 @@ static int ffm_launch(lctr_ctx* c, Slot& s, int64_t rb, int64_t re, bool train, 
         LCTR_CUDA(cudaGetLastError());
         return 0;
     }
-    // default training kernel for k % 4 == 0: rows staged through shared memory by the TMA (cp.async.bulk + mbarrier ring);
-    // LCTR_FFM_TMA=0 selects the register-staged kernel below
-    static const bool use_tma = !(getenv("LCTR_FFM_TMA") && atoi(getenv("LCTR_FFM_TMA")) == 0);
+    // LCTR_FFM_TMA=1 selects the TMA-staged kernel (cp.async.bulk rows + mbarrier).  It is parity-green but NOT the
+    // default: ncu (profiles/ncu_r02_ffm_c3_summary.txt) shows both kernels are ISSUE-bound, not memory-bound (C3:
+    // 26 K / 16 K warp instructions per sample, DRAM at 2-3 % of peak); staging whole rows in shared memory cuts the
+    // instruction count by 37 % but leaves 2 CTAs = 4 warps per SM next to the field-pair tile, against 16 warps of the
+    // register-staged kernel: 664 vs 437 us on C3, 6.10 vs 5.74 ms on C5.
+    static const bool use_tma = getenv("LCTR_FFM_TMA") && atoi(getenv("LCTR_FFM_TMA")) == 1;
     if (use_tma && train && vec == 4 && !bulk) {
         // rows per chunk: as many as leave 3 (narrow rows) or 2 CTAs per SM, at least 40, at most 96
         const size_t stage_bytes = ((size_t)A * 16 + 127) / 128 * 128;

@@ -41,6 +41,12 @@ dist)
   timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus $N --steps 100 --warmup 10 \
       > $O/bench_${TAG}_fm_c2_n$N.json 2> $O/bench_${TAG}_fm_c2_n$N.err; echo "dist bench rc=$?"
   tail -c 1500 $O/bench_${TAG}_fm_c2_n$N.err ;;
+ncuffm)
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:"ffm_tma_kernel|ffm_fused_kernel" -s 8 -c 2 \
+      -o $O/prof_${TAG}_ffm_c3_tma -f python bench.py --workload ffm_c3 --steps 4 --warmup 3 --no-cpu-baseline > $O/ncu_ffm_tma_$TAG.log 2>&1
+  LCTR_FFM_TMA=0 timeout 900 ncu --set full --clock-control none --import-source on -k regex:"ffm_tma_kernel|ffm_fused_kernel" -s 8 -c 2 \
+      -o $O/prof_${TAG}_ffm_c3_old -f python bench.py --workload ffm_c3 --steps 4 --warmup 3 --no-cpu-baseline > $O/ncu_ffm_old_$TAG.log 2>&1
+  echo "ncu rc=$?" ;;
 lab)
   bash scripts/lab/run_lab.sh > /dev/null 2>&1; cp $O/lab_b4096.txt $O/lab_${TAG}_b4096.txt; cp $O/lab_b65536.txt $O/lab_${TAG}_b65536.txt ;;
 esac
