@@ -188,9 +188,12 @@ def ncu_traffic(wname, kernel):
     if not os.path.exists(p):
         return None, None
     d = json.load(open(p)).get(wname, {})
+    import re
+    pat = {"fm_fused": r"fm_fused_kernel<\d+, \d, 1,", "fm_forward": r"fm_fused_kernel<\d+, \d, 0,|fm_forward", "apply_compact": r"apply_compact",
+           "ffm_fused": r"ffm_fused_kernel|ffm_tma_kernel", "apply": r"apply_kernel", "fm_backward_red": r"fm_backward_kernel"}.get(kernel, re.escape(kernel))
     for name, rec in d.get("kernels", {}).items():
-        if kernel in name:
-            return rec.get("dram_bytes"), "profiles/ncu_traffic.json <- %s" % d.get("source", "?")
+        if re.search(pat, name):
+            return rec.get("dram_bytes"), "profiles/ncu_traffic.json <- %s (%s)" % (d.get("source", "?"), name.strip())
     return None, None
 
 
@@ -466,6 +469,8 @@ def main():
                        "algorithmic_bytes_per_launch": gather_bps * B, "peak_source": peak_src}
         tr, src = ncu_traffic(wname, "fm_forward") if not args.batch else (None, None)
         roof_gather["traffic"] = tr
+        if src:
+            roof_gather["traffic_source"] = src
     kernels = {name: {"ms": v[0] / max(v[1], 1), "launches": v[1]} for name, v in prof.items()}
     bw_desc = ("RED scatter + sparse apply" if not (wl["model"] == "fm" and world == 1) else
                "order-free fused step: one gather, RED scatter into the batch-compact buffer (hot-slot replicas), compact updater")

@@ -136,6 +136,19 @@ int lctr_download_sumvx(lctr_ctx* ctx, int slot, float* sumVX);
 int lctr_download_pred(lctr_ctx* ctx, int slot, float* pred);
 
 /* ---- MLP (Fully_Conn_Layer chain, fullyconnLayer.h) ------------------------------------------ */
+/* The chain as a stand-alone operator -- what a DL_Algo_Abst subclass calls per minibatch (dl_algo_abst.h:46-49:
+ * Predict / BP / applyBP) and what Layer_Base::forward / backward / applyBatchGradient do per sample
+ * (layer_abst.h:45-67, fullyconnLayer.h:80-206), batched over `rows` samples, fp32 reference-order arithmetic:
+ *   forward   x [rows][in0] (in0 = factor_cnt, or field_cnt * factor_cnt for Wide&Deep) -> out [rows] = the last layer's
+ *             linear output (:116); hidden activations stay on the device for the backward.  out may be NULL.
+ *   backward  dout [rows] = outputDelta of the last layer; clips to +-15 (:129-131), accumulates weightDelta / biasDelta
+ *             (:165-179) in the fused dense-gradient buffer, returns the first layer's inputDelta in dx [rows][in0]
+ *             (NULL to skip the copy).  Must follow a forward of the same row count.
+ *   apply     applyBatchGradient (:194-197): Adagrad on bias then weights with divisor `minibatch`, deltas zeroed.
+ *             With world > 1 the registered dense all-reduce runs first.  (Dropout masks: lctr_mlp_set_mask.) */
+int lctr_mlp_forward(lctr_ctx* ctx, int64_t rows, const float* x, float* out);
+int lctr_mlp_backward(lctr_ctx* ctx, int64_t rows, const float* dout, float* dx);
+int lctr_mlp_apply(lctr_ctx* ctx, uint64_t minibatch);
 /* layer l: weight [out][in] row-major (fullyconnLayer.h:211-216), bias[out], dropout mask[out] (1/0). */
 int lctr_mlp_upload(lctr_ctx* ctx, int layer, const float* weight, const float* bias);
 int lctr_mlp_download(lctr_ctx* ctx, int layer, float* weight, float* bias);

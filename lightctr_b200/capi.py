@@ -24,7 +24,7 @@ SYMBOLS = [
     "lctr_last_error", "lctr_abi_version", "lctr_create", "lctr_destroy", "lctr_sync", "lctr_upload_params",
     "lctr_download_params", "lctr_fill_params", "lctr_download_opt_state", "lctr_upload_opt_state", "lctr_upload_batch",
     "lctr_train_step", "lctr_train_batch", "lctr_train_batch_async", "lctr_wait", "lctr_predict", "lctr_download_sumvx", "lctr_download_pred",
-    "lctr_mlp_upload", "lctr_mlp_download", "lctr_mlp_set_mask", "lctr_mlp_download_grad", "lctr_set_dense_allreduce", "lctr_save_checkpoint", "lctr_load_checkpoint",
+    "lctr_mlp_forward", "lctr_mlp_backward", "lctr_mlp_apply", "lctr_mlp_upload", "lctr_mlp_download", "lctr_mlp_set_mask", "lctr_mlp_download_grad", "lctr_set_dense_allreduce", "lctr_save_checkpoint", "lctr_load_checkpoint",
     "lctr_save_dataset_bin", "lctr_load_dataset_bin", "lctr_eval", "lctr_upload_pred", "lctr_ipc_export", "lctr_ipc_import",
     "lctr_dense_grad_buffer", "lctr_device_bytes", "lctr_load_libffm", "lctr_free_dataset", "lctr_launch_count", "lctr_stream", "lctr_profile", "lctr_profile_read",
 ]
@@ -81,6 +81,9 @@ def load_library():
     L.lctr_mlp_upload.argtypes = [vp, C.c_int, f32p, f32p]
     L.lctr_mlp_download.argtypes = [vp, C.c_int, f32p, f32p]
     L.lctr_mlp_set_mask.argtypes = [vp, C.c_int, f32p]
+    L.lctr_mlp_forward.argtypes = [vp, i64, vp, vp]
+    L.lctr_mlp_backward.argtypes = [vp, i64, vp, vp]
+    L.lctr_mlp_apply.argtypes = [vp, C.c_uint64]
     L.lctr_mlp_download_grad.argtypes = [vp, C.c_int, f32p, f32p]
     L.lctr_set_dense_allreduce.argtypes = [vp, ALLREDUCE_FN, vp]
     L.lctr_eval.argtypes = [vp, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_int64), C.POINTER(C.c_float)]
@@ -354,6 +357,21 @@ class Context:
         w, b = np.empty(n_in * n_out, np.float32), np.empty(n_out, np.float32)
         _chk(self.L.lctr_mlp_download_grad(self.h, layer, w.ctypes.data, b.ctypes.data))
         return w, b
+
+    def mlp_forward(self, x):
+        x = np.ascontiguousarray(x, np.float32)
+        out = np.empty(x.shape[0], np.float32)
+        _chk(self.L.lctr_mlp_forward(self.h, x.shape[0], x.ctypes.data, out.ctypes.data))
+        return out
+
+    def mlp_backward(self, dout, in0):
+        dout = np.ascontiguousarray(dout, np.float32)
+        dx = np.empty((len(dout), in0), np.float32)
+        _chk(self.L.lctr_mlp_backward(self.h, len(dout), dout.ctypes.data, dx.ctypes.data))
+        return dx
+
+    def mlp_apply(self, minibatch):
+        _chk(self.L.lctr_mlp_apply(self.h, minibatch))
 
     def mlp_set_mask(self, layer, mask):
         m = np.ascontiguousarray(mask, np.float32)

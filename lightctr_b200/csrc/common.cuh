@@ -159,6 +159,7 @@ struct lctr_ctx {
     float *z = nullptr, *dz = nullptr;  // [B][k] NFM bi-interaction output and its gradient
     float* mlp_out = nullptr;           // [B]
     size_t mlp_cap_rows = 0;
+    int64_t mlp_fwd_rows = 0;      // rows of the last lctr_mlp_forward (lctr_mlp_backward must match)
     uint32_t* wnd_src = nullptr;   // Wide&Deep: fid of the first entry of each field, [rows][Fc]
     size_t wnd_cap_rows = 0;
     void* auc_scratch = nullptr;  // metrics.cu: histograms + lists of lctr_eval

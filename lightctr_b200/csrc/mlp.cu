@@ -203,55 +203,67 @@ int mlp_sync_dense_grad(lctr_ctx* c) {
     return 0;
 }
 
+static inline unsigned mlp_blocks(int64_t n) { return (unsigned)((n + 255) / 256); }
+
+// Fully_Conn_Layer::forward down the chain (fullyconnLayer.h:80-118) on B rows of c->z; layer l's output in layers[l].act
+static void mlp_forward_dev(lctr_ctx* c, int B) {
+    const int nl = c->n_layers;
+    const float* x = c->z;
+    for (int l = 0; l < nl; l++) {
+        MlpLayer& L = c->layers[l];
+        fc_forward_kernel<<<mlp_blocks((int64_t)B * L.out), 256, 0, c->stream>>>(x, L.w, L.b, L.mask, L.act, B, L.in, L.out,
+                                                                                 l + 1 < nl ? 1 : 0, c->cfg.activation);
+        c->launches++;
+        x = L.act;
+    }
+}
+// Fully_Conn_Layer::backward up the chain (fullyconnLayer.h:120-180) from layers[nl-1].delta: clip, inputDelta into
+// c->dz (first layer) / the previous layer's delta, weightDelta / biasDelta accumulated in the fused dense-gradient buffer
+static void mlp_backward_dev(lctr_ctx* c, int B) {
+    const int nl = c->n_layers;
+    for (int l = nl - 1; l >= 0; l--) {
+        MlpLayer& L = c->layers[l];
+        const bool has_next = l + 1 < nl;
+        const float* xin = l == 0 ? c->z : c->layers[l - 1].act;
+        clip_kernel<<<mlp_blocks((int64_t)B * L.out), 256, 0, c->stream>>>(L.delta, (int64_t)B * L.out);
+        float* dx = l == 0 ? c->dz : c->layers[l - 1].delta;
+        fc_input_delta_kernel<<<mlp_blocks((int64_t)B * L.in), 256, 0, c->stream>>>(
+            L.delta, L.w, L.mask, l > 0 ? c->layers[l - 1].act : nullptr, dx, B, L.in, L.out, has_next ? 1 : 0,
+            c->cfg.activation);
+        fc_weight_grad_kernel<<<mlp_blocks((int64_t)L.out * (L.in + 1)), 256, 0, c->stream>>>(xin, L.delta, L.dw, L.db, B,
+                                                                                              L.in, L.out);
+        c->launches += 3;
+    }
+}
+// Fully_Conn_Layer::applyBatchGradient (fullyconnLayer.h:194-197): Adagrad on bias then weights, per layer; deltas zeroed
+static void mlp_apply_dev(lctr_ctx* c, uint64_t mb) {
+    const float invB = (float)(1.0 / (double)mb);
+    for (int l = 0; l < c->n_layers; l++) {
+        MlpLayer& L = c->layers[l];
+        const size_t nw = (size_t)L.out * L.in;
+        adagrad_dense_kernel<<<mlp_blocks(L.out), 256, 0, c->stream>>>(L.b, L.db, L.acc_b, L.out, invB, c->cfg.learning_rate);
+        adagrad_dense_kernel<<<mlp_blocks((int64_t)nw), 256, 0, c->stream>>>(L.w, L.dw, L.acc_w, nw, invB, c->cfg.learning_rate);
+        c->launches += 2;
+    }
+}
+
 // forward MLP on c->z, loss, backward to c->dz, accumulate dW/db, Adagrad on the MLP (fp32, reference order).
 int launch_nfm_mlp(lctr_ctx* c, Slot& s, int64_t rb, int64_t re, int64_t rows_divisor) {
     const int B = (int)(re - rb);
     const int nl = c->n_layers;
     if (c->cfg.mlp_precision == LCTR_MLP_BF16) return launch_nfm_mlp_bf16(c, s, rb, re, rows_divisor);
     LCTR_CHECK(c->cfg.mlp_precision == LCTR_MLP_FP32, "mlp_precision=%d unknown", c->cfg.mlp_precision);
-    auto blocks = [](int64_t n) { return (unsigned)((n + 255) / 256); };
     ProfScope prof(c, PROF_MLP);
-    // ---- forward
-    const float* x = c->z;
-    for (int l = 0; l < nl; l++) {
-        MlpLayer& L = c->layers[l];
-        fc_forward_kernel<<<blocks((int64_t)B * L.out), 256, 0, c->stream>>>(x, L.w, L.b, L.mask, L.act, B, L.in, L.out,
-                                                                             l + 1 < nl ? 1 : 0, c->cfg.activation);
-        c->launches++;
-        x = L.act;
-    }
+    mlp_forward_dev(c, B);
     // ---- loss, delta of the output layer
     double* out_slot = c->stats + 2 * (c->step % kStatRing);
     MlpLayer& last = c->layers[nl - 1];
-    nfm_loss_kernel<<<blocks(B), 256, 0, c->stream>>>(s.wide, last.act, s.label, s.pred, last.delta, rb, B,
-                                                      c->stat_partial, c->stat_done, out_slot);
+    nfm_loss_kernel<<<mlp_blocks(B), 256, 0, c->stream>>>(s.wide, last.act, s.label, s.pred, last.delta, rb, B,
+                                                          c->stat_partial, c->stat_done, out_slot);
     c->launches++;
-    // ---- backward, output layer first (fullyconnLayer.h:120-180)
-    for (int l = nl - 1; l >= 0; l--) {
-        MlpLayer& L = c->layers[l];
-        const bool has_next = l + 1 < nl;
-        const float* xin = l == 0 ? c->z : c->layers[l - 1].act;
-        clip_kernel<<<blocks((int64_t)B * L.out), 256, 0, c->stream>>>(L.delta, (int64_t)B * L.out);
-        float* dx = l == 0 ? c->dz : c->layers[l - 1].delta;
-        fc_input_delta_kernel<<<blocks((int64_t)B * L.in), 256, 0, c->stream>>>(
-            L.delta, L.w, L.mask, l > 0 ? c->layers[l - 1].act : nullptr, dx, B, L.in, L.out, has_next ? 1 : 0,
-            c->cfg.activation);
-        fc_weight_grad_kernel<<<blocks((int64_t)L.out * (L.in + 1)), 256, 0, c->stream>>>(xin, L.delta, L.dw, L.db, B,
-                                                                                          L.in, L.out);
-        c->launches += 3;
-    }
+    mlp_backward_dev(c, B);
     if (mlp_sync_dense_grad(c)) return 1;
-    // ---- Adagrad on bias then weights, per layer (fullyconnLayer.h:194-197)
-    const uint64_t mb = c->cfg.minibatch_size ? c->cfg.minibatch_size : (uint64_t)rows_divisor;
-    const float invB = (float)(1.0 / (double)mb);
-    for (int l = 0; l < nl; l++) {
-        MlpLayer& L = c->layers[l];
-        const size_t nw = (size_t)L.out * L.in;
-        adagrad_dense_kernel<<<blocks(L.out), 256, 0, c->stream>>>(L.b, L.db, L.acc_b, L.out, invB, c->cfg.learning_rate);
-        adagrad_dense_kernel<<<blocks((int64_t)nw), 256, 0, c->stream>>>(L.w, L.dw, L.acc_w, nw, invB,
-                                                                        c->cfg.learning_rate);
-        c->launches += 2;
-    }
+    if (!c->mlp_skip_update) mlp_apply_dev(c, c->cfg.minibatch_size ? c->cfg.minibatch_size : (uint64_t)rows_divisor);
     LCTR_CUDA(cudaGetLastError());
     return 0;
 }
@@ -260,6 +272,46 @@ int launch_nfm_mlp(lctr_ctx* c, Slot& s, int64_t rb, int64_t re, int64_t rows_di
 
 using namespace lctr;
 extern "C" {
+// ---- the Fully_Conn_Layer chain as a stand-alone operator (fp32 reference-order mode) ---------------------------------
+int lctr_mlp_forward(lctr_ctx* c, int64_t rows, const float* x, float* out) {
+    LCTR_CHECK(c && x && rows > 0, "lctr_mlp_forward: null / empty input");
+    LCTR_CHECK(c->n_layers > 0, "lctr_mlp_forward: the context has no dense layers (model NFM / WND with hidden[])");
+    LCTR_CHECK(c->cfg.mlp_precision == LCTR_MLP_FP32, "lctr_mlp_forward/backward/apply run the fp32 reference-order layers");
+    if (mlp_reserve(c, rows)) return 1;
+    const size_t in0 = mlp_in0(c->cfg);
+    LCTR_CUDA(cudaMemcpyAsync(c->z, x, (size_t)rows * in0 * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    mlp_forward_dev(c, (int)rows);
+    LCTR_CUDA(cudaGetLastError());
+    c->mlp_fwd_rows = rows;
+    if (out) {
+        MlpLayer& last = c->layers[c->n_layers - 1];
+        LCTR_CUDA(cudaMemcpyAsync(out, last.act, (size_t)rows * last.out * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+        LCTR_CUDA(cudaStreamSynchronize(c->stream));
+    }
+    return 0;
+}
+int lctr_mlp_backward(lctr_ctx* c, int64_t rows, const float* dout, float* dx) {
+    LCTR_CHECK(c && dout, "lctr_mlp_backward: null input");
+    LCTR_CHECK(c->n_layers > 0 && rows > 0 && rows == c->mlp_fwd_rows, "lctr_mlp_backward: %lld rows, but the last lctr_mlp_forward "
+               "ran %lld", (long long)rows, (long long)c->mlp_fwd_rows);
+    MlpLayer& last = c->layers[c->n_layers - 1];
+    LCTR_CUDA(cudaMemcpyAsync(last.delta, dout, (size_t)rows * last.out * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    mlp_backward_dev(c, (int)rows);
+    LCTR_CUDA(cudaGetLastError());
+    if (dx) {
+        LCTR_CUDA(cudaMemcpyAsync(dx, c->dz, (size_t)rows * mlp_in0(c->cfg) * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+        LCTR_CUDA(cudaStreamSynchronize(c->stream));
+    }
+    return 0;
+}
+int lctr_mlp_apply(lctr_ctx* c, uint64_t minibatch) {
+    LCTR_CHECK(c && c->n_layers > 0, "lctr_mlp_apply: the context has no dense layers");
+    LCTR_CHECK(minibatch > 0, "lctr_mlp_apply: minibatch divisor must be > 0");
+    if (mlp_sync_dense_grad(c)) return 1;
+    mlp_apply_dev(c, minibatch);
+    LCTR_CUDA(cudaGetLastError());
+    return 0;
+}
 int lctr_mlp_upload(lctr_ctx* c, int layer, const float* weight, const float* bias) {
     LCTR_CHECK(c && layer >= 0 && layer < c->n_layers, "mlp layer %d out of range", layer);
     MlpLayer& L = c->layers[layer];

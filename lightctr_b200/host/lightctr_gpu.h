@@ -7,6 +7,9 @@
 //     Train_FFM_Algo      LightCTR/train/train_ffm_algo.h:22-66
 //     Train_NFM_Algo      LightCTR/train/train_nfm_algo.h:18-77
 //     FM_Predict          LightCTR/predict/fm_predict.h:17-39
+//     Layer_Base / Fully_Conn_Layer / DL_Algo_Abst   LightCTR/train/layer/layer_abst.h:25-83, fullyconnLayer.h:15-238,
+//                         dl_algo_abst.h:25-246 (minibatch-batched: see the comment above Layer_Base below)
+//     Distributed_Algo_Abst   LightCTR/distributed_algo_abst.h:86-292 (one process per GPU instead of ZeroMQ workers)
 //     GradientUpdater / MomentumUpdater statics   LightCTR/util/gradientUpdater.h:36-42, main.cpp:64-73
 // but every Train()/Predict() lowers to the C ABI of include/lightctr_b200.h (CUDA, sm_100a).  A caller
 // such as the reference's main.cpp:144-162,228-253 compiles unchanged against this header inside
@@ -21,6 +24,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <fstream>
 #include <iomanip>
 #include <iostream>
@@ -419,6 +423,246 @@ private:
     std::vector<uint16_t> field;
     std::vector<float> val;
     std::vector<int32_t> test_label;
+};
+
+// ==========================================================================================================
+// dl_algo_abst.h / train/layer/layer_abst.h / fullyconnLayer.h: the dense-layer surface
+// ==========================================================================================================
+// The reference drives these classes one SAMPLE at a time from a thread pool (dl_algo_abst.h:70-105): Predict(rid) ->
+// Layer_Base::forward down the chain, BP(rid) -> backward up the chain, applyBP once per minibatch.  On the GPU the unit
+// of work is the minibatch, so the same methods take the minibatch's rows at once (row-major [rows][dimension] floats)
+// and lower to lctr_mlp_forward / lctr_mlp_backward / lctr_mlp_apply; names, call order, chaining through
+// prevLayer / nextLayer, initialisation order of the rand() stream (fullyconnLayer.h:48-54) and the re-drawn dropout
+// masks of applyBatchGradient (:200-202) are the reference's.
+struct Sigmoid { static const int code = LCTR_ACT_SIGMOID; };
+struct Tanh { static const int code = LCTR_ACT_TANH; };
+
+class Layer_Base {  // layer_abst.h:25-83
+public:
+    Layer_Base(Layer_Base* _prevLayer, size_t _input_dimension, size_t _output_dimension)
+        : input_dimension(_input_dimension), output_dimension(_output_dimension) {
+        nextLayer = prevLayer = NULL;
+        if (_prevLayer != NULL) {
+            if (_prevLayer->output_dimension != this->input_dimension) { std::cout << "layer dimension mismatch" << std::endl; exit(1); }
+            this->prevLayer = _prevLayer;
+            _prevLayer->nextLayer = this;
+            bInputLayer = false;
+            printf("Init %zux%zu ", _input_dimension, _output_dimension);
+        } else {
+            bInputLayer = true;
+            printf("Init Input %zux%zu ", _input_dimension, _output_dimension);
+        }
+    }
+    virtual ~Layer_Base() {}
+    // rows x input_dimension in, the chain's last output (rows x its output_dimension) back -- call on the input layer
+    virtual std::vector<float>& forward(const std::vector<float>& prevLOutput, size_t rows) = 0;
+    // rows x output_dimension deltas of the LAST layer in -- call on the output layer; walks back to the input layer
+    virtual void backward(const std::vector<float>& outputDelta, size_t rows) = 0;
+    virtual void applyBatchGradient() { if (nextLayer) nextLayer->applyBatchGradient(); }
+    Layer_Base *nextLayer, *prevLayer;
+    size_t input_dimension, output_dimension;
+    bool bInputLayer;
+};
+
+template <typename ActivationFunction>
+class Fully_Conn_Layer : public Layer_Base {  // fullyconnLayer.h:15-238
+public:
+    Fully_Conn_Layer(Layer_Base* _prevLayer, size_t _input_dimension, size_t _output_dimension)
+        : Layer_Base(_prevLayer, _input_dimension, _output_dimension), needInputDelta(false), ctx(NULL), index(0) {
+        weight = new float[input_dimension * output_dimension];
+        bias = new float[output_dimension];
+        dropout_mask = new float[output_dimension];
+        for (size_t i = 0; i < output_dimension; i++) {  // init(), :48-54: bias, mask, then the row of weights
+            bias[i] = 0.0;
+            dropout_mask[i] = SampleBinary(GradientUpdater::__global_sparse_rate) ? 1. : 0.;
+            for (size_t j = 0; j < input_dimension; j++) *getWeight(i, j) = UniformNumRand() - 0.5f;
+        }
+        if (_prevLayer) index = static_cast<Fully_Conn_Layer*>(_prevLayer)->index + 1;
+        printf("Fully Connected Layer\n");
+    }
+    ~Fully_Conn_Layer() {
+        delete[] weight; delete[] bias; delete[] dropout_mask;
+        if (bInputLayer && ctx) lctr_destroy(ctx);
+    }
+    std::vector<float>& forward(const std::vector<float>& x, size_t rows) {
+        if (!bInputLayer) { std::cout << "forward(): call on the input layer of the chain" << std::endl; exit(1); }
+        ensure_ctx();
+        Fully_Conn_Layer* last = this;
+        while (last->nextLayer) last = static_cast<Fully_Conn_Layer*>(last->nextLayer);
+        out_buf.resize(rows * last->output_dimension);
+        LCTR_OK(lctr_mlp_forward(ctx, (int64_t)rows, x.data(), out_buf.data()));
+        return out_buf;  // output layer returns wx + b without activator (:116)
+    }
+    void backward(const std::vector<float>& outputDelta, size_t rows) {
+        Fully_Conn_Layer* first = this;
+        while (first->prevLayer) first = static_cast<Fully_Conn_Layer*>(first->prevLayer);
+        if (nextLayer || !first->ctx) { std::cout << "backward(): call on the output layer after forward()" << std::endl; exit(1); }
+        first->input_delta.resize(rows * first->input_dimension);
+        LCTR_OK(lctr_mlp_backward(first->ctx, (int64_t)rows, outputDelta.data(), first->needInputDelta ? first->input_delta.data() : NULL));
+    }
+    const std::vector<float>& inputDelta() const { return input_delta; }  // :189-192 (needInputDelta)
+    void applyBatchGradient() {  // :194-206, on the input layer: updater, then every layer re-draws its mask in order
+        if (bInputLayer) {
+            ensure_ctx();
+            LCTR_OK(lctr_mlp_apply(ctx, GradientUpdater::__global_minibatch_size));
+        }
+        for (size_t i = 0; i < output_dimension; i++) dropout_mask[i] = SampleBinary(GradientUpdater::__global_sparse_rate) ? 1. : 0.;
+        Fully_Conn_Layer* first = this;
+        while (first->prevLayer) first = static_cast<Fully_Conn_Layer*>(first->prevLayer);
+        LCTR_OK(lctr_mlp_set_mask(first->ctx, (int)index, dropout_mask));
+        if (nextLayer) nextLayer->applyBatchGradient();
+    }
+    // host copies of the parameters (pulled from the device on demand)
+    void syncFromDevice() {
+        Fully_Conn_Layer* first = this;
+        while (first->prevLayer) first = static_cast<Fully_Conn_Layer*>(first->prevLayer);
+        if (first->ctx) LCTR_OK(lctr_mlp_download(first->ctx, (int)index, weight, bias));
+    }
+    inline float* getWeight(size_t out_idx, size_t in_idx) const { return &weight[out_idx * input_dimension + in_idx]; }  // :211-216
+    bool needInputDelta;
+    float *weight, *bias, *dropout_mask;
+
+private:
+    void ensure_ctx() {  // the chain is complete once forward() is called: one device context for all its layers
+        if (ctx) return;
+        std::vector<Fully_Conn_Layer*> chain;
+        for (Layer_Base* l = this; l; l = l->nextLayer) chain.push_back(static_cast<Fully_Conn_Layer*>(l));
+        if (chain.size() < 2 || chain.size() > LCTR_MAX_LAYERS + 1 || chain.back()->output_dimension != 1) {
+            std::cout << "Fully_Conn_Layer chain: 2.." << LCTR_MAX_LAYERS + 1 << " layers ending in one output" << std::endl;
+            exit(1);
+        }
+        lctr_cfg cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.abi_version = LCTR_ABI_VERSION;
+        cfg.model = LCTR_MODEL_NFM;       // dense chain on a factor_cnt-wide input; the embedding side stays unused
+        cfg.feature_cnt = 1;
+        cfg.factor_cnt = (uint32_t)input_dimension;
+        cfg.learning_rate = GradientUpdater::__global_learning_rate;
+        cfg.minibatch_size = GradientUpdater::__global_minibatch_size;
+        cfg.n_hidden = (int32_t)chain.size() - 1;
+        for (size_t l = 0; l + 1 < chain.size(); l++) cfg.hidden[l] = (uint32_t)chain[l]->output_dimension;
+        cfg.activation = ActivationFunction::code;
+        cfg.mlp_precision = LCTR_MLP_FP32;
+        LCTR_OK(lctr_create(&cfg, &ctx));
+        for (size_t l = 0; l < chain.size(); l++) {
+            LCTR_OK(lctr_mlp_upload(ctx, (int)l, chain[l]->weight, chain[l]->bias));
+            LCTR_OK(lctr_mlp_set_mask(ctx, (int)l, chain[l]->dropout_mask));
+        }
+    }
+    lctr_ctx* ctx;  // owned by the input layer
+    size_t index;   // position in the chain
+    std::vector<float> out_buf, input_delta;
+};
+
+struct Logistic {};  // util/loss.h: gradient = pred - label on the sigmoid output
+enum DL_Algo { DNN, CNN, RNN };
+
+// dl_algo_abst.h:25-246.  Same constructor, members and Train() / validate() flow; Predict / BP take the minibatch's row
+// ids at once.  `shuffle` (default true = the reference's random_shuffle per epoch, :62) can be switched off for parity runs.
+template <typename LossFunction, typename ActivationFunction, typename OutputActivationFunction>
+class DL_Algo_Abst {
+public:
+    DL_Algo_Abst(std::string dataPath, size_t _epoch, size_t _feature_cnt, size_t hidden_size, size_t _multiclass_output_cnt = 1)
+        : shuffle(true), feature_cnt(_feature_cnt), multiclass_output_cnt(_multiclass_output_cnt), epoch(_epoch) {
+        (void)hidden_size;
+        if (_multiclass_output_cnt != 1) { std::cout << "the GPU dense path covers the single-output (CTR) case" << std::endl; exit(1); }
+        this->dl_algo = DNN;
+        loadDataRow(dataPath);
+    }
+    virtual ~DL_Algo_Abst() { for (size_t i = 0; i < network.size(); i++) delete network[i]; }
+    virtual void initNetwork(size_t hidden_size) = 0;
+    virtual const std::vector<float>& Predict(const std::vector<size_t>& rids, std::vector<std::vector<float> >& dataSet) = 0;
+    virtual void BP(const std::vector<size_t>& rids, const std::vector<float>& grad) = 0;
+    virtual void applyBP(size_t epoch) const = 0;
+    void appendNNLayer(Layer_Base* layer) { network.push_back(layer); }
+
+    void Train() {  // :53-134
+        size_t batch_epoch = 0;
+        const size_t mb = GradientUpdater::__global_minibatch_size;
+        for (size_t p = 0; p < epoch; p++) {
+            GradientUpdater::__global_bTraining = true;
+            std::vector<size_t> inner_order(dataRow_cnt);
+            for (size_t i = 0; i < dataRow_cnt; i++) inner_order[i] = i;
+            if (shuffle) std::random_shuffle(inner_order.begin(), inner_order.end());
+            for (size_t b = 0; b < dataRow_cnt; b += mb) {
+                std::vector<size_t> rids(inner_order.begin() + b, inner_order.begin() + std::min(b + mb, dataRow_cnt));
+                std::vector<float> pred = Predict(rids, dataSet);
+                std::vector<float> grad(pred.size());
+                for (size_t i = 0; i < pred.size(); i++) {
+                    pred[i] = sigmoid_forward(pred[i]);            // outputActivFun.forward (:79)
+                    grad[i] = pred[i] - (float)label[rids[i]];     // lossFun.gradient, Logistic (:91)
+                }
+                BP(rids, grad);
+                applyBP(batch_epoch);
+                validate(batch_epoch++);
+            }
+        }
+    }
+    void validate(size_t batch_epoch) {  // :136-176
+        if (batch_epoch % 50 != 0) return;
+        GradientUpdater::__global_bTraining = false;
+        std::vector<size_t> all(dataRow_cnt);
+        for (size_t i = 0; i < dataRow_cnt; i++) all[i] = i;
+        std::vector<float> pred = Predict(all, dataSet);
+        float loss = 0.0f;
+        int correct = 0;
+        for (size_t i = 0; i < dataRow_cnt; i++) {
+            const float p = sigmoid_forward(pred[i]);
+            // argmax over one output is index 0 (:150-154): "correct" counts label == 0 exactly like the reference
+            if (label[i] == 0) correct++;
+            loss += (label[i] == 1) ? -log(p) : -log(1.0f - p);
+        }
+        printf("Epoch %zu Loss = %f correct = %.3f\n", batch_epoch, loss, 1.0f * correct / dataRow_cnt);
+        last_loss = loss;
+        GradientUpdater::__global_bTraining = true;
+    }
+    virtual void loadDataRow(std::string dataPath) {  // :178-226, MNIST rows "label p0 p1 ..." (binary: label < 5 -> 0)
+        dataSet.clear();
+        std::ifstream fin_;
+        std::string line;
+        int nchar, y, val;
+        size_t fid = 0;
+        fin_.open(dataPath, std::ios::in);
+        if (!fin_.is_open()) { std::cout << "open file error!" << std::endl; exit(1); }
+        while (!fin_.eof()) {
+            std::vector<float> tmp(feature_cnt, 0.f);
+            getline(fin_, line);
+            const char* pline = line.c_str();
+            if (sscanf(pline, "%d%n", &y, &nchar) >= 1) {
+                pline += nchar + 1;
+                y = y < 5 ? 0 : 1;
+                label.push_back(y);
+                fid = 0;
+                while (pline < line.c_str() + (int)line.length() && sscanf(pline, "%d%n", &val, &nchar) >= 1) {
+                    pline += nchar + 1;
+                    if (*pline == ',') pline += 1;
+                    if (val != 0 && fid < feature_cnt) tmp[fid] = val / 255.0;
+                    fid++;
+                    if (fid > feature_cnt) break;
+                }
+                dataSet.push_back(tmp);
+                if (dataSet.size() > 500) break;
+            }
+        }
+        this->dataRow_cnt = this->dataSet.size();
+        if (dataRow_cnt == 0 || label.size() != dataRow_cnt) { std::cout << "empty dataset" << std::endl; exit(1); }
+    }
+    bool shuffle;
+    float last_loss;
+
+protected:
+    static float sigmoid_forward(float x) {  // util/activations.h:65-72
+        if (x < -16.f) return 1e-7f;
+        if (x > 16.f) return (float)(1.0 - 1e-7);
+        return 1.0f / (1.0f + expf(-x));
+    }
+    DL_Algo dl_algo;
+    std::vector<Layer_Base*> network;
+    Layer_Base *inputLayer, *outputLayer;
+    size_t feature_cnt, multiclass_output_cnt, dataRow_cnt;
+    size_t epoch;
+    std::vector<std::vector<float> > dataSet;
+    std::vector<int> label;
 };
 
 }  // namespace lightctr_b200

@@ -33,7 +33,7 @@ others)
 ncu)
   timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 120 -c 200 --csv --log-file $O/launches_${TAG}_fm_c2.csv \
       python bench.py --steps 30 --warmup 5 --no-cpu-baseline --no-c5 > $O/ncu_launch_$TAG.log 2>&1
-  timeout 900 ncu --set full --clock-control none --import-source on -k regex:"fm_fused_kernel|apply_compact" -s 30 -c 6 \
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:"fm_fused_kernel|apply_compact" -s 6 -c 40 \
       -o $O/prof_${TAG}_fm_c2 -f python bench.py --steps 6 --warmup 3 --no-cpu-baseline --no-c5 > $O/ncu_full_$TAG.log 2>&1
   echo "ncu rc=$?" ;;
 dist)
