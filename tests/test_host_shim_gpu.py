@@ -82,22 +82,15 @@ def test_cxx_nfm_driver(exe, files, oracle_api):
         assert abs(g - w) <= 1e-5 * abs(w), (got, want)
 
 
-def test_cxx_nfm_layer_chain_fp32_and_bf16(exe, files):
+def test_cxx_nfm_layer_chain_fp32_and_bf16(exe, files, oracle_api):
     """Config C4 through the C++ surface: Train_NFM_Algo(path, epoch, k, {64, 32}) (the Fully_Conn_Layer chain) in the
-    fp32 parity mode must print the same losses as the Python mirror of the same class (same rand() stream, same C ABI
-    calls), and the bf16 tensor-core mode must track it (dropout masks are identical in both modes)."""
-    from lightctr_b200 import trainers as T
+    fp32 parity mode against the ORACLE's chain (same rand() stream: V, then the layers input to output), and the bf16
+    tensor-core mode must track it (dropout masks are identical in both modes)."""
     a = subprocess.check_output([exe, "nfmc", files["train"], files["test"], "2", "16", "64,32", "1"], text=True)
     b = subprocess.check_output([exe, "nfmc_bf16", files["train"], files["test"], "2", "16", "64,32", "1"], text=True)
     la, lb = _losses(a, "loss"), _losses(b, "loss")
-    T.srand(1)
-    T.GradientUpdater.minibatch_size = 50
-    T.GradientUpdater.learning_rate = 0.05
-    nfm = T.Train_NFM_Algo(files["train"], 1, 16, [64, 32])
-    want = []
-    for _ in range(2):
-        nfm.Train()
-        want.append(nfm.loss_curve[-1])
+    o = oracle_api.NFMOracle(files["tr"], 16, [64, 32], seed=1)
+    want = [o.epoch()[0] for _ in range(2)]
     assert len(la) == 2 and len(lb) == 2
     for g, w in zip(la, want):
         assert abs(g - w) <= 1e-5 * abs(w), (la, want)
