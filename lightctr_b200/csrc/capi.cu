@@ -414,7 +414,7 @@ static int upload_batch_on(lctr_ctx* c, cudaStream_t st, int slot, int64_t rows,
         }
     }
     s.fused_valid = false;
-    if ((fused_supported(c) || c->cfg.world > 1) && rows > 0 && nnz > 0) {
+    if ((fused_supported(c) || c->cfg.world > 1) && rows > 0 && nnz > 0) {  // fused_supported: FM and NFM, one GPU
         // slot map of the batch: the gradient rows of the order-free fused step; on several GPUs also the key set of the
         // pull / push exchange, whose per-owner lists go out right away (posted stores, overlapping the previous step)
         if (fused_reserve(c, s, nnz) || fused_build_slot(c, s, st, nullptr, rows, nnz)) return 1;
@@ -511,6 +511,15 @@ int lctr_train_step(lctr_ctx* c, int slot, int64_t rb, int64_t re, float* loss_s
                  launch_nfm_mlp(c, s, rb, re, re - rb) || launch_wnd_backward(c, s, rb, re) || launch_apply(c, re - rb);
             break;
         case LCTR_MODEL_NFM:
+            if (fused_kernels_ok(c) && s.fused_valid) {
+                // order-free embedding side (fm_fused.cu) around the dense layers; on several GPUs the rows come from the
+                // batch-compact cache and the gradient rows go to their owners (dist.cu)
+                const bool multi = c->cfg.world > 1;
+                rc = (multi && dist_pre_step(c, s, slot, true)) || mlp_reserve(c, re - rb) || launch_nfm_forward_fused(c, s, rb, re) ||
+                     launch_nfm_mlp(c, s, rb, re, re - rb) || launch_nfm_backward_fused(c, s, rb, re) ||
+                     (multi ? dist_post_step(c, s, slot, re - rb) : launch_apply_compact(c, s, re - rb, nullptr, nullptr));
+                break;
+            }
             if (c->cfg.world > 1) {
                 // embeddings: owner-sharded pull / push like FM; dense layers: replicated, gradients all-reduced
                 rc = dist_pre_step(c, s, slot, false) || mlp_reserve(c, re - rb) || launch_fm_forward(c, s, rb, re, true, false) ||

@@ -346,6 +346,8 @@ int fused_build_slot(lctr_ctx* c, Slot& s, cudaStream_t st, const int64_t* hdr, 
 void dist_wait_info(lctr_ctx* c, const unsigned long long** flags, int* n, unsigned long long* epoch);
 int launch_fm_fused(lctr_ctx* c, Slot& s, int64_t rb, int64_t re, bool stats, const int64_t* hdr, double* out_slot_override);
 int launch_fm_forward_tree(lctr_ctx* c, Slot& s, int64_t rb, int64_t re, bool stats);
+int launch_nfm_forward_fused(lctr_ctx* c, Slot& s, int64_t rb, int64_t re);
+int launch_nfm_backward_fused(lctr_ctx* c, Slot& s, int64_t rb, int64_t re);
 int launch_apply_compact(lctr_ctx* c, Slot& s, int64_t rows_in_step, const OptParams* P_host, const OptParams* dP);
 void fused_opt_params(lctr_ctx* c, int64_t rows, void* out);
 void* fused_dev_opt(lctr_ctx* c);

@@ -10,11 +10,12 @@
 
 namespace lctr {
 
-// the fused kernels exist for FM with K in {4, 8, 16, 32}, order-free mode; on one GPU they read the tables directly,
+// the fused kernels exist for FM and NFM (embedding side) with K in {4, 8, 16, 32}, order-free mode; on one GPU they read the tables directly,
 // on several (dist.cu) the batch-compact cache of the pulled rows
 bool fused_kernels_ok(const lctr_ctx* c) {
     const int k = (int)c->cfg.factor_cnt;
-    return c->cfg.model == LCTR_MODEL_FM && c->cfg.deterministic == 0 && (k == 4 || k == 8 || k == 16 || k == 32);
+    return (c->cfg.model == LCTR_MODEL_FM || c->cfg.model == LCTR_MODEL_NFM) && c->cfg.deterministic == 0 &&
+           (k == 4 || k == 8 || k == 16 || k == 32);
 }
 bool fused_supported(const lctr_ctx* c) { return c->cfg.world == 1 && fused_kernels_ok(c); }
 
@@ -119,8 +120,9 @@ int fused_build_slot(lctr_ctx* c, Slot& s, cudaStream_t st, const int64_t* hdr, 
     return 0;
 }
 
+// mode 1: FM forward + backward;  2: NFM forward (z, wide part);  3: NFM backward from dz
 template <int K>
-static void fused_go(lctr_ctx* c, Slot& s, int64_t rb, int64_t re, int stats, double* out_slot, const int64_t* hdr) {
+static void fused_go(lctr_ctx* c, Slot& s, int64_t rb, int64_t re, int stats, double* out_slot, const int64_t* hdr, int mode) {
     FusedState* f = c->fused;
     const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>((re - rb + 3) / 4, (int64_t)c->sm_count * 4));
     // one GPU: parameters straight from the tables (index = fid); several: from the batch-compact cache the owners filled
@@ -129,30 +131,49 @@ static void fused_go(lctr_ctx* c, Slot& s, int64_t rb, int64_t re, int stats, do
     const unsigned long long* wf = nullptr;
     int nw = 0;
     unsigned long long ep = 0;
-    if (multi) dist_wait_info(c, &wf, &nw, &ep);
+    if (multi && mode != 3) dist_wait_info(c, &wf, &nw, &ep);
 #define FUSED_ARGS s.row_ptr, multi ? s.ent_pslot : s.fid, s.ent_slot, s.val, s.label, c->cW, c->cV, s.pred, s.sumvx, nullptr, f->G, \
                    f->Ghot, f->GS, c->cfg.l2_reg, rb, re, hdr, c->stat_partial, c->stat_done, out_slot, stats, wf, nw, ep
-    if (s.has_val) fm_fused_kernel<K, true, 1, false><<<grid, 128, 0, c->stream>>>(FUSED_ARGS);
-    else fm_fused_kernel<K, false, 1, false><<<grid, 128, 0, c->stream>>>(FUSED_ARGS);
+#define FUSED_LAUNCH(HV)                                                                                                         \
+    do {                                                                                                                         \
+        if (mode == 1) fm_fused_kernel<K, HV, 1, false><<<grid, 128, 0, c->stream>>>(FUSED_ARGS);                                \
+        else if (mode == 2) fm_fused_kernel<K, HV, 2, false><<<grid, 128, 0, c->stream>>>(FUSED_ARGS, c->z, s.wide);             \
+        else fm_fused_kernel<K, HV, 3, false><<<grid, 128, 0, c->stream>>>(FUSED_ARGS, c->dz, nullptr);                          \
+    } while (0)
+    if (s.has_val) FUSED_LAUNCH(true); else FUSED_LAUNCH(false);
+#undef FUSED_LAUNCH
 #undef FUSED_ARGS
+}
+
+static int launch_fused_mode(lctr_ctx* c, Slot& s, int64_t rb, int64_t re, bool stats, const int64_t* hdr, double* out_slot_override,
+                             int mode, int prof_id) {
+    if (re - rb <= 0) return 0;
+    LCTR_CHECK(s.fused_valid, "fused FM step on a slot without its slot map (uploaded before the context supported it?)");
+    double* out_slot = out_slot_override ? out_slot_override : c->stats + 2 * (c->step % kStatRing);
+    ProfScope prof(c, prof_id);
+    switch ((int)c->cfg.factor_cnt) {
+        case 4: fused_go<4>(c, s, rb, re, stats ? 1 : 0, out_slot, hdr, mode); break;
+        case 8: fused_go<8>(c, s, rb, re, stats ? 1 : 0, out_slot, hdr, mode); break;
+        case 16: fused_go<16>(c, s, rb, re, stats ? 1 : 0, out_slot, hdr, mode); break;
+        default: fused_go<32>(c, s, rb, re, stats ? 1 : 0, out_slot, hdr, mode); break;
+    }
+    c->launches++;
+    LCTR_CUDA(cudaGetLastError());
+    return 0;
 }
 
 // forward + RED backward of rows [rb, re) of the slot.  hdr != nullptr: `re` only sizes the grid, the row count comes
 // from hdr[0].
 int launch_fm_fused(lctr_ctx* c, Slot& s, int64_t rb, int64_t re, bool stats, const int64_t* hdr, double* out_slot_override) {
-    if (re - rb <= 0) return 0;
-    LCTR_CHECK(s.fused_valid, "fused FM step on a slot without its slot map (uploaded before the context supported it?)");
-    double* out_slot = out_slot_override ? out_slot_override : c->stats + 2 * (c->step % kStatRing);
-    ProfScope prof(c, PROF_FM_FUSED);
-    switch ((int)c->cfg.factor_cnt) {
-        case 4: fused_go<4>(c, s, rb, re, stats ? 1 : 0, out_slot, hdr); break;
-        case 8: fused_go<8>(c, s, rb, re, stats ? 1 : 0, out_slot, hdr); break;
-        case 16: fused_go<16>(c, s, rb, re, stats ? 1 : 0, out_slot, hdr); break;
-        default: fused_go<32>(c, s, rb, re, stats ? 1 : 0, out_slot, hdr); break;
-    }
-    c->launches++;
-    LCTR_CUDA(cudaGetLastError());
-    return 0;
+    return launch_fused_mode(c, s, rb, re, stats, hdr, out_slot_override, 1, PROF_FM_FUSED);
+}
+// NFM embedding side around the dense layers: forward fills c->z (bi-interaction) and the slot's wide part; backward reads
+// c->dz (the first dense layer's input delta) and the predictions the loss kernel left in the slot
+int launch_nfm_forward_fused(lctr_ctx* c, Slot& s, int64_t rb, int64_t re) {
+    return launch_fused_mode(c, s, rb, re, false, nullptr, nullptr, 2, PROF_FM_FWD);
+}
+int launch_nfm_backward_fused(lctr_ctx* c, Slot& s, int64_t rb, int64_t re) {
+    return launch_fused_mode(c, s, rb, re, false, nullptr, nullptr, 3, PROF_FM_FUSED);
 }
 
 // order-free forward alone (predictions, sumVX, statistics): the throughput predictor of cfg.deterministic == 0 contexts and

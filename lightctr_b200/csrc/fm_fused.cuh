@@ -193,7 +193,10 @@ slotmap_assign_kernel(const uint32_t* __restrict__ fid, const int64_t* __restric
 // ---------------------------------------------------------------------------------------------------------------
 // fused forward (+ RED backward)
 // ---------------------------------------------------------------------------------------------------------------
-// MODE 0: forward only (pred, sumVX, d = pred - label, statistics).  MODE 1: forward + RED backward into G / Ghot.
+// MODE 0: FM forward only (pred, sumVX, d = pred - label, statistics).  MODE 1: FM forward + RED backward into G / Ghot.
+// MODE 2: NFM forward (train_nfm_algo.cpp:78-94): wide part, sumVX and the bi-interaction z = 0.5 (sumVX^2 - sum (xV)^2) for
+// the dense layers.  MODE 3: NFM backward (accumWideGrad / accumDeepGrad, :126-159) from the dense layers' input delta dz:
+// the rows are gathered again (L2 hits), sumVX comes back from memory, gradients leave as REDs like MODE 1.
 // pidx: per-entry index of the PARAMETER row (the fid; or the slot when the rows live in a batch-compact cache),
 // gidx: per-entry gradient row: slot, or kHotBit | replica block (slotmap_assign_kernel).  SAME_IDX: pidx == gidx.
 //
@@ -208,7 +211,10 @@ fm_fused_kernel(const int64_t* __restrict__ row_ptr, const uint32_t* __restrict_
                 const float* __restrict__ V, float* __restrict__ pred, float* __restrict__ sumvx, float* __restrict__ dvec,
                 float* __restrict__ G, float* __restrict__ Ghot, int GS, float l2, int64_t rb, int64_t re_arg,
                 const int64_t* __restrict__ hdr, double* partial, unsigned int* done, double* out_slot, int do_stats,
-                const unsigned long long* wait_flags = nullptr, int n_wait = 0, unsigned long long wait_epoch = 0) {
+                const unsigned long long* wait_flags = nullptr, int n_wait = 0, unsigned long long wait_epoch = 0,
+                float* __restrict__ zbuf = nullptr /* MODE 2: z out, MODE 3: dz in; [re - rb][K] */,
+                float* __restrict__ wide = nullptr /* MODE 2: wide part out [rows] */) {
+    constexpr bool FWD = MODE != 3, BWD = MODE == 1 || MODE == 3, NFM = MODE >= 2;
     static_assert(K % 4 == 0 && K <= 32 && (K / 4 & (K / 4 - 1)) == 0, "fused FM step: K in {4, 8, 16, 32}");
     if (wait_flags) {  // multi-GPU: the owners' rows of this step must have landed in the cache (dist.cu)
         if (threadIdx.x < n_wait) {
@@ -249,7 +255,7 @@ fm_fused_kernel(const int64_t* __restrict__ row_ptr, const uint32_t* __restrict_
                 const int i = p * 32 + lane;
                 const bool ok = i < n;
                 pf[p] = ok ? ldg_u32_pinned(pidx + b + i) : 0u;
-                gs[p] = SAME_IDX ? pf[p] : ((ok && MODE == 1) ? ldg_u32_pinned(gidx + b + i) : 0u);
+                gs[p] = SAME_IDX ? pf[p] : ((ok && BWD) ? ldg_u32_pinned(gidx + b + i) : 0u);
                 xs[p] = ok ? (HAS_VAL ? ldg_f32_pinned(val + b + i) : 1.f) : 0.f;
             }
         }
@@ -288,76 +294,110 @@ fm_fused_kernel(const int64_t* __restrict__ row_ptr, const uint32_t* __restrict_
                     const int i = p * 32 + lane;
                     const bool ok = i < nn;
                     npf[p] = ok ? ldg_u32_pinned(pidx + bn + i) : 0u;
-                    ngs[p] = SAME_IDX ? npf[p] : ((ok && MODE == 1) ? ldg_u32_pinned(gidx + bn + i) : 0u);
+                    ngs[p] = SAME_IDX ? npf[p] : ((ok && BWD) ? ldg_u32_pinned(gidx + bn + i) : 0u);
                     nxs[p] = ok ? (HAS_VAL ? ldg_f32_pinned(val + bn + i) : 1.f) : 0.f;
                 }
             }
             // ---- interaction sums (order-free): s = sum x V (this lane's 4 factors over its rows), sq = sum |xV|^2
             float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+            float4 sqv = make_float4(0.f, 0.f, 0.f, 0.f);  // NFM: per-factor sum (xV)^2
             float sq = 0.f, wsum = 0.f;
+            if (FWD) {
 #pragma unroll
-            for (int p = 0; p < NPASS; p++) {
-                if (p * 32 < n) {
-                    wsum = __fmaf_rn(ws[p], HAS_VAL ? xs[p] : (p * 32 + lane < n ? 1.f : 0.f), wsum);                        // fm_pred += W[fid] * X   train_fm_algo.cpp:74
+                for (int p = 0; p < NPASS; p++) {
+                    if (p * 32 < n) {
+                        wsum = __fmaf_rn(ws[p], HAS_VAL ? xs[p] : (p * 32 + lane < n ? 1.f : 0.f), wsum);  // fm_pred += W[fid] * X   train_fm_algo.cpp:74
 #pragma unroll
-                    for (int it = 0; it < LPR; it++) {
-                        const float xj = HAS_VAL ? __shfl_sync(kFull, xs[p], it * GR + g)
-                                                 : (p * 32 + it * GR + g < n ? 1.f : 0.f);  // 0 beyond n
-                        const float4 tt = make_float4(v[p][it].x * xj, v[p][it].y * xj, v[p][it].z * xj, v[p][it].w * xj);
-                        s.x += tt.x; s.y += tt.y; s.z += tt.z; s.w += tt.w;      // sumVX += tmp            :77
-                        sq = __fmaf_rn(tt.x, tt.x, sq); sq = __fmaf_rn(tt.y, tt.y, sq);
-                        sq = __fmaf_rn(tt.z, tt.z, sq); sq = __fmaf_rn(tt.w, tt.w, sq);  // dot(tmp, tmp)  :78
+                        for (int it = 0; it < LPR; it++) {
+                            const float xj = HAS_VAL ? __shfl_sync(kFull, xs[p], it * GR + g)
+                                                     : (p * 32 + it * GR + g < n ? 1.f : 0.f);  // 0 beyond n
+                            const float4 tt = make_float4(v[p][it].x * xj, v[p][it].y * xj, v[p][it].z * xj, v[p][it].w * xj);
+                            s.x += tt.x; s.y += tt.y; s.z += tt.z; s.w += tt.w;      // sumVX += tmp            :77
+                            if (NFM) {
+                                sqv.x = __fmaf_rn(tt.x, tt.x, sqv.x); sqv.y = __fmaf_rn(tt.y, tt.y, sqv.y);
+                                sqv.z = __fmaf_rn(tt.z, tt.z, sqv.z); sqv.w = __fmaf_rn(tt.w, tt.w, sqv.w);
+                            } else {
+                                sq = __fmaf_rn(tt.x, tt.x, sq); sq = __fmaf_rn(tt.y, tt.y, sq);
+                                sq = __fmaf_rn(tt.z, tt.z, sq); sq = __fmaf_rn(tt.w, tt.w, sq);  // dot(tmp, tmp)  :78
+                            }
+                        }
                     }
                 }
-            }
-            for (int base = NPASS * 32; base < n; base += 32) {  // samples longer than the register window
-                const int i = base + lane;
-                const bool ok = i < n;
-                const uint32_t f = ok ? __ldg(pidx + b + i) : 0u;
-                const float x = ok ? (HAS_VAL ? __ldg(val + b + i) : 1.f) : 0.f;
-                wsum = __fmaf_rn(__ldg(W + f), x, wsum);
-                float4 vv[LPR];
+                for (int base = NPASS * 32; base < n; base += 32) {  // samples longer than the register window
+                    const int i = base + lane;
+                    const bool ok = i < n;
+                    const uint32_t f = ok ? __ldg(pidx + b + i) : 0u;
+                    const float x = ok ? (HAS_VAL ? __ldg(val + b + i) : 1.f) : 0.f;
+                    wsum = __fmaf_rn(__ldg(W + f), x, wsum);
+                    float4 vv[LPR];
 #pragma unroll
-                for (int it = 0; it < LPR; it++) {
-                    const uint32_t fj = __shfl_sync(kFull, f, it * GR + g);
-                    vv[it] = ldg_f4(V + (size_t)fj * K + 4 * q);
+                    for (int it = 0; it < LPR; it++) {
+                        const uint32_t fj = __shfl_sync(kFull, f, it * GR + g);
+                        vv[it] = ldg_f4(V + (size_t)fj * K + 4 * q);
+                    }
+#pragma unroll
+                    for (int it = 0; it < LPR; it++) {
+                        const float xj = __shfl_sync(kFull, x, it * GR + g);
+                        const float4 tt = make_float4(vv[it].x * xj, vv[it].y * xj, vv[it].z * xj, vv[it].w * xj);
+                        s.x += tt.x; s.y += tt.y; s.z += tt.z; s.w += tt.w;
+                        if (NFM) {
+                            sqv.x = __fmaf_rn(tt.x, tt.x, sqv.x); sqv.y = __fmaf_rn(tt.y, tt.y, sqv.y);
+                            sqv.z = __fmaf_rn(tt.z, tt.z, sqv.z); sqv.w = __fmaf_rn(tt.w, tt.w, sqv.w);
+                        } else {
+                            sq = __fmaf_rn(tt.x, tt.x, sq); sq = __fmaf_rn(tt.y, tt.y, sq);
+                            sq = __fmaf_rn(tt.z, tt.z, sq); sq = __fmaf_rn(tt.w, tt.w, sq);
+                        }
+                    }
                 }
 #pragma unroll
-                for (int it = 0; it < LPR; it++) {
-                    const float xj = __shfl_sync(kFull, x, it * GR + g);
-                    const float4 tt = make_float4(vv[it].x * xj, vv[it].y * xj, vv[it].z * xj, vv[it].w * xj);
-                    s.x += tt.x; s.y += tt.y; s.z += tt.z; s.w += tt.w;
-                    sq = __fmaf_rn(tt.x, tt.x, sq); sq = __fmaf_rn(tt.y, tt.y, sq);
-                    sq = __fmaf_rn(tt.z, tt.z, sq); sq = __fmaf_rn(tt.w, tt.w, sq);
+                for (int o = LPR; o < 32; o <<= 1) {  // over the row groups: every lane ends with the full sumVX of its 4 factors
+                    s.x += __shfl_xor_sync(kFull, s.x, o); s.y += __shfl_xor_sync(kFull, s.y, o);
+                    s.z += __shfl_xor_sync(kFull, s.z, o); s.w += __shfl_xor_sync(kFull, s.w, o);
+                    if (NFM) {
+                        sqv.x += __shfl_xor_sync(kFull, sqv.x, o); sqv.y += __shfl_xor_sync(kFull, sqv.y, o);
+                        sqv.z += __shfl_xor_sync(kFull, sqv.z, o); sqv.w += __shfl_xor_sync(kFull, sqv.w, o);
+                    }
                 }
+                wsum = warp_sum(wsum);
+                if (lane < LPR) *reinterpret_cast<float4*>(sumvx + (size_t)r * K + 4 * q) = s;  // FM_Algo_Abst::sumVX (:145)
             }
+            float d = 0.f;
+            float4 dz4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (!NFM) {
+                sq = warp_sum(sq);
+                float dot = s.x * s.x + s.y * s.y + s.z * s.z + s.w * s.w;  // |sumVX|^2 over the LPR lanes of a row group
 #pragma unroll
-            for (int o = LPR; o < 32; o <<= 1) {  // over the row groups: every lane ends with the full sumVX of its 4 factors
-                s.x += __shfl_xor_sync(kFull, s.x, o); s.y += __shfl_xor_sync(kFull, s.y, o);
-                s.z += __shfl_xor_sync(kFull, s.z, o); s.w += __shfl_xor_sync(kFull, s.w, o);
-            }
-            sq = warp_sum(sq);
-            wsum = warp_sum(wsum);
-            float dot = s.x * s.x + s.y * s.y + s.z * s.z + s.w * s.w;  // |sumVX|^2 over the LPR lanes of a row group
-#pragma unroll
-            for (int o = 1; o < LPR; o <<= 1) dot += __shfl_xor_sync(kFull, dot, o);
-            const float fm = wsum - 0.5f * sq + 0.5f * dot;             // :78, :82
-            const float pr = ref_sigmoid(fm);                           // :84
-            const float y = __ldg(label + r);
-            const float d = pr - y;                                     // LogisticGradW  fm_algo_abst.h:159-161
-            if (lane < LPR) *reinterpret_cast<float4*>(sumvx + (size_t)r * K + 4 * q) = s;  // FM_Algo_Abst::sumVX (:145)
-            if (lane == 0) {
-                pred[r] = pr;
-                if (dvec) dvec[r] = d;
-                if (do_stats) {
-                    double l1, c1;
-                    loss_terms(pr, y, l1, c1);
-                    loss += l1;
-                    correct += c1;
+                for (int o = 1; o < LPR; o <<= 1) dot += __shfl_xor_sync(kFull, dot, o);
+                const float fm = wsum - 0.5f * sq + 0.5f * dot;             // :78, :82
+                const float pr = ref_sigmoid(fm);                           // :84
+                const float y = __ldg(label + r);
+                d = pr - y;                                                 // LogisticGradW  fm_algo_abst.h:159-161
+                if (lane == 0) {
+                    pred[r] = pr;
+                    if (dvec) dvec[r] = d;
+                    if (do_stats) {
+                        double l1, c1;
+                        loss_terms(pr, y, l1, c1);
+                        loss += l1;
+                        correct += c1;
+                    }
                 }
+            } else if (MODE == 2) {
+                // z = sum -0.5 (xV)^2 + 0.5 sumVX^2 per factor (train_nfm_algo.cpp:87-94); wide part = sum W x (:83)
+                if (lane < LPR) {
+                    const float4 z4 = make_float4(0.5f * (s.x * s.x - sqv.x), 0.5f * (s.y * s.y - sqv.y),
+                                                  0.5f * (s.z * s.z - sqv.z), 0.5f * (s.w * s.w - sqv.w));
+                    *reinterpret_cast<float4*>(zbuf + (size_t)(r - rb) * K + 4 * q) = z4;
+                }
+                if (lane == 0) wide[r] = wsum;
+            } else {  // MODE 3
+                s = __ldg(reinterpret_cast<const float4*>(sumvx + (size_t)r * K + 4 * q));
+                dz4 = __ldg(reinterpret_cast<const float4*>(zbuf + (size_t)(r - rb) * K + 4 * q));
+                d = __ldg(pred + r) - __ldg(label + r);
             }
-            if (MODE == 1) {
-                // ---- backward from the register-resident rows (train_fm_algo.cpp:101-116), vector REDs into G / Ghot
+            if (BWD) {
+                // ---- backward from the register-resident rows (train_fm_algo.cpp:101-116; NFM: train_nfm_algo.cpp:126-159),
+                // vector REDs into G / Ghot.  FM: gV = (sumVX - xV) gradW + l2 V;  NFM: gV = (sumVX - xV) (dz x) + l2 V
 #pragma unroll
                 for (int p = 0; p < NPASS; p++) {
                     if (p * 32 < n) {
@@ -370,11 +410,12 @@ fm_fused_kernel(const int64_t* __restrict__ row_ptr, const uint32_t* __restrict_
                             if (p * 32 + j < n) {
                                 const float gw = __fmaf_rn(d, xj, l2 * wj);                       // :108
                                 const float4 vv = v[p][it];
+                                const float4 mu = NFM ? make_float4(dz4.x * xj, dz4.y * xj, dz4.z * xj, dz4.w * xj) : make_float4(gw, gw, gw, gw);
                                 float4 gv;
-                                gv.x = __fmaf_rn(__fmaf_rn(-xj, vv.x, s.x), gw, l2 * vv.x);       // :112-115
-                                gv.y = __fmaf_rn(__fmaf_rn(-xj, vv.y, s.y), gw, l2 * vv.y);
-                                gv.z = __fmaf_rn(__fmaf_rn(-xj, vv.z, s.z), gw, l2 * vv.z);
-                                gv.w = __fmaf_rn(__fmaf_rn(-xj, vv.w, s.w), gw, l2 * vv.w);
+                                gv.x = __fmaf_rn(__fmaf_rn(-xj, vv.x, s.x), mu.x, l2 * vv.x);     // :112-115
+                                gv.y = __fmaf_rn(__fmaf_rn(-xj, vv.y, s.y), mu.y, l2 * vv.y);
+                                gv.z = __fmaf_rn(__fmaf_rn(-xj, vv.z, s.z), mu.z, l2 * vv.z);
+                                gv.w = __fmaf_rn(__fmaf_rn(-xj, vv.w, s.w), mu.w, l2 * vv.w);
                                 float* dst = (sj & kHotBit) ? Ghot + ((size_t)(sj & ~kHotBit) * kHotRep + rep) * GS
                                                             : G + (size_t)sj * GS;
                                 red_add_v4(dst + 4 * q, gv);
@@ -400,11 +441,12 @@ fm_fused_kernel(const int64_t* __restrict__ row_ptr, const uint32_t* __restrict_
                         if (base + j < n) {
                             const float4 vv = ldg_f4(V + (size_t)fj * K + 4 * q);
                             const float gw = __fmaf_rn(d, xj, l2 * wj);
+                            const float4 mu = NFM ? make_float4(dz4.x * xj, dz4.y * xj, dz4.z * xj, dz4.w * xj) : make_float4(gw, gw, gw, gw);
                             float4 gv;
-                            gv.x = __fmaf_rn(__fmaf_rn(-xj, vv.x, s.x), gw, l2 * vv.x);
-                            gv.y = __fmaf_rn(__fmaf_rn(-xj, vv.y, s.y), gw, l2 * vv.y);
-                            gv.z = __fmaf_rn(__fmaf_rn(-xj, vv.z, s.z), gw, l2 * vv.z);
-                            gv.w = __fmaf_rn(__fmaf_rn(-xj, vv.w, s.w), gw, l2 * vv.w);
+                            gv.x = __fmaf_rn(__fmaf_rn(-xj, vv.x, s.x), mu.x, l2 * vv.x);
+                            gv.y = __fmaf_rn(__fmaf_rn(-xj, vv.y, s.y), mu.y, l2 * vv.y);
+                            gv.z = __fmaf_rn(__fmaf_rn(-xj, vv.z, s.z), mu.z, l2 * vv.z);
+                            gv.w = __fmaf_rn(__fmaf_rn(-xj, vv.w, s.w), mu.w, l2 * vv.w);
                             float* dst = (sj & kHotBit) ? Ghot + ((size_t)(sj & ~kHotBit) * kHotRep + rep) * GS
                                                         : G + (size_t)sj * GS;
                             red_add_v4(dst + 4 * q, gv);
