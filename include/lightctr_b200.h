@@ -32,7 +32,13 @@ typedef struct lctr_ctx lctr_ctx;
 enum { LCTR_MODEL_FM = 1, LCTR_MODEL_FFM = 2, LCTR_MODEL_NFM = 3, LCTR_MODEL_WND = 4 };
 /* updater = the reference's `_Num` family member (gradientUpdater.h:128-154 Adagrad, :200-233 RMSprop,
  * :235-278 FTRL; momentumUpdater.h:74-111 Adadelta, :172-215 Adam) */
-enum { LCTR_OPT_ADAGRAD = 0, LCTR_OPT_FTRL = 1, LCTR_OPT_ADAM = 2, LCTR_OPT_RMSPROP = 3, LCTR_OPT_ADADELTA = 4 };
+enum { LCTR_OPT_ADAGRAD = 0, LCTR_OPT_FTRL = 1, LCTR_OPT_ADAM = 2, LCTR_OPT_RMSPROP = 3, LCTR_OPT_ADADELTA = 4,
+       /* the parameter server's own update rules (distribut/paramserver.h:232-300), applied by the owner of a row to the
+        * step's summed gradient as ONE push of worker 0: SGD (:295-300, the PS default :49; Wide&Deep tensors use the tensor
+        * form :232-237), Adagrad (:288-294), DCASGD / DCASGDA (:252-286; shadow copy and accumulator kept per coordinate).
+        * The synchronous exchange has no staleness, so the delay-compensation term of DCASGD* sees the parameter change
+        * since the previous step. */
+       LCTR_OPT_PS_SGD = 5, LCTR_OPT_PS_ADAGRAD = 6, LCTR_OPT_PS_DCASGD = 7, LCTR_OPT_PS_DCASGDA = 8 };
 enum { LCTR_ACT_SIGMOID = 0, LCTR_ACT_TANH = 1 };
 enum { LCTR_MLP_FP32 = 0, LCTR_MLP_BF16 = 1 };
 

@@ -14,6 +14,7 @@ LIB_PATH = os.path.join(HERE, "lib", "liblightctr_b200.so")
 
 MODEL_FM, MODEL_FFM, MODEL_NFM, MODEL_WND = 1, 2, 3, 4
 OPT_ADAGRAD, OPT_FTRL, OPT_ADAM, OPT_RMSPROP, OPT_ADADELTA = 0, 1, 2, 3, 4
+OPT_PS_SGD, OPT_PS_ADAGRAD, OPT_PS_DCASGD, OPT_PS_DCASGDA = 5, 6, 7, 8
 ACT_SIGMOID, ACT_TANH = 0, 1
 MLP_FP32, MLP_BF16 = 0, 1
 MAX_LAYERS = 8

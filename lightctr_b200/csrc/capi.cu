@@ -58,6 +58,10 @@ static int slot_reserve(lctr_ctx* c, Slot& s, int64_t rows, int64_t nnz) {
     return 0;
 }
 
+__global__ void fill_value_kernel(float* p, size_t n, float v) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v;
+}
+
 __global__ void label_to_float_kernel(const int32_t* in, float* out, int64_t n_arg, const int64_t* hdr) {
     const int64_t n = hdr ? hdr[0] : n_arg;
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -168,7 +172,7 @@ int lctr_create(const lctr_cfg* cfg, lctr_ctx** out) {
     LCTR_CHECK(cfg->abi_version == LCTR_ABI_VERSION, "lctr_create: abi_version %u != %u", cfg->abi_version,
                LCTR_ABI_VERSION);
     LCTR_CHECK(cfg->model >= LCTR_MODEL_FM && cfg->model <= LCTR_MODEL_WND, "lctr_create: bad model %d", cfg->model);
-    LCTR_CHECK(cfg->optimizer >= LCTR_OPT_ADAGRAD && cfg->optimizer <= LCTR_OPT_ADADELTA, "lctr_create: bad optimizer %d",
+    LCTR_CHECK(cfg->optimizer >= LCTR_OPT_ADAGRAD && cfg->optimizer <= LCTR_OPT_PS_DCASGDA, "lctr_create: bad optimizer %d",
                cfg->optimizer);
     LCTR_CHECK(cfg->feature_cnt > 0 && cfg->feature_cnt < (1ull << 32), "lctr_create: feature_cnt out of range");
     LCTR_CHECK(cfg->factor_cnt > 0, "lctr_create: factor_cnt must be > 0");
@@ -203,7 +207,8 @@ int lctr_create(const lctr_cfg* cfg, lctr_ctx** out) {
     LCTR_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     const size_t FL = c->Fl;
     const size_t nv = FL * c->rowlen;
-    const bool two = cfg->optimizer == LCTR_OPT_FTRL || cfg->optimizer == LCTR_OPT_ADAM || cfg->optimizer == LCTR_OPT_ADADELTA;
+    const bool two = cfg->optimizer == LCTR_OPT_FTRL || cfg->optimizer == LCTR_OPT_ADAM || cfg->optimizer == LCTR_OPT_ADADELTA ||
+                     cfg->optimizer == LCTR_OPT_PS_DCASGD || cfg->optimizer == LCTR_OPT_PS_DCASGDA;
     int rc = 0;
     rc |= dalloc(&c->W, FL); rc |= dalloc(&c->V, nv);
     rc |= dalloc(&c->gW, FL); rc |= dalloc(&c->gV, nv);
@@ -227,6 +232,10 @@ int lctr_create(const lctr_cfg* cfg, lctr_ctx** out) {
     if (two) {
         LCTR_CUDA(cudaMemsetAsync(c->s2W, 0, FL * sizeof(float), c->stream));
         LCTR_CUDA(cudaMemsetAsync(c->s2V, 0, nv * sizeof(float), c->stream));
+    }
+    if (cfg->optimizer == LCTR_OPT_PS_ADAGRAD || cfg->optimizer == LCTR_OPT_PS_DCASGDA) {  // data_accum = 1e-7 (paramserver.h:323)
+        fill_value_kernel<<<c->sm_count * 4, 256, 0, c->stream>>>(c->s1W, FL, 1e-7f);
+        fill_value_kernel<<<c->sm_count * 4, 256, 0, c->stream>>>(c->s1V, nv, 1e-7f);
     }
     LCTR_CUDA(cudaMemsetAsync(c->touched, 0, FL + 512, c->stream));
     if (c->cfg.world > 1) {

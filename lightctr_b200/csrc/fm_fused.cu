@@ -214,7 +214,11 @@ static void apply_go(lctr_ctx* c, Slot& s, const OptParams& P, const OptParams* 
         case LCTR_OPT_FTRL: apply_compact_kernel<K, LCTR_OPT_FTRL><<<grid, 256, 0, c->stream>>>(AC_ARGS); break;
         case LCTR_OPT_ADAM: apply_compact_kernel<K, LCTR_OPT_ADAM><<<grid, 256, 0, c->stream>>>(AC_ARGS); break;
         case LCTR_OPT_RMSPROP: apply_compact_kernel<K, LCTR_OPT_RMSPROP><<<grid, 256, 0, c->stream>>>(AC_ARGS); break;
-        default: apply_compact_kernel<K, LCTR_OPT_ADADELTA><<<grid, 256, 0, c->stream>>>(AC_ARGS); break;
+        case LCTR_OPT_ADADELTA: apply_compact_kernel<K, LCTR_OPT_ADADELTA><<<grid, 256, 0, c->stream>>>(AC_ARGS); break;
+        case LCTR_OPT_PS_SGD: apply_compact_kernel<K, LCTR_OPT_PS_SGD><<<grid, 256, 0, c->stream>>>(AC_ARGS); break;
+        case LCTR_OPT_PS_ADAGRAD: apply_compact_kernel<K, LCTR_OPT_PS_ADAGRAD><<<grid, 256, 0, c->stream>>>(AC_ARGS); break;
+        case LCTR_OPT_PS_DCASGD: apply_compact_kernel<K, LCTR_OPT_PS_DCASGD><<<grid, 256, 0, c->stream>>>(AC_ARGS); break;
+        default: apply_compact_kernel<K, LCTR_OPT_PS_DCASGDA><<<grid, 256, 0, c->stream>>>(AC_ARGS); break;
     }
 #undef AC_ARGS
 }

@@ -479,7 +479,8 @@ apply_compact_kernel(const uint32_t* __restrict__ uniq, const unsigned int* __re
     constexpr int LPR = K / 4, GR = 32 / LPR, U = 2;
     OptParams P = P_dev ? *P_dev : P_in;
     P.opt = OPT;
-    constexpr bool two = OPT == LCTR_OPT_FTRL || OPT == LCTR_OPT_ADAM || OPT == LCTR_OPT_ADADELTA;
+    constexpr bool two = OPT == LCTR_OPT_FTRL || OPT == LCTR_OPT_ADAM || OPT == LCTR_OPT_ADADELTA || OPT == LCTR_OPT_PS_DCASGD ||
+                         OPT == LCTR_OPT_PS_DCASGDA;
     const int lane = threadIdx.x & 31;
     // ---- hot slots: the blocks BEYOND main_blocks, one warp per hot slot (the two kinds of work have equally long
     // dependent-load chains, so they run side by side instead of one after the other).  The kHotRep replica rows form a

@@ -216,7 +216,8 @@ int launch_apply(lctr_ctx* c, int64_t rows_in_step) {
             case LCTR_OPT_FTRL: APPLY_GO(L, VV, S, UU, LCTR_OPT_FTRL); break;         \
             case LCTR_OPT_ADAM: APPLY_GO(L, VV, S, UU, LCTR_OPT_ADAM); break;         \
             case LCTR_OPT_RMSPROP: APPLY_GO(L, VV, S, UU, LCTR_OPT_RMSPROP); break;   \
-            default: APPLY_GO(L, VV, S, UU, LCTR_OPT_ADADELTA); break;                \
+            case LCTR_OPT_ADADELTA: APPLY_GO(L, VV, S, UU, LCTR_OPT_ADADELTA); break; \
+            default: APPLY_GO(L, VV, S, UU, -1); break;                               \
         }                                                                    \
     } while (0)
     if (vec == 4) {

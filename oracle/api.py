@@ -69,6 +69,7 @@ def lib():
     L.orc_free_data.argtypes = [C.POINTER(_Data)]
     L.orc_adagrad.argtypes = [C.c_size_t, _f32p, _f32p, _f32p, C.c_size_t, C.c_float]
     L.orc_ftrl.argtypes = [C.c_size_t, _f32p, _f32p, _f32p, _f32p, C.c_int]
+    L.orc_ps_update.argtypes = [C.c_int, C.c_size_t, _f32p, _f32p, _f32p, _f32p, C.c_size_t, C.c_float, C.c_int]
     L.orc_adadelta.argtypes = [C.c_size_t, _f32p, _f32p, _f32p, _f32p, C.c_size_t, C.c_float]
     L.orc_rmsprop.argtypes = [C.c_size_t, _f32p, _f32p, _f32p, C.c_size_t, C.c_float, C.c_float]
     L.orc_adam.argtypes = [C.c_size_t, _f32p, _f32p, _f32p, _f32p, C.POINTER(C.c_size_t), C.c_size_t,
@@ -194,9 +195,14 @@ class FMOracle:
         # trainer's `updater` member (adagrad is the shipped one); W call first, then V call, as in the reference
         opt = getattr(self, "opt", "adagrad")
         B = self.ds.rows
-        if opt in ("ftrl", "adam", "adadelta") and not hasattr(self, "s2"):
+        if opt in ("ftrl", "adam", "adadelta", "ps_dcasgd", "ps_dcasgda") and not hasattr(self, "s2"):
             self.s2 = np.zeros(F * (k + 1), np.float32)
             self.iter = C.c_size_t(0)
+        if opt in ("ps_adagrad", "ps_dcasgda") and not getattr(self, "_ps_init", False):
+            self.accum[:] = np.float32(1e-7)  # data_accum = TValue(1e-7), paramserver.h:323
+            self._ps_init = True
+        if not hasattr(self, "s2"):
+            self.s2 = np.zeros(1, np.float32)
         for (w, lo, hi) in ((self.W, 0, F), (self.V, F, F * (k + 1))):
             g, a = self.update_g[lo:hi], self.accum[lo:hi]
             if opt == "adagrad":
@@ -210,6 +216,10 @@ class FMOracle:
             elif opt == "adam":
                 L.orc_adam(hi - lo, w, g, a, self.s2[lo:hi], C.byref(self.iter), B, self.lr,
                            np.float32(getattr(self, "beta1", 0.8)), np.float32(getattr(self, "beta2", 0.999)))
+            elif opt.startswith("ps_"):
+                kind = {"ps_sgd": 0, "ps_adagrad": 1, "ps_dcasgd": 2, "ps_dcasgda": 3}[opt]
+                sh = self.s2[lo:hi] if kind >= 2 else self.s2[:1]
+                L.orc_ps_update(kind, hi - lo, w, g, a, sh, B, self.lr, 0)
             else:
                 raise ValueError(opt)
 

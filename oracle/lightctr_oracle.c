@@ -704,6 +704,37 @@ void orc_predict(int64_t rows, const int64_t* row_ptr, const uint32_t* fid, cons
     *auc_out = orc_auc(pctr_out, label, (size_t)rows);
 }
 
+/* ParamServer push handler, per coordinate (distribut/paramserver.h:232-300), one push of worker 0 carrying the step's
+ * summed gradient.  PARITY UNPINNED: paramserver.h pulls in the ZeroMQ transport and cannot be compiled here; the Value
+ * operators mutate their left operand (distributed_algo_abst.h:39-72), which the sequences below follow literally.
+ * kind: 0 SGD (:295-300; tensor != 0: tensor SGD :232-237), 1 Adagrad (:288-294), 2 DCASGD (:252-267), 3 DCASGDA (:268-286).
+ * accum starts at 1e-7 (:323), shadow at 0 (:327). */
+void orc_ps_update(int kind, size_t len, float* w, const float* g, float* accum, float* shadow, size_t minibatch, float lr,
+                   int tensor) {
+    const float mb = (float)minibatch;
+    for (size_t i = 0; i < len; i++) {
+        if (kind == 0) {
+            if (tensor) { const float scaler = (float)(-1.0 * (double)lr / (double)minibatch); float t = g[i] * scaler; w[i] = w[i] + t; }
+            else { float den = mb / lr; float t = g[i] / den; w[i] = w[i] - t; }
+        } else if (kind == 1) {
+            float grad = g[i] / mb; grad = grad * grad; accum[i] = accum[i] + grad;
+            float sq = (float)sqrt((double)accum[i] + 1e-7); sq = sq / lr;
+            float t = g[i] / sq; w[i] = w[i] - t;
+        } else if (kind == 2) {
+            float grad = g[i] / mb, reserve = grad;
+            grad = grad * grad; float cur = w[i] - shadow[i]; grad = grad * cur; grad = grad * 0.1f;
+            reserve = reserve + grad; reserve = reserve * lr; w[i] = w[i] - reserve; shadow[i] = w[i];
+        } else {
+            float grad = g[i] / mb;
+            accum[i] = accum[i] * 0.95f; grad = grad * grad; grad = grad * (1 - 0.95f); accum[i] = accum[i] + grad;
+            float reserve = grad; /* :277 copies grad after it was overwritten */
+            float sq = (float)sqrt((double)accum[i] + 1e-7);
+            grad = grad * grad; float cur = w[i] - shadow[i]; grad = grad * cur; grad = grad * 0.1f; grad = grad / sq;
+            reserve = reserve + grad; reserve = reserve * lr; w[i] = w[i] - reserve; shadow[i] = w[i];
+        }
+    }
+}
+
 /* ============================ distributed semantics =========================================== */
 uint32_t orc_murmur_u64(uint64_t k) { /* hash.h:51-58 */
     k ^= k >> 33; k *= 0xff51afd7ed558ccdULL; k ^= k >> 33; k *= 0xc4ceb9fe1a85ec53ULL; k ^= k >> 33;

@@ -114,3 +114,38 @@ def test_fm_exact_order_mode_with_ftrl_and_adam(oracle_api, opt):
     assert np.max(np.abs(s1 - o.accum)) < 1e-5 * max(1.0, float(np.max(np.abs(o.accum))))
     assert np.max(np.abs(s2 - o.s2)) < 1e-5 * max(1.0, float(np.max(np.abs(o.s2))))
     ctx.close()
+
+
+@pytest.mark.parametrize("opt", ["ps_sgd", "ps_adagrad", "ps_dcasgd", "ps_dcasgda"])
+def test_fm_parameter_server_update_rules(oracle_api, opt):
+    """The ParamServer's own per-coordinate rules (distribut/paramserver.h:232-300: SGD -- the default --, Adagrad, DCASGD,
+    DCASGDA with their mutating Value arithmetic) as the trainer's updater, exact-order mode, against the oracle's
+    restatement (unpinned: the PS cannot be compiled without its ZeroMQ transport).  The learning rate is raised so that
+    the SGD-type rules (step = lr * g / minibatch) move the loss."""
+    from lightctr_b200 import capi
+    ds = load_csr("train_sparse_csr.npz", field_cnt=68)
+    k = 8
+    lr = 5.0 if opt != "ps_adagrad" else 0.05
+    W0, V0 = oracle_api.init_params(1, ds.feature_cnt, k)
+    o = oracle_api.FMOracle(ds, k, W0, V0, lr=lr)
+    o.opt = opt
+    code = {"ps_sgd": capi.OPT_PS_SGD, "ps_adagrad": capi.OPT_PS_ADAGRAD, "ps_dcasgd": capi.OPT_PS_DCASGD,
+            "ps_dcasgda": capi.OPT_PS_DCASGDA}[opt]
+    ctx = capi.Context(capi.MODEL_FM, ds.feature_cnt, k, optimizer=code, deterministic=1, lr=lr)
+    ctx.upload_params(W0, V0)
+    ctx.upload_batch(0, ds.row_ptr, ds.fid, None, None, ds.label)
+    losses = []
+    for e in range(5):
+        lg = ctx.train_step(0)[0]
+        lo, _ = o.epoch()
+        losses.append(lo)
+        assert _rel(lg, lo) < 1e-5, (opt, e, lg, lo)
+    assert abs(losses[-1] - losses[0]) > 1e-3 * abs(losses[0])  # the rule actually trains
+    W, V = ctx.download_params()
+    assert np.max(np.abs(W - o.W)) < 1e-5 and np.max(np.abs(V - o.V)) < 1e-5
+    s1, s2 = ctx.download_opt_state()
+    if opt in ("ps_adagrad", "ps_dcasgda"):
+        assert np.max(np.abs(s1 - o.accum)) <= 1e-5 * max(1.0, float(np.max(np.abs(o.accum))))
+    if opt in ("ps_dcasgd", "ps_dcasgda"):
+        assert np.max(np.abs(s2 - o.s2)) < 1e-5
+    ctx.close()
