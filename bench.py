@@ -236,7 +236,7 @@ def measure(wname, wl, args, rank, world, local_rank, dist, steps, warmup, do_e2
         os.environ["LCTR_CSC_IN_STEP"] = "1"
     mlp_bf16 = wl["model"] == "nfm" and os.environ.get("LCTR_BENCH_MLP", "bf16") == "bf16"
     ctx = capi.Context(model, F, k, Fc, optimizer=opt, device=local_rank, deterministic=det, rank=rank, world=world,
-                       minibatch_size=(world * B if world > 1 else 0), max_nnz=B * 120, hidden=wl.get("hidden", ()),
+                       minibatch_size=(world * B if world > 1 else 0), max_nnz=B * 100, hidden=wl.get("hidden", ()),
                        mlp_precision=capi.MLP_BF16 if mlp_bf16 else capi.MLP_FP32)
     if wl["model"] == "nfm":  # FC chain initialised like fullyconnLayer.h:48-54 (U(-0.5,0.5), bias 0), masks all-ones
         rng0 = np.random.default_rng(99)

@@ -36,6 +36,7 @@ enum { PROF_FM_FWD = 0, PROF_FM_BWD_RED = 1, PROF_APPLY = 2, PROF_FFM_FUSED = 3,
 constexpr int kStatRing = 64;
 constexpr int kHotRep = 32;      // fm_fused: replica rows per hot slot of the batch-compact gradient buffer
 constexpr int kHotMax = 2048;    // hot slots per batch (ids beyond the cap stay ordinary slots)
+constexpr uint32_t kHotBit = 0x80000000u;  // gradient index of an entry of a hot slot: kHotBit | replica block
 constexpr unsigned kFull = 0xffffffffu;
 
 // One resident CSR batch / dataset (FM_Algo_Abst::dataSet + label, fm_algo_abst.h:156,170).
@@ -140,6 +141,7 @@ struct lctr_ctx {
     float *cW = nullptr, *cV = nullptr, *cgW = nullptr, *cgV = nullptr;
     lctr::DistState* dist = nullptr;
     lctr::FusedState* fused = nullptr;  // order-free fused FM step (fm_fused.cu)
+    size_t dist_rows = 0;               // world > 1: rows of the exchange index space (gradient / cache rows are indexed by it)
     uint32_t* touch_list = nullptr;      // compacted fids of the step (stage A of the sparse apply)
     unsigned int* n_touch = nullptr;     // list length (device)
     unsigned int* apply_done = nullptr;  // block-completion counter of stage B

@@ -12,21 +12,24 @@
 // (row = slot of the batch's key set, fm_fused.cu's slot map) instead of full-size copies of the tables.
 //
 //   upload (depends only on the batch; on the upload stream, overlaps the previous step)
-//     slot map of my batch (mark / compact / assign) and, per owner o, the list {shard-local row, my slot} of the keys
-//     o owns, written straight into o's key inbox with posted stores + a generation flag        (send_keys_kernel)
+//     slot map of my batch (mark / compact / assign) and, per owner o, the list of the shard-local rows o owns, written
+//     straight into o's key inbox with posted stores + a generation flag (send_keys_kernel).  From then on a row of the
+//     exchange is addressed by p = o * cap_pair + its position in that list, by requester and owner alike: the entries of
+//     the batch are re-indexed to p (remap_entries_kernel), so the cache rows of one owner and the gradient rows for one
+//     owner are CONTIGUOUS and both transfers are long coalesced streams instead of scattered 64 B packets (the first
+//     version of this protocol wrote pulled rows to scattered cache slots: 48 us for the 3 MB of an FM C2 step).
 //   step
 //     1 serve   OWNER-driven pull: I read the key lists my peers posted and WRITE the rows they asked for into their
 //               caches (posted peer stores instead of read round trips), then raise "rows delivered" on each peer
 //                                                                                                (serve_pull_kernel)
 //     2 compute the single-GPU kernels on the cache; the first one waits (in-kernel) for every owner's flag
-//     3 push    FM (64 B rows): the slot's gradient row (hot replicas folded) is added into the owner's update_g with
-//               peer vector REDs; FFM (1.2 KB rows): plain posted stores into the owner's gradient inbox at the
-//               position of the key in the list it received -- no slot reservation; then "pushes landed" flags
-//                                                                              (push_fused_kernel / push_rows_kernel)
-//     4 owner   wide rows: inbox rows are added into update_g (local REDs)                        (merge_kernel)
-//               sparse updater on the shard; its first kernel waits for every requester's flag   (opt.cu)
-// Launches per step: 5 (FM) / 6 (FFM); the barriers of the r01 protocol are flags written at the tail of one kernel and
-// polled at the head of the next -- no barrier launches, no host involvement.
+//     3 push    owner by owner, my gradient rows [gV | gW] (hot replicas folded) stream into the owner's gradient inbox
+//               at the positions of the list it received -- no slot reservation, no atomics on the wire; then "pushes
+//               landed" flags                                                                    (push_rows_kernel)
+//     4 owner   inbox rows are added into update_g with local REDs (waits for the flags)          (merge_kernel)
+//               sparse updater on the shard                                                      (opt.cu)
+// Launches per step: 6; the barriers of the r01 protocol are flags written at the tail of one kernel and polled at the
+// head of the next -- no barrier launches, no host involvement.
 #include <stdlib.h>
 #include <string.h>
 
@@ -55,9 +58,9 @@ struct ArenaLayout {
                          // by a slower owner's merge when its sender already uploads the slot's next batch):
                          // 64 B header {u32 count} + cap_pair x uint2 {row, requester slot}
     size_t key_region;   // bytes per region
-    size_t cacheW;       // cap_keys floats
-    size_t cacheV;       // cap_keys x rowlen floats
-    size_t grad_inbox;   // [world] regions of cap_pair x recw floats (wide rows only)
+    size_t cacheW;       // world * cap_pair floats (row p)
+    size_t cacheV;       // world * cap_pair x rowlen floats
+    size_t grad_inbox;   // [world] regions of cap_pair x recw floats
     size_t grad_region;  // bytes per region
     size_t total;
 };
@@ -70,12 +73,14 @@ struct DistState {
     PeerTable peers;
     size_t cap_keys = 0, cap_pair = 0;
     int recw = 0;                     // floats per gradient-inbox record: rowlen + 4 ([gV | gW | pad])
-    bool mailbox = false;             // wide rows: stores into the owner's inbox + owner-side merge
+    size_t rows_x = 0;                // world * cap_pair: rows of the exchange index space p
     unsigned int* send_cnt = nullptr; // [kMaxWorld] records appended per owner by the running send_keys
-    uint32_t* opos = nullptr;         // [kNumSlots][cap_keys]: position of my slot's key in its owner's list
+    unsigned int* seg_cnt = nullptr;  // [kNumSlots][kMaxWorld]: keys per owner of each slot's batch
+    uint32_t* opos = nullptr;         // [kNumSlots][cap_keys]: exchange row p of each of my slots
+    uint32_t* hot_p = nullptr;        // [kNumSlots][rows_x]: replica block of hot exchange rows (fused kernels), else ~0
     unsigned int* done_ctr = nullptr; // [4] last-block counters
     int* overflow = nullptr;          // device flag: a key list outgrew cap_pair
-    float *cgV = nullptr, *cgW = nullptr;  // [cap_keys][rowlen], [cap_keys]: compact gradient rows of the non-fused kernels
+    float *cgV = nullptr, *cgW = nullptr;  // [rows_x][rowlen], [rows_x]: compact gradient rows of the non-fused kernels
     void* opened[kMaxWorld][kNumHandles] = {{nullptr}};
     bool imported = false;
     unsigned long long epoch = 0;
@@ -115,7 +120,8 @@ __device__ __forceinline__ void raise_flags_last_block(const PeerTable& P, const
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// upload: per owner, the list of {shard-local row, my slot} -> the owner's key inbox
+// upload: per owner, the list of shard-local rows -> the owner's key inbox; rows of the exchange are then addressed by
+// p = owner * cap_pair + position in that list, on both sides
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 send_keys_kernel(const uint32_t* __restrict__ uniq, const unsigned int* __restrict__ n_uniq, PeerTable P, ArenaLayout A,
@@ -143,24 +149,27 @@ send_keys_kernel(const uint32_t* __restrict__ uniq, const unsigned int* __restri
             if (j < cap_pair) {
                 uint2* pairs = reinterpret_cast<uint2*>(P.p[o].arena + A.key_inbox + ((size_t)slot * world + me) * A.key_region + 64);
                 pairs[j] = make_uint2(f >> shift, i);
-                opos[i] = j;
+                opos[i] = o * cap_pair + j;
             } else {
-                *overflow = 1;
-                opos[i] = 0xffffffffu;
+                *overflow = 1;  // reported at the next host synchronisation; the row index stays in bounds
+                opos[i] = o * cap_pair;
             }
         }
         __syncthreads();
     }
     __threadfence_system();
 }
-// counts into the owners' headers, counters re-armed, then the generation flag of (slot, me) on every owner
+// counts into the owners' headers (and kept locally for the push), counters re-armed, then the generation flag of
+// (slot, me) on every owner
 __global__ void send_keys_finish_kernel(PeerTable P, ArenaLayout A, int me, int world, int slot, int flag_slot, unsigned cap_pair,
-                                        unsigned int* send_cnt, unsigned long long gen) {
+                                        unsigned int* send_cnt, unsigned int* seg_cnt, unsigned long long gen) {
     const int o = threadIdx.x;
     __threadfence_system();
     if (o < world) {
         unsigned int* hdr = reinterpret_cast<unsigned int*>(P.p[o].arena + A.key_inbox + ((size_t)slot * world + me) * A.key_region);
-        hdr[0] = min(send_cnt[o], cap_pair);
+        const unsigned n = min(send_cnt[o], cap_pair);
+        hdr[0] = n;
+        seg_cnt[o] = n;
         send_cnt[o] = 0;
         __threadfence_system();
         volatile unsigned long long* f = flag_ptr(P.p[o].arena, A, FLAG_KEYS + flag_slot, me);
@@ -168,15 +177,44 @@ __global__ void send_keys_finish_kernel(PeerTable P, ArenaLayout A, int me, int 
     }
     __threadfence_system();
 }
+// entries: slot -> exchange row p (plain index of the parameter cache; gradient index unless the slot is hot); and the
+// replica block of every hot exchange row
+__global__ void __launch_bounds__(256)
+remap_entries_kernel(const int64_t* __restrict__ hdr, int64_t nnz_arg, const uint32_t* __restrict__ opos,
+                     uint32_t* __restrict__ ent_pslot, uint32_t* __restrict__ ent_slot, const uint32_t* __restrict__ hot_of,
+                     const unsigned int* __restrict__ n_uniq, uint32_t* __restrict__ hot_p) {
+    const int64_t nnz = hdr ? hdr[1] : nnz_arg;
+    const int64_t t0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nt = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = t0; i < nnz; i += nt) {
+        const uint32_t pp = opos[ent_pslot[i]];
+        ent_pslot[i] = pp;
+        if (!(ent_slot[i] & kHotBit)) ent_slot[i] = pp;
+    }
+    if (hot_p) {
+        const unsigned n = *n_uniq;
+        for (int64_t i = t0; i < n; i += nt) {
+            const uint32_t h = hot_of[i];
+            if (h != 0xffffffffu) hot_p[opos[i]] = h;
+        }
+    }
+}
+// undo the hot marks of the previous batch of the slot (hot_p is all ~0 between uploads)
+__global__ void __launch_bounds__(256)
+clear_hot_p_kernel(const uint32_t* __restrict__ opos_prev, const uint32_t* __restrict__ hot_of_prev, unsigned n_prev,
+                   uint32_t* __restrict__ hot_p) {
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n_prev; i += gridDim.x * blockDim.x)
+        if (hot_of_prev[i] != 0xffffffffu) hot_p[opos_prev[i]] = 0xffffffffu;
+}
 
 // ---------------------------------------------------------------------------------------------------------------
-// step 1: owner-driven pull
+// step 1: owner-driven pull.  Requester r's rows from me land at its cache rows [me * cap_pair, me * cap_pair + n):
+// consecutive list positions are consecutive rows, so a warp's stores form long contiguous runs on the wire
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int kMaxSl = 4;
 __global__ void __launch_bounds__(256)
 serve_pull_kernel(PeerTable P, ArenaLayout A, int me, int world, int slot, int flag_slot, unsigned long long gen,
-                  unsigned long long epoch, int rowlen, const float* __restrict__ W, const float* __restrict__ V,
-                  unsigned int* done_ctr) {
+                  unsigned long long epoch, int rowlen, unsigned cap_pair, const float* __restrict__ W,
+                  const float* __restrict__ V, unsigned int* done_ctr) {
     wait_flags(P.p[me].arena, A, FLAG_KEYS + flag_slot, world, gen);  // every requester's key list of this upload has landed
     const int lane = threadIdx.x & 31;
     const unsigned warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -190,212 +228,114 @@ serve_pull_kernel(PeerTable P, ArenaLayout A, int me, int world, int slot, int f
         const unsigned char* region = P.p[me].arena + A.key_inbox + ((size_t)slot * world + r) * A.key_region;
         const unsigned n = *reinterpret_cast<const volatile unsigned int*>(region);
         const uint2* pairs = reinterpret_cast<const uint2*>(region + 64);
-        float* cW = reinterpret_cast<float*>(P.p[r].arena + A.cacheW);
-        float* cV = reinterpret_cast<float*>(P.p[r].arena + A.cacheV);
+        float* cW = reinterpret_cast<float*>(P.p[r].arena + A.cacheW) + (size_t)me * cap_pair;
+        float* cV = reinterpret_cast<float*>(P.p[r].arena + A.cacheV) + (size_t)me * cap_pair * rowlen;
         if (vec == 4 && slices <= lpr * kMaxSl) {
             constexpr int U = 4;  // row groups in flight before the first (posted) store leaves
             for (unsigned b0 = warp * (G * U); b0 < n; b0 += nwarps * (G * U)) {
-                uint2 pr[U];
+                unsigned l[U];
                 float4 v[U][kMaxSl];
                 float w[U];
 #pragma unroll
                 for (int u = 0; u < U; u++) {
                     const unsigned j = b0 + u * G + g;
-                    pr[u] = j < n ? pairs[j] : make_uint2(0xffffffffu, 0);
-                    if (pr[u].x == 0xffffffffu) continue;
-                    const float* src = V + (size_t)pr[u].x * rowlen;
+                    l[u] = j < n ? pairs[j].x : 0xffffffffu;
+                    if (l[u] == 0xffffffffu) continue;
+                    const float* src = V + (size_t)l[u] * rowlen;
 #pragma unroll
                     for (int i = 0; i < kMaxSl; i++) {
                         const int sl = q + i * lpr;
                         if (sl < slices) v[u][i] = *reinterpret_cast<const float4*>(src + 4 * sl);
                     }
-                    if (q == 0) w[u] = W[pr[u].x];
+                    if (q == 0) w[u] = W[l[u]];
                 }
 #pragma unroll
                 for (int u = 0; u < U; u++) {
-                    if (pr[u].x == 0xffffffffu) continue;
-                    float* dst = cV + (size_t)pr[u].y * rowlen;
+                    if (l[u] == 0xffffffffu) continue;
+                    const unsigned j = b0 + u * G + g;
+                    float* dst = cV + (size_t)j * rowlen;
 #pragma unroll
                     for (int i = 0; i < kMaxSl; i++) {
                         const int sl = q + i * lpr;
                         if (sl < slices) *reinterpret_cast<float4*>(dst + 4 * sl) = v[u][i];
                     }
-                    if (q == 0) cW[pr[u].y] = w[u];
+                    if (q == 0) cW[j] = w[u];
                 }
             }
         } else {
             for (unsigned j = warp * G + g; j < n; j += nwarps * G) {  // generic fallback (odd row lengths)
-                const uint2 pr = pairs[j];
-                const float* src = V + (size_t)pr.x * rowlen;
-                float* dst = cV + (size_t)pr.y * rowlen;
+                const float* src = V + (size_t)pairs[j].x * rowlen;
+                float* dst = cV + (size_t)j * rowlen;
                 for (int sl = q * vec; sl < rowlen; sl += lpr * vec)
                     for (int c = 0; c < vec; c++) dst[sl + c] = src[sl + c];
-                if (q == 0) cW[pr.y] = W[pr.x];
+                if (q == 0) cW[j] = W[pairs[j].x];
             }
         }
     }
     raise_flags_last_block(P, A, FLAG_PULLED, me, world, epoch, done_ctr);
 }
 
-// stand-alone wait for compute kernels without an in-kernel wait (FFM / NFM / non-fused FM)
+// stand-alone wait for compute kernels without an in-kernel wait (FFM / non-fused FM and NFM)
 __global__ void wait_flags_kernel(PeerTable P, ArenaLayout A, int me, int row, int world, unsigned long long value) {
     wait_flags(P.p[me].arena, A, row, world, value);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// step 3: push
+// step 3: push.  The gradient rows of owner o are rows [o * cap_pair, o * cap_pair + n_o) of my compact buffer, in the
+// order of the list o received: one contiguous stream of records [gV (rowlen) | gW | pad] into o's gradient inbox.
 // ---------------------------------------------------------------------------------------------------------------
-// FM fused path: row i of G (stride GS, [gV (K) | gW]) + the replica rows of hot slots -> the owner's update_g (peer REDs).
-// Blocks < main_blocks walk the ordinary slots, LPR lanes per row; the others fold one hot slot per warp (lane = column).
-template <int K>
+// gv / gw: row p at gv + p * gvs (rowlen floats) and gw + p * gws.  hot_p (fused FM / NFM kernels): rows whose entries were
+// accumulated in kHotRep replica rows of Ghot -- folded here.  Local rows (and replicas) are re-zeroed.
 __global__ void __launch_bounds__(256)
-push_fused_kernel(const uint32_t* __restrict__ uniq, const unsigned int* __restrict__ n_uniq, float* __restrict__ G,
-                  const uint32_t* __restrict__ hot_of, const uint32_t* __restrict__ hot_slot,
-                  const unsigned int* __restrict__ n_hot, float* __restrict__ Ghot, int GS, int main_blocks, PeerTable P,
-                  ArenaLayout A, int me, int world, int shift, unsigned long long epoch, unsigned int* done_ctr) {
-    constexpr int LPR = K / 4, GR = 32 / LPR, U = 4;
-    const unsigned mask = (unsigned)world - 1;
-    const int lane = threadIdx.x & 31;
-    if ((int)blockIdx.x >= main_blocks) {
-        const unsigned hwarp = (blockIdx.x - main_blocks) * (blockDim.x >> 5) + (threadIdx.x >> 5);
-        const unsigned nhw = (gridDim.x - main_blocks) * (blockDim.x >> 5);
-        const unsigned nh = min(*n_hot, (unsigned)kHotMaxD);
-        for (unsigned h = hwarp; h < nh; h += nhw) {
-            const uint32_t f = __ldg(uniq + __ldg(hot_slot + h));
-            const unsigned o = f & mask;
-            const size_t l = f >> shift;
-            float* tile = Ghot + (size_t)h * kHotRepD * GS;
-            for (int c0 = 0; c0 < K + 1; c0 += 32) {
-                const int ncol = GS < 32 ? GS : 32;
-                const int col = c0 + lane % ncol;
-                const int grp = lane / ncol, ngrp = 32 / ncol;
-                float sum = 0.f;
-#pragma unroll 8
-                for (int i = 0; i < kHotRepD; i++) {
-                    if (i < kHotRepD / ngrp) {
-                        float* p = tile + (size_t)(grp + i * ngrp) * GS + col;
-                        sum += __ldcg(p);
-                        *p = 0.f;
-                    }
-                }
-                for (int o2 = ncol; o2 < 32; o2 <<= 1) sum += __shfl_xor_sync(kFull, sum, o2);
-                if (grp == 0 && col <= K && sum != 0.f) {
-                    red_add_f32(col < K ? P.p[o].gV + l * K + col : P.p[o].gW + l, sum);
-                    P.p[o].touched[l] = 1;  // (idempotent byte store; every lane that sent something marks the row)
-                }
-            }
-        }
-    } else {
-        const int q = lane % LPR, g = lane / LPR;
-        const unsigned warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-        const unsigned nwarps = (unsigned)main_blocks * (blockDim.x >> 5);
-        const unsigned total = *n_uniq;
-        for (unsigned b0 = warp * (GR * U); b0 < total; b0 += nwarps * (GR * U)) {
-            uint32_t f[U];
-            float4 v[U];
-            float w[U];
-            bool ok[U];
-#pragma unroll
-            for (int u = 0; u < U; u++) {
-                const unsigned idx = b0 + u * GR + g;
-                ok[u] = idx < total && __ldg(hot_of + idx) == 0xffffffffu;
-                f[u] = ok[u] ? __ldg(uniq + idx) : 0u;
-                v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-                w[u] = 0.f;
-                if (ok[u]) {
-                    v[u] = *reinterpret_cast<const float4*>(G + (size_t)idx * GS + 4 * q);
-                    if (q == 0) w[u] = G[(size_t)idx * GS + K];
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < U; u++) {
-                if (!ok[u]) continue;
-                const unsigned idx = b0 + u * GR + g;
-                const unsigned o = f[u] & mask;
-                const size_t l = f[u] >> shift;
-                if (v[u].x != 0.f || v[u].y != 0.f || v[u].z != 0.f || v[u].w != 0.f) {
-                    red_add_v4(P.p[o].gV + l * K + 4 * q, v[u]);
-                    *reinterpret_cast<float4*>(G + (size_t)idx * GS + 4 * q) = make_float4(0.f, 0.f, 0.f, 0.f);
-                    P.p[o].touched[l] = 1;  // (idempotent byte store; every lane that sent something marks the row)
-                }
-                if (q == 0 && w[u] != 0.f) {
-                    red_add_f32(P.p[o].gW + l, w[u]);
-                    G[(size_t)idx * GS + K] = 0.f;
-                    P.p[o].touched[l] = 1;
-                }
-            }
-        }
-    }
-    raise_flags_last_block(P, A, FLAG_PUSHED, me, world, epoch, done_ctr);
-}
-
-// generic path (FFM / NFM / non-fused FM): compact rows cgV[slot][rowlen], cgW[slot].  MAILBOX: posted stores into the
-// owner's gradient inbox at the position of the key in the list the owner received (opos); otherwise peer REDs into the
-// owner's update_g.  One warp per row, 16 B slices, all loads of a row before its stores; the local rows are re-zeroed.
-template <bool MAILBOX>
-__global__ void __launch_bounds__(256)
-push_rows_kernel(const uint32_t* __restrict__ uniq, const unsigned int* __restrict__ n_uniq, const uint32_t* __restrict__ opos,
-                 float* __restrict__ cgW, float* __restrict__ cgV, int rowlen, int recw, PeerTable P, ArenaLayout A, int me,
-                 int world, int shift, unsigned long long epoch, unsigned int* done_ctr) {
-    const unsigned n = *n_uniq;
-    const unsigned mask = (unsigned)world - 1;
+push_rows_kernel(const unsigned int* __restrict__ seg_cnt, float* __restrict__ gv, int gvs, float* __restrict__ gw, int gws,
+                 const uint32_t* __restrict__ hot_p, float* __restrict__ Ghot, int GS, int rowlen, int recw, unsigned cap_pair,
+                 PeerTable P, ArenaLayout A, int me, int world, unsigned long long epoch, unsigned int* done_ctr) {
     const int lane = threadIdx.x & 31;
     const unsigned warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const unsigned nwarps = gridDim.x * (blockDim.x >> 5);
-    const bool vec4 = rowlen % 4 == 0 && rowlen <= 128 * kMaxSl;
-    const int slices = rowlen / 4;
-    for (unsigned i = warp; i < n; i += nwarps) {
-        const uint32_t f = uniq[i];
-        const unsigned o = f & mask;
-        const size_t l = f >> shift;
-        float* gsrc = cgV + (size_t)i * rowlen;
-        const float gw = cgW[i];
-        float* dstrow;
-        if (MAILBOX) {
-            const uint32_t j = opos[i];
-            if (j == 0xffffffffu) continue;  // list overflow: reported through the overflow flag at upload
-            dstrow = reinterpret_cast<float*>(P.p[o].arena + A.grad_inbox + (size_t)me * A.grad_region) + (size_t)j * recw;
-        } else {
-            dstrow = P.p[o].gV + l * rowlen;
-        }
-        if (vec4) {
-            float4 v[kMaxSl];
-#pragma unroll
-            for (int s = 0; s < kMaxSl; s++) {
-                const int sl = lane + 32 * s;
-                if (sl < slices) v[s] = *reinterpret_cast<const float4*>(gsrc + 4 * sl);
-            }
-#pragma unroll
-            for (int s = 0; s < kMaxSl; s++) {
-                const int sl = lane + 32 * s;
-                if (sl < slices) {
-                    if (MAILBOX) *reinterpret_cast<float4*>(dstrow + 4 * sl) = v[s];
-                    else if (v[s].x != 0.f || v[s].y != 0.f || v[s].z != 0.f || v[s].w != 0.f) red_add_v4(dstrow + 4 * sl, v[s]);
-                    *reinterpret_cast<float4*>(gsrc + 4 * sl) = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int slices = rowlen / 4;  // rowlen % 4 == 0 is required by dist_alloc
+    int lpr = 1;
+    while (lpr < slices && lpr < 32) lpr <<= 1;
+    const int G = 32 / lpr, q = lane % lpr, g = lane / lpr;
+    for (int o = 0; o < world; o++) {
+        const unsigned n = seg_cnt[o];
+        float* inbox = reinterpret_cast<float*>(P.p[o].arena + A.grad_inbox + (size_t)me * A.grad_region);
+        for (unsigned j = warp * G + g; j < n; j += nwarps * G) {
+            const size_t pr = (size_t)o * cap_pair + j;
+            float* src = gv + pr * gvs;
+            float* dst = inbox + (size_t)j * recw;
+            const uint32_t h = hot_p ? __ldg(hot_p + pr) : 0xffffffffu;
+            float gwv = q == 0 ? gw[pr * gws] : 0.f;
+            for (int sl = q; sl < slices; sl += lpr) {
+                float4 v = *reinterpret_cast<const float4*>(src + 4 * sl);
+                if (h != 0xffffffffu) {  // fold (and re-zero) the replica rows of a hot slot: column block sl, + gW at column rowlen
+                    float* tile = Ghot + (size_t)h * kHotRep * GS;
+#pragma unroll 8
+                    for (int rp = 0; rp < kHotRep; rp++) {
+                        float4* p4 = reinterpret_cast<float4*>(tile + (size_t)rp * GS + 4 * sl);
+                        const float4 t = __ldcg(p4);
+                        v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
+                        *p4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
                 }
+                *reinterpret_cast<float4*>(dst + 4 * sl) = v;
+                *reinterpret_cast<float4*>(src + 4 * sl) = make_float4(0.f, 0.f, 0.f, 0.f);
             }
-        } else {
-            for (int c = lane; c < rowlen; c += 32) {
-                const float v = gsrc[c];
-                if (MAILBOX) dstrow[c] = v;
-                else if (v != 0.f) red_add_f32(dstrow + c, v);
-                gsrc[c] = 0.f;
+            if (q == 0) {
+                if (h != 0xffffffffu) {
+                    float* tile = Ghot + (size_t)h * kHotRep * GS;
+                    for (int rp = 0; rp < kHotRep; rp++) { gwv += __ldcg(tile + (size_t)rp * GS + rowlen); tile[(size_t)rp * GS + rowlen] = 0.f; }
+                }
+                dst[rowlen] = gwv;
+                gw[pr * gws] = 0.f;
             }
-        }
-        if (lane == 0) {
-            if (MAILBOX) dstrow[rowlen] = gw;
-            else {
-                red_add_f32(P.p[o].gW + l, gw);
-                P.p[o].touched[l] = 1;
-            }
-            cgW[i] = 0.f;
         }
     }
     raise_flags_last_block(P, A, FLAG_PUSHED, me, world, epoch, done_ctr);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// step 4 (wide rows): owner folds the R gradient inboxes into its shard's update_g (local REDs) and marks the rows
+// step 4: owner folds the R gradient inboxes into its shard's update_g (local REDs) and marks the rows
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 merge_kernel(PeerTable P, ArenaLayout A, int me, int world, int slot, unsigned long long epoch, int rowlen, int recw,
@@ -404,36 +344,29 @@ merge_kernel(PeerTable P, ArenaLayout A, int me, int world, int slot, unsigned l
     const int lane = threadIdx.x & 31;
     const unsigned warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const unsigned nwarps = gridDim.x * (blockDim.x >> 5);
-    const bool vec4 = rowlen % 4 == 0 && recw % 4 == 0 && rowlen <= 128 * kMaxSl;
     const int slices = rowlen / 4;
+    int lpr = 1;
+    while (lpr < slices && lpr < 32) lpr <<= 1;
+    const int G = 32 / lpr, q = lane % lpr, g = lane / lpr;
     for (int src = 0; src < world; src++) {
         const unsigned char* region = P.p[me].arena + A.key_inbox + ((size_t)slot * world + src) * A.key_region;
         const unsigned n = *reinterpret_cast<const volatile unsigned int*>(region);
         const uint2* pairs = reinterpret_cast<const uint2*>(region + 64);
         const float* recs = reinterpret_cast<const float*>(P.p[me].arena + A.grad_inbox + (size_t)src * A.grad_region);
-        for (unsigned j = warp; j < n; j += nwarps) {
+        for (unsigned j = warp * G + g; j < n; j += nwarps * G) {
             const float* rec = recs + (size_t)j * recw;
             const size_t l = pairs[j].x;
             float* gdst = gV + l * (size_t)rowlen;
-            if (vec4) {
-                float4 v[kMaxSl];
-#pragma unroll
-                for (int s = 0; s < kMaxSl; s++) {
-                    const int sl = lane + 32 * s;
-                    if (sl < slices) v[s] = __ldcg(reinterpret_cast<const float4*>(rec + 4 * sl));
-                }
-#pragma unroll
-                for (int s = 0; s < kMaxSl; s++) {
-                    const int sl = lane + 32 * s;
-                    if (sl < slices && (v[s].x != 0.f || v[s].y != 0.f || v[s].z != 0.f || v[s].w != 0.f)) red_add_v4(gdst + 4 * sl, v[s]);
-                }
-            } else {
-                for (int c = lane; c < rowlen; c += 32) red_add_f32(gdst + c, __ldcg(rec + c));
+            bool any = false;
+            for (int sl = q; sl < slices; sl += lpr) {
+                const float4 v = __ldcg(reinterpret_cast<const float4*>(rec + 4 * sl));
+                if (v.x != 0.f || v.y != 0.f || v.z != 0.f || v.w != 0.f) { red_add_v4(gdst + 4 * sl, v); any = true; }
             }
-            if (lane == 0) {
-                red_add_f32(gW + l, __ldcg(rec + rowlen));
-                touched[l] = 1;
+            if (q == 0) {
+                const float w = __ldcg(rec + rowlen);
+                if (w != 0.f) { red_add_f32(gW + l, w); any = true; }
             }
+            if (any) touched[l] = 1;  // (idempotent byte store; every lane that added something marks the row)
         }
     }
 }
@@ -448,21 +381,21 @@ int dist_alloc(lctr_ctx* c) {
     c->dist = d;
     d->rank = c->cfg.rank; d->world = R;
     while ((1 << d->shift) < R) d->shift++;
+    LCTR_CHECK(c->rowlen % 4 == 0, "multi-GPU exchange moves rows in 16 B slices: rowlen %zu must be a multiple of 4", c->rowlen);
     // keys of one batch: at most its entry count (cfg.max_nnz), at most the id space
     d->cap_keys = c->cfg.max_nnz ? std::min<size_t>(c->cfg.max_nnz, c->F) : c->F;
-    // keys one requester sends one owner: U / R on average (owner = fid mod R); twice that plus slack, at most the shard
-    d->cap_pair = std::min<size_t>(c->Fl, 2 * d->cap_keys / R + 4096);
+    // keys one requester sends one owner: U / R on average (owner = fid mod R, binomially tight); 1.5x that plus slack
+    d->cap_pair = std::min<size_t>(c->Fl, 3 * d->cap_keys / (2 * R) + 4096);
+    d->rows_x = (size_t)R * d->cap_pair;
     d->recw = (int)((c->rowlen + 4 + 3) / 4 * 4);
-    const char* pm0 = getenv("LCTR_DIST_PUSH");
-    d->mailbox = pm0 ? strcmp(pm0, "mailbox") == 0 : c->rowlen >= 64;
     ArenaLayout& A = d->A;
     size_t off = 0;
     A.flags = off; off = align_up(off + (size_t)(3 + kNumSlots) * kMaxWorld * sizeof(unsigned long long), 256);
     A.key_region = align_up(64 + d->cap_pair * sizeof(uint2), 256);
     A.key_inbox = off; off += A.key_region * kNumSlots * 2 * R;
-    A.cacheW = off; off = align_up(off + d->cap_keys * sizeof(float), 256);
-    A.cacheV = off; off = align_up(off + d->cap_keys * c->rowlen * sizeof(float), 256);
-    A.grad_region = d->mailbox ? align_up(d->cap_pair * (size_t)d->recw * sizeof(float), 256) : 0;
+    A.cacheW = off; off = align_up(off + d->rows_x * sizeof(float), 256);
+    A.cacheV = off; off = align_up(off + d->rows_x * c->rowlen * sizeof(float), 256);
+    A.grad_region = align_up(d->cap_pair * (size_t)d->recw * sizeof(float), 256);
     A.grad_inbox = off; off += A.grad_region * R;
     A.total = off;
     LCTR_CUDA(cudaMalloc((void**)&d->arena, A.total));
@@ -470,20 +403,27 @@ int dist_alloc(lctr_ctx* c) {
     d->bytes += A.total;
     LCTR_CUDA(cudaMalloc((void**)&d->send_cnt, kMaxWorld * sizeof(unsigned int)));
     LCTR_CUDA(cudaMemsetAsync(d->send_cnt, 0, kMaxWorld * sizeof(unsigned int), c->stream));
+    LCTR_CUDA(cudaMalloc((void**)&d->seg_cnt, (size_t)kNumSlots * kMaxWorld * sizeof(unsigned int)));
+    LCTR_CUDA(cudaMemsetAsync(d->seg_cnt, 0, (size_t)kNumSlots * kMaxWorld * sizeof(unsigned int), c->stream));
     LCTR_CUDA(cudaMalloc((void**)&d->opos, (size_t)kNumSlots * d->cap_keys * sizeof(uint32_t)));
     d->bytes += (size_t)kNumSlots * d->cap_keys * sizeof(uint32_t);
     LCTR_CUDA(cudaMalloc((void**)&d->done_ctr, 4 * sizeof(unsigned int)));
     LCTR_CUDA(cudaMemsetAsync(d->done_ctr, 0, 4 * sizeof(unsigned int), c->stream));
     LCTR_CUDA(cudaMalloc((void**)&d->overflow, sizeof(int)));
     LCTR_CUDA(cudaMemsetAsync(d->overflow, 0, sizeof(int), c->stream));
-    if (!fused_kernels_ok(c)) {  // the fused FM kernels keep their gradients in fm_fused.cu's G / Ghot
-        LCTR_CUDA(cudaMalloc((void**)&d->cgW, d->cap_keys * sizeof(float)));
-        LCTR_CUDA(cudaMalloc((void**)&d->cgV, d->cap_keys * c->rowlen * sizeof(float)));
-        LCTR_CUDA(cudaMemsetAsync(d->cgW, 0, d->cap_keys * sizeof(float), c->stream));
-        LCTR_CUDA(cudaMemsetAsync(d->cgV, 0, d->cap_keys * c->rowlen * sizeof(float), c->stream));
-        d->bytes += d->cap_keys * (c->rowlen + 1) * sizeof(float);
+    if (fused_kernels_ok(c)) {  // the fused FM / NFM kernels keep their gradients in fm_fused.cu's G / Ghot (rows p)
+        LCTR_CUDA(cudaMalloc((void**)&d->hot_p, (size_t)kNumSlots * d->rows_x * sizeof(uint32_t)));
+        LCTR_CUDA(cudaMemsetAsync(d->hot_p, 0xff, (size_t)kNumSlots * d->rows_x * sizeof(uint32_t), c->stream));
+        d->bytes += (size_t)kNumSlots * d->rows_x * sizeof(uint32_t);
+    } else {
+        LCTR_CUDA(cudaMalloc((void**)&d->cgW, d->rows_x * sizeof(float)));
+        LCTR_CUDA(cudaMalloc((void**)&d->cgV, d->rows_x * c->rowlen * sizeof(float)));
+        LCTR_CUDA(cudaMemsetAsync(d->cgW, 0, d->rows_x * sizeof(float), c->stream));
+        LCTR_CUDA(cudaMemsetAsync(d->cgV, 0, d->rows_x * c->rowlen * sizeof(float), c->stream));
+        d->bytes += d->rows_x * (c->rowlen + 1) * sizeof(float);
     }
-    // compute view: the batch-compact cache and gradient rows (indexed by slot)
+    c->dist_rows = d->rows_x;
+    // compute view: the batch-compact cache and gradient rows (indexed by exchange row p)
     c->cW = reinterpret_cast<float*>(d->arena + A.cacheW);
     c->cV = reinterpret_cast<float*>(d->arena + A.cacheV);
     c->cgW = d->cgW;
@@ -500,7 +440,8 @@ int dist_free(lctr_ctx* c) {
     for (int r = 0; r < d->world; r++)
         for (int j = 0; j < kNumHandles; j++)
             if (d->opened[r][j]) cudaIpcCloseMemHandle(d->opened[r][j]);
-    cudaFree(d->arena); cudaFree(d->send_cnt); cudaFree(d->opos); cudaFree(d->done_ctr); cudaFree(d->overflow);
+    cudaFree(d->arena); cudaFree(d->send_cnt); cudaFree(d->seg_cnt); cudaFree(d->opos); cudaFree(d->done_ctr); cudaFree(d->overflow);
+    if (d->hot_p) cudaFree(d->hot_p);
     if (d->cgW) cudaFree(d->cgW);
     if (d->cgV) cudaFree(d->cgV);
     c->cW = c->cV = c->cgW = c->cgV = nullptr;
@@ -527,10 +468,16 @@ int dist_send_keys(lctr_ctx* c, Slot& s, int slot, cudaStream_t st) {
     d->gen[slot]++;
     const int slot2 = slot * 2 + (int)(d->gen[slot] & 1);
     const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>((std::min<int64_t>(s.nnz, (int64_t)c->F) + 255) / 256, (int64_t)c->sm_count * 4));
+    uint32_t* opos = d->opos + (size_t)slot * d->cap_keys;
+    uint32_t* hot_p = d->hot_p ? d->hot_p + (size_t)slot * d->rows_x : nullptr;
+    if (hot_p) LCTR_CUDA(cudaMemsetAsync(hot_p, 0xff, d->rows_x * sizeof(uint32_t), st));  // the previous batch's hot rows
     send_keys_kernel<<<grid, 256, 0, st>>>(s.uniq, s.n_uniq, d->peers, d->A, d->rank, d->world, slot2, d->shift, (unsigned)d->cap_pair,
-                                           d->send_cnt, d->opos + (size_t)slot * d->cap_keys, d->overflow);
-    send_keys_finish_kernel<<<1, 32, 0, st>>>(d->peers, d->A, d->rank, d->world, slot2, slot, (unsigned)d->cap_pair, d->send_cnt, d->gen[slot]);
-    c->launches += 2;
+                                           d->send_cnt, opos, d->overflow);
+    send_keys_finish_kernel<<<1, 32, 0, st>>>(d->peers, d->A, d->rank, d->world, slot2, slot, (unsigned)d->cap_pair, d->send_cnt,
+                                              d->seg_cnt + (size_t)slot * kMaxWorld, d->gen[slot]);
+    const unsigned rg = (unsigned)std::max<int64_t>(1, std::min<int64_t>((s.nnz + 255) / 256, (int64_t)c->sm_count * 8));
+    remap_entries_kernel<<<rg, 256, 0, st>>>(nullptr, s.nnz, opos, s.ent_pslot, s.ent_slot, hot_p ? s.hot_of : nullptr, s.n_uniq, hot_p);
+    c->launches += 3;
     LCTR_CUDA(cudaGetLastError());
     return 0;
 }
@@ -553,7 +500,8 @@ int dist_pre_step(lctr_ctx* c, Slot& s, int slot, bool in_kernel_wait) {
     d->epoch++;
     { ProfScope prof(c, PROF_DIST_PULL);
     serve_pull_kernel<<<c->sm_count * 4, 256, 0, c->stream>>>(d->peers, d->A, d->rank, d->world, slot * 2 + (int)(d->gen[slot] & 1), slot,
-                                                             d->gen[slot], d->epoch, (int)c->rowlen, c->W, c->V, d->done_ctr + 0); }
+                                                             d->gen[slot], d->epoch, (int)c->rowlen, (unsigned)d->cap_pair, c->W, c->V,
+                                                             d->done_ctr + 0); }
     c->launches++;
     if (!in_kernel_wait) {
         ProfScope prof(c, PROF_DIST_BAR1);
@@ -564,53 +512,27 @@ int dist_pre_step(lctr_ctx* c, Slot& s, int slot, bool in_kernel_wait) {
     return 0;
 }
 
-template <int K>
-static void push_fused_go(lctr_ctx* c, Slot& s) {
-    DistState* d = c->dist;
-    FusedState* f = c->fused;
-    const int main_blocks = c->sm_count * 2;
-    push_fused_kernel<K><<<main_blocks + kHotMaxD / 8, 256, 0, c->stream>>>(s.uniq, s.n_uniq, f->G, s.hot_of, s.hot_slot, s.n_hot, f->Ghot,
-                                                                          f->GS, main_blocks, d->peers, d->A, d->rank, d->world,
-                                                                          d->shift, d->epoch, d->done_ctr + 1);
-}
-
 int dist_post_step(lctr_ctx* c, Slot& s, int slot, int64_t rows_divisor) {
     DistState* d = c->dist;
+    (void)s;
+    const unsigned int* seg = d->seg_cnt + (size_t)slot * kMaxWorld;
+    { ProfScope prof(c, PROF_DIST_PUSH);
     if (fused_kernels_ok(c)) {
-        ProfScope prof(c, PROF_DIST_PUSH);
-        switch ((int)c->cfg.factor_cnt) {
-            case 4: push_fused_go<4>(c, s); break;
-            case 8: push_fused_go<8>(c, s); break;
-            case 16: push_fused_go<16>(c, s); break;
-            default: push_fused_go<32>(c, s); break;
-        }
-        c->launches++;
+        FusedState* f = c->fused;
+        push_rows_kernel<<<c->sm_count * 4, 256, 0, c->stream>>>(seg, f->G, f->GS, f->G + c->rowlen, f->GS, d->hot_p + (size_t)slot * d->rows_x,
+                                                                 f->Ghot, f->GS, (int)c->rowlen, d->recw, (unsigned)d->cap_pair, d->peers,
+                                                                 d->A, d->rank, d->world, d->epoch, d->done_ctr + 1);
     } else {
-        { ProfScope prof(c, PROF_DIST_PUSH);
-        const uint32_t* opos = d->opos + (size_t)slot * d->cap_keys;
-        if (d->mailbox)
-            push_rows_kernel<true><<<c->sm_count * 4, 256, 0, c->stream>>>(s.uniq, s.n_uniq, opos, d->cgW, d->cgV, (int)c->rowlen, d->recw,
-                                                                           d->peers, d->A, d->rank, d->world, d->shift, d->epoch, d->done_ctr + 1);
-        else
-            push_rows_kernel<false><<<c->sm_count * 4, 256, 0, c->stream>>>(s.uniq, s.n_uniq, opos, d->cgW, d->cgV, (int)c->rowlen, d->recw,
-                                                                            d->peers, d->A, d->rank, d->world, d->shift, d->epoch, d->done_ctr + 1); }
-        c->launches++;
-        if (d->mailbox) {
-            ProfScope prof(c, PROF_DIST_MERGE);
-            merge_kernel<<<c->sm_count * 4, 256, 0, c->stream>>>(d->peers, d->A, d->rank, d->world, slot * 2 + (int)(d->gen[slot] & 1), d->epoch, (int)c->rowlen, d->recw,
-                                                                 c->gW, c->gV, c->touched);
-            c->launches++;
-        }
-    }
+        push_rows_kernel<<<c->sm_count * 4, 256, 0, c->stream>>>(seg, d->cgV, (int)c->rowlen, d->cgW, 1, nullptr, nullptr, 0, (int)c->rowlen,
+                                                                 d->recw, (unsigned)d->cap_pair, d->peers, d->A, d->rank, d->world, d->epoch,
+                                                                 d->done_ctr + 1);
+    } }
+    { ProfScope prof(c, PROF_DIST_MERGE);
+    merge_kernel<<<c->sm_count * 4, 256, 0, c->stream>>>(d->peers, d->A, d->rank, d->world, slot * 2 + (int)(d->gen[slot] & 1), d->epoch,
+                                                         (int)c->rowlen, d->recw, c->gW, c->gV, c->touched); }
+    c->launches += 2;
     LCTR_CUDA(cudaGetLastError());
-    // owner: sparse updater on the shard; its first kernel waits for "pushes landed" unless the merge already did
-    const unsigned long long* pushed = reinterpret_cast<const unsigned long long*>(d->arena + d->A.flags) + (size_t)FLAG_PUSHED * kMaxWorld;
-    c->apply_wait_flags = (fused_kernels_ok(c) || !d->mailbox) ? pushed : nullptr;
-    c->apply_wait_n = d->world;
-    c->apply_wait_epoch = d->epoch;
-    const int rc = launch_apply(c, rows_divisor);
-    c->apply_wait_flags = nullptr;
-    return rc;
+    return launch_apply(c, rows_divisor);  // sparse updater on the shard (the merge waited for every requester's pushes)
 }
 
 }  // namespace lctr

@@ -307,7 +307,7 @@ __global__ void ffm_tma_kernel(const int64_t* __restrict__ row_ptr, const uint32
                                int Fc, int k, float* __restrict__ pred, float* __restrict__ gW, float* __restrict__ gV,
                                uint8_t* __restrict__ touched, float l2, int64_t rb, double* partial, unsigned int* done,
                                double* out_slot, int do_stats, int CR /* rows per chunk */) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
+    extern __shared__ __align__(16) unsigned char smem_raw[];  // (dynamic shared memory starts 1024 B aligned)
     const int A = Fc * k / 4;     // 16 B slots per row
     const int PPF = k / 4;        // slots per field
     const uint32_t rowbytes = (uint32_t)A * 16u;

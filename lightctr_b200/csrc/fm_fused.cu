@@ -80,12 +80,14 @@ int fused_reserve(lctr_ctx* c, Slot& s, int64_t nnz) {
         LCTR_CUDA(cudaMemset(f->cnt, 0, (size_t)(s.cap_uniq + 64) * sizeof(unsigned int)));
         f->cnt_cap = (size_t)s.cap_uniq;
     }
-    if (f->GS && (size_t)s.cap_uniq > f->G_rows) {
+    // gradient rows: one per slot; on several GPUs one per exchange row (dist.cu re-indexes the entries)
+    const size_t g_rows = c->cfg.world > 1 ? c->dist_rows : (size_t)s.cap_uniq;
+    if (f->GS && g_rows > f->G_rows) {
         LCTR_CUDA(cudaStreamSynchronize(c->stream));
         if (f->G) cudaFree(f->G);
-        LCTR_CUDA(cudaMalloc((void**)&f->G, (size_t)(s.cap_uniq + 64) * f->GS * sizeof(float)));
-        LCTR_CUDA(cudaMemset(f->G, 0, (size_t)(s.cap_uniq + 64) * f->GS * sizeof(float)));
-        f->G_rows = (size_t)s.cap_uniq;
+        LCTR_CUDA(cudaMalloc((void**)&f->G, (g_rows + 64) * f->GS * sizeof(float)));
+        LCTR_CUDA(cudaMemset(f->G, 0, (g_rows + 64) * f->GS * sizeof(float)));
+        f->G_rows = g_rows;
     }
     return 0;
 }

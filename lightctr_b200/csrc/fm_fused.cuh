@@ -29,7 +29,6 @@
 namespace lctr {
 
 constexpr int kHotSampleRows = 512;
-constexpr uint32_t kHotBit = 0x80000000u;
 // stride (floats) of a compact gradient row [gV (k) | gW | pad]: power of two >= k + 1 (rows never straddle a 128 B line)
 __host__ __device__ constexpr int grad_stride(int k) { return k < 8 ? 8 : (k < 16 ? 16 : (k < 32 ? 32 : 64)); }
 
