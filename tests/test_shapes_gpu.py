@@ -125,7 +125,7 @@ def test_fm_parameter_server_update_rules(oracle_api, opt):
     from lightctr_b200 import capi
     ds = load_csr("train_sparse_csr.npz", field_cnt=68)
     k = 8
-    lr = {"ps_sgd": 5.0, "ps_adagrad": 0.05, "ps_dcasgd": 5.0, "ps_dcasgda": 0.5}[opt]
+    lr = {"ps_sgd": 5.0, "ps_adagrad": 0.05, "ps_dcasgd": 5.0, "ps_dcasgda": 0.01}[opt]
     W0, V0 = oracle_api.init_params(1, ds.feature_cnt, k)
     o = oracle_api.FMOracle(ds, k, W0, V0, lr=lr)
     o.opt = opt
