@@ -91,29 +91,33 @@ struct DistState {
 __device__ __forceinline__ unsigned long long* flag_ptr(unsigned char* arena, const ArenaLayout& A, int row, int col) {
     return reinterpret_cast<unsigned long long*>(arena + A.flags) + (size_t)row * kMaxWorld + col;
 }
+// System-scope fences are executed by the few threads that poll / raise flags, never by whole CTAs: membar.sys drains the
+// issuing SM's outstanding peer traffic, and hundreds of CTAs x 256 threads doing it cost ~40 us per kernel (measured: the
+// pull / push kernels of an FM C2 step, 3 MB each, took 46 us with per-thread fences).  The CTA barrier before / after
+// makes the fence cumulative over the other threads' accesses (PTX memory model: causality order through bar.sync).
 __device__ __forceinline__ void wait_flags(unsigned char* my_arena, const ArenaLayout& A, int row, int world,
                                            unsigned long long value) {
     if ((int)threadIdx.x < world) {
         const volatile unsigned long long* f = flag_ptr(my_arena, A, row, threadIdx.x);
         while (*f < value) __nanosleep(40);
+        __threadfence_system();
     }
     __syncthreads();
-    __threadfence_system();
 }
-// every block: fence its stores, count in; the last block raises flag[row][me] = value on every peer
+// every block: one thread fences the block's stores and counts in; the last block raises flag[row][me] = value on every peer
 __device__ __forceinline__ void raise_flags_last_block(const PeerTable& P, const ArenaLayout& A, int row, int me, int world,
                                                        unsigned long long value, unsigned int* ctr) {
-    __threadfence_system();
-    __syncthreads();
     __shared__ bool last;
-    if (threadIdx.x == 0) last = atomicAdd(ctr, 1u) == gridDim.x - 1;
     __syncthreads();
-    if (last) {
+    if (threadIdx.x == 0) {
         __threadfence_system();
-        if ((int)threadIdx.x < world) {
-            volatile unsigned long long* f = flag_ptr(P.p[threadIdx.x].arena, A, row, me);
-            *f = value;
-        }
+        last = atomicAdd(ctr, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (last && (int)threadIdx.x < world) {
+        __threadfence_system();
+        volatile unsigned long long* f = flag_ptr(P.p[threadIdx.x].arena, A, row, me);
+        *f = value;
         if (threadIdx.x == 0) *ctr = 0;
         __threadfence_system();
     }
@@ -157,7 +161,7 @@ send_keys_kernel(const uint32_t* __restrict__ uniq, const unsigned int* __restri
         }
         __syncthreads();
     }
-    __threadfence_system();
+    if (threadIdx.x == 0) __threadfence_system();  // after the loop's last CTA barrier: cumulative over the CTA's stores
 }
 // counts into the owners' headers (and kept locally for the push), counters re-armed, then the generation flag of
 // (slot, me) on every owner

@@ -219,9 +219,9 @@ fm_fused_kernel(const int64_t* __restrict__ row_ptr, const uint32_t* __restrict_
         if (threadIdx.x < n_wait) {
             const volatile unsigned long long* f = wait_flags + threadIdx.x;
             while (*f < wait_epoch) __nanosleep(40);
+            __threadfence_system();  // by the polling threads only; the CTA barrier extends it to the others
         }
         __syncthreads();
-        __threadfence_system();
     }
     constexpr int LPR = K / 4;                           // lanes per V row (one float4 each)
     constexpr int GR = 32 / LPR;                         // rows per gather instruction

@@ -29,9 +29,9 @@ compact_touched_kernel(uint8_t* __restrict__ touched, size_t F, uint32_t* __rest
         if ((int)threadIdx.x < n_wait) {
             const volatile unsigned long long* f = wait_flags + threadIdx.x;
             while (*f < wait_epoch) __nanosleep(40);
+            __threadfence_system();
         }
         __syncthreads();
-        __threadfence_system();
     }
     const int lane = threadIdx.x & 31;
     const size_t warp = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
