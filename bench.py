@@ -271,6 +271,12 @@ def measure(wname, wl, args, rank, world, local_rank, dist, steps, warmup, do_e2
         with torch.cuda.stream(stream):
             if do_flush:
                 flush.zero_()
+            if world > 1 and do_flush:
+                # the 256 MB flush saturates THIS GPU's memory system for ~80 us; a peer that is already inside its step
+                # would have its NVLink stores into this GPU queue behind it (measured: 3 MB pull / push kernels stretched
+                # from ~10 to ~45 us).  Ranks therefore leave the flush together; the timed region starts after it.
+                stream.synchronize()
+                dist.barrier()
             if timed_events is not None:
                 timed_events[0].record(stream)
         ctx.train_step(i % NB, want_stats=False)
@@ -481,7 +487,7 @@ def main():
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16 dense layers (fp32 accumulate, fp32 masters) + f32 embeddings" if mlp_bf16 else "f32",
             "data": "synthetic",
-            "config": {"workload": wl["desc"], "l2": "flushed between timed steps (256 MB write)", "batch_per_gpu": B,
+            "config": {"workload": wl["desc"], "l2": "flushed between timed steps (256 MB write)" + ("; ranks barrier after the flush, before the timed region" if world > 1 else ""), "batch_per_gpu": B,
                        "global_batch": world * B, "nnz_per_row": n,
                        **({"mlp": "bf16 mma, fused fwd+bwd per 128-sample tile" if mlp_bf16 else "fp32 reference-order"}
                           if wl["model"] == "nfm" else {}),

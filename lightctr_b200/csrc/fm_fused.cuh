@@ -219,7 +219,7 @@ fm_fused_kernel(const int64_t* __restrict__ row_ptr, const uint32_t* __restrict_
         if (threadIdx.x < n_wait) {
             const volatile unsigned long long* f = wait_flags + threadIdx.x;
             while (*f < wait_epoch) __nanosleep(40);
-            __threadfence_system();  // by the polling threads only; the CTA barrier extends it to the others
+            __threadfence();  // the flags and the delivered rows live in this GPU's memory: device scope suffices on the acquire side
         }
         __syncthreads();
     }

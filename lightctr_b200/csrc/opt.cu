@@ -29,7 +29,7 @@ compact_touched_kernel(uint8_t* __restrict__ touched, size_t F, uint32_t* __rest
         if ((int)threadIdx.x < n_wait) {
             const volatile unsigned long long* f = wait_flags + threadIdx.x;
             while (*f < wait_epoch) __nanosleep(40);
-            __threadfence_system();
+            __threadfence();
         }
         __syncthreads();
     }

@@ -47,6 +47,12 @@ ncuffm)
   LCTR_FFM_TMA=0 timeout 900 ncu --set full --clock-control none --import-source on -k regex:"ffm_tma_kernel|ffm_fused_kernel" -s 8 -c 2 \
       -o $O/prof_${TAG}_ffm_c3_old -f python bench.py --workload ffm_c3 --steps 4 --warmup 3 --no-cpu-baseline > $O/ncu_ffm_old_$TAG.log 2>&1
   echo "ncu rc=$?" ;;
+distq)
+  N=${NGPU:-2}
+  for v in gpu; do
+  LCTR_DIST_FENCE=$v timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus $N --steps 100 --warmup 10 --no-c5 \
+      > $O/bench_${TAG}_fm_c2_n${N}_$v.json 2> $O/bench_${TAG}_fm_c2_n${N}_$v.err; echo "dist bench $v rc=$?"
+  done ;;
 lab)
   bash scripts/lab/run_lab.sh > /dev/null 2>&1; cp $O/lab_b4096.txt $O/lab_${TAG}_b4096.txt; cp $O/lab_b65536.txt $O/lab_${TAG}_b65536.txt ;;
 esac
