@@ -179,7 +179,7 @@ int lctr_create(const lctr_cfg* cfg, lctr_ctx** out) {
     LCTR_CHECK(cfg->model != LCTR_MODEL_FFM || cfg->field_cnt > 0, "lctr_create: FFM needs field_cnt > 0");
     if (cfg->model == LCTR_MODEL_WND) {
         LCTR_CHECK(cfg->field_cnt > 0 && cfg->field_cnt <= 2048, "lctr_create: Wide&Deep needs 0 < field_cnt <= 2048");
-        LCTR_CHECK(cfg->world <= 1 && cfg->deterministic == 0, "lctr_create: Wide&Deep is single-GPU, RED scatter only");
+        LCTR_CHECK(cfg->deterministic == 0, "lctr_create: Wide&Deep uses the RED scatter (deterministic = 0)");
     }
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
@@ -516,8 +516,13 @@ int lctr_train_step(lctr_ctx* c, int slot, int64_t rb, int64_t re, float* loss_s
                 rc = launch_ffm_forward(c, s, rb, re, true) || launch_ffm_backward(c, s, rb, re) || launch_apply(c, re - rb);
             break;
         case LCTR_MODEL_WND:
-            rc = mlp_reserve(c, re - rb) || wnd_reserve(c, re - rb) || launch_wnd_forward(c, s, rb, re) ||
-                 launch_nfm_mlp(c, s, rb, re, re - rb) || launch_wnd_backward(c, s, rb, re) || launch_apply(c, re - rb);
+            if (c->cfg.world > 1)  // rows from the owners' shards into the batch-compact cache, gradients back to the owners
+                rc = dist_pre_step(c, s, slot, false) || mlp_reserve(c, re - rb) || wnd_reserve(c, re - rb) ||
+                     launch_wnd_forward(c, s, rb, re) || launch_nfm_mlp(c, s, rb, re, re - rb) || launch_wnd_backward(c, s, rb, re) ||
+                     dist_post_step(c, s, slot, re - rb);
+            else
+                rc = mlp_reserve(c, re - rb) || wnd_reserve(c, re - rb) || launch_wnd_forward(c, s, rb, re) ||
+                     launch_nfm_mlp(c, s, rb, re, re - rb) || launch_wnd_backward(c, s, rb, re) || launch_apply(c, re - rb);
             break;
         case LCTR_MODEL_NFM:
             if (fused_kernels_ok(c) && s.fused_valid) {
@@ -723,11 +728,24 @@ int lctr_wait(lctr_ctx* c, uint64_t ticket, float* loss_sum, float* acc_cnt) {
 int lctr_predict(lctr_ctx* c, int slot, int quirk_sumvx_slot, float* pctr) {
     LCTR_CHECK(c, "null ctx");
     LCTR_CHECK(slot >= 0 && slot < kNumSlots, "slot %d out of range", slot);
+    Slot& s = c->slots[slot];
+    int rc = 0;
+    if (c->cfg.model == LCTR_MODEL_WND) {
+        // Distributed_Algo_Abst::Predict (distributed_algo_abst.h:163-174): a forward pass over the slot; with several
+        // ranks a collective call (every rank serves the rows its peers need)
+        const float* out = nullptr;
+        rc = (c->cfg.world > 1 && dist_pre_step(c, s, slot, false)) || mlp_reserve(c, s.rows) || wnd_reserve(c, s.rows) ||
+             launch_wnd_forward(c, s, 0, s.rows) || mlp_forward_only(c, s.rows, &out) || launch_wnd_pred(c, s, out, 0, s.rows);
+        if (rc) return 1;
+        if (pctr) {
+            LCTR_CUDA(cudaMemcpyAsync(pctr, s.pred, (size_t)s.rows * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+            LCTR_CUDA(cudaStreamSynchronize(c->stream));
+        }
+        return 0;
+    }
     // world > 1: the compute view only holds the rows pulled by the last train step, at their pre-update values
     LCTR_CHECK(c->cfg.world == 1, "lctr_predict: multi-GPU contexts keep sharded tables; download the parameters "
                                   "(lctr_download_params) into a single-GPU context to predict");
-    Slot& s = c->slots[slot];
-    int rc = 0;
     if (c->cfg.model == LCTR_MODEL_FFM) {
         // parity mode: the reference's own pair loop order; otherwise the field-pair factorised forward
         rc = c->cfg.deterministic == 1 ? launch_ffm_predict_inorder(c, s) : launch_ffm_forward(c, s, 0, s.rows, false);

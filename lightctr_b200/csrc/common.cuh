@@ -377,6 +377,8 @@ int wnd_reserve(lctr_ctx* c, int64_t rows);
 void wnd_free(lctr_ctx* c);
 int launch_wnd_forward(lctr_ctx* c, Slot& s, int64_t rb, int64_t re);
 int launch_wnd_backward(lctr_ctx* c, Slot& s, int64_t rb, int64_t re);
+int launch_wnd_pred(lctr_ctx* c, Slot& s, const float* mlp_out, int64_t rb, int64_t re);
+int mlp_forward_only(lctr_ctx* c, int64_t rows, const float** out);
 // width of the dense chain's input: k (NFM bi-interaction) or Fc * d (Wide&Deep concat)
 inline size_t mlp_in0(const lctr_cfg& cf) {
     return cf.model == LCTR_MODEL_WND ? (size_t)cf.field_cnt * cf.factor_cnt : (size_t)cf.factor_cnt;

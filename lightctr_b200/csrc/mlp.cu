@@ -193,9 +193,12 @@ int mlp_reserve(lctr_ctx* c, int64_t rows) {
     return 0;
 }
 
-// world > 1: the dense gradients of the ranks are summed before the updater (data-parallel dense layers)
+// world > 1: the dense gradients of the ranks are summed before the updater (data-parallel dense layers).  Wide&Deep without
+// a registered hook keeps the reference's behaviour: every worker trains its OWN dense layers, only the wide weights and the
+// tensors are shared through the parameter servers (distributed_algo_abst.h:115-118,279)
 int mlp_sync_dense_grad(lctr_ctx* c) {
     if (c->cfg.world <= 1) return 0;
+    if (c->cfg.model == LCTR_MODEL_WND && !c->dense_allreduce) return 0;
     LCTR_CHECK(c->dense_allreduce, "NFM with world=%d needs lctr_set_dense_allreduce (dense gradients are all-reduced "
                "between the MLP backward and its updater)", c->cfg.world);
     LCTR_CHECK(c->dense_allreduce(c->dense_allreduce_user, c->dense_grad, c->dense_grad_n, (void*)c->stream) == 0,
@@ -245,6 +248,15 @@ static void mlp_apply_dev(lctr_ctx* c, uint64_t mb) {
         adagrad_dense_kernel<<<mlp_blocks((int64_t)nw), 256, 0, c->stream>>>(L.w, L.dw, L.acc_w, nw, invB, c->cfg.learning_rate);
         c->launches += 2;
     }
+}
+
+// forward only (fp32 reference-order layers) on the rows staged in c->z; *out = the last layer's output [rows]
+int mlp_forward_only(lctr_ctx* c, int64_t rows, const float** out) {
+    LCTR_CHECK(c->cfg.mlp_precision == LCTR_MLP_FP32, "forward-only dense layers run in the fp32 mode");
+    mlp_forward_dev(c, (int)rows);
+    *out = c->layers[c->n_layers - 1].act;
+    LCTR_CUDA(cudaGetLastError());
+    return 0;
 }
 
 // forward MLP on c->z, loss, backward to c->dz, accumulate dW/db, Adagrad on the MLP (fp32, reference order).

@@ -79,7 +79,7 @@ wnd_backward_kernel(const int64_t* __restrict__ row_ptr, const uint32_t* __restr
         const uint32_t f = __ldg(fid + i);
         const float x = val ? __ldg(val + i) : 1.f;
         red_add_f32(gW + f, lossv * x + l2 * __ldg(W + f));  // gradW = loss * X + L2Reg_ratio * w (:256)
-        touched[f] = 1;
+        if (touched) touched[f] = 1;
     }
     const uint32_t* sr = zsrc + (size_t)(r - rb) * Fc;
     const float* dr = dz + (size_t)(r - rb) * Fc * d;
@@ -87,7 +87,7 @@ wnd_backward_kernel(const int64_t* __restrict__ row_ptr, const uint32_t* __restr
         const uint32_t f = sr[a];
         if (f == 0xffffffffu) continue;
         for (int c = 0; c < d; c++) red_add_f32(gE + (size_t)f * d + c, dr[(size_t)a * d + c]);  // :274-276
-        touched[f] = 1;
+        if (touched) touched[f] = 1;
     }
 }
 
@@ -111,9 +111,22 @@ int launch_wnd_forward(lctr_ctx* c, Slot& s, int64_t rb, int64_t re) {
     if (rows <= 0) return 0;
     LCTR_CHECK(s.has_field, "Wide&Deep batch uploaded without the field array");
     ProfScope prof(c, PROF_FM_FWD);
-    wnd_forward_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, c->stream>>>(s.row_ptr, s.fid, s.field, s.has_val ? s.val : nullptr,
+    wnd_forward_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, c->stream>>>(s.row_ptr, c->cfg.world > 1 ? s.ent_pslot : s.fid, s.field, s.has_val ? s.val : nullptr,
                                                                          c->cW, c->cV, (int)c->cfg.field_cnt, (int)c->cfg.factor_cnt,
                                                                          c->z, c->wnd_src, s.wide, rb, re);
+    c->launches++;
+    LCTR_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// Distributed_Algo_Abst::Predict (distributed_algo_abst.h:163-174): pCTR = sigmoid(wide + chain output), no gradients
+__global__ void wnd_pred_kernel(const float* __restrict__ wide, const float* __restrict__ out, float* __restrict__ pred, int64_t rb, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) pred[rb + i] = ref_sigmoid(wide[rb + i] + out[i]);  // :236
+}
+int launch_wnd_pred(lctr_ctx* c, Slot& s, const float* mlp_out, int64_t rb, int64_t re) {
+    if (re - rb <= 0) return 0;
+    wnd_pred_kernel<<<(unsigned)((re - rb + 255) / 256), 256, 0, c->stream>>>(s.wide, mlp_out, s.pred, rb, re - rb);
     c->launches++;
     LCTR_CUDA(cudaGetLastError());
     return 0;
@@ -123,9 +136,9 @@ int launch_wnd_backward(lctr_ctx* c, Slot& s, int64_t rb, int64_t re) {
     const int64_t rows = re - rb;
     if (rows <= 0) return 0;
     ProfScope prof(c, PROF_FM_BWD_RED);
-    wnd_backward_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, c->stream>>>(s.row_ptr, s.fid, s.has_val ? s.val : nullptr, s.label, s.pred,
+    wnd_backward_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, c->stream>>>(s.row_ptr, c->cfg.world > 1 ? s.ent_pslot : s.fid, s.has_val ? s.val : nullptr, s.label, s.pred,
                                                                           c->cW, c->wnd_src, c->dz, (int)c->cfg.field_cnt,
-                                                                          (int)c->cfg.factor_cnt, c->cgW, c->cgV, c->touched,
+                                                                          (int)c->cfg.factor_cnt, c->cgW, c->cgV, c->cfg.world > 1 ? nullptr : c->touched,
                                                                           c->cfg.l2_reg, rb, re);
     c->launches++;
     LCTR_CUDA(cudaGetLastError());

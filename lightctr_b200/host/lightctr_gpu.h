@@ -23,11 +23,13 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 
 #include <algorithm>
 #include <fstream>
 #include <iomanip>
 #include <iostream>
+#include <sstream>
 #include <string>
 #include <vector>
 
@@ -663,6 +665,187 @@ protected:
     size_t epoch;
     std::vector<std::vector<float> > dataSet;
     std::vector<int> label;
+};
+
+// ==========================================================================================================
+// distributed_algo_abst.h:86-340 -- Wide&Deep worker: one process per GPU instead of ZeroMQ workers + parameter servers
+// ==========================================================================================================
+// Same constructor (`<dataPath>_<rank>.csv`, :95-101), members and Train() / Predict() flow.  What the reference keeps
+// on parameter-server processes -- the wide weights (scalar SGD, paramserver.h:295-300) and the per-feature tensors
+// (tensor SGD, :232-237) -- lives in owner-sharded tables across the ranks' GPUs (owner = fid mod world) and moves
+// over NVLink peer memory; every worker trains its OWN dense layers, as in the reference (:115-118, :279).
+// Rank / world come from LIGHTCTR_B200_RANK / LIGHTCTR_B200_WORLD (the reference: `worker.Rank()` from its master); with
+// world > 1 the CUDA-IPC handles and the global feature / field counts are exchanged through files in the directory
+// LIGHTCTR_B200_RDV (any channel works: the blobs are opaque).
+class Distributed_Algo_Abst {
+public:
+    Distributed_Algo_Abst(std::string _dataPath, size_t _epoch_cnt) : epoch(_epoch_cnt), ctx(NULL), ds(NULL) {
+        const char* er = getenv("LIGHTCTR_B200_RANK");
+        const char* ew = getenv("LIGHTCTR_B200_WORLD");
+        rank = er ? atoi(er) : 0;
+        world = ew ? atoi(ew) : 1;
+        std::stringstream ss;
+        ss << _dataPath << "_" << rank << ".csv";
+        loadDataRow(ss.str());
+        L2Reg_ratio = 0.f;
+        batch_size = GradientUpdater::__global_minibatch_size;
+        if (world > 1) exchange_counts();
+        // dense layers: input layer first, then the output layer (:115-117) -- the order of the rand() stream
+        for (int l = 0; l < 2; l++) {
+            const size_t in = l == 0 ? field_cnt * factor_dim : 50, out = l == 0 ? 50 : 1;
+            layers.push_back(Fully_Conn_Layer_Host(in, out));
+        }
+        make_ctx();
+    }
+    ~Distributed_Algo_Abst() {
+        if (ds) lctr_free_dataset(ds);
+        if (ctx) lctr_destroy(ctx);
+    }
+    void Train() {  // :130-161
+        GradientUpdater::__global_bTraining = true;
+        std::vector<float> loss_curve, accuracy_curve;
+        for (size_t i = 0; i < this->epoch; i++) {
+            train_loss = 0;
+            accuracy = 0;
+            const size_t minibatch_epoch = (this->dataRow_cnt + this->batch_size - 1) / this->batch_size;
+            for (size_t p = 0; p < minibatch_epoch; p++) {
+                const size_t start_pos = p * batch_size;
+                float l = 0, c = 0;
+                LCTR_OK(lctr_train_step(ctx, 0, (int64_t)start_pos, (int64_t)std::min(start_pos + batch_size, this->dataRow_cnt), &l, &c));
+                train_loss += l;
+                accuracy += (size_t)c;
+                for (size_t li = 0; li < layers.size(); li++) {  // applyBatchGradient re-draws the masks (:279)
+                    layers[li].resample();
+                    LCTR_OK(lctr_mlp_set_mask(ctx, (int)li, layers[li].mask.data()));
+                }
+            }
+            printf("[Worker Train] epoch = %zu loss = %f accuracy = %f\n", i, train_loss, 1.0 * accuracy / dataRow_cnt);
+            loss_curve.push_back(train_loss);
+            accuracy_curve.push_back(1.0 * accuracy / dataRow_cnt);
+        }
+        for (size_t i = 0; i < this->epoch; i++) printf("%f(%.3f) ", loss_curve[i], accuracy_curve[i]);
+        puts("");
+        puts("Train Task Complete");
+        GradientUpdater::__global_bTraining = false;
+    }
+    void Predict() {  // :163-174
+        GradientUpdater::__global_bTraining = false;
+        train_loss = 0;
+        accuracy = 0;
+        std::vector<float> p(dataRow_cnt);
+        LCTR_OK(lctr_predict(ctx, 0, -1, p.data()));
+        for (size_t rid = 0; rid < dataRow_cnt; rid++) {
+            const float pCTR = p[rid];
+            train_loss += (int)ds->label[rid] == 1 ? -log(pCTR) : -log(1.0 - pCTR);
+            if (pCTR >= 0.5 && ds->label[rid] == 1) accuracy++;        // (>= here, > in the trainers: :239-243)
+            else if (pCTR < 0.5 && ds->label[rid] == 0) accuracy++;
+        }
+        printf("[Worker Predict] loss = %f accuracy = %f\n", train_loss, 1.0 * accuracy / dataRow_cnt);
+    }
+    float last_loss() const { return train_loss; }
+    size_t feature_cnt, field_cnt, dataRow_cnt;
+    float L2Reg_ratio;
+    static const size_t factor_dim = 4;  // :327
+    std::vector<Fully_Conn_Layer_Host> layers;
+    lctr_ctx* ctx;
+
+private:
+    void loadDataRow(std::string dataPath) {  // :283-318 (libffm rows; counts from the data)
+        if (lctr_load_libffm(dataPath.c_str(), 0, 0, &ds) != 0) { std::cout << "open file error!" << std::endl; exit(1); }
+        feature_cnt = ds->feature_cnt;
+        field_cnt = 0;
+        for (int64_t i = 0; i < ds->nnz; i++) field_cnt = std::max(field_cnt, (size_t)ds->field[i] + 1);
+        dataRow_cnt = (size_t)ds->rows;
+    }
+    std::string rdv(const char* what, int r) const {
+        const char* dir = getenv("LIGHTCTR_B200_RDV");
+        if (!dir) { std::cout << "world > 1 needs LIGHTCTR_B200_RDV (a directory all ranks can write)" << std::endl; exit(1); }
+        std::stringstream ss;
+        ss << dir << "/" << what << "_" << r << ".bin";
+        return ss.str();
+    }
+    void put(const char* what, const void* data, size_t bytes) const {
+        const std::string path = rdv(what, rank), tmp = path + ".tmp";
+        FILE* f = fopen(tmp.c_str(), "wb");
+        if (!f || fwrite(data, 1, bytes, f) != bytes) { std::cout << "rendezvous write error" << std::endl; exit(1); }
+        fclose(f);
+        rename(tmp.c_str(), path.c_str());
+    }
+    void get(const char* what, int r, void* data, size_t bytes) const {
+        const std::string path = rdv(what, r);
+        for (int tries = 0; tries < 60000; tries++) {
+            FILE* f = fopen(path.c_str(), "rb");
+            if (f) {
+                const size_t n = fread(data, 1, bytes, f);
+                fclose(f);
+                if (n == bytes) return;
+            }
+            struct timespec ts = {0, 1000000};
+            nanosleep(&ts, NULL);
+        }
+        std::cout << "rendezvous timeout: " << path << std::endl;
+        exit(1);
+    }
+    void exchange_counts() {  // the tables are sized for the largest id any rank has seen (the PS grows on demand)
+        size_t mine[2] = {feature_cnt, field_cnt};
+        put("counts", mine, sizeof(mine));
+        for (int r = 0; r < world; r++) {
+            size_t other[2];
+            get("counts", r, other, sizeof(other));
+            feature_cnt = std::max(feature_cnt, other[0]);
+            field_cnt = std::max(field_cnt, other[1]);
+        }
+    }
+    void make_ctx() {
+        lctr_cfg cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.abi_version = LCTR_ABI_VERSION;
+        cfg.model = LCTR_MODEL_WND;
+        cfg.optimizer = LCTR_OPT_PS_SGD;  // ParamServer(UpdaterType::SGD), paramserver.h:49
+        const char* dev = getenv("LIGHTCTR_B200_DEVICE");
+        cfg.device = dev ? atoi(dev) : rank;
+        cfg.feature_cnt = feature_cnt;
+        cfg.field_cnt = (uint32_t)field_cnt;
+        cfg.factor_cnt = (uint32_t)factor_dim;
+        cfg.learning_rate = GradientUpdater::__global_learning_rate;
+        cfg.l2_reg = L2Reg_ratio;
+        cfg.minibatch_size = GradientUpdater::__global_minibatch_size;
+        cfg.n_hidden = 1;
+        cfg.hidden[0] = 50;
+        cfg.activation = LCTR_ACT_TANH;  // Fully_Conn_Layer<Tanh> input layer (:115)
+        cfg.mlp_precision = LCTR_MLP_FP32;
+        cfg.rank = rank;
+        cfg.world = world;
+        cfg.max_nnz = (uint64_t)ds->nnz;
+        LCTR_OK(lctr_create(&cfg, &ctx));
+        // wide weights start at 0 (Value::initParam, :73-75), tensors at GaussRand() (TensorWrapper, paramserver.h:41-45);
+        // drawn here per feature in id order, identically on every rank, after the layers' draws
+        std::vector<float> W(feature_cnt, 0.f), E(feature_cnt * factor_dim);
+        for (size_t i = 0; i < E.size(); i++) E[i] = GaussRand();
+        LCTR_OK(lctr_upload_params(ctx, W.data(), E.data()));
+        for (size_t l = 0; l < layers.size(); l++) {
+            LCTR_OK(lctr_mlp_upload(ctx, (int)l, layers[l].weight.data(), layers[l].bias.data()));
+            LCTR_OK(lctr_mlp_set_mask(ctx, (int)l, layers[l].mask.data()));
+        }
+        if (world > 1) {
+            size_t n = 0;
+            LCTR_OK(lctr_ipc_export(ctx, NULL, 0, &n));
+            std::vector<char> mine(n), all((size_t)world * n);
+            LCTR_OK(lctr_ipc_export(ctx, mine.data(), n, &n));
+            put("ipc", mine.data(), n);
+            for (int r = 0; r < world; r++) get("ipc", r, all.data() + (size_t)r * n, n);
+            LCTR_OK(lctr_ipc_import(ctx, all.data(), n));
+            char done = 1;  // every rank has mapped its peers before anybody's first key list goes out
+            put("mapped", &done, 1);
+            for (int r = 0; r < world; r++) get("mapped", r, &done, 1);
+        }
+        LCTR_OK(lctr_upload_batch(ctx, 0, ds->rows, ds->nnz, ds->row_ptr, ds->fid, ds->field, ds->val, ds->label));
+    }
+    size_t epoch, batch_size;
+    int rank, world;
+    float train_loss;
+    size_t accuracy;
+    lctr_dataset* ds;
 };
 
 }  // namespace lightctr_b200

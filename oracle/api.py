@@ -341,8 +341,10 @@ class WNDOracle:
     """Wide&Deep with per-field concat input (Distributed_Algo_Abst::batchGradCompute restated as one synchronous
     process; parity unpinned, see lightctr_oracle.c).  dims = [Fc*d, H.., 1]."""
 
-    def __init__(self, ds, d, hidden, W, E, lr=0.05, l2=0.001, batch_size=50, minibatch=50, sparse_rate=0.8, act=0):
+    def __init__(self, ds, d, hidden, W, E, lr=0.05, l2=0.001, batch_size=50, minibatch=50, sparse_rate=0.8, act=0,
+                 optimizer="adagrad"):
         self.ds, self.d = ds, d
+        self.ps_rule = 1 if optimizer == "ps_sgd" else 0
         F, Fc = ds.feature_cnt, ds.field_cnt
         self.W, self.E = W.copy(), E.copy()
         hidden = list(hidden) if isinstance(hidden, (list, tuple)) else [hidden]
@@ -354,6 +356,7 @@ class WNDOracle:
     def epoch(self):
         ds = self.ds
         loss, acc = C.c_float(0), C.c_size_t(0)
+        lib().orc_set_wnd_ps_rule(self.ps_rule)
         lib().orc_wnd_epoch(ds.rows, ds.row_ptr, ds.fid, ds.field, ds.val, ds.label, ds.feature_cnt, ds.field_cnt, self.d,
                             self.W, self.E, self.update_g, self.accum, self.mlp.p, self.bs, self.mb, self.lr, self.l2,
                             self.sr, C.byref(loss), C.byref(acc))

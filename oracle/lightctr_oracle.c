@@ -581,6 +581,9 @@ void orc_nfm_epoch(int64_t rows, const int64_t* row_ptr, const uint32_t* fid, co
  *   pCTR = sigmoid(pred + MLP(input)) (:236); loss / accuracy (:237-245, note >= 0.5)
  *   gradW = loss * X + L2 * w (:256), pushed per entry; MLP backward from `loss` (:270-273); inputDelta is the
  *   gradient of the first-entry tensors (:274-276); MLP applyBatchGradient after the batch (:283). */
+void orc_ps_update(int kind, size_t len, float* w, const float* g, float* accum, float* shadow, size_t minibatch, float lr, int tensor);
+static int orc_wnd_ps_rule = 0;
+void orc_set_wnd_ps_rule(int on) { orc_wnd_ps_rule = on; }
 void orc_wnd_epoch(int64_t rows, const int64_t* row_ptr, const uint32_t* fid, const uint32_t* field,
                    const float* val, const int* label, size_t F, size_t Fc, size_t d, float* W, float* E,
                    float* update_g, float* accum, orc_mlp* mlp, size_t batch_size, size_t minibatch, float lr,
@@ -625,8 +628,15 @@ void orc_wnd_epoch(int64_t rows, const int64_t* row_ptr, const uint32_t* fid, co
                 for (size_t c = 0; c < d; c++) gE[(size_t)first[a] * d + c] = gE[(size_t)first[a] * d + c] + delta[a * d + c];
             }
         }
-        orc_adagrad(F, W, update_g, accum, minibatch, lr);
-        orc_adagrad(F * d, E, gE, accum + F, minibatch, lr);
+        if (orc_wnd_ps_rule) { /* the parameter server's default rules: scalar SGD for w (paramserver.h:295-300), tensor SGD for
+                                  the tensors (:232-237); a zero gradient leaves a coordinate unchanged, so the dense sweep
+                                  equals the PS touching the pushed keys only */
+            orc_ps_update(0, F, W, update_g, accum, accum, minibatch, lr, 0);
+            orc_ps_update(0, F * d, E, gE, accum, accum, minibatch, lr, 1);
+        } else {
+            orc_adagrad(F, W, update_g, accum, minibatch, lr);
+            orc_adagrad(F * d, E, gE, accum + F, minibatch, lr);
+        }
         orc_mlp_apply(mlp, minibatch, lr, sparse_rate);
     }
     free(deep); free(first);
