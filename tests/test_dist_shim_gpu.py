@@ -66,10 +66,12 @@ def test_one_worker_against_the_oracle(exe, oracle_api, tmp_path):
     text = subprocess.check_output([exe, prefix, str(epochs), str(seed)], text=True, env=env)
     got = [float(v) for v in re.findall(r"\[Worker Train\] epoch = \d+ loss = ([0-9.eE+-]+)", text)]
     gpred = float(re.search(r"\[Worker Predict\] loss = ([0-9.eE+-]+)", text).group(1))
-    mlp, W0, E0 = _worker_init(api, seed, Fd, Fcd)
     ds = api.Dataset(rp, fid, fld, np.ones(len(fid), np.float32), lab, Fd, Fcd)
-    o = api.WNDOracle(ds, 4, [50], W0, E0, lr=0.05, l2=0.0, batch_size=50, minibatch=50, act=1, optimizer="ps_sgd")
-    for l in range(2):  # adopt the chain drawn above (WNDOracle created its own)
+    o = api.WNDOracle(ds, 4, [50], np.zeros(Fd, np.float32), np.zeros(Fd * 4, np.float32), lr=0.05, l2=0.0, batch_size=50,
+                      minibatch=50, act=1, optimizer="ps_sgd")   # (its constructor draws a chain of its own: discarded)
+    mlp, W0, E0 = _worker_init(api, seed, Fd, Fcd)               # re-seeds: from here the rand() stream is the worker's
+    o.W[:], o.E[:] = W0, E0
+    for l in range(2):
         for name in ("weight", "bias", "mask"):
             o.mlp.arrays(name, l)[:] = mlp.arrays(name, l)
     want = [o.epoch()[0] for _ in range(epochs)]
