@@ -105,6 +105,7 @@ struct MlpLayer {
     float* act = nullptr;                               // [B][out] activations (post-activation for hidden layers)
     float* delta = nullptr;                             // [B][out] dL/d(pre-activation)
     void* w16 = nullptr;                                // bf16 copy of w (tensor-core mode, hidden layers)
+    void* w16t = nullptr;                               // the same, as the chunk-major tile mlp_umma.cu stages by bulk copy
 };
 
 }  // namespace lctr
@@ -173,6 +174,8 @@ struct lctr_ctx {
     void* dense_allreduce_user = nullptr;
     int mlp_tm = 0;             // bf16 mode: samples per CTA tile (128 or 64)
     size_t mlp_smem = 0;        // bf16 mode: dynamic shared memory per CTA
+    int mlp_umma = 0;           // bf16 mode: the tcgen05 kernel (mlp_umma.cu) takes this chain
+    size_t mlp_umma_smem = 0;
     int mlp_has_mask = 0;       // any dropout mask entry == 0
     int mlp_skip_update = 0;    // LCTR_MLP_SKIP_UPDATE=1: leave the dense gradients in place (tests read them)
     int sm_count = 148;

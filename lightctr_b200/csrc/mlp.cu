@@ -164,7 +164,7 @@ int mlp_free(lctr_ctx* c) {
         MlpLayer& L = c->layers[l];
         if (L.w) cudaFree(L.w); if (L.b) cudaFree(L.b); if (L.mask) cudaFree(L.mask);
         if (L.acc_w) cudaFree(L.acc_w); if (L.acc_b) cudaFree(L.acc_b);
-        if (L.act) cudaFree(L.act); if (L.delta) cudaFree(L.delta); if (L.w16) cudaFree(L.w16);
+        if (L.act) cudaFree(L.act); if (L.delta) cudaFree(L.delta); if (L.w16) cudaFree(L.w16); if (L.w16t) cudaFree(L.w16t);
         L = MlpLayer();
     }
     if (c->dense_grad) cudaFree(c->dense_grad);

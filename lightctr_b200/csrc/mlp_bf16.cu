@@ -21,6 +21,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "mlp_umma.cuh"
 
 namespace lctr {
 
@@ -341,9 +342,13 @@ nfm_mlp_fused_kernel(MlpDev P, const float* __restrict__ z, float* __restrict__ 
 }
 
 // fp32 -> bf16 copy of one weight matrix
-__global__ void to_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, size_t n) {
+__global__ void to_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, __nv_bfloat16* __restrict__ dst_tiled,
+                               int in, int out, size_t n) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) dst[i] = __float2bfloat16(src[i]);
+    if (i >= n) return;
+    const __nv_bfloat16 v = __float2bfloat16(src[i]);
+    dst[i] = v;
+    if (dst_tiled) dst_tiled[umma::tiled_index(i, in, out)] = v;
 }
 
 // AdagradUpdater_Num::update (gradientUpdater.h:139-150) over every dense segment in ONE launch; the gradient buffer is
@@ -354,6 +359,8 @@ struct DenseSegs {
     float* w[2 * kMaxDense];
     float* acc[2 * kMaxDense];
     __nv_bfloat16* w16[2 * kMaxDense];
+    __nv_bfloat16* w16t[2 * kMaxDense];  // chunk-major copy (mlp_umma.cu), or null
+    int in[2 * kMaxDense], out[2 * kMaxDense];
 };
 __global__ void adagrad_dense_all_kernel(DenseSegs S, float* __restrict__ g, float invB, float lr) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -368,6 +375,7 @@ __global__ void adagrad_dense_all_kernel(DenseSegs S, float* __restrict__ g, flo
         const float wn = (float)((double)S.w[s][j] - (double)(lr * g1) / sqrt((double)a + 1e-7));
         S.w[s][j] = wn;
         if (S.w16[s]) S.w16[s][j] = __float2bfloat16(wn);
+        if (S.w16t[s]) S.w16t[s][umma::tiled_index(j, S.in[s], S.out[s])] = __float2bfloat16(wn);
     }
     g[i] = 0.f;
 }
@@ -397,9 +405,13 @@ int mlp_bf16_prepare(lctr_ctx* c) {
     for (int l = 0; l < nl; l++) {
         LCTR_CHECK(c->layers[l].in % 16 == 0 && c->layers[l].in <= 512,
                    "bf16 MLP: layer %d input width %d must be a multiple of 16 (<= 512)", l, c->layers[l].in);
-        if (l < nh && !c->layers[l].w16)
+        if (l < nh && !c->layers[l].w16) {
             LCTR_CUDA(cudaMalloc((void**)&c->layers[l].w16, (size_t)c->layers[l].out * c->layers[l].in * 2));
+            LCTR_CUDA(cudaMalloc((void**)&c->layers[l].w16t, (size_t)c->layers[l].out * c->layers[l].in * 2));
+        }
     }
+    c->mlp_umma = mlp_umma_supported(c) ? 1 : 0;
+    if (c->mlp_umma && mlp_umma_prepare(c)) return 1;
     LCTR_CHECK(c->layers[nh].in <= 256, "bf16 MLP: last hidden layer wider than 256");
     MlpDev P;
     size_t need = bf16_layout(c, 128, P);
@@ -418,7 +430,7 @@ int mlp_bf16_refresh(lctr_ctx* c, int layer) {
     MlpLayer& L = c->layers[layer];
     if (!L.w16) return 0;
     const size_t n = (size_t)L.out * L.in;
-    to_bf16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(L.w, (__nv_bfloat16*)L.w16, n);
+    to_bf16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(L.w, (__nv_bfloat16*)L.w16, (__nv_bfloat16*)L.w16t, L.in, L.out, n);
     LCTR_CUDA(cudaGetLastError());
     return 0;
 }
@@ -437,13 +449,15 @@ int launch_nfm_mlp_bf16(lctr_ctx* c, Slot& s, int64_t rb, int64_t re, int64_t ro
     P.w32_last = c->layers[nh].w;
     double* out_slot = c->stats + 2 * (c->step % kStatRing);
     const unsigned grid = (unsigned)((B + c->mlp_tm - 1) / c->mlp_tm);
-    if (c->mlp_tm == 128)
+    if (c->mlp_umma && !c->mlp_has_mask) {  // tcgen05 / TMEM kernel (mlp_umma.cu); dropout masks stay on the mma.sync kernel
+        if (launch_mlp_umma(c, s, rb, B, out_slot)) return 1;
+    } else if (c->mlp_tm == 128)
         nfm_mlp_fused_kernel<128><<<grid, 256, c->mlp_smem, c->stream>>>(P, c->z, c->dz, s.wide, s.label, s.pred, rb, B,
                                                                         c->stat_partial, c->stat_done, out_slot);
     else
         nfm_mlp_fused_kernel<64><<<grid, 128, c->mlp_smem, c->stream>>>(P, c->z, c->dz, s.wide, s.label, s.pred, rb, B,
                                                                        c->stat_partial, c->stat_done, out_slot);
-    c->launches++;
+    if (!(c->mlp_umma && !c->mlp_has_mask)) c->launches++;
     LCTR_CUDA(cudaGetLastError());
     if (mlp_sync_dense_grad(c)) return 1;
     if (!c->mlp_skip_update) {
@@ -453,6 +467,8 @@ int launch_nfm_mlp_bf16(lctr_ctx* c, Slot& s, int64_t rb, int64_t re, int64_t ro
         for (int l = 0; l < nl; l++) {
             MlpLayer& L = c->layers[l];
             S.off[2 * l] = off; S.w[2 * l] = L.w; S.acc[2 * l] = L.acc_w; S.w16[2 * l] = (__nv_bfloat16*)L.w16;
+            S.w16t[2 * l] = (__nv_bfloat16*)L.w16t; S.in[2 * l] = L.in; S.out[2 * l] = L.out;
+            S.w16t[2 * l + 1] = nullptr; S.in[2 * l + 1] = 1; S.out[2 * l + 1] = L.out;
             off += (size_t)L.out * L.in;
             S.off[2 * l + 1] = off; S.w[2 * l + 1] = L.b; S.acc[2 * l + 1] = L.acc_b; S.w16[2 * l + 1] = nullptr;
             off += L.out;

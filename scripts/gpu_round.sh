@@ -53,6 +53,26 @@ distq)
   LCTR_DIST_FENCE=$v timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus $N --steps 100 --warmup 10 --no-c5 \
       > $O/bench_${TAG}_fm_c2_n${N}_$v.json 2> $O/bench_${TAG}_fm_c2_n${N}_$v.err; echo "dist bench $v rc=$?"
   done ;;
+umma)
+  timeout 120 scripts/lab/umma_lab > $O/umma_lab_$TAG.txt 2>&1; echo "rc=$?" >> $O/umma_lab_$TAG.txt; cat $O/umma_lab_$TAG.txt
+  timeout 600 python -m pytest tests/test_mlp_bf16_gpu.py -m gpu -q ${PYTEST_X:--x} > $O/pytest_umma_$TAG.log 2>&1; echo "pytest rc=$?" >> $O/pytest_umma_$TAG.log
+  tail -n 30 $O/pytest_umma_$TAG.log
+  timeout 600 python bench.py --workload nfm_c4 --steps 20 --warmup 3 --no-cpu-baseline > $O/bench_${TAG}_nfm_c4.json 2> $O/bench_${TAG}_nfm_c4.err; echo "bench rc=$?"
+  LCTR_MLP_UMMA=0 timeout 600 python bench.py --workload nfm_c4 --steps 20 --warmup 3 --no-cpu-baseline > $O/bench_${TAG}_nfm_c4_mmasync.json 2> $O/bench_${TAG}_nfm_c4_mmasync.err
+  python -c "
+import json
+for f in ('$O/bench_${TAG}_nfm_c4.json','$O/bench_${TAG}_nfm_c4_mmasync.json'):
+    try:
+        d=json.loads(open(f).read().strip().splitlines()[-1]); print(f, d['value'], d['ms_per_step'], d.get('kernels_ms'))
+    except Exception as e: print(f, 'ERR', e)
+" ;;
+ummaprof)
+  LCTR_MLP_UMMA_TRACE=1 timeout 300 python bench.py --workload nfm_c4 --steps 6 --warmup 3 --no-cpu-baseline > /dev/null 2> $O/umma_trace_$TAG.txt; tail -n 8 $O/umma_trace_$TAG.txt
+  timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 60 -c 60 --csv --log-file $O/launches_${TAG}_nfm_c4.csv \
+      python bench.py --workload nfm_c4 --steps 8 --warmup 3 --no-cpu-baseline > $O/ncu_launch_nfm_$TAG.log 2>&1
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:"nfm_mlp_umma|adagrad_dense" -s 6 -c 4 \
+      -o $O/prof_${TAG}_nfm_c4 -f python bench.py --workload nfm_c4 --steps 4 --warmup 3 --no-cpu-baseline > $O/ncu_full_nfm_$TAG.log 2>&1
+  echo "ncu rc=$?" ;;
 lab)
   bash scripts/lab/run_lab.sh > /dev/null 2>&1; cp $O/lab_b4096.txt $O/lab_${TAG}_b4096.txt; cp $O/lab_b65536.txt $O/lab_${TAG}_b65536.txt ;;
 esac
