@@ -111,12 +111,22 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
     return *reinterpret_cast<uint32_t*>(&v);
 }
 __device__ __forceinline__ float2 unpack2(uint32_t u) { return __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&u)); }
-__device__ __forceinline__ float fwd_act(float v, int act) {  // activations.h:71-90,126-143, fast-math forms as in mlp_bf16.cu
-    if (act == LCTR_ACT_SIGMOID) return v < -16.f ? 1e-7f : (v > 16.f ? 0.99999988f : __fdividef(1.0f, 1.0f + __expf(-v)));
-    const float t1 = __expf(v), t2 = __expf(-v);
-    return fabsf(v) > 15.f ? copysignf(1.f, v) : __fdividef(t1 - t2, t1 + t2);
+// activations.h:71-90,126-143 in the fast-math forms of mlp_bf16.cu, branch free (selects) so that the MUFU chains of a
+// 32-column group interleave instead of serialising behind per-element branches
+template <int ACT>
+__device__ __forceinline__ float fwd_act(float v) {
+    if (ACT == LCTR_ACT_SIGMOID) {
+        float s = __fdividef(1.0f, 1.0f + __expf(-v));
+        s = v < -16.f ? 1e-7f : s;
+        return v > 16.f ? 0.99999988f : s;
+    } else {
+        const float t1 = __expf(v), t2 = __expf(-v);
+        const float r = __fdividef(t1 - t2, t1 + t2);
+        return fabsf(v) > 15.f ? copysignf(1.f, v) : r;
+    }
 }
-__device__ __forceinline__ float bwd_act(float fo, int act) { return act == LCTR_ACT_SIGMOID ? fo * (1.0f - fo) : 1.0f - fo * fo; }
+template <int ACT>
+__device__ __forceinline__ float bwd_act(float fo) { return ACT == LCTR_ACT_SIGMOID ? fo * (1.0f - fo) : 1.0f - fo * fo; }
 __device__ __forceinline__ float clip15(float v) { return fminf(fmaxf(v, -15.f), 15.f); }
 
 // Column sums over the 32 lanes of a warp for 32 columns held one row per lane: on return lane j holds the sum of
@@ -135,6 +145,7 @@ __device__ __forceinline__ float transpose_reduce32(float (&v)[32], int lane) {
     return v[0];
 }
 
+template <int ACT>
 __global__ void __launch_bounds__(kThreads, 1)
 nfm_mlp_umma_kernel(Dev P, const float* __restrict__ z, float* __restrict__ dz, const float* __restrict__ wide,
                     const float* __restrict__ label, float* __restrict__ pred, int64_t rb, int B, double* partial,
@@ -153,6 +164,11 @@ nfm_mlp_umma_kernel(Dev P, const float* __restrict__ z, float* __restrict__ dz, 
     float* s_part = reinterpret_cast<float*>(smem + P.part_off);  // [2][128] partial output-layer dot products
     const uint32_t bar_w = sbase + P.bar_off, bar_m = bar_w + 8;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + P.bar_off + 16);
+    // the row's wide term and label are independent of the dense chain: request them now, use them after the forward pass
+    const int64_t gi = rb + row0 + row;
+    const float wide_r = row < valid ? wide[gi] : 0.f;
+    const float label_r = row < valid ? label[gi] : 0.f;
+    const float b_last = P.bias[nh][0];
 
     if (tid == 0) {
         bar_init(bar_w, 1);
@@ -216,19 +232,25 @@ nfm_mlp_umma_kernel(Dev P, const float* __restrict__ z, float* __restrict__ dz, 
         for (int c0 = h * (N / 2); c0 < (h + 1) * (N / 2); c0 += 32) {
             uint32_t r[32];
             tmem_ld32(tlane + c0, r);
+            float a[32];
+#pragma unroll
+            for (int g = 0; g < 8; g++) {
+                const float4 b4 = *reinterpret_cast<const float4*>(bias + c0 + g * 4);
+                a[g * 4 + 0] = fwd_act<ACT>(__uint_as_float(r[g * 4 + 0]) + b4.x);
+                a[g * 4 + 1] = fwd_act<ACT>(__uint_as_float(r[g * 4 + 1]) + b4.y);
+                a[g * 4 + 2] = fwd_act<ACT>(__uint_as_float(r[g * 4 + 2]) + b4.z);
+                a[g * 4 + 3] = fwd_act<ACT>(__uint_as_float(r[g * 4 + 3]) + b4.w);
+            }
 #pragma unroll
             for (int g = 0; g < 4; g++) {
                 uint32_t pk[4];
 #pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    const int c = c0 + g * 8 + 2 * j;
-                    const float a0 = fwd_act(__uint_as_float(r[g * 8 + 2 * j]) + bias[c], P.act);
-                    const float a1 = fwd_act(__uint_as_float(r[g * 8 + 2 * j + 1]) + bias[c + 1], P.act);
-                    pk[j] = pack2(a0, a1);
-                    if (last) {  // output layer (linear, out = 1) on the rounded activations, like the other operands
-                        const float2 ar = unpack2(pk[j]);
-                        part += ar.x * s_wl[c] + ar.y * s_wl[c + 1];
-                    }
+                for (int j = 0; j < 4; j++) pk[j] = pack2(a[g * 8 + 2 * j], a[g * 8 + 2 * j + 1]);
+                if (last) {  // output layer (linear, out = 1) on the rounded activations, like the other operands
+                    const float4 w0 = *reinterpret_cast<const float4*>(s_wl + c0 + g * 8);
+                    const float4 w1 = *reinterpret_cast<const float4*>(s_wl + c0 + g * 8 + 4);
+                    const float2 a0 = unpack2(pk[0]), a1 = unpack2(pk[1]), a2 = unpack2(pk[2]), a3 = unpack2(pk[3]);
+                    part += a0.x * w0.x + a0.y * w0.y + a1.x * w0.z + a1.y * w0.w + a2.x * w1.x + a2.y * w1.y + a3.x * w1.z + a3.y * w1.w;
                 }
                 *reinterpret_cast<uint4*>(y + (c0 / 8 + g) * kChunk + row * 16) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
             }
@@ -241,20 +263,15 @@ nfm_mlp_umma_kernel(Dev P, const float* __restrict__ z, float* __restrict__ dz, 
     }
 
     // ---- output layer, loss, delta of the last hidden layer in place, dW/db of the output layer, db of the last hidden
-    double loss = 0.0, correct = 0.0;
+    float p_row = 0.5f;
     {
         const int K = P.in[nh];
         float d3 = 0.f;
         if (row < valid) {
-            const int64_t gi = rb + row0 + row;
-            const float o = s_part[row] + s_part[kTM + row] + P.bias[nh][0];
-            const float p = ref_sigmoid(wide[gi] + o);  // train_nfm_algo.cpp:101-116
-            const float yv = label[gi];
-            if (h == 0) {
-                pred[gi] = p;
-                loss_terms(p, yv, loss, correct);
-            }
-            d3 = clip15(p - yv);
+            const float o = s_part[row] + s_part[kTM + row] + b_last;
+            p_row = ref_sigmoid(wide_r + o);  // train_nfm_algo.cpp:101-116
+            if (h == 0) pred[gi] = p_row;
+            d3 = clip15(p_row - label_r);
         }
         unsigned char* x = smem + P.x_off[nh];
         for (int c0 = h * (K / 2); c0 < (h + 1) * (K / 2); c0 += 32) {
@@ -272,7 +289,7 @@ nfm_mlp_umma_kernel(Dev P, const float* __restrict__ z, float* __restrict__ dz, 
                     gw[g * 8 + 2 * j] = d3 * a.x;  // weightDelta of the output layer (:165-178)
                     gw[g * 8 + 2 * j + 1] = d3 * a.y;
                     // no mask on the output layer's dX; previous activation' (:139-156)
-                    pk[j] = pack2(clip15(d3 * s_wl[c] * bwd_act(a.x, P.act)), clip15(d3 * s_wl[c + 1] * bwd_act(a.y, P.act)));
+                    pk[j] = pack2(clip15(d3 * s_wl[c] * bwd_act<ACT>(a.x)), clip15(d3 * s_wl[c + 1] * bwd_act<ACT>(a.y)));
                     const float2 e = unpack2(pk[j]);
                     gd[g * 8 + 2 * j] = e.x;
                     gd[g * 8 + 2 * j + 1] = e.y;
@@ -338,8 +355,8 @@ nfm_mlp_umma_kernel(Dev P, const float* __restrict__ z, float* __restrict__ dz, 
 #pragma unroll
                     for (int j = 0; j < 4; j++) {
                         const float2 a = unpack2(uu[j]);
-                        pk[j] = pack2(clip15(__uint_as_float(r[g * 8 + 2 * j]) * bwd_act(a.x, P.act)),
-                                      clip15(__uint_as_float(r[g * 8 + 2 * j + 1]) * bwd_act(a.y, P.act)));
+                        pk[j] = pack2(clip15(__uint_as_float(r[g * 8 + 2 * j]) * bwd_act<ACT>(a.x)),
+                                      clip15(__uint_as_float(r[g * 8 + 2 * j + 1]) * bwd_act<ACT>(a.y)));
                         const float2 e = unpack2(pk[j]);
                         gd[g * 8 + 2 * j] = e.x;
                         gd[g * 8 + 2 * j + 1] = e.y;
@@ -363,13 +380,36 @@ nfm_mlp_umma_kernel(Dev P, const float* __restrict__ z, float* __restrict__ dz, 
         stamp(P, ns);
         // dW_l -> dense gradient buffer (weightDelta, :165-178); fire-and-forget REDs
         if (dw_normal) {
+            // thread = weight row: a direct RED would touch 32 lines per warp instruction.  32 x 32 tiles go through a
+            // per-warp staging buffer (the delta_l tile, dead once this layer's MMAs have completed; 16 B chunks XOR-ed
+            // with the row so that both sides are conflict free) and leave as 4 full 128 B lines per instruction.
+            float* stage = reinterpret_cast<float*>(smem + P.x_off[l + 1] + wid * 4096);
             for (int m = 0; m < N / 128; m++) {
-                float* drow = P.dw[l] + (size_t)(m * 128 + row) * K;
-                for (int c0 = h * (K / 2); c0 < (h + 1) * (K / 2); c0 += 8) {
-                    uint32_t r[8];
-                    tmem_ld8(tlane + kColsDW + m * K + c0, r);
-                    red_add_v4(drow + c0, __uint_as_float(r[0]), __uint_as_float(r[1]), __uint_as_float(r[2]), __uint_as_float(r[3]));
-                    red_add_v4(drow + c0 + 4, __uint_as_float(r[4]), __uint_as_float(r[5]), __uint_as_float(r[6]), __uint_as_float(r[7]));
+                float* dbase = P.dw[l] + (size_t)(m * 128 + q * 32) * K;
+                if ((K / 2) % 32 == 0) {
+                    for (int c0 = h * (K / 2); c0 < (h + 1) * (K / 2); c0 += 32) {
+                        uint32_t r[32];
+                        tmem_ld32(tlane + kColsDW + m * K + c0, r);
+#pragma unroll
+                        for (int j = 0; j < 8; j++)
+                            *reinterpret_cast<uint4*>(stage + lane * 32 + ((j ^ (lane & 7)) << 2)) = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+                        __syncwarp();
+#pragma unroll
+                        for (int i = 0; i < 8; i++) {
+                            const int rr = 4 * i + (lane >> 3), j = lane & 7;
+                            const float4 v = *reinterpret_cast<const float4*>(stage + rr * 32 + ((j ^ (rr & 7)) << 2));
+                            red_add_v4(dbase + (size_t)rr * K + c0 + j * 4, v.x, v.y, v.z, v.w);
+                        }
+                        __syncwarp();
+                    }
+                } else {
+                    float* drow = dbase + (size_t)lane * K;
+                    for (int c0 = h * (K / 2); c0 < (h + 1) * (K / 2); c0 += 8) {
+                        uint32_t r[8];
+                        tmem_ld8(tlane + kColsDW + m * K + c0, r);
+                        red_add_v4(drow + c0, __uint_as_float(r[0]), __uint_as_float(r[1]), __uint_as_float(r[2]), __uint_as_float(r[3]));
+                        red_add_v4(drow + c0 + 4, __uint_as_float(r[4]), __uint_as_float(r[5]), __uint_as_float(r[6]), __uint_as_float(r[7]));
+                    }
                 }
             }
         } else {
@@ -389,6 +429,8 @@ nfm_mlp_umma_kernel(Dev P, const float* __restrict__ z, float* __restrict__ dz, 
         stamp(P, ns);
     }
     if (wid == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+    double loss = 0.0, correct = 0.0;  // the double-precision log sits here, behind the last REDs, off the dependent chain
+    if (h == 0 && row < valid) loss_terms(p_row, label_r, loss, correct);
     publish_stats(loss, correct, partial, done, out_slot, false);
     stamp(P, ns);
 }
@@ -438,7 +480,8 @@ int mlp_umma_prepare(lctr_ctx* c) {
     umma::Dev P;
     const size_t need = umma::layout(c, P);
     c->mlp_umma_smem = need;
-    LCTR_CUDA(cudaFuncSetAttribute(umma::nfm_mlp_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
+    LCTR_CUDA(cudaFuncSetAttribute(umma::nfm_mlp_umma_kernel<LCTR_ACT_SIGMOID>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
+    LCTR_CUDA(cudaFuncSetAttribute(umma::nfm_mlp_umma_kernel<LCTR_ACT_TANH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
     return 0;
 }
 
@@ -461,8 +504,12 @@ int launch_mlp_umma(lctr_ctx* c, Slot& s, int64_t rb, int B, double* out_slot) {
         P.trace = d_trace;
     }
     const unsigned grid = (unsigned)((B + umma::kTM - 1) / umma::kTM);
-    umma::nfm_mlp_umma_kernel<<<grid, umma::kThreads, c->mlp_umma_smem, c->stream>>>(P, c->z, c->dz, s.wide, s.label, s.pred, rb, B,
-                                                                                    c->stat_partial, c->stat_done, out_slot);
+    if (P.act == LCTR_ACT_SIGMOID)
+        umma::nfm_mlp_umma_kernel<LCTR_ACT_SIGMOID><<<grid, umma::kThreads, c->mlp_umma_smem, c->stream>>>(
+            P, c->z, c->dz, s.wide, s.label, s.pred, rb, B, c->stat_partial, c->stat_done, out_slot);
+    else
+        umma::nfm_mlp_umma_kernel<LCTR_ACT_TANH><<<grid, umma::kThreads, c->mlp_umma_smem, c->stream>>>(
+            P, c->z, c->dz, s.wide, s.label, s.pred, rb, B, c->stat_partial, c->stat_done, out_slot);
     c->launches++;
     LCTR_CUDA(cudaGetLastError());
     if (trace) {  // phase boundaries of CTA 0: setup | per layer (mma wait, epilogue) | output | per layer (mma wait, dX, dW) | stats

@@ -66,6 +66,18 @@ for f in ('$O/bench_${TAG}_nfm_c4.json','$O/bench_${TAG}_nfm_c4_mmasync.json'):
         d=json.loads(open(f).read().strip().splitlines()[-1]); print(f, d['value'], d['ms_per_step'], d.get('kernels_ms'))
     except Exception as e: print(f, 'ERR', e)
 " ;;
+ummaq)
+  timeout 600 python -m pytest tests/test_mlp_bf16_gpu.py -m gpu -q ${PYTEST_X:--x} > $O/pytest_umma_$TAG.log 2>&1; echo "pytest rc=$?" >> $O/pytest_umma_$TAG.log
+  tail -n 12 $O/pytest_umma_$TAG.log
+  LCTR_MLP_UMMA_TRACE=1 timeout 300 python bench.py --workload nfm_c4 --steps 6 --warmup 3 --no-cpu-baseline > /dev/null 2> $O/umma_trace_$TAG.txt; tail -n 3 $O/umma_trace_$TAG.txt
+  timeout 600 python bench.py --workload nfm_c4 --steps 20 --warmup 3 --no-cpu-baseline > $O/bench_${TAG}_nfm_c4.json 2> $O/bench_${TAG}_nfm_c4.err; echo "bench rc=$?"
+  python -c "
+import json
+for f in ('$O/bench_${TAG}_nfm_c4.json',):
+    try:
+        d=json.loads(open(f).read().strip().splitlines()[-1]); print(f, d['value'], d['ms_per_step'], d.get('kernels_ms'))
+    except Exception as e: print(f, 'ERR', e)
+" ;;
 ummaprof)
   LCTR_MLP_UMMA_TRACE=1 timeout 300 python bench.py --workload nfm_c4 --steps 6 --warmup 3 --no-cpu-baseline > /dev/null 2> $O/umma_trace_$TAG.txt; tail -n 8 $O/umma_trace_$TAG.txt
   timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 60 -c 60 --csv --log-file $O/launches_${TAG}_nfm_c4.csv \
