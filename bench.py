@@ -463,7 +463,9 @@ def main():
         flops = 6.0 * sum(dims[i] * dims[i + 1] for i in range(len(dims) - 1)) * B
         tpeak, tsrc = measured_tensor_peak()
         achieved = flops / (ms / cnt * 1e-3) / 1e12
-        roof = {"bound": "tensor", "kernel": "mlp (nfm_mlp_fused_kernel + dense Adagrad)", "achieved": achieved, "peak": tpeak,
+        umma = os.environ.get("LCTR_MLP_UMMA", "1") != "0"
+        roof = {"bound": "tensor", "kernel": ("mlp (nfm_mlp_umma_kernel: tcgen05.mma, TMEM accumulators; + dense Adagrad)" if umma
+                                              else "mlp (nfm_mlp_fused_kernel: mma.sync; + dense Adagrad)"), "achieved": achieved, "peak": tpeak,
                 "unit": "TFLOP/s", "frac": achieved / tpeak, "traffic": None, "peak_source": tsrc,
                 "algorithmic_flops_per_launch": flops, "kernel_ms": ms / cnt}
     roof_gather = None
@@ -489,7 +491,8 @@ def main():
             "data": "synthetic",
             "config": {"workload": wl["desc"], "l2": "flushed between timed steps (256 MB write)" + ("; ranks barrier after the flush, before the timed region" if world > 1 else ""), "batch_per_gpu": B,
                        "global_batch": world * B, "nnz_per_row": n,
-                       **({"mlp": "bf16 mma, fused fwd+bwd per 128-sample tile" if mlp_bf16 else "fp32 reference-order"}
+                       **({"mlp": ("bf16 tcgen05.mma with TMEM accumulators, fused fwd+bwd per 128-sample CTA" if os.environ.get("LCTR_MLP_UMMA", "1") != "0"
+                                   else "bf16 mma.sync, fused fwd+bwd per 128-sample tile") if mlp_bf16 else "fp32 reference-order"}
                           if wl["model"] == "nfm" else {}),
                        "backward": bw_desc,
                        "parallelism": "1 GPU" if world == 1 else

@@ -111,18 +111,26 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
     return *reinterpret_cast<uint32_t*>(&v);
 }
 __device__ __forceinline__ float2 unpack2(uint32_t u) { return __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&u)); }
-// activations.h:71-90,126-143 in the fast-math forms of mlp_bf16.cu, branch free (selects) so that the MUFU chains of a
-// 32-column group interleave instead of serialising behind per-element branches
+// activations.h:71-90,126-143 on the MUFU unit, branch free and without the denormal fix-ups of __expf / __fdividef (the
+// epilogues are issue bound: 18 instructions per element with the intrinsics, 6 here).
+//   Sigmoid: 1 / (1 + 2^t), t = -log2(e) * (acc + b) clamped to +-16 log2(e); the bias arrives pre-multiplied by -log2(e)
+//            so that t is one FFMA.  The reference's clamp values (1e-7, 1 - 1e-7 beyond |x| = 16) become sigmoid(+-16)
+//            = 1.1e-7 / 0.9999999: the same bf16 number above, 1.13e-7 instead of 1.0e-7 below.
+//   Tanh:    tanh.approx (relative error 2^-11, an eighth of a bf16 ulp); saturates to +-1 by itself.
+__device__ __forceinline__ float ex2_ftz(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rcp_ftz(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+constexpr float kLog2e = 1.4426950408889634f;
 template <int ACT>
-__device__ __forceinline__ float fwd_act(float v) {
+__device__ __forceinline__ float bias_scale() { return ACT == LCTR_ACT_SIGMOID ? -kLog2e : 1.0f; }
+template <int ACT>
+__device__ __forceinline__ float fwd_act(float acc, float b_scaled) {
     if (ACT == LCTR_ACT_SIGMOID) {
-        float s = __fdividef(1.0f, 1.0f + __expf(-v));
-        s = v < -16.f ? 1e-7f : s;
-        return v > 16.f ? 0.99999988f : s;
+        const float t = fminf(fmaxf(fmaf(acc, -kLog2e, b_scaled), -16.f * kLog2e), 16.f * kLog2e);
+        return rcp_ftz(1.0f + ex2_ftz(t));
     } else {
-        const float t1 = __expf(v), t2 = __expf(-v);
-        const float r = __fdividef(t1 - t2, t1 + t2);
-        return fabsf(v) > 15.f ? copysignf(1.f, v) : r;
+        float y;
+        asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(acc + b_scaled));
+        return y;
     }
 }
 template <int ACT>
@@ -184,7 +192,7 @@ nfm_mlp_umma_kernel(Dev P, const float* __restrict__ z, float* __restrict__ dz, 
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     for (int l = 0; l < nh; l++)
-        for (int j = tid; j < P.out[l]; j += kThreads) s_bias[P.vec_off[l] + j] = P.bias[l][j];
+        for (int j = tid; j < P.out[l]; j += kThreads) s_bias[P.vec_off[l] + j] = P.bias[l][j] * bias_scale<ACT>();
     for (int i = tid; i < P.in[nh]; i += kThreads) s_wl[i] = P.w32_last[i];
     {   // z tile -> bf16, chunk-major
         const int k = P.in[0], chunks = k / 8;
@@ -236,10 +244,10 @@ nfm_mlp_umma_kernel(Dev P, const float* __restrict__ z, float* __restrict__ dz, 
 #pragma unroll
             for (int g = 0; g < 8; g++) {
                 const float4 b4 = *reinterpret_cast<const float4*>(bias + c0 + g * 4);
-                a[g * 4 + 0] = fwd_act<ACT>(__uint_as_float(r[g * 4 + 0]) + b4.x);
-                a[g * 4 + 1] = fwd_act<ACT>(__uint_as_float(r[g * 4 + 1]) + b4.y);
-                a[g * 4 + 2] = fwd_act<ACT>(__uint_as_float(r[g * 4 + 2]) + b4.z);
-                a[g * 4 + 3] = fwd_act<ACT>(__uint_as_float(r[g * 4 + 3]) + b4.w);
+                a[g * 4 + 0] = fwd_act<ACT>(__uint_as_float(r[g * 4 + 0]), b4.x);
+                a[g * 4 + 1] = fwd_act<ACT>(__uint_as_float(r[g * 4 + 1]), b4.y);
+                a[g * 4 + 2] = fwd_act<ACT>(__uint_as_float(r[g * 4 + 2]), b4.z);
+                a[g * 4 + 3] = fwd_act<ACT>(__uint_as_float(r[g * 4 + 3]), b4.w);
             }
 #pragma unroll
             for (int g = 0; g < 4; g++) {
@@ -264,6 +272,7 @@ nfm_mlp_umma_kernel(Dev P, const float* __restrict__ z, float* __restrict__ dz, 
 
     // ---- output layer, loss, delta of the last hidden layer in place, dW/db of the output layer, db of the last hidden
     float p_row = 0.5f;
+    double loss = 0.0, correct = 0.0;
     {
         const int K = P.in[nh];
         float d3 = 0.f;
@@ -310,32 +319,40 @@ nfm_mlp_umma_kernel(Dev P, const float* __restrict__ z, float* __restrict__ dz, 
     }
 
     // ---- backward through the hidden layers (fullyconnLayer.h:120-180)
+    // TMEM columns of a layer's accumulators: dX at cx, dW at cw.  By default (0, 256); a layer whose two accumulators fit
+    // into the 256 columns the previous layer's dX has vacated is issued EARLY -- before the previous layer's dW leaves
+    // for global memory -- so that its MMAs run under that epilogue.
+    auto dw_cols = [&](int l) { return (P.out[l] % 128 == 0) ? (P.out[l] / 128) * P.in[l] : (P.in[l] / 128) * P.out[l]; };
+    auto issue_backward = [&](int l, uint32_t cx, uint32_t cw) {  // one thread
+        const int K = P.in[l], N = P.out[l];
+        tc_after();
+        const uint32_t xd = sbase + P.x_off[l + 1], xl = sbase + P.x_off[l], wl = sbase + P.w_off[l];
+        if (N % 128 == 0) {  // dW_l = delta_l^T . X_l, rows = out
+            const uint32_t id = idesc(K, 1, 1);
+            for (int m = 0; m < N / 128; m++)
+                for (int k = 0; k < kTM / 16; k++)
+                    mma(tmem + cw + m * K, sdesc(xd + m * 16 * kChunk + k * 256, 128, kChunk), sdesc(xl + k * 256, 128, kChunk), id, k > 0);
+        } else {             // transposed: X_l^T . delta_l, rows = in
+            const uint32_t id = idesc(N, 1, 1);
+            for (int m = 0; m < K / 128; m++)
+                for (int k = 0; k < kTM / 16; k++)
+                    mma(tmem + cw + m * N, sdesc(xl + m * 16 * kChunk + k * 256, 128, kChunk), sdesc(xd + k * 256, 128, kChunk), id, k > 0);
+        }
+        {   // dX_l = delta_l . W_l
+            const uint32_t id = idesc(K, 0, 1);
+            for (int k = 0; k < N / 16; k++)
+                mma(tmem + cx, sdesc(xd + k * 2 * kChunk, kChunk, 128), sdesc(wl + k * 256, 128, N * 16), id, k > 0);
+        }
+        commit(bar_m);
+    };
+    uint32_t cx = kColsDX, cw = kColsDW;
+    bool issued = false;
     for (int l = nh - 1; l >= 0; l--) {
         const int K = P.in[l], N = P.out[l];
         const bool dw_normal = (N % 128) == 0;  // else transposed: rows = in_l
-        if (tid == 0) {
-            tc_after();
-            const uint32_t xd = sbase + P.x_off[l + 1], xl = sbase + P.x_off[l], wl = sbase + P.w_off[l];
-            // dW first: it must have read X_l before the dX epilogue overwrites it (both complete before the commit fires)
-            if (dw_normal) {
-                const uint32_t id = idesc(K, 1, 1);
-                for (int m = 0; m < N / 128; m++)
-                    for (int k = 0; k < kTM / 16; k++)
-                        mma(tmem + kColsDW + m * K, sdesc(xd + m * 16 * kChunk + k * 256, 128, kChunk), sdesc(xl + k * 256, 128, kChunk), id, k > 0);
-            } else {
-                const uint32_t id = idesc(N, 1, 1);
-                for (int m = 0; m < K / 128; m++)
-                    for (int k = 0; k < kTM / 16; k++)
-                        mma(tmem + kColsDW + m * N, sdesc(xl + m * 16 * kChunk + k * 256, 128, kChunk), sdesc(xd + k * 256, 128, kChunk), id, k > 0);
-            }
-            {   // dX_l = delta_l . W_l
-                const uint32_t id = idesc(K, 0, 1);
-                for (int k = 0; k < N / 16; k++)
-                    mma(tmem + kColsDX, sdesc(xd + k * 2 * kChunk, kChunk, 128), sdesc(wl + k * 256, 128, N * 16), id, k > 0);
-            }
-            commit(bar_m);
-        }
+        if (!issued && tid == 0) issue_backward(l, cx, cw);
         __syncwarp();
+        if (l == nh - 1 && h == 0 && row < valid) loss_terms(p_row, label_r, loss, correct);  // double-precision log, under the MMAs
         bar_wait(bar_m, phase); phase ^= 1;
         __syncwarp();
         tc_after();
@@ -345,7 +362,7 @@ nfm_mlp_umma_kernel(Dev P, const float* __restrict__ z, float* __restrict__ dz, 
             for (int c0 = h * (K / 2); c0 < (h + 1) * (K / 2); c0 += 32) {
                 uint32_t r[32];
                 float gd[32];
-                tmem_ld32(tlane + kColsDX + c0, r);
+                tmem_ld32(tlane + cx + c0, r);
 #pragma unroll
                 for (int g = 0; g < 4; g++) {
                     uint4* px = reinterpret_cast<uint4*>(xl + (c0 / 8 + g) * kChunk + row * 16);
@@ -369,7 +386,7 @@ nfm_mlp_umma_kernel(Dev P, const float* __restrict__ z, float* __restrict__ dz, 
         } else {  // dz: the gradient handed back to the embedding backward, fp32
             for (int c0 = h * (K / 2); c0 < (h + 1) * (K / 2); c0 += 8) {
                 uint32_t r[8];
-                tmem_ld8(tlane + kColsDX + c0, r);
+                tmem_ld8(tlane + cx + c0, r);
                 if (row < valid) {
                     float4* dst = reinterpret_cast<float4*>(dz + (size_t)(row0 + row) * K + c0);
                     dst[0] = make_float4(__uint_as_float(r[0]), __uint_as_float(r[1]), __uint_as_float(r[2]), __uint_as_float(r[3]));
@@ -378,6 +395,22 @@ nfm_mlp_umma_kernel(Dev P, const float* __restrict__ z, float* __restrict__ dz, 
             }
         }
         stamp(P, ns);
+        const uint32_t cw_l = cw;
+        issued = false;
+        if (l > 0) {
+            const uint32_t ncw = (uint32_t)((P.in[l - 1] + 31) & ~31);
+            if (cw_l >= kColsDW && ncw + dw_cols(l - 1) <= kColsDW) {  // uniform over the CTA; this layer's dW is outside [0, 256)
+                fence_async_smem();
+                tc_before();
+                __syncthreads();
+                cx = 0; cw = ncw;
+                if (tid == 0) issue_backward(l - 1, cx, cw);
+                __syncwarp();
+                issued = true;
+            } else {
+                cx = kColsDX; cw = kColsDW;
+            }
+        }
         // dW_l -> dense gradient buffer (weightDelta, :165-178); fire-and-forget REDs
         if (dw_normal) {
             // thread = weight row: a direct RED would touch 32 lines per warp instruction.  32 x 32 tiles go through a
@@ -389,7 +422,7 @@ nfm_mlp_umma_kernel(Dev P, const float* __restrict__ z, float* __restrict__ dz, 
                 if ((K / 2) % 32 == 0) {
                     for (int c0 = h * (K / 2); c0 < (h + 1) * (K / 2); c0 += 32) {
                         uint32_t r[32];
-                        tmem_ld32(tlane + kColsDW + m * K + c0, r);
+                        tmem_ld32(tlane + cw_l + m * K + c0, r);
 #pragma unroll
                         for (int j = 0; j < 8; j++)
                             *reinterpret_cast<uint4*>(stage + lane * 32 + ((j ^ (lane & 7)) << 2)) = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
@@ -398,7 +431,7 @@ nfm_mlp_umma_kernel(Dev P, const float* __restrict__ z, float* __restrict__ dz, 
                         for (int i = 0; i < 8; i++) {
                             const int rr = 4 * i + (lane >> 3), j = lane & 7;
                             const float4 v = *reinterpret_cast<const float4*>(stage + rr * 32 + ((j ^ (rr & 7)) << 2));
-                            red_add_v4(dbase + (size_t)rr * K + c0 + j * 4, v.x, v.y, v.z, v.w);
+                            if (!P.debug_no_dw) red_add_v4(dbase + (size_t)rr * K + c0 + j * 4, v.x, v.y, v.z, v.w);
                         }
                         __syncwarp();
                     }
@@ -406,7 +439,7 @@ nfm_mlp_umma_kernel(Dev P, const float* __restrict__ z, float* __restrict__ dz, 
                     float* drow = dbase + (size_t)lane * K;
                     for (int c0 = h * (K / 2); c0 < (h + 1) * (K / 2); c0 += 8) {
                         uint32_t r[8];
-                        tmem_ld8(tlane + kColsDW + m * K + c0, r);
+                        tmem_ld8(tlane + cw_l + m * K + c0, r);
                         red_add_v4(drow + c0, __uint_as_float(r[0]), __uint_as_float(r[1]), __uint_as_float(r[2]), __uint_as_float(r[3]));
                         red_add_v4(drow + c0 + 4, __uint_as_float(r[4]), __uint_as_float(r[5]), __uint_as_float(r[6]), __uint_as_float(r[7]));
                     }
@@ -417,7 +450,7 @@ nfm_mlp_umma_kernel(Dev P, const float* __restrict__ z, float* __restrict__ dz, 
                 float* dcol = P.dw[l] + m * 128 + row;  // thread = input index; lanes are contiguous in memory
                 for (int c0 = h * (N / 2); c0 < (h + 1) * (N / 2); c0 += 8) {
                     uint32_t r[8];
-                    tmem_ld8(tlane + kColsDW + m * N + c0, r);
+                    tmem_ld8(tlane + cw_l + m * N + c0, r);
 #pragma unroll
                     for (int j = 0; j < 8; j++) red_add(dcol + (size_t)(c0 + j) * K, __uint_as_float(r[j]));
                 }
@@ -429,8 +462,6 @@ nfm_mlp_umma_kernel(Dev P, const float* __restrict__ z, float* __restrict__ dz, 
         stamp(P, ns);
     }
     if (wid == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
-    double loss = 0.0, correct = 0.0;  // the double-precision log sits here, behind the last REDs, off the dependent chain
-    if (h == 0 && row < valid) loss_terms(p_row, label_r, loss, correct);
     publish_stats(loss, correct, partial, done, out_slot, false);
     stamp(P, ns);
 }
@@ -496,7 +527,9 @@ int launch_mlp_umma(lctr_ctx* c, Slot& s, int64_t rb, int B, double* out_slot) {
     }
     P.w32_last = c->layers[nh].w;
     P.trace = nullptr;
-    static const bool trace = getenv("LCTR_MLP_UMMA_TRACE") && getenv("LCTR_MLP_UMMA_TRACE")[0] == '1';
+    const bool no_dw = getenv("LCTR_MLP_UMMA_NODW") && getenv("LCTR_MLP_UMMA_NODW")[0] == '1';
+    P.debug_no_dw = no_dw ? 1 : 0;
+    const bool trace = getenv("LCTR_MLP_UMMA_TRACE") && getenv("LCTR_MLP_UMMA_TRACE")[0] == '1';
     static unsigned long long* d_trace = nullptr;
     if (trace) {
         if (!d_trace) LCTR_CUDA(cudaMalloc((void**)&d_trace, 64 * sizeof(unsigned long long)));

@@ -78,6 +78,18 @@ for f in ('$O/bench_${TAG}_nfm_c4.json',):
         d=json.loads(open(f).read().strip().splitlines()[-1]); print(f, d['value'], d['ms_per_step'], d.get('kernels_ms'))
     except Exception as e: print(f, 'ERR', e)
 " ;;
+ummanodw)
+  for v in 0 1; do
+  LCTR_MLP_UMMA_NODW=$v timeout 600 python bench.py --workload nfm_c4 --steps 30 --warmup 3 --no-cpu-baseline > $O/bench_${TAG}_nfm_c4_nodw$v.json 2> $O/bench_${TAG}_nfm_c4_nodw$v.err
+  LCTR_MLP_UMMA_NODW=$v LCTR_MLP_UMMA_TRACE=1 timeout 300 python bench.py --workload nfm_c4 --steps 4 --warmup 3 --no-cpu-baseline 2>&1 >/dev/null | tail -n 1
+  done
+  python -c "
+import json
+for f in ('$O/bench_${TAG}_nfm_c4_nodw0.json','$O/bench_${TAG}_nfm_c4_nodw1.json'):
+    try:
+        d=json.loads(open(f).read().strip().splitlines()[-1]); print(f, d['value'], d['ms_per_step'], d.get('kernels_ms'))
+    except Exception as e: print(f, 'ERR', e)
+" ;;
 ummaprof)
   LCTR_MLP_UMMA_TRACE=1 timeout 300 python bench.py --workload nfm_c4 --steps 6 --warmup 3 --no-cpu-baseline > /dev/null 2> $O/umma_trace_$TAG.txt; tail -n 8 $O/umma_trace_$TAG.txt
   timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 60 -c 60 --csv --log-file $O/launches_${TAG}_nfm_c4.csv \

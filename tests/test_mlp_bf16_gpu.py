@@ -89,12 +89,18 @@ def _emulate(torch, capi, rp, fid, label, W, V, k, layers, act, masks):
     return p.numpy(), [(g[0].numpy(), g[1].numpy()) for g in grads], dz.numpy()
 
 
-@pytest.mark.parametrize("hidden,act_name,rows,masked", [((64, 32), "sigmoid", 300, False),
-                                                         ((256, 128, 64), "sigmoid", 257, False),
-                                                         ((256, 128, 64), "tanh", 129, True)])
-def test_bf16_mlp_matches_emulation(hidden, act_name, rows, masked):
+# which kernel takes the chain: "umma" = tcgen05 / TMEM (mlp_umma.cu: hidden widths multiples of 64, every layer's dW
+# expressible with M = 128, no dropout mask), "mma" = the mma.sync kernel of mlp_bf16.cu (everything else)
+@pytest.mark.parametrize("hidden,act_name,rows,masked,kernel", [((64, 32), "sigmoid", 300, False, "mma"),
+                                                                ((256, 128, 64), "sigmoid", 257, False, "umma"),
+                                                                ((256, 128, 64), "tanh", 200, False, "umma"),
+                                                                ((128, 64), "sigmoid", 300, False, "umma"),
+                                                                ((128, 128), "tanh", 130, False, "umma"),
+                                                                ((256, 128, 64), "tanh", 129, True, "mma")])
+def test_bf16_mlp_matches_emulation(hidden, act_name, rows, masked, kernel, capfd, monkeypatch):
     torch = pytest.importorskip("torch")
     from lightctr_b200 import capi
+    monkeypatch.setenv("LCTR_MLP_UMMA_TRACE", "1")  # the tcgen05 kernel reports its phase timings on stderr when it runs
     F, k = 3000, 16
     act = capi.ACT_SIGMOID if act_name == "sigmoid" else capi.ACT_TANH
     dims = [k] + list(hidden) + [1]
@@ -110,6 +116,7 @@ def test_bf16_mlp_matches_emulation(hidden, act_name, rows, masked):
     c.upload_batch(0, rp, fid, None, None, label)
     loss, acc = c.train_step(0)
     pred = c.download_pred(0)
+    assert ("[mlp_umma trace" in capfd.readouterr().err) == (kernel == "umma")
     p_ref, g_ref, _ = _emulate(torch, capi, rp, fid, label, W, V, k, layers, act, masks)
     assert np.max(np.abs(pred - p_ref)) < 3e-3, np.max(np.abs(pred - p_ref))  # bf16-ulp flips of single activations
     y = label.astype(np.float64)
@@ -125,6 +132,34 @@ def test_bf16_mlp_matches_emulation(hidden, act_name, rows, masked):
             # and the bulk of the entries is much tighter than the max
             assert np.median(np.abs(got - ref)) / scale < 1e-3, (l, name)
     c.close()
+
+
+def test_tcgen05_and_mma_sync_kernels_agree(monkeypatch):
+    """The two tensor-core kernels (mlp_umma.cu: tcgen05.mma + TMEM; mlp_bf16.cu: mma.sync) round at the same points; on the
+    C4 chain they must agree to a few bf16 ulps of single activations (the sigmoid is 1/(1+2^t) on MUFU in one and
+    __expf/__fdividef in the other)."""
+    from lightctr_b200 import capi
+    F, k, hidden, rows = 3000, 16, (256, 128, 64), 1000
+    dims = [k] + list(hidden) + [1]
+    rp, fid, label = _batch(21, rows, F, 24)
+    W, V, layers = _params(23, F, k, dims)
+    out = {}
+    monkeypatch.setenv("LCTR_MLP_SKIP_UPDATE", "1")
+    for flag in ("0", "1"):
+        monkeypatch.setenv("LCTR_MLP_UMMA", flag)  # read when the context prepares its dense layers
+        c = _ctx(capi, capi.MLP_BF16, F, k, hidden, capi.ACT_SIGMOID, rows, W, V, layers)
+        c.upload_batch(0, rp, fid, None, None, label)
+        loss, _ = c.train_step(0)
+        out[flag] = (loss, c.download_pred(0), [c.mlp_download_grad(l, dims[l], dims[l + 1]) for l in range(len(dims) - 1)])
+        c.close()
+    (l0, p0, g0), (l1, p1, g1) = out["0"], out["1"]
+    assert abs(l0 - l1) < 1e-3 * abs(l0), (l0, l1)
+    assert np.max(np.abs(p0 - p1)) < 3e-3
+    for l in range(len(dims) - 1):
+        for a, b, name in ((g0[l][0], g1[l][0], "dW"), (g0[l][1], g1[l][1], "db")):
+            scale = np.max(np.abs(a)) + 1e-12
+            assert np.max(np.abs(a - b)) / scale < 1e-2, (l, name)
+            assert np.median(np.abs(a - b)) / scale < 1e-3, (l, name)
 
 
 def test_bf16_first_step_signs_match_fp32_mode():
