@@ -387,6 +387,7 @@ inline size_t mlp_in0(const lctr_cfg& cf) {
     return cf.model == LCTR_MODEL_WND ? (size_t)cf.field_cnt * cf.factor_cnt : (size_t)cf.factor_cnt;
 }
 int mlp_sync_dense_grad(lctr_ctx* c);
+int launch_ffm_warp(lctr_ctx* c, Slot& s, int64_t rb, int64_t re, bool stats);  // 0 launched, -1 shape not covered, 1 error
 int mlp_bf16_prepare(lctr_ctx* c);
 int mlp_bf16_refresh(lctr_ctx* c, int layer);
 int launch_nfm_mlp_bf16(lctr_ctx* c, Slot& s, int64_t rb, int64_t re, int64_t rows_divisor);

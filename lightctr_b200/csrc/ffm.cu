@@ -565,6 +565,11 @@ static int ffm_launch(lctr_ctx* c, Slot& s, int64_t rb, int64_t re, bool train, 
         LCTR_CUDA(cudaGetLastError());
         return 0;
     }
+    // default for k % 4 == 0: the warp-per-sample kernel of ffm_warp.cu (LCTR_FFM_WARP=0 keeps the CTA-per-sample kernel below)
+    if (train && !bulk && vec == 4) {
+        const int rc = launch_ffm_warp(c, s, rb, re, stats);
+        if (rc >= 0) return rc;
+    }
 #define FFM_GO(VECN, HV, TR)                                                                                          \
     do {                                                                                                              \
         auto kern = bulk ? ffm_fused_kernel<VECN, HV, TR, (VECN == 4) && TR> : ffm_fused_kernel<VECN, HV, TR, false>; \
