@@ -76,12 +76,15 @@ __device__ __forceinline__ void update_one(const OptParams& P, float corr, float
                 w = w - g / (P.mb / P.lr);
             }
         } else if (P.opt == LCTR_OPT_PS_ADAGRAD) {  // :288-294 (s1 = data_accum, initialised to 1e-7 :323)
-            float grad = g / P.mb;
-            grad = grad * grad;
+            // `TValue grad = data_pair.second / minibatch` divides the PUSHED value in place (Value::operator/ mutates and
+            // returns *this, distributed_algo_abst.h:56-63), so the step below uses g / minibatch, not g -- pinned by the
+            // reference cluster's Adagrad curve (tests/golden/wnd_ref_curve.json)
+            const float gm = g / P.mb;
+            float grad = gm * gm;
             s1 = s1 + grad;
             float sq = (float)sqrt((double)s1 + 1e-7);
             sq = sq / P.lr;
-            w = w - g / sq;
+            w = w - gm / sq;
         } else if (P.opt == LCTR_OPT_PS_DCASGD) {   // :252-267 (s2 = shadow copy of worker 0)
             float grad = g / P.mb;
             float reserve = grad;

@@ -8,7 +8,7 @@
 //          first-entry tensors (:274-276, no L2 on tensors)
 // Both gathers are HBM-bound row reads; the scatter uses the same RED + touched-map + sparse-apply path as FM.
 // The reference runs this against asynchronous parameter servers; the synchronous restatement it is checked against
-// is oracle/lightctr_oracle.c:orc_wnd_epoch (parity unpinned: the class cannot be compiled here).
+// is oracle/lightctr_oracle.c:orc_wnd_epoch (synchronous schedule of the worker pinned in tests/test_oracle_wnd_pin_cpu.py).
 #include "common.cuh"
 
 namespace lctr {

@@ -24,6 +24,7 @@ def build(ref=True):
     subprocess.check_call(["make", "-s", "-C", HERE, "oracle"])
     if ref and os.path.isdir("/root/reference/LightCTR"):
         subprocess.check_call(["make", "-s", "-C", HERE, "ref"])
+        subprocess.check_call(["make", "-s", "-C", HERE, "refdist"])  # cluster roles; skipped by the Makefile without a libzmq
 
 
 class _Data(C.Structure):
@@ -92,6 +93,11 @@ def lib():
     L.orc_wnd_epoch.argtypes = [C.c_int64, _i64p, _u32p, _u32p, _f32p, _i32p, C.c_size_t, C.c_size_t, C.c_size_t, _f32p,
                                 _f32p, _f32p, _f32p, C.POINTER(_Mlp), C.c_size_t, C.c_size_t, C.c_float, C.c_float,
                                 C.c_float, C.POINTER(C.c_float), C.POINTER(C.c_size_t)]
+    L.orc_wnd_epoch_ref.argtypes = [C.c_int64, _i64p, _u32p, _u32p, _f32p, _i32p, C.c_size_t, C.c_size_t, C.c_size_t, _f32p,
+                                    _f32p, _f32p, _f32p, C.POINTER(_Mlp), C.c_size_t, C.c_size_t, C.c_float, C.c_float, C.c_int,
+                                    _f32p, _f32p, C.POINTER(C.c_float), C.POINTER(C.c_size_t)]
+    L.orc_wire_f16.argtypes = [C.c_float]
+    L.orc_wire_f16.restype = C.c_float
     L.orc_predict.argtypes = [C.c_int64, _i64p, _u32p, _u32p, _f32p, _i32p, C.c_size_t, C.c_size_t, _f32p, _f32p,
                               C.c_void_p, C.c_int, _f32p, C.POINTER(C.c_float), C.POINTER(C.c_int),
                               C.POINTER(C.c_float)]
@@ -338,13 +344,21 @@ class NFMOracle:
 
 
 class WNDOracle:
-    """Wide&Deep with per-field concat input (Distributed_Algo_Abst::batchGradCompute restated as one synchronous
-    process; parity unpinned, see lightctr_oracle.c).  dims = [Fc*d, H.., 1]."""
+    """Wide&Deep with per-field concat input (Distributed_Algo_Abst::batchGradCompute).  dims = [Fc*d, H.., 1].
+    schedule="sync" (default): one synchronous process, gradients applied once per minibatch -- what the CUDA path implements.
+    schedule="reference": the cluster's own schedule (binary16 wire, per-sample tensor SGD on the server, wide weights pulled
+    and pushed once per minibatch; optimizer is the server's SGD, l2 = 0) -- PINNED against a real Master + ParamServer +
+    worker run, tests/golden/wnd_ref_curve.json / tests/test_oracle_wnd_pin_cpu.py."""
 
     def __init__(self, ds, d, hidden, W, E, lr=0.05, l2=0.001, batch_size=50, minibatch=50, sparse_rate=0.8, act=0,
-                 optimizer="adagrad"):
+                 optimizer="adagrad", schedule="sync"):
         self.ds, self.d = ds, d
+        self.schedule = schedule
         self.ps_rule = 1 if optimizer == "ps_sgd" else 0
+        self.ps_kind = {"ps_sgd": 0, "ps_adagrad": 1, "ps_dcasgd": 2, "ps_dcasgda": 3}.get(optimizer, 0)
+        if schedule == "reference":  # the server's per-key state: data_accum starts at 1e-7, shadow copies at 0 (paramserver.h:318-327)
+            self.ps_accum = np.full(ds.feature_cnt, 1e-7, np.float32)
+            self.ps_shadow = np.zeros(ds.feature_cnt, np.float32)
         F, Fc = ds.feature_cnt, ds.field_cnt
         self.W, self.E = W.copy(), E.copy()
         hidden = list(hidden) if isinstance(hidden, (list, tuple)) else [hidden]
@@ -356,6 +370,12 @@ class WNDOracle:
     def epoch(self):
         ds = self.ds
         loss, acc = C.c_float(0), C.c_size_t(0)
+        if self.schedule == "reference":
+            pulled = np.zeros(ds.feature_cnt, np.float32)
+            lib().orc_wnd_epoch_ref(ds.rows, ds.row_ptr, ds.fid, ds.field, ds.val, ds.label, ds.feature_cnt, ds.field_cnt, self.d,
+                                    self.W, self.E, self.update_g[:ds.feature_cnt], pulled, self.mlp.p, self.bs, self.mb, self.lr,
+                                    self.sr, self.ps_kind, self.ps_accum, self.ps_shadow, C.byref(loss), C.byref(acc))
+            return loss.value, acc.value / ds.rows
         lib().orc_set_wnd_ps_rule(self.ps_rule)
         lib().orc_wnd_epoch(ds.rows, ds.row_ptr, ds.fid, ds.field, ds.val, ds.label, ds.feature_cnt, ds.field_cnt, self.d,
                             self.W, self.E, self.update_g, self.accum, self.mlp.p, self.bs, self.mb, self.lr, self.l2,

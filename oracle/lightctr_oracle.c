@@ -573,9 +573,9 @@ void orc_nfm_epoch(int64_t rows, const int64_t* row_ptr, const uint32_t* fid, co
 /* Distributed_Algo_Abst::batchGradCompute (distributed_algo_abst.h:176-280) restated as ONE synchronous process:
  * what a worker computes per row, with the pull = "read the current parameters" and the push = "add into update_g",
  * applied once per minibatch by the trainer's updater (the reference applies pushes on asynchronous parameter
- * servers with fp16 transport; SURVEY.md 8e lists those deltas).  PARITY UNPINNED: this class links ZeroMQ
- * (third/zeromq, a Mach-O archive in the reference tree) and cannot be compiled here, so this restatement is checked
- * against the source text only, not against reference outputs.
+ * servers with fp16 transport; SURVEY.md 8e lists those deltas).  This SCHEDULE is the product's, not the reference's; every
+ * function it is made of is PINNED through orc_wnd_epoch_ref below -- the same worker and server rules in the cluster's own
+ * schedule, held digit for digit against a real Master + ParamServer + worker run (tests/test_oracle_wnd_pin_cpu.py).
  *   wide:  pred += w[fid] * X over the row's entries (:205-211)
  *   deep:  input[field*d .. +d) = tensor of the FIRST entry of each field (:213-216, :224-229), 0 for absent fields
  *   pCTR = sigmoid(pred + MLP(input)) (:236); loss / accuracy (:237-245, note >= 0.5)
@@ -638,6 +638,123 @@ void orc_wnd_epoch(int64_t rows, const int64_t* row_ptr, const uint32_t* fid, co
             orc_adagrad(F * d, E, gE, accum + F, minibatch, lr);
         }
         orc_mlp_apply(mlp, minibatch, lr, sparse_rate);
+    }
+    free(deep); free(first);
+    *loss_out = loss; *acc_out = accuracy;
+}
+
+/* ---- the worker + parameter server in the REFERENCE'S OWN schedule (pinned) ------------------------------------------------
+ * orc_wnd_epoch above is the synchronous batch restatement the CUDA path implements.  What the unmodified cluster does
+ * differs in three places, all restated here so that this function can be held against the loss curve of a real
+ * Master + ParamServer + worker run over ZeroMQ (tests/golden/wnd_ref_curve.json, made by tests/golden/make_wnd_ref_curve.py
+ * from oracle/ref_dist_driver.cpp):
+ *   1. every number that crosses the wire is a binary16: pulled parameters (distribut/paramserver.h:160-162,177, read back by
+ *      pull.h:111-112,150), pushed gradients (push.h, read by paramserver.h:217-220,241) -- common/float16.h:105-152 rounds to
+ *      nearest even, flushes nothing, maps -0 to +0;
+ *   2. the wide weights are pulled ONCE per minibatch (distributed_algo_abst.h:178-193) and their gradients pushed once
+ *      (:275-278), but a sample's per-field tensors are pulled (:217) and their gradients pushed (:272) PER SAMPLE: the server
+ *      applies plain SGD to a tensor right away (paramserver.h:229-237), so the next sample sees it;
+ *   3. a tensor is created on the server the first time it is pulled, from the SERVER's rand() stream (paramserver.h:40-46):
+ *      the caller passes E already initialised in that order (oracle/umap_order.cpp).
+ * Wide parameters start at 0 (Value::initParam, distributed_algo_abst.h:70-72), L2Reg_ratio = 0 (:103). */
+static uint16_t orc_f32_to_f16(float src) {            /* float16.h:105-152 */
+    uint32_t s; memcpy(&s, &src, 4);
+    const uint16_t sign = (uint16_t)((s >> 16) & 0x8000);
+    int exp = (int)((s >> 23) & 0xff) - 127;
+    int mant = (int)(s & 0x7fffff);
+    if ((s & 0x7fffffff) == 0) return 0;               /* +-0 -> +0 */
+    if (exp > 15) return (exp == 128 && mant) ? 0x7fff : (uint16_t)(sign | 0x7c00);
+    uint16_t u = 0; int sticky = 0;
+    if (exp >= -14) { u = (uint16_t)((((exp + 15) & 0x1f) << 10) | (mant >> 13)); }
+    else {
+        const int rshift = -(exp + 14);
+        if (rshift < 32) { mant |= 1 << 23; sticky = (mant & ((1 << rshift) - 1)) != 0; mant >>= rshift; u = (uint16_t)((mant >> 13) & 0x3ff); }
+        else { mant = 0; u = 0; }
+    }
+    const int round_bit = (mant >> 12) & 1;
+    sticky |= (mant & ((1 << 12) - 1)) != 0;
+    if ((round_bit && sticky) || (round_bit && (u & 1))) u = (uint16_t)(u + 1);
+    return (uint16_t)(u | sign);
+}
+static float orc_f16_to_f32(uint16_t h) {              /* float16.h:65-100 */
+    const uint32_t sign = (h >> 15) & 1; int exp = (h >> 10) & 0x1f; uint32_t mant = h & 0x3ff, f = 0;
+    if (exp > 0 && exp < 31) f = (sign << 31) | ((uint32_t)(exp + 112) << 23) | (mant << 13);
+    else if (exp == 0) {
+        if (mant) { exp += 113; while ((mant & (1u << 10)) == 0) { mant <<= 1; exp--; } mant &= 0x3ff; f = (sign << 31) | ((uint32_t)exp << 23) | (mant << 13); }
+        else f = sign << 31;
+    } else f = mant ? 0x7fffffffu : ((0xffu << 23) | (sign << 31));
+    float r; memcpy(&r, &f, 4); return r;
+}
+float orc_wire_f16(float x) { return orc_f16_to_f32(orc_f32_to_f16(x)); }
+
+void orc_wnd_epoch_ref(int64_t rows, const int64_t* row_ptr, const uint32_t* fid, const uint32_t* field, const float* val,
+                       const int* label, size_t F, size_t Fc, size_t d, float* W, float* E, float* push_g, float* pulled,
+                       orc_mlp* mlp, size_t batch_size, size_t minibatch, float lr, float sparse_rate, int ps_kind, float* accum,
+                       float* shadow, float* loss_out, size_t* acc_out) {
+    float loss = 0; size_t accuracy = 0;
+    float* deep = (float*)malloc(sizeof(float) * Fc * d);
+    int64_t* first = (int64_t*)malloc(sizeof(int64_t) * Fc);
+    const float scaler = (float)(-1.0 * (double)lr / (double)minibatch);       /* paramserver.h:232-233 */
+    const float den = (float)minibatch / lr;                                     /* :297-299 */
+    size_t n_batches = ((size_t)rows + batch_size - 1) / batch_size;
+    for (size_t p = 0; p < n_batches; p++) {
+        int64_t rb = (int64_t)(p * batch_size), re = rb + (int64_t)batch_size;
+        if (re > rows) re = rows;
+        /* pull_op.sync: one binary16 copy of every wide weight of the minibatch (distributed_algo_abst.h:178-193) */
+        for (int64_t i = row_ptr[rb]; i < row_ptr[re]; i++) { pulled[fid[i]] = orc_wire_f16(W[fid[i]]); push_g[fid[i]] = 0.0f; }
+        for (int64_t rid = rb; rid < re; rid++) {
+            float pred = 0.0f;
+            memset(deep, 0, sizeof(float) * Fc * d);
+            for (size_t a = 0; a < Fc; a++) first[a] = -1;
+            for (int64_t i = row_ptr[rid]; i < row_ptr[rid + 1]; i++) {         /* :201-212 */
+                const size_t f = fid[i], a = field[i];
+                float wx = pulled[f] * val[i];
+                pred += wx;
+                if (first[a] < 0) {                                              /* pull_tensor_op.sync (:217), binary16 */
+                    first[a] = (int64_t)f;
+                    for (size_t c = 0; c < d; c++) deep[a * d + c] = orc_wire_f16(E[f * d + c]);
+                }
+            }
+            const float fc = orc_mlp_forward(mlp, deep);
+            const float pCTR = orc_sigmoid(pred + fc);
+            {
+                double term = (label[rid] == 1) ? (double)(-logf(pCTR)) : -log(1.0 - (double)pCTR);
+                loss = (float)((double)loss + term);
+                if (pCTR >= 0.5 && label[rid] == 1) accuracy++;
+                else if (pCTR < 0.5 && label[rid] == 0) accuracy++;
+            }
+            if (minibatch == 0) continue;                                        /* predicting */
+            const float lossv = pCTR - (float)label[rid];
+            for (int64_t i = row_ptr[rid]; i < row_ptr[rid + 1]; i++) {         /* :250-266, L2Reg_ratio == 0 */
+                const size_t f = fid[i];
+                float a = lossv * val[i], c = 0.0f * pulled[f];
+                push_g[f] = push_g[f] + (a + c);
+            }
+            orc_mlp_backward(mlp, lossv);
+            const float* delta = mlp->in_delta[0];
+            for (size_t a = 0; a < Fc; a++) {                                    /* push_tensor_op.sync (:272) -> SGD on the server */
+                if (first[a] < 0) continue;
+                for (size_t c = 0; c < d; c++) {
+                    float t = orc_wire_f16(delta[a * d + c]) * scaler;
+                    E[(size_t)first[a] * d + c] = E[(size_t)first[a] * d + c] + t;
+                }
+            }
+        }
+        if (minibatch == 0) continue;
+        /* push_op.sync (:276-278): binary16 gradient sums, scalar SGD on the server (paramserver.h:295-300).  A key occurs once
+         * in push_map; walk the batch's entries and clear each sum after use. */
+        for (int64_t i = row_ptr[rb]; i < row_ptr[re]; i++) {
+            const size_t f = fid[i];
+            if (pulled[f] != pulled[f]) continue;                                /* already applied (marked NaN below) */
+            pulled[f] = NAN;
+            /* push.h:62-65: a gradient outside 1e-7 < |g| < 15 (Value::checkPreferredValue, distributed_algo_abst.h:76-79) is
+             * not sent at all -- a feature present in most rows of the minibatch easily sums to |g| >= 15 */
+            if (!((double)fabsf(push_g[f]) > 1e-7 && fabsf(push_g[f]) < 15.0f)) continue;
+            const float g16 = orc_wire_f16(push_g[f]);
+            if (ps_kind == 0) { float t = g16 / den; W[f] = W[f] - t; }                /* SGD, the server's default */
+            else orc_ps_update(ps_kind, 1, W + f, &g16, accum + f, shadow + f, minibatch, lr, 0);  /* Adagrad / DCASGD / DCASGDA */
+        }
+        orc_mlp_apply(mlp, minibatch, lr, sparse_rate);                          /* :280 */
     }
     free(deep); free(first);
     *loss_out = loss; *acc_out = accuracy;
@@ -715,8 +832,10 @@ void orc_predict(int64_t rows, const int64_t* row_ptr, const uint32_t* fid, cons
 }
 
 /* ParamServer push handler, per coordinate (distribut/paramserver.h:232-300), one push of worker 0 carrying the step's
- * summed gradient.  PARITY UNPINNED: paramserver.h pulls in the ZeroMQ transport and cannot be compiled here; the Value
- * operators mutate their left operand (distributed_algo_abst.h:39-72), which the sequences below follow literally.
+ * summed gradient.  PINNED: all four rules reproduce the loss curves of the reference cluster run with the corresponding
+ * UpdaterType (tests/golden/wnd_ref_curve.json, tests/test_oracle_wnd_pin_cpu.py; the pin caught that Adagrad steps by
+ * g / minibatch).  The Value operators mutate their left operand (distributed_algo_abst.h:39-72), which the sequences below
+ * follow literally.
  * kind: 0 SGD (:295-300; tensor != 0: tensor SGD :232-237), 1 Adagrad (:288-294), 2 DCASGD (:252-267), 3 DCASGDA (:268-286).
  * accum starts at 1e-7 (:323), shadow at 0 (:327). */
 void orc_ps_update(int kind, size_t len, float* w, const float* g, float* accum, float* shadow, size_t minibatch, float lr,
@@ -727,9 +846,11 @@ void orc_ps_update(int kind, size_t len, float* w, const float* g, float* accum,
             if (tensor) { const float scaler = (float)(-1.0 * (double)lr / (double)minibatch); float t = g[i] * scaler; w[i] = w[i] + t; }
             else { float den = mb / lr; float t = g[i] / den; w[i] = w[i] - t; }
         } else if (kind == 1) {
-            float grad = g[i] / mb; grad = grad * grad; accum[i] = accum[i] + grad;
+            /* :288-294.  `TValue grad = data_pair.second / minibatch` divides the pushed value IN PLACE (Value::operator/ mutates
+             * and returns *this), so the step is (g / minibatch) / (sqrt(accum) / lr) -- pinned: wnd_ref_curve.json "adagrad" */
+            const float gm = g[i] / mb; float grad = gm * gm; accum[i] = accum[i] + grad;
             float sq = (float)sqrt((double)accum[i] + 1e-7); sq = sq / lr;
-            float t = g[i] / sq; w[i] = w[i] - t;
+            float t = gm / sq; w[i] = w[i] - t;
         } else if (kind == 2) {
             float grad = g[i] / mb, reserve = grad;
             grad = grad * grad; float cur = w[i] - shadow[i]; grad = grad * cur; grad = grad * 0.1f;

@@ -1,7 +1,7 @@
 """Distributed_Algo_Abst (distributed_algo_abst.h:86-340) through its C++ shim (lightctr_b200/host/lightctr_gpu.h), compiled
 with plain g++ (dist_example.cpp = the worker part of the reference's main.cpp:253):
   * one worker: loss curve against the oracle's synchronous restatement orc_wnd_epoch with the parameter server's default
-    SGD rules (parity unpinned: the class links ZeroMQ and cannot be compiled here);
+    SGD rules (synchronous schedule; the worker and the rules themselves are pinned in tests/test_oracle_wnd_pin_cpu.py);
   * two workers, one process each (sharing cuda:0 through CUDA IPC): the owner-sharded wide weights / tensors must come out
     identical to a one-process emulation that applies both workers' minibatch gradients per step while each worker keeps
     its own dense layers -- the semantics of the reference's workers + parameter servers when run in lock step."""

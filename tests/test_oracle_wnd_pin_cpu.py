@@ -1,0 +1,102 @@
+"""PIN of the Wide&Deep worker + parameter-server restatement (oracle.api.WNDOracle(schedule="reference"),
+oracle/lightctr_oracle.c:orc_wnd_epoch_ref) against the UNMODIFIED reference cluster.
+
+tests/golden/wnd_ref_curve.json holds the per-epoch loss / accuracy printed by a real Master + ParamServer + one
+Distributed_Algo_Abst worker run over ZeroMQ (oracle/ref_dist_driver.cpp, compiled from the sources where they lie under
+/root/reference; tests/golden/make_wnd_ref_curve.py) on the reference's data/train_sparse.csv, once per server updater
+(SGD -- main.cpp's default --, Adagrad, DCASGD, DCASGDA; distribut/paramserver.h:22-27,244-300).  The restatement has to
+reproduce every printed digit: that covers the worker (distributed_algo_abst.h:170-282: wide sum on the pulled copies,
+first-feature-per-field tensors, Tanh / linear Fully_Conn_Layer pair with dropout, loss, per-sample tensor push, per-batch
+wide push with the checkPreferredValue filter of push.h:62-65), the binary16 wire format (common/float16.h) and all four
+server rules with their mutating Value arithmetic.
+
+The CUDA path implements the synchronous-minibatch schedule of the same rules (WNDOracle(schedule="sync"), tests/
+test_parity_gpu.py, tests/test_dist_shim_gpu.py); the two schedules share every function pinned here."""
+import json
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from golden_util import GOLDEN, load_csr
+
+UPDATERS = ["sgd", "adagrad", "dcasgd", "dcasgda"]
+
+
+def _golden():
+    with open(os.path.join(GOLDEN, "wnd_ref_curve.json")) as f:
+        return json.load(f)
+
+
+def _replay(api, g, ds, updater):
+    """WNDOracle in the cluster's schedule, initialised like the two processes: the server's tensors in first-pull order from
+    the server's rand() stream, the worker's dense layers from the worker's (each process spends `*_rand_skip` draws on its
+    listen port first, common/network.h:366-383)."""
+    L = api.lib()
+    F, d = ds.feature_cnt, g["factor_dim"]
+    L.orc_srand(g["seed_ps"])
+    for _ in range(g["ps_rand_skip"]):
+        L.orc_rand()
+    L.orc_gauss_reset()
+    E = np.zeros(F * d, np.float32)
+    for key in g["first_touch"]:
+        for c in range(d):
+            E[key * d + c] = np.float32(L.orc_gauss())  # TensorWrapper(length), paramserver.h:40-46
+    o = api.WNDOracle(ds, d, [g["hidden"]], np.zeros(F, np.float32), E, lr=g["learning_rate"], l2=0.0, batch_size=g["minibatch"],
+                      minibatch=g["minibatch"], sparse_rate=g["sparse_rate"], act=1, optimizer="ps_" + updater, schedule="reference")
+    L.orc_srand(g["seed_worker"])  # (the constructor above drew a chain of its own: replaced by the worker's)
+    for _ in range(g["worker_rand_skip"]):
+        L.orc_rand()
+    L.orc_gauss_reset()
+    o.mlp = api.Mlp([ds.field_cnt * d, g["hidden"], 1], 1, g["sparse_rate"])
+    return o
+
+
+@pytest.mark.parametrize("updater", UPDATERS)
+def test_reference_cluster_curve_is_reproduced(oracle_api, updater):
+    g = _golden()
+    ds = load_csr("train_sparse_csr.npz", field_cnt=68)
+    o = _replay(oracle_api, g, ds, updater)
+    want = g["curves"][updater]
+    for e in range(g["epochs"]):
+        loss, acc = o.epoch()
+        # the reference prints %f: 6 decimals of a float32 in the hundreds -- every printed digit must agree
+        assert abs(loss - want["loss"][e]) <= 1.5e-6 * max(1.0, abs(want["loss"][e])), (updater, e, loss, want["loss"][e])
+        assert abs(acc - want["accuracy"][e]) < 1e-9, (updater, e, acc, want["accuracy"][e])
+
+
+def test_binary16_wire_rounding(oracle_api):
+    """common/float16.h:105-152 is round-to-nearest-even with subnormals (and -0 -> +0): equal to numpy's float16 everywhere else"""
+    L = oracle_api.lib()
+    rng = np.random.default_rng(5)
+    xs = np.concatenate([rng.standard_normal(4000).astype(np.float32) * np.float32(s) for s in (1e-9, 1e-6, 1e-4, 1e-2, 1, 50, 7e4)])
+    xs = np.concatenate([xs, np.array([0.0, 65504.0, 65519.9, 65520.0, 6.1e-5, 5.96e-8, 2.98e-8, 2.99e-8, 1.0009766, 1.0004883], np.float32)])
+    with np.errstate(over="ignore"):
+        want = xs.astype(np.float16).astype(np.float32)
+    got = np.array([L.orc_wire_f16(float(x)) for x in xs], np.float32)
+    assert np.array_equal(got, want)
+    assert L.orc_wire_f16(-0.0) == 0.0 and not np.signbit(np.float32(L.orc_wire_f16(-0.0)))
+
+
+REF = os.path.join(os.path.dirname(GOLDEN), "..", "oracle", "_ref")
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(REF, "role_worker")), reason="reference cluster roles not built (make -C oracle refdist)")
+def test_committed_curve_is_what_the_reference_prints(tmp_path):
+    """where the roles are built (this container: /root/reference + pyzmq's libzmq), re-run the default (SGD) cluster and compare
+    with the committed fixture -- the golden file is an output of the reference, not of the oracle"""
+    import sys
+    sys.path.insert(0, GOLDEN)
+    import make_wnd_ref_curve as gen
+    from golden_util import write_libffm
+    g = _golden()
+    ds = load_csr("train_sparse_csr.npz", field_cnt=68)
+    prefix = str(tmp_path / "ad_data")
+    write_libffm(ds, prefix + "_1.csv")
+    try:
+        loss, acc, skip_ps, skip_w = gen.run_cluster(prefix, str(tmp_path), 2, g["seed_ps"], g["seed_worker"], 0)
+    except (OSError, subprocess.SubprocessError, AssertionError) as e:  # no loopback networking / libzmq on this box
+        pytest.skip("could not run the reference cluster here: %r" % (e,))
+    assert (skip_ps, skip_w) == (g["ps_rand_skip"], g["worker_rand_skip"])
+    assert loss == g["curves"]["sgd"]["loss"][:2] and acc == g["curves"]["sgd"]["accuracy"][:2]

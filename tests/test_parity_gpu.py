@@ -509,7 +509,8 @@ def test_upload_batch_rejects_malformed_input():
 @pytest.mark.parametrize("with_val", [False, True])
 def test_wide_and_deep_concat_variant(oracle_api, with_val):
     """LCTR_MODEL_WND (csrc/wnd.cu): Distributed_Algo_Abst's per-field concat input against the
-    oracle's synchronous restatement orc_wnd_epoch (parity UNPINNED: that reference class cannot be compiled here).
+    oracle's synchronous restatement orc_wnd_epoch (its worker / server functions are pinned against the reference cluster in
+    tests/test_oracle_wnd_pin_cpu.py; the synchronous schedule is the product's).
     Rows with repeated fields (only the first entry of a field feeds the deep part) and absent fields."""
     from lightctr_b200 import capi
     rng = np.random.default_rng(31)

@@ -120,7 +120,7 @@ def test_fm_exact_order_mode_with_ftrl_and_adam(oracle_api, opt):
 def test_fm_parameter_server_update_rules(oracle_api, opt):
     """The ParamServer's own per-coordinate rules (distribut/paramserver.h:232-300: SGD -- the default --, Adagrad, DCASGD,
     DCASGDA with their mutating Value arithmetic) as the trainer's updater, exact-order mode, against the oracle's
-    restatement (unpinned: the PS cannot be compiled without its ZeroMQ transport).  The learning rate is raised so that
+    restatement (pinned: tests/test_oracle_wnd_pin_cpu.py reproduces the reference cluster's curve for each rule).  The learning rate is raised so that
     the SGD-type rules (step = lr * g / minibatch) move the loss."""
     from lightctr_b200 import capi
     ds = load_csr("train_sparse_csr.npz", field_cnt=68)
