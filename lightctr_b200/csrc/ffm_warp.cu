@@ -80,8 +80,29 @@ ffm_warp_kernel(const int64_t* __restrict__ row_ptr, const uint32_t* __restrict_
     }
 
     double loss = 0.0, correct = 0.0;
-    for (int64_t r = rb + (int64_t)blockIdx.x * nwarp + wid; r < rb + rows; r += (int64_t)gridDim.x * nwarp) {
-        const int64_t b0 = row_ptr[r], e0 = row_ptr[r + 1];
+    const int64_t r_end = rb + rows, r_step = (int64_t)gridDim.x * nwarp;
+    int64_t r = rb + (int64_t)blockIdx.x * nwarp + wid;
+    int64_t nb0 = 0, ne0 = 0;
+    if (r < r_end) { nb0 = row_ptr[r]; ne0 = row_ptr[r + 1]; }
+    for (; r < r_end; r += r_step) {
+        const int64_t b0 = nb0, e0 = ne0;
+        if (r + r_step < r_end) { nb0 = row_ptr[r + r_step]; ne0 = row_ptr[r + r_step + 1]; }  // the next sample's extent: off the chain
+        // the sample's (fid, field, x, W[fid]) live in registers, lane j of chunk c holding entry 32 c + j of a 128-entry
+        // window: one round trip for the whole sample, and the gradient phase reuses them when the sample fits one window
+        uint32_t f_c[4]; int a_c[4]; float x_c[4], w_c[4];
+        auto load_window = [&](int64_t s0) {
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                const int64_t e = s0 + 32 * c + lane;
+                const bool ok = e < e0;
+                f_c[c] = ok ? __ldg(fid + e) : 0u;
+                a_c[c] = ok ? (int)__ldg(field + e) : 0;
+                x_c[c] = ok ? (HAS_VAL ? __ldg(val + e) : 1.f) : 0.f;
+            }
+#pragma unroll
+            for (int c = 0; c < 4; c++) w_c[c] = (s0 + 32 * c + lane < e0) ? __ldg(W + f_c[c]) : 0.f;
+        };
+        const bool one_window = e0 - b0 <= 128;
         // ---- phase 1: gather, T, wide sum, diagonal, per-field counts ---------------------------------------------
         float4 acc[PASSES];
         int cntf[PASSES];
@@ -107,15 +128,18 @@ ffm_warp_kernel(const int64_t* __restrict__ row_ptr, const uint32_t* __restrict_
             }
             seen |= 1ull << a;
         };
-        for (int64_t c0 = b0; c0 < e0; c0 += 32) {
+        for (int64_t s0 = b0; s0 < e0; s0 += 128) {
+          load_window(s0);
+#pragma unroll
+          for (int c = 0; c < 4; c++) wsum = fmaf(w_c[c], x_c[c], wsum);  // fm_pred += W[fid] * X  (train_ffm_algo.cpp:60)
+#pragma unroll 1
+          for (int c = 0; c < 4; c++) {
+            const int64_t c0 = s0 + 32 * c;
+            if (c0 >= e0) break;
             const int nst = (int)min((int64_t)32, e0 - c0);
-            uint32_t f_l = 0u; int a_l = 0; float x_l = 0.f;
-            if (lane < nst) {
-                f_l = __ldg(fid + c0 + lane);
-                a_l = (int)__ldg(field + c0 + lane);
-                x_l = HAS_VAL ? __ldg(val + c0 + lane) : 1.f;
-                wsum = fmaf(__ldg(W + f_l), x_l, wsum);  // fm_pred += W[fid] * X  (train_ffm_algo.cpp:60)
-            }
+            const uint32_t f_l = c == 0 ? f_c[0] : (c == 1 ? f_c[1] : (c == 2 ? f_c[2] : f_c[3]));
+            const int a_l = c == 0 ? a_c[0] : (c == 1 ? a_c[1] : (c == 2 ? a_c[2] : a_c[3]));
+            const float x_l = c == 0 ? x_c[0] : (c == 1 ? x_c[1] : (c == 2 ? x_c[2] : x_c[3]));
             auto group = [&](auto tag, int i) {
                 constexpr int UU = decltype(tag)::value;
                 float4 v[UU][PASSES];
@@ -148,8 +172,10 @@ ffm_warp_kernel(const int64_t* __restrict__ row_ptr, const uint32_t* __restrict_
             };
             int i = 0;
             for (; i + KU <= nst; i += KU) group(std::integral_constant<int, KU>{}, i);
+            for (; i + 4 <= nst; i += 4) group(std::integral_constant<int, 4>{}, i);  // tails in 4 / 2 / 1: each group is one round trip
             for (; i + 2 <= nst; i += 2) group(std::integral_constant<int, 2>{}, i);
             for (; i < nst; i++) group(std::integral_constant<int, 1>{}, i);
+          }
         }
         if (cur >= 0) flush(cur);
         {   // fields the sample does not have: their T rows are read by the pair sum and the gradient phase as zeros
@@ -198,16 +224,22 @@ ffm_warp_kernel(const int64_t* __restrict__ row_ptr, const uint32_t* __restrict_
             lc0[p] = l2 * (float)cntf[p]; lc1[p] = l2 * (float)(cntf[p] - 1);
             go0[p] = sb[p] >= 0 && cntf[p] > 0; go1[p] = sb[p] >= 0 && cntf[p] > 1;
         }
-        for (int64_t c0 = b0; c0 < e0; c0 += 32) {
+        for (int64_t s0 = b0; s0 < e0; s0 += 128) {
+          if (!one_window) load_window(s0);
+#pragma unroll
+          for (int c = 0; c < 4; c++)
+              if (s0 + 32 * c + lane < e0) {
+                  red_add_f32(gW + f_c[c], fmaf(l2, w_c[c], d * x_c[c]));  // train_ffm_algo.cpp:98
+                  if (touched) touched[f_c[c]] = 1;
+              }
+#pragma unroll 1
+          for (int c = 0; c < 4; c++) {
+            const int64_t c0 = s0 + 32 * c;
+            if (c0 >= e0) break;
             const int nst = (int)min((int64_t)32, e0 - c0);
-            uint32_t f_l = 0u; int a_l = 0; float x_l = 0.f;
-            if (lane < nst) {
-                f_l = __ldg(fid + c0 + lane);
-                a_l = (int)__ldg(field + c0 + lane);
-                x_l = HAS_VAL ? __ldg(val + c0 + lane) : 1.f;
-                red_add_f32(gW + f_l, fmaf(l2, __ldg(W + f_l), d * x_l));  // train_ffm_algo.cpp:98
-                if (touched) touched[f_l] = 1;
-            }
+            const uint32_t f_l = c == 0 ? f_c[0] : (c == 1 ? f_c[1] : (c == 2 ? f_c[2] : f_c[3]));
+            const int a_l = c == 0 ? a_c[0] : (c == 1 ? a_c[1] : (c == 2 ? a_c[2] : a_c[3]));
+            const float x_l = c == 0 ? x_c[0] : (c == 1 ? x_c[1] : (c == 2 ? x_c[2] : x_c[3]));
             auto group = [&](auto tag, int i) {
                 constexpr int UU = decltype(tag)::value;
                 float4 v[UU][PASSES];
@@ -240,8 +272,10 @@ ffm_warp_kernel(const int64_t* __restrict__ row_ptr, const uint32_t* __restrict_
             };
             int i = 0;
             for (; i + KU <= nst; i += KU) group(std::integral_constant<int, KU>{}, i);
+            for (; i + 4 <= nst; i += 4) group(std::integral_constant<int, 4>{}, i);  // tails in 4 / 2 / 1: each group is one round trip
             for (; i + 2 <= nst; i += 2) group(std::integral_constant<int, 2>{}, i);
             for (; i < nst; i++) group(std::integral_constant<int, 1>{}, i);
+          }
         }
         __syncwarp();  // T is rewritten by the next sample
     }
