@@ -7,6 +7,7 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <string>
 #include <vector>
 
 #include "common.cuh"
@@ -55,8 +56,9 @@ int lctr_save_checkpoint(lctr_ctx* c, const char* path) {
     LCTR_CHECK(c && path, "null argument");
     LCTR_CHECK(c->cfg.world == 1, "checkpoints are written per single-GPU trainer (world == 1)");
     LCTR_CUDA(cudaStreamSynchronize(c->stream));
-    FILE* f = fopen(path, "wb");
-    LCTR_CHECK(f, "open file error! (%s)", path);
+    const std::string tmp = std::string(path) + ".tmp";  // written beside the target and renamed: no torn checkpoint
+    FILE* f = fopen(tmp.c_str(), "wb");
+    LCTR_CHECK(f, "open file error! (%s)", tmp.c_str());
     CkptHeader h;
     memset(&h, 0, sizeof(h));
     memcpy(h.magic, "LCTRCKP1", 8);
@@ -76,8 +78,18 @@ int lctr_save_checkpoint(lctr_ctx* c, const char* path) {
         rc = dev_to_file(c, f, L.w, nw) || dev_to_file(c, f, L.b, L.out) || dev_to_file(c, f, L.acc_w, nw) ||
              dev_to_file(c, f, L.acc_b, L.out) || dev_to_file(c, f, L.mask, L.out);
     }
-    fclose(f);
-    return rc;
+    if (fclose(f) != 0) rc = 1;
+    if (rc) {
+        remove(tmp.c_str());
+        set_error("lctr_save_checkpoint: short write (%s)", tmp.c_str());
+        return 1;
+    }
+    if (rename(tmp.c_str(), path) != 0) {
+        remove(tmp.c_str());
+        set_error("lctr_save_checkpoint: cannot rename %s to %s", tmp.c_str(), path);
+        return 1;
+    }
+    return 0;
 }
 
 int lctr_load_checkpoint(lctr_ctx* c, const char* path) {
@@ -114,7 +126,8 @@ int lctr_load_checkpoint(lctr_ctx* c, const char* path) {
     }
     fclose(f);
     if (rc) return 1;
-    if (c->n_layers) {  // the masked code path of the tensor-core mode is keyed on "any mask entry == 0"
+    if (c->n_layers) {  // the masked code path of the tensor-core mode is keyed on "any mask entry == 0": recomputed, not accumulated
+        c->mlp_has_mask = 0;
         for (int l = 0; l < c->n_layers; l++) {
             std::vector<float> m(c->layers[l].out);
             LCTR_CUDA(cudaMemcpy(m.data(), c->layers[l].mask, m.size() * sizeof(float), cudaMemcpyDeviceToHost));
@@ -153,8 +166,25 @@ int lctr_load_dataset_bin(const char* path, lctr_dataset** out) {
         set_error("%s is not a lightctr_b200 CSR cache", path);
         return 1;
     }
+    // the header is not trusted: the counts must be consistent with each other and with the length of the file
+    long long flen = -1;
+    {
+        const long here = ftell(f);
+        if (here >= 0 && fseek(f, 0, SEEK_END) == 0) { flen = ftell(f); fseek(f, here, SEEK_SET); }
+    }
+    const uint64_t rows = hdr[0], nnz = hdr[1], labels = hdr[2];
+    const uint64_t kMax = (uint64_t)1 << 40;
+    const bool sane = rows < kMax && nnz < kMax && labels < kMax && labels >= rows &&
+                      (flen < 0 || (unsigned long long)flen == 8 + sizeof(hdr) + 8 * (rows + 1) + 10 * nnz + 4 * labels);
+    if (!sane) {
+        fclose(f);
+        set_error("%s: inconsistent CSR cache header (rows %llu, nnz %llu, labels %llu, file %lld bytes)", path,
+                  (unsigned long long)rows, (unsigned long long)nnz, (unsigned long long)labels, flen);
+        return 1;
+    }
     lctr_dataset* d = (lctr_dataset*)calloc(1, sizeof(lctr_dataset));
-    d->rows = (int64_t)hdr[0]; d->nnz = (int64_t)hdr[1]; d->label_cnt = (int64_t)hdr[2];
+    if (!d) { fclose(f); set_error("lctr_load_dataset_bin: out of memory"); return 1; }
+    d->rows = (int64_t)rows; d->nnz = (int64_t)nnz; d->label_cnt = (int64_t)labels;
     d->feature_cnt = hdr[3]; d->field_cnt = hdr[4];
     const size_t nn = d->nnz ? (size_t)d->nnz : 1, nl = d->label_cnt ? (size_t)d->label_cnt : 1;
     d->row_ptr = (int64_t*)malloc(sizeof(int64_t) * (size_t)(d->rows + 1));
@@ -162,6 +192,11 @@ int lctr_load_dataset_bin(const char* path, lctr_dataset** out) {
     d->field = (uint16_t*)malloc(sizeof(uint16_t) * nn);
     d->val = (float*)malloc(sizeof(float) * nn);
     d->label = (int32_t*)malloc(sizeof(int32_t) * nl);
+    if (!d->row_ptr || !d->fid || !d->field || !d->val || !d->label) {
+        fclose(f); lctr_free_dataset(d);
+        set_error("lctr_load_dataset_bin: out of memory for %llu entries", (unsigned long long)nnz);
+        return 1;
+    }
     bool ok = get(f, d->row_ptr, sizeof(int64_t) * (size_t)(d->rows + 1)) && get(f, d->fid, sizeof(uint32_t) * (size_t)d->nnz) &&
               get(f, d->field, sizeof(uint16_t) * (size_t)d->nnz) && get(f, d->val, sizeof(float) * (size_t)d->nnz) &&
               get(f, d->label, sizeof(int32_t) * (size_t)d->label_cnt);

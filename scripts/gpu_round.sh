@@ -29,7 +29,11 @@ sweep)
 others)
   for w in ffm_c3 nfm_c4 ffm_c5; do
     timeout 900 python bench.py --workload $w --steps 20 --warmup 3 --no-cpu-baseline > $O/bench_${TAG}_$w.json 2> $O/bench_${TAG}_$w.err
-  done ;;
+  done
+  for w in ffm_c3 ffm_c5; do
+    LCTR_FFM_WARP=0 timeout 900 python bench.py --workload $w --steps 20 --warmup 3 --no-cpu-baseline > $O/bench_${TAG}_${w}_cta_per_sample.json 2> $O/bench_${TAG}_${w}_cta_per_sample.err
+  done
+  LCTR_MLP_UMMA=0 timeout 900 python bench.py --workload nfm_c4 --steps 20 --warmup 3 --no-cpu-baseline > $O/bench_${TAG}_nfm_c4_mmasync.json 2> $O/bench_${TAG}_nfm_c4_mmasync.err ;;
 ncu)
   timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 120 -c 200 --csv --log-file $O/launches_${TAG}_fm_c2.csv \
       python bench.py --steps 30 --warmup 5 --no-cpu-baseline --no-c5 > $O/ncu_launch_$TAG.log 2>&1

@@ -33,3 +33,27 @@ def test_bin_cache_rejects_foreign_files(tmp_path):
     p.write_bytes(b"not a cache" * 10)
     with pytest.raises(capi.LctrError):
         capi.load_dataset_bin(str(p))
+
+
+def test_bin_cache_header_is_not_trusted(tmp_path):
+    """a cache whose counts disagree with each other or with the file length is an error, not an allocation of whatever the
+    header says (rows / nnz / label count are checked before any buffer is sized from them)"""
+    import struct
+    import pytest
+    from golden_util import load_csr, write_libffm
+    from lightctr_b200 import capi
+    ds = load_csr("train_sparse_csr.npz", field_cnt=68)
+    txt, binp = str(tmp_path / "t.csv"), str(tmp_path / "t.bin")
+    write_libffm(ds, txt)
+    capi.libffm_to_bin(txt, binp, 68, 0)
+    good = open(binp, "rb").read()
+    rows, nnz, labels = struct.unpack_from("<3Q", good, 8)
+    for bad_hdr in ((rows, nnz + 1, labels), (rows + 5, nnz, labels), (rows, nnz, rows - 1), (1 << 62, nnz, labels)):
+        p = tmp_path / "bad.bin"
+        p.write_bytes(good[:8] + struct.pack("<3Q", *bad_hdr) + good[32:])
+        with pytest.raises(capi.LctrError):
+            capi.load_dataset_bin(str(p))
+    p = tmp_path / "short.bin"
+    p.write_bytes(good[:-100])
+    with pytest.raises(capi.LctrError):
+        capi.load_dataset_bin(str(p))
