@@ -190,7 +190,7 @@ def ncu_traffic(wname, kernel):
     d = json.load(open(p)).get(wname, {})
     import re
     pat = {"fm_fused": r"fm_fused_kernel<\d+, \d, 1,", "fm_forward": r"fm_fused_kernel<\d+, \d, 0,|fm_forward", "apply_compact": r"apply_compact",
-           "ffm_fused": r"ffm_fused_kernel|ffm_tma_kernel", "apply": r"apply_kernel", "fm_backward_red": r"fm_backward_kernel"}.get(kernel, re.escape(kernel))
+           "ffm_fused": r"ffm_warp_kernel|ffm_fused_kernel|ffm_tma_kernel", "apply": r"apply_kernel", "fm_backward_red": r"fm_backward_kernel"}.get(kernel, re.escape(kernel))
     for name, rec in d.get("kernels", {}).items():
         if re.search(pat, name):
             return rec.get("dram_bytes"), "profiles/ncu_traffic.json <- %s (%s)" % (d.get("source", "?"), name.strip())
@@ -468,6 +468,10 @@ def main():
                                               else "mlp (nfm_mlp_fused_kernel: mma.sync; + dense Adagrad)"), "achieved": achieved, "peak": tpeak,
                 "unit": "TFLOP/s", "frac": achieved / tpeak, "traffic": None, "peak_source": tsrc,
                 "algorithmic_flops_per_launch": flops, "kernel_ms": ms / cnt}
+        if world == 1:
+            tr, src = ncu_traffic(wname, "nfm_mlp_umma" if umma else "nfm_mlp_fused")
+            if tr is not None:
+                roof["traffic"], roof["traffic_source"] = tr, src
     roof_gather = None
     if m["gather"]:
         gms = m["gather"]["ms"]

@@ -210,19 +210,33 @@ static void apply_go(lctr_ctx* c, Slot& s, const OptParams& P, const OptParams* 
     FusedState* f = c->fused;
     const int main_blocks = c->sm_count * 3;
     const unsigned grid = (unsigned)(main_blocks + kHotMax / 8);  // + one warp per possible hot slot
-#define AC_ARGS s.uniq, s.n_uniq, f->G, s.hot_of, s.hot_slot, s.n_hot, f->Ghot, f->GS, main_blocks, c->W, c->V, c->s1W, c->s1V, c->s2W, c->s2V, P, P_dev
+    // Programmatic dependent launch behind the gradient kernel (one GPU; LCTR_PDL=0 turns it off): the updater's CTAs start as
+    // the gradient kernel's retire, request their ids, parameter and state rows, and only then wait for its completion.
+    const char* pdl_env = getenv("LCTR_PDL");  // read per launch: the tests toggle it
+    const bool pdl_off = pdl_env && atoi(pdl_env) == 0;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = 0; cfg.stream = c->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = (c->cfg.world == 1 && !pdl_off) ? 1 : 0;
+#define AC_GO(OPTC)                                                                                                          \
+    cudaLaunchKernelEx(&cfg, apply_compact_kernel<K, OPTC>, (const uint32_t*)s.uniq, (const unsigned int*)s.n_uniq, f->G,          \
+                       (const uint32_t*)s.hot_of, (const uint32_t*)s.hot_slot, (const unsigned int*)s.n_hot, f->Ghot, f->GS,     \
+                       main_blocks, c->W, c->V, c->s1W, c->s1V, c->s2W, c->s2V, P, P_dev)
     switch (P.opt) {
-        case LCTR_OPT_ADAGRAD: apply_compact_kernel<K, LCTR_OPT_ADAGRAD><<<grid, 256, 0, c->stream>>>(AC_ARGS); break;
-        case LCTR_OPT_FTRL: apply_compact_kernel<K, LCTR_OPT_FTRL><<<grid, 256, 0, c->stream>>>(AC_ARGS); break;
-        case LCTR_OPT_ADAM: apply_compact_kernel<K, LCTR_OPT_ADAM><<<grid, 256, 0, c->stream>>>(AC_ARGS); break;
-        case LCTR_OPT_RMSPROP: apply_compact_kernel<K, LCTR_OPT_RMSPROP><<<grid, 256, 0, c->stream>>>(AC_ARGS); break;
-        case LCTR_OPT_ADADELTA: apply_compact_kernel<K, LCTR_OPT_ADADELTA><<<grid, 256, 0, c->stream>>>(AC_ARGS); break;
-        case LCTR_OPT_PS_SGD: apply_compact_kernel<K, LCTR_OPT_PS_SGD><<<grid, 256, 0, c->stream>>>(AC_ARGS); break;
-        case LCTR_OPT_PS_ADAGRAD: apply_compact_kernel<K, LCTR_OPT_PS_ADAGRAD><<<grid, 256, 0, c->stream>>>(AC_ARGS); break;
-        case LCTR_OPT_PS_DCASGD: apply_compact_kernel<K, LCTR_OPT_PS_DCASGD><<<grid, 256, 0, c->stream>>>(AC_ARGS); break;
-        default: apply_compact_kernel<K, LCTR_OPT_PS_DCASGDA><<<grid, 256, 0, c->stream>>>(AC_ARGS); break;
+        case LCTR_OPT_ADAGRAD: AC_GO(LCTR_OPT_ADAGRAD); break;
+        case LCTR_OPT_FTRL: AC_GO(LCTR_OPT_FTRL); break;
+        case LCTR_OPT_ADAM: AC_GO(LCTR_OPT_ADAM); break;
+        case LCTR_OPT_RMSPROP: AC_GO(LCTR_OPT_RMSPROP); break;
+        case LCTR_OPT_ADADELTA: AC_GO(LCTR_OPT_ADADELTA); break;
+        case LCTR_OPT_PS_SGD: AC_GO(LCTR_OPT_PS_SGD); break;
+        case LCTR_OPT_PS_ADAGRAD: AC_GO(LCTR_OPT_PS_ADAGRAD); break;
+        case LCTR_OPT_PS_DCASGD: AC_GO(LCTR_OPT_PS_DCASGD); break;
+        default: AC_GO(LCTR_OPT_PS_DCASGDA); break;
     }
-#undef AC_ARGS
+#undef AC_GO
 }
 
 // updater over the slot's key set.  P_host (optional) / dP: parameters already staged in device memory (graph launches).

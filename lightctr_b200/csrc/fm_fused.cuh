@@ -215,6 +215,10 @@ fm_fused_kernel(const int64_t* __restrict__ row_ptr, const uint32_t* __restrict_
                 float* __restrict__ wide = nullptr /* MODE 2: wide part out [rows] */) {
     constexpr bool FWD = MODE != 3, BWD = MODE == 1 || MODE == 3, NFM = MODE >= 2;
     static_assert(K % 4 == 0 && K <= 32 && (K / 4 & (K / 4 - 1)) == 0, "fused FM step: K in {4, 8, 16, 32}");
+    // programmatic dependent launch: a kernel launched behind this one with the serialisation attribute (the compact
+    // updater, launch_apply_compact) may start its CTAs as soon as ours retire; it synchronises on our COMPLETION itself
+    // (cudaGridDependencySynchronize) before it touches G.  Without the attribute this is a no-op.
+    cudaTriggerProgrammaticLaunchCompletion();
     if (wait_flags) {  // multi-GPU: the owners' rows of this step must have landed in the cache (dist.cu)
         if (threadIdx.x < n_wait) {
             const volatile unsigned long long* f = wait_flags + threadIdx.x;
@@ -498,18 +502,19 @@ apply_compact_kernel(const uint32_t* __restrict__ uniq, const unsigned int* __re
                 const int ncol = GS < 32 ? GS : 32;             // columns covered per pass
                 const int col = c0 + lane % ncol;
                 const int grp = lane / ncol, ngrp = 32 / ncol;  // GS < 32: several replica rows per load
-                float t[kHotRep];
-#pragma unroll
-                for (int i = 0; i < kHotRep; i++)
-                    t[i] = (i < kHotRep / ngrp) ? __ldcg(tile + (size_t)(grp + i * ngrp) * GS + col) : 0.f;
                 float wv = 0.f, av = 0.f, bv = 0.f;
                 const bool mine = grp == 0 && col <= K;
                 const size_t o = col < K ? (size_t)f * K + col : (size_t)f;
-                if (mine) {
+                if (mine) {  // parameters and updater state: not written by the gradient kernel, requested before the dependency
                     wv = col < K ? V[o] : W[o];
                     av = col < K ? s1V[o] : s1W[o];
                     if (two) bv = col < K ? s2V[o] : s2W[o];
                 }
+                cudaGridDependencySynchronize();  // the gradient kernel has completed (returns at once after the first time)
+                float t[kHotRep];
+#pragma unroll
+                for (int i = 0; i < kHotRep; i++)
+                    t[i] = (i < kHotRep / ngrp) ? __ldcg(tile + (size_t)(grp + i * ngrp) * GS + col) : 0.f;
                 float sum = 0.f;
 #pragma unroll
                 for (int i = 0; i < kHotRep; i++) {
@@ -524,6 +529,7 @@ apply_compact_kernel(const uint32_t* __restrict__ uniq, const unsigned int* __re
                 }
             }
         }
+        cudaGridDependencySynchronize();
         return;
     }
     const unsigned warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -543,17 +549,24 @@ apply_compact_kernel(const uint32_t* __restrict__ uniq, const unsigned int* __re
             f[u] = ok[u] ? __ldg(uniq + idx) : 0u;
             g4[u] = v4[u] = a4[u] = b4[u] = make_float4(0.f, 0.f, 0.f, 0.f);
             gw[u] = w[u] = a[u] = bb[u] = 0.f;
-            if (ok[u]) {
-                const float* grow = G + (size_t)idx * GS;
+            if (ok[u]) {  // parameters and state first: the gradient kernel does not write them
                 const size_t o = (size_t)f[u] * K + 4 * q;
-                g4[u] = *reinterpret_cast<const float4*>(grow + 4 * q);
                 v4[u] = *reinterpret_cast<const float4*>(V + o);
                 a4[u] = *reinterpret_cast<const float4*>(s1V + o);
                 if (two) b4[u] = *reinterpret_cast<const float4*>(s2V + o);
                 if (q == 0) {
-                    gw[u] = grow[K]; w[u] = W[f[u]]; a[u] = s1W[f[u]];
+                    w[u] = W[f[u]]; a[u] = s1W[f[u]];
                     if (two) bb[u] = s2W[f[u]];
                 }
+            }
+        }
+        cudaGridDependencySynchronize();  // G is complete from here on (immediate after the first iteration)
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            if (ok[u]) {
+                const float* grow = G + (size_t)(b0 + u * GR + g) * GS;
+                g4[u] = *reinterpret_cast<const float4*>(grow + 4 * q);
+                if (q == 0) gw[u] = grow[K];
             }
         }
 #pragma unroll
@@ -578,6 +591,7 @@ apply_compact_kernel(const uint32_t* __restrict__ uniq, const unsigned int* __re
             }
         }
     }
+    cudaGridDependencySynchronize();
 }
 
 }  // namespace lctr

@@ -200,3 +200,34 @@ def test_fused_sub_ranges_of_a_resident_slot(oracle_api):
     Wg, Vg = ctx.download_params()
     assert np.max(np.abs(Wg - W)) < 2e-5 and np.max(np.abs(Vg - V)) < 2e-5
     ctx.close()
+
+
+def test_dependent_launch_of_the_updater_changes_nothing(oracle_api, monkeypatch):
+    """The compact updater is launched programmatically dependent on the gradient kernel (it starts early and synchronises on
+    the gradient kernel's completion itself, fm_fused.cu: apply_go).  Many short steps back to back -- where an updater that
+    read G too early, or a gradient kernel that read parameters mid-update, would show -- with the attribute on and off
+    (LCTR_PDL), from identical state: the order-free path reproduces itself to re-association noise per step."""
+    from lightctr_b200 import capi
+    F, k, B = 20000, 16, 2048
+    rp, fid, fld, lab, _ = _synth(F, B, 77)
+    rng = np.random.default_rng(8)
+    W0 = (rng.standard_normal(F) * 0.01).astype(np.float32)
+    V0 = (rng.standard_normal(F * k) * 0.05).astype(np.float32)
+    curves = {}
+    for flag in ("0", "1"):
+        monkeypatch.setenv("LCTR_PDL", flag)
+        ctx = capi.Context(capi.MODEL_FM, F, k, deterministic=0, lr=0.02)
+        ctx.upload_params(W0, V0)
+        ctx.upload_batch(0, rp, fid, None, None, lab)
+        curves[flag] = [ctx.train_step(0)[0] for _ in range(150)]
+        W, V = ctx.download_params()
+        curves[flag + "p"] = (W, V)
+        ctx.close()
+    a, b = np.array(curves["0"]), np.array(curves["1"])
+    assert np.all(np.isfinite(a)) and b[-1] < b[0]
+    assert np.max(np.abs(a - b) / np.abs(a)) < 2e-4, np.max(np.abs(a - b) / np.abs(a))  # 150 chaotic steps apart, not a race
+    assert np.max(np.abs(a[:10] - b[:10]) / np.abs(a[:10])) < 5e-6
+    ds = oracle_api.Dataset(rp, fid, fld.astype(np.uint32), np.ones(len(fid), np.float32), lab, F, 0)
+    o = oracle_api.FMOracle(ds, k, W0, V0, lr=0.02)
+    lo = [o.epoch()[0] for _ in range(10)]
+    assert np.max(np.abs(b[:10] - np.array(lo)) / np.array(lo)) < 1e-5
