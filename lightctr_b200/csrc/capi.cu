@@ -289,7 +289,8 @@ int lctr_destroy(lctr_ctx* c) {
         if (g.d_stat) cudaFree(g.d_stat); if (g.h_stat) cudaFreeHost(g.h_stat);
     }
     if (c->copy_stream) {
-        for (int i = 0; i < 2; i++) { cudaEventDestroy(c->ev_copied[i]); cudaEventDestroy(c->ev_computed[i]); }
+        for (int i = 0; i < 2; i++) { cudaEventDestroy(c->ev_copied[i]); cudaEventDestroy(c->ev_computed[i]); cudaEventDestroy(c->ev_h2d[i]); }
+        if (c->build_stream) cudaStreamDestroy(c->build_stream);
         for (int i = 0; i < kStatRing; i++) cudaEventDestroy(c->ev_stat[i]);
         cudaStreamDestroy(c->copy_stream);
     }
@@ -564,9 +565,11 @@ int lctr_train_batch(lctr_ctx* c, int64_t rows, int64_t nnz, const int64_t* row_
 static int pipe_init(lctr_ctx* c) {
     if (c->copy_stream) return 0;
     LCTR_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    LCTR_CUDA(cudaStreamCreateWithFlags(&c->build_stream, cudaStreamNonBlocking));
     for (int i = 0; i < 2; i++) {
         LCTR_CUDA(cudaEventCreateWithFlags(&c->ev_copied[i], cudaEventDisableTiming));
         LCTR_CUDA(cudaEventCreateWithFlags(&c->ev_computed[i], cudaEventDisableTiming));
+        LCTR_CUDA(cudaEventCreateWithFlags(&c->ev_h2d[i], cudaEventDisableTiming));
     }
     for (int i = 0; i < kStatRing; i++) LCTR_CUDA(cudaEventCreateWithFlags(&c->ev_stat[i], cudaEventDisableTiming));
     LCTR_CUDA(cudaMallocHost((void**)&c->h_stat_ring, sizeof(double) * 2 * kStatRing));
@@ -647,6 +650,7 @@ static int train_batch_async_graph(lctr_ctx* c, int64_t rows, int64_t nnz, const
         g.cap_nnz != s.cap_nnz) {
         LCTR_CUDA(cudaStreamSynchronize(c->stream));
         LCTR_CUDA(cudaStreamSynchronize(c->copy_stream));
+        LCTR_CUDA(cudaStreamSynchronize(c->build_stream));
         if (rows > s.cap_rows || nnz > s.cap_nnz)  // head-room so that slightly larger batches do not re-capture
             if (slot_reserve(c, s, std::max(rows, s.cap_rows) + rows / 8 + 64, std::max(nnz, s.cap_nnz) + nnz / 8 + 1024)) return 1;
         if (fused_supported(c) ? fused_reserve(c, s, s.cap_nnz) : csc_reserve(c, s, s.cap_nnz)) return 1;
@@ -660,8 +664,12 @@ static int train_batch_async_graph(lctr_ctx* c, int64_t rows, int64_t nnz, const
     if (val) LCTR_CUDA(cudaMemcpyAsync(s.val, val, (size_t)nnz * sizeof(float), cudaMemcpyHostToDevice, c->copy_stream));
     LCTR_CUDA(cudaMemcpyAsync(s.pred, label, (size_t)rows * sizeof(int32_t), cudaMemcpyHostToDevice, c->copy_stream));
     g.h_hdr[0] = rows; g.h_hdr[1] = nnz;
-    LCTR_CUDA(cudaGraphLaunch(g.build, c->copy_stream));
-    LCTR_CUDA(cudaEventRecord(c->ev_copied[p], c->copy_stream));
+    // the batch's slot map is built on its own stream: the copy engine moves batch t+1 while the SMs build batch t's map (the
+    // build kernels share scratch buffers, so they stay serialised among themselves -- on this one stream)
+    LCTR_CUDA(cudaEventRecord(c->ev_h2d[p], c->copy_stream));
+    LCTR_CUDA(cudaStreamWaitEvent(c->build_stream, c->ev_h2d[p], 0));
+    LCTR_CUDA(cudaGraphLaunch(g.build, c->build_stream));
+    LCTR_CUDA(cudaEventRecord(c->ev_copied[p], c->build_stream));
     LCTR_CUDA(cudaStreamWaitEvent(c->stream, c->ev_copied[p], 0));
     const bool fused = fused_supported(c);
     if (fused) fused_opt_params(c, rows, g.h_opt); else csc_opt_params(c, rows, g.h_opt);
@@ -689,6 +697,8 @@ int lctr_train_batch_async(lctr_ctx* c, int64_t rows, int64_t nnz, const int64_t
     const int slot = kNumSlots - 2 + p;
     // the copy may only overwrite the slot once the step that last used it has finished
     if (c->pipe_issued >= 2) LCTR_CUDA(cudaStreamWaitEvent(c->copy_stream, c->ev_computed[p], 0));
+    if (c->pipe_issued >= 1) LCTR_CUDA(cudaStreamWaitEvent(c->copy_stream, c->ev_copied[p ^ 1], 0));  // a graph-path build of the
+                                                                   // other slot (build_stream) shares the slot-map scratch
     if (upload_batch_on(c, c->copy_stream, slot, rows, nnz, row_ptr, fid, field, val, label)) return 1;
     LCTR_CUDA(cudaEventRecord(c->ev_copied[p], c->copy_stream));
     LCTR_CUDA(cudaStreamWaitEvent(c->stream, c->ev_copied[p], 0));

@@ -195,6 +195,8 @@ struct lctr_ctx {
     // streamed training pipeline (lctr_train_batch_async): copy stream, per-slot events, pinned result ring
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_computed[2] = {nullptr, nullptr};
+    cudaStream_t build_stream = nullptr;                  // graph pipeline: the slot-map kernels of batch t run here while the copy
+    cudaEvent_t ev_h2d[2] = {nullptr, nullptr};           // engine already moves batch t+1 on copy_stream
     cudaEvent_t ev_stat[lctr::kStatRing] = {nullptr};
     double* h_stat_ring = nullptr;
     uint64_t pipe_issued = 0, pipe_waited = 0;
