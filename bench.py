@@ -352,14 +352,16 @@ def measure(wname, wl, args, rank, world, local_rank, dist, steps, warmup, do_e2
         if world > 1:
             dist.barrier()
         t0 = time.time()
-        prev = None
+        from collections import deque
+        from lightctr_b200 import capi as _capi
+        pending = deque()  # the API's pipeline depth: step t computes, t+1 has its slot map built, t+2 is being copied
         e2e_loss = 0.0
         for i in range(steps):
-            t = ctx.train_batch_async(*host[i % NB])
-            if prev is not None:
-                e2e_loss += ctx.wait(prev)[0]
-            prev = t
-        e2e_loss += ctx.wait(prev)[0]
+            pending.append(ctx.train_batch_async(*host[i % NB]))
+            if len(pending) >= _capi.PIPE_DEPTH:
+                e2e_loss += ctx.wait(pending.popleft())[0]
+        while pending:
+            e2e_loss += ctx.wait(pending.popleft())[0]
         ctx.sync()
         e2e_s = time.time() - t0
         if world > 1:

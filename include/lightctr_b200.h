@@ -125,10 +125,12 @@ int lctr_train_batch(lctr_ctx* ctx, int64_t rows, int64_t nnz, const int64_t* ro
                      const uint16_t* field, const float* val, const int32_t* label, float* loss_sum,
                      float* acc_cnt);
 /* Streamed training (host buffers in, results out, every step) with the copy of batch i+1 overlapping the kernels of
- * batch i: the batch is copied on a second stream into one of two pipeline slots, the step is enqueued behind it
- * and its (loss, acc) are copied back into a pinned ring; returns immediately with a ticket.  At most two tickets
- * may be outstanding; the host buffers must stay valid until the ticket has been waited for.  lctr_wait blocks
- * until that step's results are on the host. */
+ * batch i: the batch is copied on a second stream into one of LCTR_PIPE_DEPTH pipeline slots (its slot map is built on a
+ * third stream), the step is enqueued behind it and its (loss, acc) are copied back into a pinned ring; returns immediately
+ * with a ticket.  At most LCTR_PIPE_DEPTH tickets may be outstanding; the host buffers must stay valid until the ticket has
+ * been waited for.  lctr_wait blocks until that step's results are on the host.  (Depth 3: while step t computes, batch
+ * t+1 has its slot map built and batch t+2 is on the copy engine.) */
+#define LCTR_PIPE_DEPTH 3
 int lctr_train_batch_async(lctr_ctx* ctx, int64_t rows, int64_t nnz, const int64_t* row_ptr, const uint32_t* fid,
                            const uint16_t* field, const float* val, const int32_t* label, uint64_t* ticket);
 int lctr_wait(lctr_ctx* ctx, uint64_t ticket, float* loss_sum, float* acc_cnt);

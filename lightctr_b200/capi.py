@@ -14,6 +14,7 @@ LIB_PATH = os.path.join(HERE, "lib", "liblightctr_b200.so")
 
 MODEL_FM, MODEL_FFM, MODEL_NFM, MODEL_WND = 1, 2, 3, 4
 OPT_ADAGRAD, OPT_FTRL, OPT_ADAM, OPT_RMSPROP, OPT_ADADELTA = 0, 1, 2, 3, 4
+PIPE_DEPTH = 3  # LCTR_PIPE_DEPTH: tickets of train_batch_async that may be outstanding
 OPT_PS_SGD, OPT_PS_ADAGRAD, OPT_PS_DCASGD, OPT_PS_DCASGDA = 5, 6, 7, 8
 ACT_SIGMOID, ACT_TANH = 0, 1
 MLP_FP32, MLP_BF16 = 0, 1

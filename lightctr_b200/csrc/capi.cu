@@ -280,7 +280,7 @@ int lctr_destroy(lctr_ctx* c) {
     csc_scratch_free(c);
     if (c->h_stats) cudaFreeHost(c->h_stats);
     if (c->h_stat_ring) cudaFreeHost(c->h_stat_ring);
-    for (int p = 0; p < 2; p++) {
+    for (int p = 0; p < kPipe; p++) {
         PipeGraph& g = c->pipe_graph[p];
         if (g.build) cudaGraphExecDestroy(g.build);
         if (g.step) cudaGraphExecDestroy(g.step);
@@ -289,7 +289,7 @@ int lctr_destroy(lctr_ctx* c) {
         if (g.d_stat) cudaFree(g.d_stat); if (g.h_stat) cudaFreeHost(g.h_stat);
     }
     if (c->copy_stream) {
-        for (int i = 0; i < 2; i++) { cudaEventDestroy(c->ev_copied[i]); cudaEventDestroy(c->ev_computed[i]); cudaEventDestroy(c->ev_h2d[i]); }
+        for (int i = 0; i < kPipe; i++) { cudaEventDestroy(c->ev_copied[i]); cudaEventDestroy(c->ev_computed[i]); cudaEventDestroy(c->ev_h2d[i]); }
         if (c->build_stream) cudaStreamDestroy(c->build_stream);
         for (int i = 0; i < kStatRing; i++) cudaEventDestroy(c->ev_stat[i]);
         cudaStreamDestroy(c->copy_stream);
@@ -566,7 +566,7 @@ static int pipe_init(lctr_ctx* c) {
     if (c->copy_stream) return 0;
     LCTR_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
     LCTR_CUDA(cudaStreamCreateWithFlags(&c->build_stream, cudaStreamNonBlocking));
-    for (int i = 0; i < 2; i++) {
+    for (int i = 0; i < kPipe; i++) {
         LCTR_CUDA(cudaEventCreateWithFlags(&c->ev_copied[i], cudaEventDisableTiming));
         LCTR_CUDA(cudaEventCreateWithFlags(&c->ev_computed[i], cudaEventDisableTiming));
         LCTR_CUDA(cudaEventCreateWithFlags(&c->ev_h2d[i], cudaEventDisableTiming));
@@ -583,7 +583,7 @@ static int pipe_init(lctr_ctx* c) {
 // costs the host three cudaMemcpyAsync, two graph launches and four event calls instead of ~20 launches.
 static int pipe_graph_capture(lctr_ctx* c, int p, bool has_val) {
     PipeGraph& g = c->pipe_graph[p];
-    Slot& s = c->slots[kNumSlots - 2 + p];
+    Slot& s = c->slots[kNumSlots - kPipe + p];
     if (g.build) { cudaGraphExecDestroy(g.build); g.build = nullptr; }
     if (g.step) { cudaGraphExecDestroy(g.step); g.step = nullptr; }
     if (!g.d_hdr) {
@@ -642,8 +642,8 @@ static int pipe_graph_capture(lctr_ctx* c, int p, bool has_val) {
 
 static int train_batch_async_graph(lctr_ctx* c, int64_t rows, int64_t nnz, const int64_t* row_ptr, const uint32_t* fid,
                                    const float* val, const int32_t* label, uint64_t* ticket) {
-    const int p = (int)(c->pipe_issued & 1);
-    const int slot = kNumSlots - 2 + p;
+    const int p = (int)(c->pipe_issued % kPipe);
+    const int slot = kNumSlots - kPipe + p;
     Slot& s = c->slots[slot];
     PipeGraph& g = c->pipe_graph[p];
     if (rows > s.cap_rows || nnz > s.cap_nnz || !g.build || g.has_val != (val != nullptr) || g.cap_rows != s.cap_rows ||
@@ -658,7 +658,7 @@ static int train_batch_async_graph(lctr_ctx* c, int64_t rows, int64_t nnz, const
         if (pipe_graph_capture(c, p, val != nullptr)) return 1;
     }
     s.rows = rows; s.nnz = nnz; s.has_val = val != nullptr; s.has_field = false;
-    if (c->pipe_issued >= 2) LCTR_CUDA(cudaStreamWaitEvent(c->copy_stream, c->ev_computed[p], 0));
+    if (c->pipe_issued >= (uint64_t)kPipe) LCTR_CUDA(cudaStreamWaitEvent(c->copy_stream, c->ev_computed[p], 0));
     LCTR_CUDA(cudaMemcpyAsync(s.row_ptr, row_ptr, (size_t)(rows + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, c->copy_stream));
     LCTR_CUDA(cudaMemcpyAsync(s.fid, fid, (size_t)nnz * sizeof(uint32_t), cudaMemcpyHostToDevice, c->copy_stream));
     if (val) LCTR_CUDA(cudaMemcpyAsync(s.val, val, (size_t)nnz * sizeof(float), cudaMemcpyHostToDevice, c->copy_stream));
@@ -689,15 +689,15 @@ int lctr_train_batch_async(lctr_ctx* c, int64_t rows, int64_t nnz, const int64_t
     LCTR_CHECK(c && ticket, "null argument");
     LCTR_CHECK(c->cfg.deterministic != 1, "streamed batches need cfg.deterministic 0 (RED scatter) or 2 (device grouping)");
     if (pipe_init(c)) return 1;
-    LCTR_CHECK(c->pipe_issued - c->pipe_waited < 2, "more than 2 streamed batches outstanding: call lctr_wait first");
+    LCTR_CHECK(c->pipe_issued - c->pipe_waited < (uint64_t)kPipe, "more than %d streamed batches outstanding: call lctr_wait first", kPipe);
     if ((c->cfg.deterministic == 2 || fused_supported(c)) && c->cfg.world == 1 && c->cfg.model == LCTR_MODEL_FM && !c->profiling &&
         rows > 0 && nnz > 0)
         return train_batch_async_graph(c, rows, nnz, row_ptr, fid, val, label, ticket);
-    const int p = (int)(c->pipe_issued & 1);
-    const int slot = kNumSlots - 2 + p;
+    const int p = (int)(c->pipe_issued % kPipe);
+    const int slot = kNumSlots - kPipe + p;
     // the copy may only overwrite the slot once the step that last used it has finished
-    if (c->pipe_issued >= 2) LCTR_CUDA(cudaStreamWaitEvent(c->copy_stream, c->ev_computed[p], 0));
-    if (c->pipe_issued >= 1) LCTR_CUDA(cudaStreamWaitEvent(c->copy_stream, c->ev_copied[p ^ 1], 0));  // a graph-path build of the
+    if (c->pipe_issued >= (uint64_t)kPipe) LCTR_CUDA(cudaStreamWaitEvent(c->copy_stream, c->ev_computed[p], 0));
+    if (c->pipe_issued >= 1) LCTR_CUDA(cudaStreamWaitEvent(c->copy_stream, c->ev_copied[(p + kPipe - 1) % kPipe], 0));  // a graph-path build of the
                                                                    // other slot (build_stream) shares the slot-map scratch
     if (upload_batch_on(c, c->copy_stream, slot, rows, nnz, row_ptr, fid, field, val, label)) return 1;
     LCTR_CUDA(cudaEventRecord(c->ev_copied[p], c->copy_stream));
@@ -718,7 +718,7 @@ int lctr_wait(lctr_ctx* c, uint64_t ticket, float* loss_sum, float* acc_cnt) {
     LCTR_CHECK(c && c->copy_stream, "lctr_wait: no streamed batch was issued");
     LCTR_CHECK(ticket < c->step && c->step - ticket <= (uint64_t)kStatRing, "lctr_wait: ticket %llu is not outstanding",
                (unsigned long long)ticket);
-    for (int p = 0; p < 2; p++) {
+    for (int p = 0; p < kPipe; p++) {
         if (c->pipe_graph[p].build && c->pipe_graph[p].ticket == ticket) {
             LCTR_CUDA(cudaEventSynchronize(c->ev_computed[p]));
             if (loss_sum) *loss_sum = (float)c->pipe_graph[p].h_stat[0];

@@ -31,6 +31,7 @@ void set_error(const char* fmt, ...);
     } while (0)
 
 constexpr int kNumSlots = 8;
+constexpr int kPipe = LCTR_PIPE_DEPTH;  // streamed pipeline: batches in flight (the last kPipe slots are its buffers)
 constexpr int kNumProf = 16;  // per-kernel timing buckets
 enum { PROF_FM_FWD = 0, PROF_FM_BWD_RED = 1, PROF_APPLY = 2, PROF_FFM_FUSED = 3, PROF_FM_BWD_CSC = 4, PROF_MLP = 5, PROF_DIST_MARK = 6, PROF_DIST_COMPACT = 7, PROF_DIST_PULL = 8, PROF_DIST_PUSH = 9, PROF_DIST_BAR0 = 10, PROF_DIST_MERGE = 11, PROF_DIST_BAR1 = 12, PROF_CSC_BUILD = 13, PROF_FM_FUSED = 14, PROF_APPLY_COMPACT = 15 };
 constexpr int kStatRing = 64;
@@ -194,13 +195,13 @@ struct lctr_ctx {
     int64_t prof_cnt[lctr::kNumProf] = {0};
     // streamed training pipeline (lctr_train_batch_async): copy stream, per-slot events, pinned result ring
     cudaStream_t copy_stream = nullptr;
-    cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_computed[2] = {nullptr, nullptr};
+    cudaEvent_t ev_copied[lctr::kPipe] = {}, ev_computed[lctr::kPipe] = {};
     cudaStream_t build_stream = nullptr;                  // graph pipeline: the slot-map kernels of batch t run here while the copy
-    cudaEvent_t ev_h2d[2] = {nullptr, nullptr};           // engine already moves batch t+1 on copy_stream
+    cudaEvent_t ev_h2d[lctr::kPipe] = {};                   // engine already moves batch t+1 on copy_stream
     cudaEvent_t ev_stat[lctr::kStatRing] = {nullptr};
     double* h_stat_ring = nullptr;
     uint64_t pipe_issued = 0, pipe_waited = 0;
-    lctr::PipeGraph pipe_graph[2];
+    lctr::PipeGraph pipe_graph[lctr::kPipe];
 };
 
 namespace lctr {
@@ -389,6 +390,7 @@ inline size_t mlp_in0(const lctr_cfg& cf) {
     return cf.model == LCTR_MODEL_WND ? (size_t)cf.field_cnt * cf.factor_cnt : (size_t)cf.factor_cnt;
 }
 int mlp_sync_dense_grad(lctr_ctx* c);
+bool pdl_on();  // LCTR_PDL != 0 (fm_fused.cu)
 int launch_ffm_warp(lctr_ctx* c, Slot& s, int64_t rb, int64_t re, bool stats);  // 0 launched, -1 shape not covered, 1 error
 int mlp_bf16_prepare(lctr_ctx* c);
 int mlp_bf16_refresh(lctr_ctx* c, int layer);

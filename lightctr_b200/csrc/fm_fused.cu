@@ -123,6 +123,13 @@ int fused_build_slot(lctr_ctx* c, Slot& s, cudaStream_t st, const int64_t* hdr, 
 }
 
 // mode 1: FM forward + backward;  2: NFM forward (z, wide part);  3: NFM backward from dz
+// programmatic dependent launches (updater behind the gradient kernel; dense kernels and the NFM backward behind their
+// predecessors): LCTR_PDL=0 turns them off; read per launch, the tests toggle it
+bool pdl_on() {
+    const char* e = getenv("LCTR_PDL");
+    return !(e && atoi(e) == 0);
+}
+
 template <int K>
 static void fused_go(lctr_ctx* c, Slot& s, int64_t rb, int64_t re, int stats, double* out_slot, const int64_t* hdr, int mode) {
     FusedState* f = c->fused;
@@ -140,7 +147,18 @@ static void fused_go(lctr_ctx* c, Slot& s, int64_t rb, int64_t re, int stats, do
     do {                                                                                                                         \
         if (mode == 1) fm_fused_kernel<K, HV, 1, false><<<grid, 128, 0, c->stream>>>(FUSED_ARGS);                                \
         else if (mode == 2) fm_fused_kernel<K, HV, 2, false><<<grid, 128, 0, c->stream>>>(FUSED_ARGS, c->z, s.wide);             \
-        else fm_fused_kernel<K, HV, 3, false><<<grid, 128, 0, c->stream>>>(FUSED_ARGS, c->dz, nullptr);                          \
+        else {  /* NFM backward: dependent on the dense kernels in front of it (it requests its batch data before their end) */ \
+            cudaLaunchConfig_t cfg = {};                                                                                         \
+            cfg.gridDim = dim3(grid); cfg.blockDim = dim3(128); cfg.stream = c->stream;                                          \
+            cudaLaunchAttribute at[1];                                                                                           \
+            at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;                                                       \
+            at[0].val.programmaticStreamSerializationAllowed = 1;                                                                \
+            cfg.attrs = at; cfg.numAttrs = (!multi && pdl_on()) ? 1 : 0;                                                         \
+            cudaLaunchKernelEx(&cfg, fm_fused_kernel<K, HV, 3, false>, (const int64_t*)s.row_ptr, (const uint32_t*)(multi ? s.ent_pslot : s.fid), \
+                               (const uint32_t*)s.ent_slot, (const float*)s.val, (const float*)s.label, (const float*)c->cW,   \
+                               (const float*)c->cV, s.pred, s.sumvx, (float*)nullptr, f->G, f->Ghot, f->GS, c->cfg.l2_reg, rb, re, hdr, \
+                               c->stat_partial, c->stat_done, out_slot, stats, wf, nw, ep, c->dz, (float*)nullptr);              \
+        }                                                                                                                        \
     } while (0)
     if (s.has_val) FUSED_LAUNCH(true); else FUSED_LAUNCH(false);
 #undef FUSED_LAUNCH
@@ -212,8 +230,7 @@ static void apply_go(lctr_ctx* c, Slot& s, const OptParams& P, const OptParams* 
     const unsigned grid = (unsigned)(main_blocks + kHotMax / 8);  // + one warp per possible hot slot
     // Programmatic dependent launch behind the gradient kernel (one GPU; LCTR_PDL=0 turns it off): the updater's CTAs start as
     // the gradient kernel's retire, request their ids, parameter and state rows, and only then wait for its completion.
-    const char* pdl_env = getenv("LCTR_PDL");  // read per launch: the tests toggle it
-    const bool pdl_off = pdl_env && atoi(pdl_env) == 0;
+    const bool pdl_off = !pdl_on();
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = 0; cfg.stream = c->stream;
     cudaLaunchAttribute attr[1];

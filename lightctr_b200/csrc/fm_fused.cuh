@@ -262,6 +262,9 @@ fm_fused_kernel(const int64_t* __restrict__ row_ptr, const uint32_t* __restrict_
                 xs[p] = ok ? (HAS_VAL ? ldg_f32_pinned(val + b + i) : 1.f) : 0.f;
             }
         }
+        // launched programmatically dependent (NFM backward behind the dense kernels): everything above is batch data; the
+        // parameters, dz and the predictions are read from here on.  A no-op for an ordinary launch.
+        cudaGridDependencySynchronize();
         for (int t = 0; t < cnt; t++) {
             const int64_t r = c0 + (int64_t)t * NW;
             const long long b = __shfl_sync(kFull, mb, t);

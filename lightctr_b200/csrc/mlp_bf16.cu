@@ -364,9 +364,11 @@ struct DenseSegs {
 };
 __global__ void adagrad_dense_all_kernel(DenseSegs S, float* __restrict__ g, float invB, float lr) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= S.off[S.n]) return;
+    cudaTriggerProgrammaticLaunchCompletion();  // the NFM embedding backward behind this kernel
     int s = 0;
-    while (i >= S.off[s + 1]) s++;
+    if (i < S.off[S.n]) while (i >= S.off[s + 1]) s++;
+    cudaGridDependencySynchronize();            // the dense kernel in front has completed: its dW / db sums are final
+    if (i >= S.off[S.n]) return;
     const size_t j = i - S.off[s];
     const float g1 = g[i] * invB;
     if (g1 != 0.f) {
@@ -475,8 +477,13 @@ int launch_nfm_mlp_bf16(lctr_ctx* c, Slot& s, int64_t rb, int64_t re, int64_t ro
         }
         S.off[2 * nl] = off;
         const uint64_t mb = c->cfg.minibatch_size ? c->cfg.minibatch_size : (uint64_t)rows_divisor;
-        adagrad_dense_all_kernel<<<(unsigned)((off + 255) / 256), 256, 0, c->stream>>>(S, c->dense_grad, (float)(1.0 / (double)mb),
-                                                                                     c->cfg.learning_rate);
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)((off + 255) / 256)); cfg.blockDim = dim3(256); cfg.stream = c->stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at; cfg.numAttrs = (c->cfg.world == 1 && pdl_on()) ? 1 : 0;
+        cudaLaunchKernelEx(&cfg, adagrad_dense_all_kernel, S, c->dense_grad, (float)(1.0 / (double)mb), c->cfg.learning_rate);
         c->launches++;
     }
     LCTR_CUDA(cudaGetLastError());

@@ -172,11 +172,9 @@ nfm_mlp_umma_kernel(Dev P, const float* __restrict__ z, float* __restrict__ dz, 
     float* s_part = reinterpret_cast<float*>(smem + P.part_off);  // [2][128] partial output-layer dot products
     const uint32_t bar_w = sbase + P.bar_off, bar_m = bar_w + 8;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + P.bar_off + 16);
-    // the row's wide term and label are independent of the dense chain: request them now, use them after the forward pass
     const int64_t gi = rb + row0 + row;
-    const float wide_r = row < valid ? wide[gi] : 0.f;
-    const float label_r = row < valid ? label[gi] : 0.f;
     const float b_last = P.bias[nh][0];
+    cudaTriggerProgrammaticLaunchCompletion();  // the dense updater behind this kernel may be scheduled as our CTAs retire
 
     if (tid == 0) {
         bar_init(bar_w, 1);
@@ -194,6 +192,13 @@ nfm_mlp_umma_kernel(Dev P, const float* __restrict__ z, float* __restrict__ dz, 
     for (int l = 0; l < nh; l++)
         for (int j = tid; j < P.out[l]; j += kThreads) s_bias[P.vec_off[l] + j] = P.bias[l][j] * bias_scale<ACT>();
     for (int i = tid; i < P.in[nh]; i += kThreads) s_wl[i] = P.w32_last[i];
+    // Everything above is independent of the kernel in front (the embedding forward that writes z and the wide term): when
+    // launched programmatically dependent, barriers, tensor memory, the weight copies and the bias vectors are under way
+    // before that kernel has finished.  (No-op for an ordinary launch.)
+    cudaGridDependencySynchronize();
+    // the row's wide term and label: requested now, used after the forward pass
+    const float wide_r = row < valid ? wide[gi] : 0.f;
+    const float label_r = row < valid ? label[gi] : 0.f;
     {   // z tile -> bf16, chunk-major
         const int k = P.in[0], chunks = k / 8;
         for (int idx = tid; idx < kTM * chunks; idx += kThreads) {
@@ -537,12 +542,18 @@ int launch_mlp_umma(lctr_ctx* c, Slot& s, int64_t rb, int B, double* out_slot) {
         P.trace = d_trace;
     }
     const unsigned grid = (unsigned)((B + umma::kTM - 1) / umma::kTM);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(umma::kThreads); cfg.dynamicSmemBytes = c->mlp_umma_smem; cfg.stream = c->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = (c->cfg.world == 1 && pdl_on()) ? 1 : 0;  // behind the embedding forward (fm_fused.cu, MODE 2)
     if (P.act == LCTR_ACT_SIGMOID)
-        umma::nfm_mlp_umma_kernel<LCTR_ACT_SIGMOID><<<grid, umma::kThreads, c->mlp_umma_smem, c->stream>>>(
-            P, c->z, c->dz, s.wide, s.label, s.pred, rb, B, c->stat_partial, c->stat_done, out_slot);
+        cudaLaunchKernelEx(&cfg, umma::nfm_mlp_umma_kernel<LCTR_ACT_SIGMOID>, P, (const float*)c->z, c->dz, (const float*)s.wide,
+                           (const float*)s.label, s.pred, rb, B, c->stat_partial, c->stat_done, out_slot);
     else
-        umma::nfm_mlp_umma_kernel<LCTR_ACT_TANH><<<grid, umma::kThreads, c->mlp_umma_smem, c->stream>>>(
-            P, c->z, c->dz, s.wide, s.label, s.pred, rb, B, c->stat_partial, c->stat_done, out_slot);
+        cudaLaunchKernelEx(&cfg, umma::nfm_mlp_umma_kernel<LCTR_ACT_TANH>, P, (const float*)c->z, c->dz, (const float*)s.wide,
+                           (const float*)s.label, s.pred, rb, B, c->stat_partial, c->stat_done, out_slot);
     c->launches++;
     LCTR_CUDA(cudaGetLastError());
     if (trace) {  // phase boundaries of CTA 0: setup | per layer (mma wait, epilogue) | output | per layer (mma wait, dX, dW) | stats

@@ -231,3 +231,39 @@ def test_dependent_launch_of_the_updater_changes_nothing(oracle_api, monkeypatch
     o = oracle_api.FMOracle(ds, k, W0, V0, lr=0.02)
     lo = [o.epoch()[0] for _ in range(10)]
     assert np.max(np.abs(b[:10] - np.array(lo)) / np.array(lo)) < 1e-5
+
+
+def test_streamed_pipeline_three_deep(oracle_api):
+    """lctr_train_batch_async with LCTR_PIPE_DEPTH = 3 tickets in flight (step t computing, batch t+1 building its slot map,
+    batch t+2 on the copy engine): every step's loss equals the synchronous lctr_train_batch sequence on a second context (the
+    order-free path reproduces itself to re-association noise), a fourth outstanding ticket is refused."""
+    from lightctr_b200 import capi
+    F, k, B, NB, steps = 30000, 16, 1024, 5, 17
+    batches = []
+    for i in range(NB):
+        rp, fid, fld, lab, _ = _synth(F, B, 100 + i)
+        batches.append((rp, fid.astype(np.uint32), None, None, lab.astype(np.int32)))
+    rng = np.random.default_rng(9)
+    W0 = (rng.standard_normal(F) * 0.01).astype(np.float32)
+    V0 = (rng.standard_normal(F * k) * 0.05).astype(np.float32)
+    a = capi.Context(capi.MODEL_FM, F, k, deterministic=0)
+    b = capi.Context(capi.MODEL_FM, F, k, deterministic=0)
+    for c in (a, b):
+        c.upload_params(W0, V0)
+    want = [a.train_batch(*batches[i % NB])[0] for i in range(steps)]
+    got, pending = [], []
+    for i in range(steps):
+        pending.append(b.train_batch_async(*batches[i % NB]))
+        if len(pending) == capi.PIPE_DEPTH:
+            if i == capi.PIPE_DEPTH - 1:  # three in flight: one more must be refused, not queued over a live slot
+                with pytest.raises(capi.LctrError):
+                    b.train_batch_async(*batches[0])
+            got.append(b.wait(pending.pop(0))[0])
+    while pending:
+        got.append(b.wait(pending.pop(0))[0])
+    want, got = np.array(want), np.array(got)
+    assert np.max(np.abs(want - got) / np.abs(want)) < 2e-5, np.max(np.abs(want - got) / np.abs(want))
+    Wa, Va = a.download_params()
+    Wb, Vb = b.download_params()
+    assert np.max(np.abs(Wa - Wb)) < 1e-4 and np.max(np.abs(Va - Vb)) < 1e-4
+    a.close(); b.close()
