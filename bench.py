@@ -356,8 +356,11 @@ def measure(wname, wl, args, rank, world, local_rank, dist, steps, warmup, do_e2
         from lightctr_b200 import capi as _capi
         pending = deque()  # the API's pipeline depth: step t computes, t+1 has its slot map built, t+2 is being copied
         e2e_loss = 0.0
+        t_issue = 0.0  # host time inside the issuing call (numpy -> pointers, copies / graph launches / events enqueued)
         for i in range(steps):
+            ti = time.perf_counter()
             pending.append(ctx.train_batch_async(*host[i % NB]))
+            t_issue += time.perf_counter() - ti
             if len(pending) >= _capi.PIPE_DEPTH:
                 e2e_loss += ctx.wait(pending.popleft())[0]
         while pending:
@@ -369,6 +372,7 @@ def measure(wname, wl, args, rank, world, local_rank, dist, steps, warmup, do_e2
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             e2e_s = float(t[0])
         e2e = {"value": world * B * steps / e2e_s, "unit": "samples/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 16,
+               "us_per_step": 1e6 * e2e_s / steps, "host_issue_us_per_step": 1e6 * t_issue / steps, "pipeline_depth": _capi.PIPE_DEPTH,
                "l2": "not flushed: every step's batch arrives from pinned host memory, parameters stay L2-resident between "
                      "steps as in a real training loop (the device-timed `value` flushes L2 before every step)"}
     clocks = sampler.finish()
