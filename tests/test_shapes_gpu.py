@@ -149,3 +149,44 @@ def test_fm_parameter_server_update_rules(oracle_api, opt):
     if opt in ("ps_dcasgd", "ps_dcasgda"):
         assert np.max(np.abs(s2 - o.s2)) < 1e-5
     ctx.close()
+
+
+@pytest.mark.parametrize("Fc,k,max_n,with_val", [(6, 4, 40, True),      # 6 slots: one pass, 26 shadow lanes
+                                                  (10, 8, 300, True),    # rows longer than the 128-entry index window
+                                                  (33, 12, 90, False),   # 99 slots: four passes, 3 parts per field
+                                                  (64, 4, 70, False)])   # the largest field count the kernel takes
+def test_ffm_warp_kernel_edge_shapes(oracle_api, Fc, k, max_n, with_val):
+    """ffm_warp.cu beyond the benchmark shapes: every pass count, values != 1, rows of 0 / 1 / hundreds of entries (the
+    whole-sample index window is 128 entries: longer rows reload it in the gradient phase), fields missing from a row,
+    several entries of one field that are NOT adjacent (the per-field register run is flushed and T[a] re-opened), rows whose
+    prediction equals the label exactly are left alone.  One step from identical state against the oracle's pair loop."""
+    from lightctr_b200 import capi
+    rng = np.random.default_rng(Fc * 100 + k)
+    F, B = 3000, 257
+    rp, fid, fld, val = [0], [], [], []
+    for r in range(B):
+        n = 0 if r % 37 == 5 else (1 if r % 41 == 7 else int(rng.integers(2, max_n + 1)))
+        fs = rng.integers(0, Fc, n)                     # unordered: the same field recurs at distance
+        if r % 3 == 0 and n > 4:
+            fs[:] = np.sort(fs)                          # and libffm-style sorted rows
+        ids = rng.choice(F, n, replace=False)
+        fid += list(ids); fld += list(fs); val += list((0.5 + rng.random(n)) if with_val else np.ones(n)); rp.append(len(fid))
+    rp = np.array(rp, np.int64); fid = np.array(fid, np.uint32); fld = np.array(fld, np.uint16)
+    val = np.array(val, np.float32); lab = (rng.random(B) < 0.4).astype(np.int32)
+    W0 = (rng.standard_normal(F) * 0.05).astype(np.float32)
+    V0 = (rng.standard_normal(F * Fc * k) * 0.1).astype(np.float32)
+    ds = oracle_api.Dataset(rp, fid, fld.astype(np.uint32), val, lab, F, Fc)
+    o = oracle_api.FFMOracle(ds, k, W0, V0)
+    ctx = capi.Context(capi.MODEL_FFM, F, k, Fc, deterministic=0)
+    ctx.upload_params(W0, V0)
+    ctx.upload_batch(0, rp, fid, fld, val if with_val else None, lab)
+    for step in range(2):
+        lg, cg = ctx.train_step(0)
+        lo, ao = o.epoch()
+        assert _rel(lg, lo) < 1e-5, (step, lg, lo)     # north-star bar on the summed logloss
+        assert abs(cg - round(ao * B)) <= 1
+        Wg, Vg = ctx.download_params()
+        assert np.max(np.abs(Wg - o.W)) < 2e-5 and np.max(np.abs(Vg - o.V)) < 2e-5
+        ctx.upload_params(o.W, o.V)                      # per-step parity from identical state (order-free path)
+        ctx.upload_opt_state(o.s1)
+    ctx.close()
