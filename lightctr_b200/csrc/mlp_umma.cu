@@ -436,7 +436,7 @@ nfm_mlp_umma_kernel(Dev P, const float* __restrict__ z, float* __restrict__ dz, 
                         for (int i = 0; i < 8; i++) {
                             const int rr = 4 * i + (lane >> 3), j = lane & 7;
                             const float4 v = *reinterpret_cast<const float4*>(stage + rr * 32 + ((j ^ (rr & 7)) << 2));
-                            if (!P.debug_no_dw) red_add_v4(dbase + (size_t)rr * K + c0 + j * 4, v.x, v.y, v.z, v.w);
+                            red_add_v4(dbase + (size_t)rr * K + c0 + j * 4, v.x, v.y, v.z, v.w);
                         }
                         __syncwarp();
                     }
@@ -532,8 +532,6 @@ int launch_mlp_umma(lctr_ctx* c, Slot& s, int64_t rb, int B, double* out_slot) {
     }
     P.w32_last = c->layers[nh].w;
     P.trace = nullptr;
-    const bool no_dw = getenv("LCTR_MLP_UMMA_NODW") && getenv("LCTR_MLP_UMMA_NODW")[0] == '1';
-    P.debug_no_dw = no_dw ? 1 : 0;
     const bool trace = getenv("LCTR_MLP_UMMA_TRACE") && getenv("LCTR_MLP_UMMA_TRACE")[0] == '1';
     static unsigned long long* d_trace = nullptr;
     if (trace) {

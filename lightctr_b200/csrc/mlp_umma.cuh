@@ -21,7 +21,6 @@ struct Dev {
     int w_off[kMaxDense];                   // byte offset of W_l, [out_l x in_l] chunk-major
     int vec_off[kMaxDense];                 // element offset of layer l in the concatenated bias vector
     int wl_off, bias_off, part_off, bar_off;
-    int debug_no_dw;                        // LCTR_MLP_UMMA_NODW=1 (timing experiments only): drop the dW REDs
     unsigned long long* trace;              // LCTR_MLP_UMMA_TRACE=1: clock64 stamps of CTA 0 per phase, else null
 };
 

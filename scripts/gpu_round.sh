@@ -82,49 +82,6 @@ for f in ('$O/bench_${TAG}_nfm_c4.json',):
         d=json.loads(open(f).read().strip().splitlines()[-1]); print(f, d['value'], d['ms_per_step'], d.get('kernels_ms'))
     except Exception as e: print(f, 'ERR', e)
 " ;;
-ummanodw)
-  for v in 0 1; do
-  LCTR_MLP_UMMA_NODW=$v timeout 600 python bench.py --workload nfm_c4 --steps 30 --warmup 3 --no-cpu-baseline > $O/bench_${TAG}_nfm_c4_nodw$v.json 2> $O/bench_${TAG}_nfm_c4_nodw$v.err
-  LCTR_MLP_UMMA_NODW=$v LCTR_MLP_UMMA_TRACE=1 timeout 300 python bench.py --workload nfm_c4 --steps 4 --warmup 3 --no-cpu-baseline 2>&1 >/dev/null | tail -n 1
-  done
-  python -c "
-import json
-for f in ('$O/bench_${TAG}_nfm_c4_nodw0.json','$O/bench_${TAG}_nfm_c4_nodw1.json'):
-    try:
-        d=json.loads(open(f).read().strip().splitlines()[-1]); print(f, d['value'], d['ms_per_step'], d.get('kernels_ms'))
-    except Exception as e: print(f, 'ERR', e)
-" ;;
-ffm)
-  timeout 900 python -m pytest tests -m gpu -q ${PYTEST_X:--x} -k "ffm or FFM or c3 or c5 or dist or ranks" > $O/pytest_ffm_$TAG.log 2>&1; echo "pytest rc=$?" >> $O/pytest_ffm_$TAG.log
-  tail -n 12 $O/pytest_ffm_$TAG.log
-  for w in ffm_c3 ffm_c5; do
-    timeout 900 python bench.py --workload $w --steps 20 --warmup 3 --no-cpu-baseline > $O/bench_${TAG}_$w.json 2> $O/bench_${TAG}_$w.err
-    LCTR_FFM_WARP=0 timeout 900 python bench.py --workload $w --steps 20 --warmup 3 --no-cpu-baseline > $O/bench_${TAG}_${w}_old.json 2> $O/bench_${TAG}_${w}_old.err
-  done
-  python -c "
-import json
-for w in ('ffm_c3','ffm_c3_old','ffm_c5','ffm_c5_old'):
-    f='$O/bench_${TAG}_%s.json'%w
-    try:
-        d=json.loads(open(f).read().strip().splitlines()[-1]); print(f, d['value'], d['ms_per_step'], {k:round(v['ms'],4) for k,v in d.get('kernels_ms',{}).items()})
-    except Exception as e: print(f, 'ERR', e)
-" ;;
-ffmq)
-  for w in ffm_c3 ffm_c5; do
-    timeout 900 python bench.py --workload $w --steps 20 --warmup 3 --no-cpu-baseline > $O/bench_${TAG}_$w.json 2> $O/bench_${TAG}_$w.err
-  done
-  python -c "
-import json
-for w in ('ffm_c3','ffm_c5'):
-    f='$O/bench_${TAG}_%s.json'%w
-    try:
-        d=json.loads(open(f).read().strip().splitlines()[-1]); print(f, d['value'], d['ms_per_step'], {k:round(v['ms'],4) for k,v in d.get('kernels_ms',{}).items()})
-    except Exception as e: print(f, 'ERR', e)
-" ;;
-ncuffmw)
-  timeout 900 ncu --set full --clock-control none --import-source on -k regex:"ffm_warp_kernel" -s 4 -c 1 \
-      -o $O/prof_${TAG}_ffm_c3_warp -f python bench.py --workload ffm_c3 --steps 4 --warmup 3 --no-cpu-baseline > $O/ncu_ffm_warp_$TAG.log 2>&1
-  echo "ncu rc=$?" ;;
 ummaprof)
   LCTR_MLP_UMMA_TRACE=1 timeout 300 python bench.py --workload nfm_c4 --steps 6 --warmup 3 --no-cpu-baseline > /dev/null 2> $O/umma_trace_$TAG.txt; tail -n 8 $O/umma_trace_$TAG.txt
   timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 60 -c 60 --csv --log-file $O/launches_${TAG}_nfm_c4.csv \
