@@ -391,6 +391,8 @@ inline size_t mlp_in0(const lctr_cfg& cf) {
 }
 int mlp_sync_dense_grad(lctr_ctx* c);
 bool pdl_on();  // LCTR_PDL != 0 (fm_fused.cu)
+// scan + clear of a permuted byte map (fm_fused.cuh): appends the ids of the set positions to uniq, counts in *n_uniq
+void launch_slotmap_compact(lctr_ctx* c, uint8_t* mark, size_t T, uint32_t* uniq, unsigned int* n_uniq, cudaStream_t st);
 int launch_ffm_warp(lctr_ctx* c, Slot& s, int64_t rb, int64_t re, bool stats);  // 0 launched, -1 shape not covered, 1 error
 int mlp_bf16_prepare(lctr_ctx* c);
 int mlp_bf16_refresh(lctr_ctx* c, int layer);

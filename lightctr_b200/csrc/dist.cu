@@ -81,6 +81,16 @@ struct DistState {
     unsigned int* done_ctr = nullptr; // [4] last-block counters
     int* overflow = nullptr;          // device flag: a key list outgrew cap_pair
     float *cgV = nullptr, *cgW = nullptr;  // [rows_x][rowlen], [rows_x]: compact gradient rows of the non-fused kernels
+    // owner side of the fused FM / NFM step: the UNION of the key lists the requesters sent for a slot's batch, built once per
+    // upload, and for every union row its position in each requester's list (~0: not asked for) -- the updater walks it and
+    // sums the gradient inboxes itself (no dense update_g, no touched map, no O(F / R) scan per step)
+    uint32_t* own_uniq = nullptr;     // [kNumSlots][cap_own] shard-local rows
+    unsigned int* n_own = nullptr;    // [kNumSlots]
+    uint32_t* own_pos = nullptr;      // [kNumSlots][world][cap_own]
+    uint32_t* posmap = nullptr;       // [world][Fl] scratch: list position of a row in requester q's current list (self-validating)
+    uint8_t* own_mark = nullptr;      // permuted byte map over the shard (128 * own_T)
+    size_t cap_own = 0, own_T = 0;
+    unsigned long long own_gen[kNumSlots] = {0};
     void* opened[kMaxWorld][kNumHandles] = {{nullptr}};
     bool imported = false;
     unsigned long long epoch = 0;
@@ -392,6 +402,111 @@ merge_kernel(PeerTable P, ArenaLayout A, int me, int world, int slot, unsigned l
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// fused FM / NFM path, owner side.  Once per upload: the union of the requesters' key lists (mark -> compact, the slot-map
+// kernels of fm_fused.cuh on the shard) and each union row's position in every list.  Every step: ONE kernel that waits for
+// the pushes, sums a row's records over the requesters in rank order (deterministic, no REDs) and applies the updater.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+own_mark_kernel(PeerTable P, ArenaLayout A, int me, int world, int slot2, int flag_slot, unsigned long long gen,
+                uint32_t* __restrict__ posmap, size_t Fl, uint8_t* __restrict__ mark, size_t T) {
+    wait_flags(P.p[me].arena, A, FLAG_KEYS + flag_slot, world, gen);  // every requester's key list of this upload has landed
+    for (int q = 0; q < world; q++) {
+        const unsigned char* region = P.p[me].arena + A.key_inbox + ((size_t)slot2 * world + q) * A.key_region;
+        const unsigned n = *reinterpret_cast<const volatile unsigned int*>(region);
+        const uint2* pairs = reinterpret_cast<const uint2*>(region + 64);
+        for (unsigned j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+            const uint32_t l = pairs[j].x;
+            posmap[(size_t)q * Fl + l] = j;  // never cleared: an entry counts only if list[entry] == row (own_pos_kernel)
+            mark[(size_t)(l & 127u) * T + (l >> 7)] = 1;
+        }
+    }
+}
+__global__ void __launch_bounds__(256)
+own_pos_kernel(PeerTable P, ArenaLayout A, int me, int world, int slot2, const uint32_t* __restrict__ own_uniq,
+               const unsigned int* __restrict__ n_own, const uint32_t* __restrict__ posmap, size_t Fl,
+               uint32_t* __restrict__ own_pos, unsigned cap_own) {
+    const unsigned total = min(*n_own, cap_own);
+    for (int q = 0; q < world; q++) {
+        const unsigned char* region = P.p[me].arena + A.key_inbox + ((size_t)slot2 * world + q) * A.key_region;
+        const unsigned n = *reinterpret_cast<const volatile unsigned int*>(region);
+        const uint2* pairs = reinterpret_cast<const uint2*>(region + 64);
+        for (unsigned u = blockIdx.x * blockDim.x + threadIdx.x; u < total; u += gridDim.x * blockDim.x) {
+            const uint32_t l = own_uniq[u];
+            const uint32_t j = posmap[(size_t)q * Fl + l];
+            own_pos[(size_t)q * cap_own + u] = (j < n && pairs[j].x == l) ? j : 0xffffffffu;
+        }
+    }
+}
+template <int K, int OPT>
+__global__ void __launch_bounds__(256)
+merge_apply_kernel(PeerTable P, ArenaLayout A, int me, int world, unsigned long long epoch, int recw,
+                   const uint32_t* __restrict__ own_uniq, const unsigned int* __restrict__ n_own,
+                   const uint32_t* __restrict__ own_pos, unsigned cap_own, float* __restrict__ W, float* __restrict__ V,
+                   float* __restrict__ s1W, float* __restrict__ s1V, float* __restrict__ s2W, float* __restrict__ s2V, OptParams Pp) {
+    wait_flags(P.p[me].arena, A, FLAG_PUSHED, world, epoch);  // every requester's records of this step have landed
+    constexpr int LPR = K / 4, GR = 32 / LPR;
+    constexpr bool two = OPT == LCTR_OPT_FTRL || OPT == LCTR_OPT_ADAM || OPT == LCTR_OPT_ADADELTA || OPT == LCTR_OPT_PS_DCASGD ||
+                         OPT == LCTR_OPT_PS_DCASGDA;
+    Pp.opt = OPT;
+    const int lane = threadIdx.x & 31, q = lane % LPR, g = lane / LPR;
+    const unsigned warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const unsigned nwarps = gridDim.x * (blockDim.x >> 5);
+    const unsigned total = min(*n_own, cap_own);
+    for (unsigned b0 = warp * GR; b0 < total; b0 += nwarps * GR) {
+        const unsigned idx = b0 + g;
+        if (idx >= total) continue;
+        const uint32_t l = own_uniq[idx];
+        const size_t o = (size_t)l * K + 4 * q;
+        float4 v4 = *reinterpret_cast<const float4*>(V + o), a4 = *reinterpret_cast<const float4*>(s1V + o);
+        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (two) b4 = *reinterpret_cast<const float4*>(s2V + o);
+        float w = 0.f, a = 0.f, bb = 0.f;
+        if (q == 0) { w = W[l]; a = s1W[l]; if (two) bb = s2W[l]; }
+        float4 g4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        float gw = 0.f;
+        for (int src = 0; src < world; src++) {  // rank order: the sum is reproducible
+            const uint32_t j = own_pos[(size_t)src * cap_own + idx];
+            if (j == 0xffffffffu) continue;
+            const float* rec = reinterpret_cast<const float*>(P.p[me].arena + A.grad_inbox + (size_t)src * A.grad_region) + (size_t)j * recw;
+            const float4 t = __ldcg(reinterpret_cast<const float4*>(rec + 4 * q));
+            g4.x += t.x; g4.y += t.y; g4.z += t.z; g4.w += t.w;
+            if (q == 0) gw += __ldcg(rec + K);
+        }
+        update_one(Pp, Pp.corrV, v4.x, g4.x, a4.x, b4.x);
+        update_one(Pp, Pp.corrV, v4.y, g4.y, a4.y, b4.y);
+        update_one(Pp, Pp.corrV, v4.z, g4.z, a4.z, b4.z);
+        update_one(Pp, Pp.corrV, v4.w, g4.w, a4.w, b4.w);
+        *reinterpret_cast<float4*>(V + o) = v4;
+        *reinterpret_cast<float4*>(s1V + o) = a4;
+        if (two) *reinterpret_cast<float4*>(s2V + o) = b4;
+        if (q == 0) {
+            update_one(Pp, Pp.corrW, w, gw, a, bb);
+            W[l] = w; s1W[l] = a;
+            if (two) s2W[l] = bb;
+        }
+    }
+}
+
+template <int K>
+static void merge_apply_go(lctr_ctx* c, DistState* d, int slot, const OptParams& Pp, unsigned grid) {
+#define MA_GO(OPTC)                                                                                                               \
+    merge_apply_kernel<K, OPTC><<<grid, 256, 0, c->stream>>>(d->peers, d->A, d->rank, d->world, d->epoch, d->recw,                 \
+        d->own_uniq + (size_t)slot * d->cap_own, d->n_own + slot, d->own_pos + (size_t)slot * d->world * d->cap_own,               \
+        (unsigned)d->cap_own, c->W, c->V, c->s1W, c->s1V, c->s2W, c->s2V, Pp)
+    switch (Pp.opt) {
+        case LCTR_OPT_ADAGRAD: MA_GO(LCTR_OPT_ADAGRAD); break;
+        case LCTR_OPT_FTRL: MA_GO(LCTR_OPT_FTRL); break;
+        case LCTR_OPT_ADAM: MA_GO(LCTR_OPT_ADAM); break;
+        case LCTR_OPT_RMSPROP: MA_GO(LCTR_OPT_RMSPROP); break;
+        case LCTR_OPT_ADADELTA: MA_GO(LCTR_OPT_ADADELTA); break;
+        case LCTR_OPT_PS_SGD: MA_GO(LCTR_OPT_PS_SGD); break;
+        case LCTR_OPT_PS_ADAGRAD: MA_GO(LCTR_OPT_PS_ADAGRAD); break;
+        case LCTR_OPT_PS_DCASGD: MA_GO(LCTR_OPT_PS_DCASGD); break;
+        default: MA_GO(LCTR_OPT_PS_DCASGDA); break;
+    }
+#undef MA_GO
+}
+
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 int dist_alloc(lctr_ctx* c) {
@@ -443,6 +558,17 @@ int dist_alloc(lctr_ctx* c) {
         LCTR_CUDA(cudaMalloc((void**)&d->hot_p, (size_t)kNumSlots * d->rows_x * sizeof(uint32_t)));
         LCTR_CUDA(cudaMemsetAsync(d->hot_p, 0xff, (size_t)kNumSlots * d->rows_x * sizeof(uint32_t), c->stream));
         d->bytes += (size_t)kNumSlots * d->rows_x * sizeof(uint32_t);
+        d->cap_own = std::min<size_t>(c->Fl, d->rows_x);
+        d->own_T = (c->Fl + 127) / 128;  // rows of the permuted byte map (fm_fused.cuh: mark_rows)
+        LCTR_CUDA(cudaMalloc((void**)&d->own_uniq, (size_t)kNumSlots * d->cap_own * sizeof(uint32_t)));
+        LCTR_CUDA(cudaMalloc((void**)&d->own_pos, (size_t)kNumSlots * R * d->cap_own * sizeof(uint32_t)));
+        LCTR_CUDA(cudaMalloc((void**)&d->n_own, kNumSlots * sizeof(unsigned int)));
+        LCTR_CUDA(cudaMemsetAsync(d->n_own, 0, kNumSlots * sizeof(unsigned int), c->stream));
+        LCTR_CUDA(cudaMalloc((void**)&d->posmap, (size_t)R * c->Fl * sizeof(uint32_t)));
+        LCTR_CUDA(cudaMemsetAsync(d->posmap, 0xff, (size_t)R * c->Fl * sizeof(uint32_t), c->stream));
+        LCTR_CUDA(cudaMalloc((void**)&d->own_mark, 128 * d->own_T));
+        LCTR_CUDA(cudaMemsetAsync(d->own_mark, 0, 128 * d->own_T, c->stream));
+        d->bytes += (size_t)kNumSlots * (R + 1) * d->cap_own * sizeof(uint32_t) + (size_t)R * c->Fl * sizeof(uint32_t) + 128 * d->own_T;
     } else {
         LCTR_CUDA(cudaMalloc((void**)&d->cgW, d->rows_x * sizeof(float)));
         LCTR_CUDA(cudaMalloc((void**)&d->cgV, d->rows_x * c->rowlen * sizeof(float)));
@@ -470,6 +596,7 @@ int dist_free(lctr_ctx* c) {
             if (d->opened[r][j]) cudaIpcCloseMemHandle(d->opened[r][j]);
     cudaFree(d->arena); cudaFree(d->send_cnt); cudaFree(d->seg_cnt); cudaFree(d->opos); cudaFree(d->done_ctr); cudaFree(d->overflow);
     if (d->hot_p) cudaFree(d->hot_p);
+    if (d->own_uniq) { cudaFree(d->own_uniq); cudaFree(d->own_pos); cudaFree(d->n_own); cudaFree(d->posmap); cudaFree(d->own_mark); }
     if (d->cgW) cudaFree(d->cgW);
     if (d->cgV) cudaFree(d->cgV);
     c->cW = c->cV = c->cgW = c->cgV = nullptr;
@@ -526,6 +653,19 @@ int dist_pre_step(lctr_ctx* c, Slot& s, int slot, bool in_kernel_wait) {
     LCTR_CHECK(d->imported, "multi-GPU step before lctr_ipc_import");
     LCTR_CHECK(s.fused_valid, "multi-GPU step on a slot without its key set");
     d->epoch++;
+    if (d->own_uniq && d->own_gen[slot] != d->gen[slot]) {  // first step on this upload of the slot: the owner-side union
+        const int slot2 = slot * 2 + (int)(d->gen[slot] & 1);
+        const unsigned g1 = (unsigned)std::max<int64_t>(8, std::min<int64_t>((int64_t)c->sm_count * 4, ((int64_t)d->cap_pair + 255) / 256));
+        LCTR_CUDA(cudaMemsetAsync(d->n_own + slot, 0, sizeof(unsigned int), c->stream));
+        own_mark_kernel<<<g1, 256, 0, c->stream>>>(d->peers, d->A, d->rank, d->world, slot2, slot, d->gen[slot], d->posmap, c->Fl,
+                                                   d->own_mark, d->own_T);
+        launch_slotmap_compact(c, d->own_mark, d->own_T, d->own_uniq + (size_t)slot * d->cap_own, d->n_own + slot, c->stream);
+        own_pos_kernel<<<g1, 256, 0, c->stream>>>(d->peers, d->A, d->rank, d->world, slot2, d->own_uniq + (size_t)slot * d->cap_own,
+                                                  d->n_own + slot, d->posmap, c->Fl, d->own_pos + (size_t)slot * d->world * d->cap_own,
+                                                  (unsigned)d->cap_own);
+        c->launches += 3;
+        d->own_gen[slot] = d->gen[slot];
+    }
     { ProfScope prof(c, PROF_DIST_PULL);
     // rows this rank serves ~ the union of what R requesters ask of it ~ (keys of a batch): one warp iteration = 32 rows (FM)
     const unsigned pull_grid = (unsigned)std::max<int64_t>(8, std::min<int64_t>((int64_t)c->sm_count * 4,
@@ -559,6 +699,20 @@ int dist_post_step(lctr_ctx* c, Slot& s, int slot, int64_t rows_divisor) {
                                                                  d->recw, (unsigned)d->cap_pair, d->peers, d->A, d->rank, d->world, d->epoch,
                                                                  d->done_ctr + 1);
     } }
+    if (d->own_uniq) {  // fused FM / NFM: merge + updater in one kernel over the owner-side union of the key lists
+        ProfScope prof(c, PROF_DIST_MERGE);
+        const OptParams Pp = make_opt_params(c, rows_divisor);
+        const unsigned mgrid = (unsigned)c->sm_count * 4;
+        switch ((int)c->cfg.factor_cnt) {
+            case 4: merge_apply_go<4>(c, d, slot, Pp, mgrid); break;
+            case 8: merge_apply_go<8>(c, d, slot, Pp, mgrid); break;
+            case 16: merge_apply_go<16>(c, d, slot, Pp, mgrid); break;
+            default: merge_apply_go<32>(c, d, slot, Pp, mgrid); break;
+        }
+        c->launches += 2;
+        LCTR_CUDA(cudaGetLastError());
+        return 0;
+    }
     { ProfScope prof(c, PROF_DIST_MERGE);
     merge_kernel<<<xgrid, 256, 0, c->stream>>>(d->peers, d->A, d->rank, d->world, slot * 2 + (int)(d->gen[slot] & 1), d->epoch,
                                                          (int)c->rowlen, d->recw, c->gW, c->gV, c->touched); }

@@ -123,6 +123,12 @@ int fused_build_slot(lctr_ctx* c, Slot& s, cudaStream_t st, const int64_t* hdr, 
 }
 
 // mode 1: FM forward + backward;  2: NFM forward (z, wide part);  3: NFM backward from dz
+void launch_slotmap_compact(lctr_ctx* c, uint8_t* mark, size_t T, uint32_t* uniq, unsigned int* n_uniq, cudaStream_t st) {
+    const size_t ntiles = (128 * T + 511) / 512;
+    const unsigned cg = (unsigned)std::max<size_t>(1, std::min<size_t>((ntiles + 7) / 8, (size_t)c->sm_count * 8));
+    slotmap_compact_kernel<<<cg, 256, 0, st>>>(mark, T, uniq, n_uniq, nullptr);
+}
+
 // programmatic dependent launches (updater behind the gradient kernel; dense kernels and the NFM backward behind their
 // predecessors): LCTR_PDL=0 turns them off; read per launch, the tests toggle it
 bool pdl_on() {

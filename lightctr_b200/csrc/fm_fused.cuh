@@ -130,7 +130,7 @@ slotmap_compact_kernel(uint8_t* __restrict__ mark, size_t T, uint32_t* __restric
             const size_t ps = base + bit;
             const uint32_t f = (uint32_t)(((ps % T) << 7) | (ps / T));
             uniq[pos] = f;
-            slot_of[f] = pos;
+            if (slot_of) slot_of[f] = pos;
             pos++;
         }
     }
