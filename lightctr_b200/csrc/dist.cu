@@ -237,6 +237,7 @@ __global__ void __launch_bounds__(256)
 serve_pull_kernel(PeerTable P, ArenaLayout A, int me, int world, int slot, int flag_slot, unsigned long long gen,
                   unsigned long long epoch, int rowlen, unsigned cap_pair, const float* __restrict__ W,
                   const float* __restrict__ V, unsigned int* done_ctr) {
+    cudaTriggerProgrammaticLaunchCompletion();  // the compute kernel behind may be scheduled early: it polls the "rows delivered" flags
     wait_flags(P.p[me].arena, A, FLAG_KEYS + flag_slot, world, gen);  // every requester's key list of this upload has landed
     const int lane = threadIdx.x & 31;
     const unsigned warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -320,6 +321,8 @@ push_rows_kernel(const unsigned int* __restrict__ seg_cnt, float* __restrict__ g
     int lpr = 1;
     while (lpr < slices && lpr < 32) lpr <<= 1;
     const int G = 32 / lpr, q = lane % lpr, g = lane / lpr;
+    cudaTriggerProgrammaticLaunchCompletion();  // the owner-side kernel behind polls the "pushes landed" flags
+    cudaGridDependencySynchronize();            // launched dependent on the gradient kernel: its G / Ghot are complete from here
     for (int o = 0; o < world; o++) {
         const unsigned n = seg_cnt[o];
         float* inbox = reinterpret_cast<float*>(P.p[o].arena + A.grad_inbox + (size_t)me * A.grad_region);
@@ -356,7 +359,7 @@ push_rows_kernel(const unsigned int* __restrict__ seg_cnt, float* __restrict__ g
 #pragma unroll
                     for (int rp = 0; rp < kHotRep; rp++) { gwv += t[rp]; tile[(size_t)rp * GS + rowlen] = 0.f; }
                 }
-                dst[rowlen] = gwv;
+                *reinterpret_cast<float4*>(dst + rowlen) = make_float4(gwv, 0.f, 0.f, 0.f);  // whole 16 B: the record leaves as full slices
                 gw[pr * gws] = 0.f;
             }
         }
@@ -444,6 +447,7 @@ merge_apply_kernel(PeerTable P, ArenaLayout A, int me, int world, unsigned long 
                    const uint32_t* __restrict__ own_pos, unsigned cap_own, float* __restrict__ W, float* __restrict__ V,
                    float* __restrict__ s1W, float* __restrict__ s1V, float* __restrict__ s2W, float* __restrict__ s2V, OptParams Pp) {
     wait_flags(P.p[me].arena, A, FLAG_PUSHED, world, epoch);  // every requester's records of this step have landed
+    cudaGridDependencySynchronize();  // (launched dependent on my own push kernel; its flag to myself is already in)
     constexpr int LPR = K / 4, GR = 32 / LPR;
     constexpr bool two = OPT == LCTR_OPT_FTRL || OPT == LCTR_OPT_ADAM || OPT == LCTR_OPT_ADADELTA || OPT == LCTR_OPT_PS_DCASGD ||
                          OPT == LCTR_OPT_PS_DCASGDA;
@@ -489,10 +493,17 @@ merge_apply_kernel(PeerTable P, ArenaLayout A, int me, int world, unsigned long 
 
 template <int K>
 static void merge_apply_go(lctr_ctx* c, DistState* d, int slot, const OptParams& Pp, unsigned grid) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(256); cfg.stream = c->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = pdl_on() ? 1 : 0;  // behind my push kernel
 #define MA_GO(OPTC)                                                                                                               \
-    merge_apply_kernel<K, OPTC><<<grid, 256, 0, c->stream>>>(d->peers, d->A, d->rank, d->world, d->epoch, d->recw,                 \
-        d->own_uniq + (size_t)slot * d->cap_own, d->n_own + slot, d->own_pos + (size_t)slot * d->world * d->cap_own,               \
-        (unsigned)d->cap_own, c->W, c->V, c->s1W, c->s1V, c->s2W, c->s2V, Pp)
+    cudaLaunchKernelEx(&cfg, merge_apply_kernel<K, OPTC>, d->peers, d->A, d->rank, d->world, d->epoch, d->recw,                    \
+        (const uint32_t*)(d->own_uniq + (size_t)slot * d->cap_own), (const unsigned int*)(d->n_own + slot),                        \
+        (const uint32_t*)(d->own_pos + (size_t)slot * d->world * d->cap_own), (unsigned)d->cap_own, c->W, c->V, c->s1W, c->s1V,   \
+        c->s2W, c->s2V, Pp)
     switch (Pp.opt) {
         case LCTR_OPT_ADAGRAD: MA_GO(LCTR_OPT_ADAGRAD); break;
         case LCTR_OPT_FTRL: MA_GO(LCTR_OPT_FTRL); break;
@@ -691,9 +702,15 @@ int dist_post_step(lctr_ctx* c, Slot& s, int slot, int64_t rows_divisor) {
     { ProfScope prof(c, PROF_DIST_PUSH);
     if (fused_kernels_ok(c)) {
         FusedState* f = c->fused;
-        push_rows_kernel<<<xgrid, 256, 0, c->stream>>>(seg, f->G, f->GS, f->G + c->rowlen, f->GS, d->hot_p + (size_t)slot * d->rows_x,
-                                                                 f->Ghot, f->GS, (int)c->rowlen, d->recw, (unsigned)d->cap_pair, d->peers,
-                                                                 d->A, d->rank, d->world, d->epoch, d->done_ctr + 1);
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(xgrid); cfg.blockDim = dim3(256); cfg.stream = c->stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at; cfg.numAttrs = pdl_on() ? 1 : 0;  // behind the gradient kernel
+        cudaLaunchKernelEx(&cfg, push_rows_kernel, seg, f->G, f->GS, f->G + c->rowlen, f->GS,
+                           (const uint32_t*)(d->hot_p + (size_t)slot * d->rows_x), f->Ghot, f->GS, (int)c->rowlen, d->recw,
+                           (unsigned)d->cap_pair, d->peers, d->A, d->rank, d->world, d->epoch, d->done_ctr + 1);
     } else {
         push_rows_kernel<<<xgrid, 256, 0, c->stream>>>(seg, d->cgV, (int)c->rowlen, d->cgW, 1, nullptr, nullptr, 0, (int)c->rowlen,
                                                                  d->recw, (unsigned)d->cap_pair, d->peers, d->A, d->rank, d->world, d->epoch,

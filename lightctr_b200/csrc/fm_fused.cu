@@ -151,7 +151,18 @@ static void fused_go(lctr_ctx* c, Slot& s, int64_t rb, int64_t re, int stats, do
                    f->Ghot, f->GS, c->cfg.l2_reg, rb, re, hdr, c->stat_partial, c->stat_done, out_slot, stats, wf, nw, ep
 #define FUSED_LAUNCH(HV)                                                                                                         \
     do {                                                                                                                         \
-        if (mode == 1) fm_fused_kernel<K, HV, 1, false><<<grid, 128, 0, c->stream>>>(FUSED_ARGS);                                \
+        if (mode == 1 && multi && pdl_on()) {  /* several GPUs: dependent on my own serve kernel; polls the owners' flags at its head */ \
+            cudaLaunchConfig_t cfg = {};                                                                                         \
+            cfg.gridDim = dim3(grid); cfg.blockDim = dim3(128); cfg.stream = c->stream;                                          \
+            cudaLaunchAttribute at[1];                                                                                           \
+            at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;                                                       \
+            at[0].val.programmaticStreamSerializationAllowed = 1;                                                                \
+            cfg.attrs = at; cfg.numAttrs = 1;                                                                                    \
+            cudaLaunchKernelEx(&cfg, fm_fused_kernel<K, HV, 1, false>, (const int64_t*)s.row_ptr, (const uint32_t*)s.ent_pslot,  \
+                               (const uint32_t*)s.ent_slot, (const float*)s.val, (const float*)s.label, (const float*)c->cW,   \
+                               (const float*)c->cV, s.pred, s.sumvx, (float*)nullptr, f->G, f->Ghot, f->GS, c->cfg.l2_reg, rb, re, hdr, \
+                               c->stat_partial, c->stat_done, out_slot, stats, wf, nw, ep, (float*)nullptr, (float*)nullptr);    \
+        } else if (mode == 1) fm_fused_kernel<K, HV, 1, false><<<grid, 128, 0, c->stream>>>(FUSED_ARGS);                         \
         else if (mode == 2) fm_fused_kernel<K, HV, 2, false><<<grid, 128, 0, c->stream>>>(FUSED_ARGS, c->z, s.wide);             \
         else {  /* NFM backward: dependent on the dense kernels in front of it (it requests its batch data before their end) */ \
             cudaLaunchConfig_t cfg = {};                                                                                         \
