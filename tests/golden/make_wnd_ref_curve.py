@@ -55,7 +55,7 @@ def free_port():
 UPDATERS = ["sgd", "adagrad", "dcasgd", "dcasgda"]  # paramserver.h:22-27; the reference's main.cpp runs the first
 
 
-def run_cluster(prefix, tmp, epochs, seed_ps, seed_worker, updater):
+def run_cluster(prefix, tmp, epochs, seed_ps, seed_worker, updater, timeout=600):
     env = dict(os.environ, LightCTR_PS_NUM="1", LightCTR_WORKER_NUM="1", LightCTR_MASTER_ADDR="127.0.0.1:%d" % free_port())
     logs = {r: open(os.path.join(tmp, r + ".log"), "w") for r in ("master", "ps")}
     procs = []
@@ -65,7 +65,7 @@ def run_cluster(prefix, tmp, epochs, seed_ps, seed_worker, updater):
         procs.append(subprocess.Popen([os.path.join(REF, "role_ps"), str(seed_ps), str(updater)], env=env, stdout=logs["ps"], stderr=subprocess.STDOUT))
         time.sleep(1.0)
         out = subprocess.run([os.path.join(REF, "role_worker"), str(seed_worker), prefix, str(epochs)], env=env, capture_output=True,
-                             text=True, timeout=1800).stdout
+                             text=True, timeout=timeout).stdout
     finally:
         for p in procs:
             p.send_signal(signal.SIGKILL)

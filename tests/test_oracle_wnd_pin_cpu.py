@@ -95,7 +95,7 @@ def test_committed_curve_is_what_the_reference_prints(tmp_path):
     prefix = str(tmp_path / "ad_data")
     write_libffm(ds, prefix + "_1.csv")
     try:
-        loss, acc, skip_ps, skip_w = gen.run_cluster(prefix, str(tmp_path), 2, g["seed_ps"], g["seed_worker"], 0)
+        loss, acc, skip_ps, skip_w = gen.run_cluster(prefix, str(tmp_path), 2, g["seed_ps"], g["seed_worker"], 0, timeout=120)
     except (OSError, subprocess.SubprocessError, AssertionError) as e:  # no loopback networking / libzmq on this box
         pytest.skip("could not run the reference cluster here: %r" % (e,))
     assert (skip_ps, skip_w) == (g["ps_rand_skip"], g["worker_rand_skip"])
