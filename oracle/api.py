@@ -105,6 +105,8 @@ def lib():
     L.orc_auc.restype = C.c_float
     L.orc_murmur_u64.argtypes = [C.c_uint64]
     L.orc_murmur_u64.restype = C.c_uint32
+    L.orc_dht_node.argtypes = [C.c_uint64, C.c_uint32]
+    L.orc_dht_node.restype = C.c_uint32
     L.orc_ring_segments.argtypes = [C.c_size_t, C.c_size_t, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
     L.orc_ring_allreduce.argtypes = [C.POINTER(C.POINTER(C.c_float)), C.c_size_t, C.c_size_t, C.c_int]
     _lib = L

@@ -871,6 +871,47 @@ uint32_t orc_murmur_u64(uint64_t k) { /* hash.h:51-58 */
     k ^= k >> 33; k *= 0xff51afd7ed558ccdULL; k ^= k >> 33; k *= 0xc4ceb9fe1a85ec53ULL; k ^= k >> 33;
     return (uint32_t)k;
 }
+uint32_t orc_murmur_str(const char* key, int len) { /* hash.h:16-49 (MurmurHash2, seed 97) */
+    const uint32_t m = 0x5bd1e995u; const int r = 24;
+    uint32_t h = 97u ^ (uint32_t)len;
+    const unsigned char* data = (const unsigned char*)key;
+    while (len >= 4) {
+        uint32_t k; memcpy(&k, data, 4);
+        k *= m; k ^= k >> r; k *= m; h *= m; h ^= k;
+        data += 4; len -= 4;
+    }
+    switch (len) {
+        case 3: h ^= (uint32_t)data[2] << 16; /* fall through */
+        case 2: h ^= (uint32_t)data[1] << 8;  /* fall through */
+        case 1: h ^= data[0]; h *= m;
+    }
+    h ^= h >> 13; h *= m; h ^= h >> 15;
+    return h;
+}
+/* ConsistentHash::getNode (distribut/consistent_hash.h:29-40,51-60): the ring holds 5 virtual nodes per server at
+ * murMurHash("<server>-<replica>") (a later insert at the same position overwrites, std::map::operator[]); a key goes to the
+ * first virtual node at or after murMurHash(key), wrapping to the ring's first.  Pinned: tests/golden/dht_nodes.json comes
+ * from the reference class itself (oracle/dht_nodes.cpp). */
+uint32_t orc_dht_node(uint64_t key, uint32_t node_cnt) {
+    uint32_t pos[5 * 64], srv[5 * 64]; int n = 0;
+    if (node_cnt > 64) node_cnt = 64;
+    for (uint32_t i = 0; i < node_cnt; i++)
+        for (uint32_t j = 0; j < 5; j++) {
+            char buf[32];
+            int len = snprintf(buf, sizeof(buf), "%u-%u", i, j);
+            uint32_t p = orc_murmur_str(buf, len);
+            int at = -1;
+            for (int t = 0; t < n; t++) if (pos[t] == p) at = t;
+            if (at >= 0) srv[at] = i; else { pos[n] = p; srv[n] = i; n++; }
+        }
+    const uint32_t part = orc_murmur_u64(key);
+    int best = -1, first = 0;
+    for (int t = 0; t < n; t++) {
+        if (pos[t] < pos[first]) first = t;
+        if (pos[t] >= part && (best < 0 || pos[t] < pos[best])) best = t;
+    }
+    return srv[best >= 0 ? best : first];
+}
 void orc_ring_segments(size_t P, size_t R, size_t* seg_size, size_t* seg_end) { /* ring_collect.h:86-109 */
     size_t s = P / R, res = P % R;
     for (size_t i = 0; i < R; i++) {
