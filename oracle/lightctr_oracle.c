@@ -921,7 +921,9 @@ void orc_ring_segments(size_t P, size_t R, size_t* seg_size, size_t* seg_end) { 
 }
 void orc_ring_allreduce(float** bufs, size_t R, size_t P, int do_average) {
     /* reduce_step ring_collect.h:114-165: at step i rank r sends segment (r - i) mod R to rank r+1,
-     * which adds it into its own copy (avx_vecAdd(buffer, begin, begin): received + local). */
+     * which adds it into its own copy (avx_vecAdd(buffer, begin, begin): received + local).
+     * PINNED bit for bit against real runs of the reference's ring master + R worker processes
+     * (oracle/ref_ring_driver.cpp, tests/golden/ring_allreduce.json, tests/test_oracle_ring_cpu.py). */
     size_t* ss = (size_t*)malloc(sizeof(size_t) * R), *se = (size_t*)malloc(sizeof(size_t) * R);
     orc_ring_segments(P, R, ss, se);
     float* wire = (float*)malloc(sizeof(float) * (P / R + 1) * R);
